@@ -1,0 +1,218 @@
+/*
+ * tinyopt_b200.h — C-ABI of the B200-native batched dense-NLLS Levenberg-Marquardt hot path.
+ *
+ * The reference (julien-michot/tinyopt, header-only C++ on Eigen) has no FFI of its own; its
+ * extension seam is the `SolverType` concept consumed by `Optimizer_<SolverType>`
+ * (include/tinyopt/optimizers/optimizer.h:34-43).  Every entry point below names the reference
+ * interface it replaces (paths relative to /root/reference/include/tinyopt/).  INTEGRATION.md shows
+ * the binding a tinyopt maintainer would add on their side.
+ *
+ * Conventions: plain pointers and sizes only; return 0 (TOB200_OK) or a negative tob200_status;
+ * nothing throws across the ABI; all data pointers are DEVICE pointers owned by the caller unless
+ * the name says `_host`; calls are asynchronous on the context's stream (tob200_sync to wait);
+ * one context per GPU, a context is not thread-safe, different contexts are independent.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * TOB200_ERR_CUDA.
+ */
+#ifndef TINYOPT_B200_H
+#define TINYOPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOB200_VERSION 100 /* 0.1.0 */
+
+typedef enum tob200_status {
+  TOB200_OK = 0,
+  TOB200_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, misaligned buffer) */
+  TOB200_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
+  TOB200_ERR_UNSUPPORTED = -3, /* shape / dtype has no kernel (see tob200_kernel_family) */
+  TOB200_ERR_NOMEM = -4        /* device allocation failed (reference: kOutOfMemory) */
+} tob200_status;
+
+typedef enum tob200_dtype { TOB200_F32 = 0, TOB200_F64 = 1 } tob200_dtype;
+
+/* Memory layout of a batch of residual blocks J (m x n per problem) and r (m per problem).
+ *   TILE32        : problems interleaved in tiles of 32 — J[tile][i][j][lane], r[tile][i][lane],
+ *                   problem p = 32*tile + lane.  Buffers hold ceil(B/32) full tiles
+ *                   (tob200_tiled_elems); pad lanes are never read back.  Native layout: one
+ *                   contiguous TMA bulk copy per row chunk, conflict-free shared-memory reads.
+ *   PROBLEM_MAJOR : J[p][i][j] (row i = d r_i / d x, the rows `J.row(i) = res[i].v` gathers in
+ *                   diff/optimize_autodiff.h:127-148), r[p][i].  Re-tiled on the device first. */
+typedef enum tob200_layout { TOB200_LAYOUT_TILE32 = 0, TOB200_LAYOUT_PROBLEM_MAJOR = 1 } tob200_layout;
+
+/* stop_reasons.h:14-43 (same values) */
+typedef enum tob200_stop_reason {
+  TOB200_STOP_OUT_OF_MEMORY = -4,
+  TOB200_STOP_SOLVER_FAILED = -3,
+  TOB200_STOP_SYSTEM_HAS_NAN_OR_INF = -2,
+  TOB200_STOP_SKIPPED = -1,
+  TOB200_STOP_NONE = 0,
+  TOB200_STOP_MIN_ERROR = 1,
+  TOB200_STOP_MIN_REL_ERROR = 2,
+  TOB200_STOP_MIN_DELTA_NORM = 3,
+  TOB200_STOP_MIN_GRAD_NORM = 4,
+  TOB200_STOP_MAX_ITERS = 5,
+  TOB200_STOP_MAX_NO_DECR = 6,
+  TOB200_STOP_MAX_CONSEC_NO_DECR = 7,
+  TOB200_STOP_TIMED_OUT = 8,
+  TOB200_STOP_USER_STOPPED = 9
+} tob200_stop_reason;
+
+/* POD mirror of the numeric subset of tinyopt::Options (optimizers/options.h:18-156), same
+ * defaults (tob200_options_default).  Thresholds are `float` as in the reference and are widened
+ * at the point of use exactly where the reference widens them. */
+typedef struct tob200_options {
+  int32_t solver_type;             /* options.h:24-30: 0 LevenbergMarquardt, 1 GaussNewton */
+  int32_t check_final_cost;        /* options.h:43 */
+  int32_t use_step_quality_approx; /* options.h:46 */
+  float grad_clipping;             /* options.h:49 */
+  int32_t use_ldlt;                /* options.h:59 (only use_ldlt = 1 is implemented) */
+  int32_t H_is_full;               /* options.h:61 */
+  float check_min_H_diag;          /* options.h:63 */
+  int32_t save_last;               /* options.h:66 */
+  int32_t use_squared_norm;        /* options.h:76 */
+  int32_t downscale_by_2;          /* options.h:77 */
+  int32_t normalize;               /* options.h:79 */
+  int32_t max_iters;               /* options.h:89 */
+  float min_error;                 /* options.h:90 */
+  float min_rerr_dec;              /* options.h:91 */
+  float min_step_norm2;            /* options.h:92 */
+  float min_grad_norm2;            /* options.h:93 */
+  int32_t max_total_failures;      /* options.h:94 */
+  int32_t max_consec_failures;     /* options.h:95 */
+  float damping_init;              /* options.h:133 */
+  float damping_min;               /* options.h:136 */
+  float damping_max;               /* options.h:136 */
+  float good_factor;               /* options.h:138 */
+  float bad_factor;                /* options.h:139 */
+} tob200_options;
+
+/* POD subset of tinyopt::Output (output.h:122-142), one per problem. */
+typedef struct tob200_result {
+  double final_cost;           /* Output::final_cost.cost */
+  double final_rerr_dec;       /* Output::final_rerr_dec */
+  double last_lambda;          /* SolverLM::lambda_ at exit (solvers/lm.h:191) */
+  double last_prev_lambda;     /* SolverLM::prev_lambda_ at exit (solvers/lm.h:192) */
+  int32_t final_num_residuals; /* Output::final_cost.num_resisuals */
+  int32_t stop_reason;         /* Output::stop_reason, tob200_stop_reason */
+  int32_t num_iters;           /* Output::num_iters (Step calls) */
+  int32_t num_failures;        /* Output::num_failures */
+  int32_t num_consec_failures; /* Output::num_consec_failures */
+  int32_t num_builds;          /* passes that rebuilt H and g (the rest were cost-only) */
+} tob200_result;
+
+typedef struct tob200_ctx tob200_ctx;
+typedef struct tob200_solver tob200_solver;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int tob200_version(void);
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on, or NULL to let the context own one. */
+int tob200_create(tob200_ctx **out, int device, void *stream);
+int tob200_destroy(tob200_ctx *ctx);
+int tob200_sync(tob200_ctx *ctx);
+/* Message of the last failure on this context (ctx == NULL: last failure of tob200_create). */
+const char *tob200_last_error(const tob200_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t tob200_launch_count(const tob200_ctx *ctx);
+/* Device time in ms of the last compute entry point (CUDA events on the context's stream;
+ * blocks until that work has finished). */
+int tob200_last_elapsed_ms(tob200_ctx *ctx, float *ms);
+
+void tob200_options_default(tob200_options *opt); /* == tinyopt::Options{} */
+
+/* Elements (not bytes) of a TILE32 buffer: ceil(B/32)*32*m*n.  r / y buffers: n = 1. */
+int64_t tob200_tiled_elems(int64_t B, int m, int n);
+/* Which kernel family serves (dtype, n): 1 thread-per-problem registers (small n),
+ * 2 warp-per-problem shared-memory tiles (mid n), 0 none. */
+int tob200_kernel_family(int dtype, int n);
+
+/* ---- layout ----------------------------------------------------------------------------------- */
+/* src[B][m][n] (problem-major) -> dst TILE32.  Use n = 1 for r / y. */
+int tob200_retile_f32(tob200_ctx *ctx, const float *src, int64_t B, int m, int n, float *dst);
+int tob200_retile_f64(tob200_ctx *ctx, const double *src, int64_t B, int m, int n, double *dst);
+
+/* ---- a1+a3+a5+a6: one Build + Solve for a batch of materialised residual blocks ---------------
+ * Replaces, per problem: `grad = J^T r; H = J^T J` (diff/optimize_autodiff.h:151-157, cost :164),
+ * SolverLM::Build's damping `H_ii *= 1 + lambda` (solvers/lm.h:108-117) and SolverGN::Solve ->
+ * SolveLDLT(H, -grad) (solvers/gn.h:150-156, math.h:232-240).
+ *   lambda : [B] per-problem damping, or NULL for Gauss-Newton (no damping)
+ *   dx     : [B][n]     cost : [B] (= |r|^2 accumulated in T, widened)     status : [B]
+ *            status 0 ok, 1 LDLT rejected (info != Success or not positive; dx untouched)
+ *   H_out  : optional [B][n][n] damped H_, full symmetric, row-major   g_out : optional [B][n] */
+int tob200_build_solve_f32(tob200_ctx *ctx, const float *J, const float *r, int layout, int64_t B,
+                           int m, int n, const float *lambda, float *dx, double *cost,
+                           float *H_out, float *g_out, int32_t *status);
+int tob200_build_solve_f64(tob200_ctx *ctx, const double *J, const double *r, int layout,
+                           int64_t B, int m, int n, const double *lambda, double *dx, double *cost,
+                           double *H_out, double *g_out, int32_t *status);
+
+/* ---- a7-a10: the whole LM loop, device resident, for the polynomial residual family ------------
+ * r_i(x) = t_i + alpha t_i^3 - y_i, t = A x.  One call == one tinyopt::Optimize()
+ * per problem (optimizers/optimizer.h:243-327 OptimizeAcc + :332-539 Step + solvers/lm.h), the
+ * Jacobian (1 + 3 alpha t_i^2) a_i^T is formed on the fly so J never exists in HBM.
+ *   A : TILE32 or PROBLEM_MAJOR [B][m][n]    y : same layout, [B][m]
+ *   x : [B][n] in (x0) / out (solution)      results : [B] */
+int tob200_lm_run_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y,
+                      float alpha, int layout, int64_t B, int m, int n, float *x,
+                      tob200_result *results);
+int tob200_lm_run_f64(tob200_ctx *ctx, const tob200_options *opt, const double *A, const double *y,
+                      double alpha, int layout, int64_t B, int m, int n, double *x,
+                      tob200_result *results);
+/* Same call with HOST buffers (pageable or pinned): H2D of A, y, x0, the run, D2H of x and
+ * results, all inside; returns when the results are in host memory. */
+int tob200_lm_run_host_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A_host,
+                           const float *y_host, float alpha, int layout, int64_t B, int m, int n,
+                           float *x_host, tob200_result *results_host);
+int tob200_lm_run_host_f64(tob200_ctx *ctx, const tob200_options *opt, const double *A_host,
+                           const double *y_host, double alpha, int layout, int64_t B, int m, int n,
+                           double *x_host, tob200_result *results_host);
+
+/* ---- the SolverType seam for user-evaluated residuals (host-driven loop) -----------------------
+ * A batched `Optimizer_<SolverLM>` whose per-problem state (x, lambda_, prev_lambda_, bad_factor_,
+ * rebuild flag, H_, grad_, Output counters) lives on the device.  Each tob200_solver_step is one
+ * Optimizer_::Step + the OptimizeAcc update (optimizer.h:266-309) for every still-running problem,
+ * fed with the residual blocks the caller's lambda produced at the current x. */
+int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob200_options *opt,
+                         tob200_solver **out);
+int tob200_solver_destroy(tob200_solver *s);
+/* Reset all problems (solvers/lm.h:46-52 reset()) and set x <- x0 ([B][n], device). */
+int tob200_solver_reset(tob200_solver *s, const void *x0);
+/* Device pointer to the current x [B][n] (dtype of the solver). */
+void *tob200_solver_x(tob200_solver *s);
+/* Device pointer to [B] int32: 1 = the next step must carry J for this problem (rebuild),
+ * 0 = cost-only (r suffices), -1 = finished. */
+const int32_t *tob200_solver_needs(tob200_solver *s);
+int tob200_solver_step_f32(tob200_solver *s, const float *J, const float *r, int layout, int m);
+int tob200_solver_step_f64(tob200_solver *s, const double *J, const double *r, int layout, int m);
+/* Number of problems still running (synchronises the stream). */
+int tob200_solver_num_active(tob200_solver *s, int64_t *n_active);
+/* Copy the per-problem results to `results` ([B], device). */
+int tob200_solver_results(tob200_solver *s, tob200_result *results);
+/* Final un-damped Hessian (solvers/lm.h:157-171 Hessian()) as doubles, [B][n][n] device. */
+int tob200_solver_final_hessian(tob200_solver *s, double *H);
+
+/* ---- synthetic problem family, generated on the device (bit-identical to the CPU oracle's) ----
+ * Any output may be NULL.  A, y in `layout`; xstar, x0: [B][n]. */
+int tob200_synth_generate_f32(tob200_ctx *ctx, uint64_t seed, int64_t p0, int64_t B, int m, int n,
+                              float alpha, float sigma, int layout, float *A, float *y,
+                              float *xstar, float *x0);
+int tob200_synth_generate_f64(tob200_ctx *ctx, uint64_t seed, int64_t p0, int64_t B, int m, int n,
+                              double alpha, double sigma, int layout, double *A, double *y,
+                              double *xstar, double *x0);
+/* Residual blocks of the family at x: r and J in `layout` (what a user lambda + AD would hand to
+ * tob200_build_solve / tob200_solver_step). */
+int tob200_synth_eval_f32(tob200_ctx *ctx, const float *A, const float *y, float alpha, int layout,
+                          int64_t B, int m, int n, const float *x, float *r, float *J);
+int tob200_synth_eval_f64(tob200_ctx *ctx, const double *A, const double *y, double alpha,
+                          int layout, int64_t B, int m, int n, const double *x, double *r,
+                          double *J);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYOPT_B200_H */

@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs.  Run on the B200 box with `pytest -m gpu`.
+
+Bars (BASELINE.json north_star): dx within 1e-10 relative (double) / 1e-4 (float), iteration
+counts identical.  The thread-per-problem kernels implement the oracle's canonical op sequence
+(DESIGN.md §4), so these tests additionally assert BIT equality, which is stronger.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-10, np.float32: 1e-4}
+TDT = {np.float64: torch.float64, np.float32: torch.float32}
+
+# float configs run with float-appropriate thresholds (SURVEY.md §7 hard part 2b / §8d)
+FLOAT_OPTS = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import tinyopt_b200 as tb
+    c = tb.Context(0)
+    yield c
+    c.close()
+
+
+def both_options(dtype, **kw):
+    import tinyopt_b200 as tb
+    if dtype == np.float32:
+        kw = {**FLOAT_OPTS, **kw}
+    return O.default_options(**kw), tb.options(**kw)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---- synthetic generator: device == oracle, bit for bit ------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("B,m,n", [(1, 1, 1), (33, 30, 6), (64, 7, 12), (100, 13, 5)])
+def test_synth_generate_bitexact(ctx, dtype, B, m, n):
+    import tinyopt_b200 as tb
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=17)
+    for layout in (tb.TILE32, tb.PROBLEM_MAJOR):
+        dA, dy, dxs, dx0 = ctx.synth_generate(B, m, n, TDT[dtype], p0=17, layout=layout)
+        if layout == tb.TILE32:
+            dA, dy = tb.from_tile32(dA, B), tb.from_tile32(dy, B)
+        assert np.array_equal(dA.cpu().numpy(), A)
+        assert np.array_equal(dy.cpu().numpy(), y)
+        assert np.array_equal(dxs.cpu().numpy(), xs)
+        assert np.array_equal(dx0.cpu().numpy(), x0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_retile_roundtrip(ctx, dtype):
+    import tinyopt_b200 as tb
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand((70, 9, 5), generator=g, dtype=TDT[dtype]).cuda()
+    t = ctx.retile(a)
+    assert torch.equal(t, tb.to_tile32(a))
+    assert torch.equal(tb.from_tile32(t, 70), a)
+    r = torch.rand((70, 9), generator=g, dtype=TDT[dtype]).cuda()
+    assert torch.equal(ctx.retile(r), tb.to_tile32(r))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_synth_eval_bitexact(ctx, dtype):
+    import tinyopt_b200 as tb
+    B, m, n = 70, 11, 4
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype)
+    r, J = O.synth_eval(A, y, x0)
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, TDT[dtype], layout=tb.TILE32)
+    dr, dJ = ctx.synth_eval(dA, dy, dx0, layout=tb.TILE32)
+    assert np.array_equal(tb.from_tile32(dr, B).cpu().numpy(), r)
+    assert np.array_equal(tb.from_tile32(dJ, B).cpu().numpy(), J)
+
+
+# ---- a1+a3+a5+a6: one Build+Solve -----------------------------------------------------------------
+SHAPES64 = [(1, 1, 1), (37, 5, 2), (96, 30, 6), (1000, 30, 6), (65, 40, 8), (50, 9, 3), (40, 3, 7)]
+SHAPES32 = SHAPES64 + [(500, 200, 12), (70, 50, 9), (33, 25, 11), (64, 64, 10)]
+
+
+def oracle_build_solve_batch(J, r, lam):
+    B, m, n = J.shape
+    dx = np.zeros((B, n), J.dtype); cost = np.zeros(B); st = np.zeros(B, np.int32)
+    H = np.zeros((B, n, n), J.dtype); g = np.zeros((B, n), J.dtype)
+    for b in range(B):
+        o = O.build_solve(J[b], r[b], float(lam[b]))
+        dx[b], cost[b], st[b], H[b], g[b] = o["dx"], o["cost"], o["status"], o["H"], o["g"]
+    return dx, cost, st, H, g
+
+
+@pytest.mark.parametrize("dtype,shapes", [(np.float64, SHAPES64), (np.float32, SHAPES32)])
+def test_build_solve_parity(ctx, dtype, shapes):
+    import tinyopt_b200 as tb
+    for (B, m, n) in shapes:
+        A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=5)
+        r, J = O.synth_eval(A, y, x0)
+        lam = np.full(B, np.float32(1e-4), dtype)
+        lam[::3] = 0  # Gauss-Newton rows
+        lam[1::7] = dtype(0.5)
+        dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+        for layout in (tb.PROBLEM_MAJOR, tb.TILE32):
+            Jd, rd = torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda()
+            if layout == tb.TILE32:
+                Jd, rd = tb.to_tile32(Jd), tb.to_tile32(rd)
+            out = ctx.build_solve(Jd, rd, torch.from_numpy(lam).cuda(), B=B, layout=layout, want_H=True, want_g=True)
+            ctx.sync()
+            assert np.array_equal(out["status"].cpu().numpy(), st), (B, m, n)
+            # the stated bar
+            assert rel_err(out["dx"].cpu().numpy(), dx) <= TOL[dtype], (B, m, n)
+            assert rel_err(out["cost"].cpu().numpy(), cost) <= TOL[dtype]
+            # the stronger property of this kernel family: same op sequence -> same bits
+            assert np.array_equal(out["dx"].cpu().numpy(), dx), (B, m, n, layout)
+            assert np.array_equal(out["cost"].cpu().numpy(), cost)
+            assert np.array_equal(out["g"].cpu().numpy(), g)
+            assert np.array_equal(out["H"].cpu().numpy(), H)
+
+
+def test_build_solve_edge_cases(ctx):
+    """zero J (H == 0: Eigen's all-zero-diagonal branch -> success, dx = 0), NaN in J (-> status 1),
+    rank-deficient J with and without damping (tests/types.cpp:94-108 situation)."""
+    import tinyopt_b200 as tb
+    B, m, n = 4, 6, 6
+    J = np.zeros((B, m, n)); r = np.ones((B, m))
+    Jt = np.array([[1, 0, 1, 0, 1, 0], [0, 1, 0, 1, 0, 1]], float)
+    J[1, :2] = Jt                      # rank 2, undamped: PSD-singular
+    J[2, :2] = Jt                      # rank 2, damped
+    J[3, 0, 0] = np.nan
+    lam = np.array([0, 0, 1e-4, 0.0])
+    dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+    out = ctx.build_solve(torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(lam).cuda())
+    ctx.sync()
+    assert np.array_equal(out["status"].cpu().numpy(), st)
+    assert list(st) == [0, 0, 0, 1]
+    ok = st == 0
+    assert np.array_equal(out["dx"].cpu().numpy()[ok], dx[ok])
+    assert np.all(dx[0] == 0)
+
+
+# ---- a7-a10: the whole LM loop ---------------------------------------------------------------------
+def run_both(ctx, dtype, B, m, n, layout=None, p0=0, **optkw):
+    import tinyopt_b200 as tb
+    layout = tb.TILE32 if layout is None else layout
+    oo, go = both_options(dtype, **optkw)
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=p0)
+    xo, ro, _ = O.synth_lm_run(A, y, x0, oo)
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, TDT[dtype], p0=p0, layout=layout)
+    out = ctx.optimize_batch(dA, dy, dx0, go, layout=layout)
+    return xo, ro, out
+
+
+def assert_lm_parity(dtype, xo, ro, out, exact=True):
+    rg = out.results
+    assert np.array_equal(rg["num_iters"], ro["num_iters"])          # iteration counts identical
+    assert np.array_equal(rg["stop_reason"], ro["stop_reason"])
+    assert np.array_equal(rg["num_failures"], ro["num_failures"])
+    xg = out.x.cpu().numpy()
+    assert rel_err(xg, xo) <= TOL[dtype]
+    assert rel_err(rg["final_cost"], ro["final_cost"]) <= TOL[dtype]
+    if exact:
+        assert np.array_equal(xg, xo)
+        assert np.array_equal(rg["final_cost"], ro["final_cost"])
+        assert np.array_equal(rg["last_lambda"], ro["last_lambda"])
+        assert np.array_equal(rg["final_rerr_dec"], ro["final_rerr_dec"])
+
+
+@pytest.mark.parametrize("B,m,n", [(2000, 30, 6), (33, 30, 6), (1, 4, 1), (257, 12, 3), (100, 20, 8), (64, 9, 7)])
+def test_lm_run_parity_f64(ctx, B, m, n):
+    """config C2 shape (n=6, m=30, double, tinyopt default options) and neighbours."""
+    xo, ro, out = run_both(ctx, np.float64, B, m, n)
+    assert_lm_parity(np.float64, xo, ro, out)
+    assert (ro["stop_reason"] > 0).all()
+
+
+@pytest.mark.parametrize("B,m,n", [(1000, 200, 12), (45, 200, 12), (300, 50, 10), (128, 30, 6), (77, 17, 11), (10, 5, 1)])
+def test_lm_run_parity_f32(ctx, B, m, n):
+    """config C3 shape (n=12, m=200, float, float-tuned thresholds) and neighbours."""
+    xo, ro, out = run_both(ctx, np.float32, B, m, n)
+    assert_lm_parity(np.float32, xo, ro, out)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_lm_run_default_options_stress(ctx, dtype):
+    """float with tinyopt's *default* (double-scaled) thresholds runs into the fp32 noise floor:
+    rejects, roll-backs, eval-only passes with a stale re-damped H.  Because the op
+    sequence is identical this must still agree exactly."""
+    import tinyopt_b200 as tb
+    B, m, n = 512, 40, 6
+    oo, go = O.default_options(), tb.options()
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=99)
+    xo, ro, _ = O.synth_lm_run(A, y, x0, oo)
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, TDT[dtype], p0=99)
+    out = ctx.optimize_batch(dA, dy, dx0, go)
+    assert_lm_parity(dtype, xo, ro, out)
+    if dtype == np.float32:
+        assert (out.results["num_builds"] < out.results["num_iters"]).any()  # eval-only passes happened
+
+
+@pytest.mark.parametrize("optkw", [
+    dict(solver_type=1),                                   # Gauss-Newton
+    dict(max_iters=2),                                     # kMaxIters
+    dict(downscale_by_2=1, normalize=1),                   # cost scaling (base.h:41-45)
+    dict(use_squared_norm=0),
+    dict(damping_init=10.0, max_consec_failures=2),
+    dict(grad_clipping=0.05),
+    dict(check_min_H_diag=1e3),                            # Build fails -> kSolverFailed
+    dict(min_error=1.0),                                   # kMinError at once
+    dict(max_total_failures=1, min_step_norm2=0, min_rerr_dec=0, min_error=0, min_grad_norm2=0),
+    dict(check_final_cost=1, max_iters=3),
+    dict(use_step_quality_approx=1),
+])
+def test_lm_run_option_variants(ctx, optkw):
+    xo, ro, out = run_both(ctx, np.float64, 200, 30, 6, **optkw)
+    # use_step_quality_approx goes through pow(): tolerance-level only (documented)
+    assert_lm_parity(np.float64, xo, ro, out, exact="use_step_quality_approx" not in optkw)
+
+
+def test_lm_run_layouts_agree(ctx):
+    import tinyopt_b200 as tb
+    xo, ro, out_t = run_both(ctx, np.float64, 100, 30, 6, layout=tb.TILE32)
+    _, _, out_p = run_both(ctx, np.float64, 100, 30, 6, layout=tb.PROBLEM_MAJOR)
+    assert torch.equal(out_t.x, out_p.x)
+    assert np.array_equal(out_t.results, out_p.results)
+
+
+def test_lm_run_no_residuals_and_errors(ctx):
+    """m == 0 -> kSkipped (tests/basic.cpp:234-242); unsupported n -> error code, never a fallback."""
+    import tinyopt_b200 as tb
+    B, n = 40, 3
+    x0 = torch.ones((B, n), dtype=torch.float64, device="cuda")
+    res = torch.empty((B, 56), dtype=torch.uint8, device="cuda")
+    # a valid non-null pointer is required even for m == 0
+    dummy = torch.zeros(64, dtype=torch.float64, device="cuda")
+    import ctypes as C
+    rc = ctx._lib.tob200_lm_run_f64(ctx._h, C.byref(tb.options()), C.c_void_p(dummy.data_ptr()),
+                                    C.c_void_p(dummy.data_ptr()), C.c_double(0.1), tb.TILE32, B, 0, n,
+                                    C.c_void_p(x0.data_ptr()), C.c_void_p(res.data_ptr()))
+    assert rc == 0
+    ctx.sync()
+    from tinyopt_b200.api import decode_results
+    r = decode_results(res)
+    assert (r["stop_reason"] == tb.StopReason.kSkipped).all() and (r["num_iters"] == 1).all()
+    assert torch.equal(x0, torch.ones_like(x0))
+    with pytest.raises(tb.TinyoptB200Error):
+        ctx.optimize_batch(torch.zeros((1, 4, 500, 32), device="cuda"), torch.zeros((1, 4, 32), device="cuda"),
+                           torch.zeros((3, 500), device="cuda"))
+
+
+# ---- BASELINE.json config sizes: exact on a slice, properties on the whole batch -------------------
+@pytest.mark.parametrize("dtype,B,m,n", [(np.float64, 100_000, 30, 6), (np.float32, 100_000, 200, 12)])
+def test_full_size_configs(ctx, dtype, B, m, n):
+    """configs[1] (C2) and configs[2] (C3) at full size."""
+    import tinyopt_b200 as tb
+    oo, go = both_options(dtype)
+    dA, dy, dxs, dx0 = ctx.synth_generate(B, m, n, TDT[dtype])
+    out = ctx.optimize_batch(dA, dy, dx0, go)
+    r = out.results
+    assert out.Succeeded().all() and out.Converged().all()
+    # (1) the first and last 2048 problems against the oracle, exactly
+    for lo in (0, B - 2048):
+        A, y, xs, x0 = O.synth_generate(2048, m, n, dtype, p0=lo)
+        xo, ro, _ = O.synth_lm_run(A, y, x0, oo)
+        sl = slice(lo, lo + 2048)
+        assert np.array_equal(r["num_iters"][sl], ro["num_iters"])
+        assert np.array_equal(r["stop_reason"][sl], ro["stop_reason"])
+        assert np.array_equal(out.x[sl].cpu().numpy(), xo)
+    # (2) size-independent properties on all B problems
+    x = out.x
+    err0 = (dx0 - dxs).norm(dim=1)
+    err1 = (x - dxs).norm(dim=1)
+    assert (err1 < err0).float().mean() > 0.999            # moved towards the truth
+    assert err1.max().item() < 0.1                          # noise-limited accuracy (sigma = 1e-2)
+    # first-order optimality: g = J^T r ~ 0 at the solution
+    rr, JJ = ctx.synth_eval(dA, dy, x)
+    bs = ctx.build_solve(JJ, rr, None, B=B, layout=tb.TILE32, want_g=True)
+    ctx.sync()
+    gn = bs["g"].norm(dim=1)
+    assert gn.max().item() < (1e-6 if dtype == np.float64 else 2e-3)
+    # cost reported == cost recomputed from the returned x (the lag of optimizer.h:428: final_cost is
+    # the cost at the last accepted x *before* the final step; the recomputed one can only be lower)
+    assert (bs["cost"].cpu().numpy() <= r["final_cost"] * (1 + 1e-6)).all()
+    # idempotence: restarting from the solution stops at once with a tiny step
+    out2 = ctx.optimize_batch(dA, dy, x, go)
+    assert (out2.results["num_iters"] <= 3).all()
+    assert (out2.x - x).abs().max().item() < (1e-6 if dtype == np.float64 else 1e-3)
+    # total work
+    assert r["num_iters"].sum() == r["num_iters"].astype(np.int64).sum()
+    assert 2 <= r["num_iters"].min() and r["num_iters"].max() <= 12

@@ -1,0 +1,359 @@
+"""Host-side interface of tinyopt_b200 over the C-ABI (ctypes + torch tensors for device memory).
+
+Names follow the reference: `Options` (optimizers/options.h), `Output` (output.h), `StopReason`
+(stop_reasons.h), `Context.optimize_batch` == one `tinyopt::Optimize()` per problem
+(optimize.h:17-77), `BatchSolver` == a batch of `Optimizer_<SolverLM>` driven from the host
+(optimizers/optimizer.h:332-539 Step).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Options  # noqa: F401
+
+TILE32 = 0
+PROBLEM_MAJOR = 1
+
+
+class TinyoptB200Error(RuntimeError):
+    pass
+
+
+class StopReason(enum.IntEnum):
+    """stop_reasons.h:14-43."""
+    kOutOfMemory = -4
+    kSolverFailed = -3
+    kSystemHasNaNOrInf = -2
+    kSkipped = -1
+    kNone = 0
+    kMinError = 1
+    kMinRelError = 2
+    kMinDeltaNorm = 3
+    kMinGradNorm = 4
+    kMaxIters = 5
+    kMaxNoDecr = 6
+    kMaxConsecNoDecr = 7
+    kTimedOut = 8
+    kUserStopped = 9
+
+
+def options(**kw) -> Options:
+    """tinyopt::Options{} with overrides (flattened names: damping_init == lm.damping_init ...)."""
+    o = Options()
+    _lib.load().tob200_options_default(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(f"tinyopt::Options has no numeric field '{k}'")
+        setattr(o, k, v)
+    return o
+
+
+RESULT_DTYPE = np.dtype(_lib.RESULT_FIELDS, align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(_lib.Result)
+
+
+@dataclass
+class Output:
+    """Batched tinyopt::Output (output.h:26-145): one entry per problem."""
+    x: torch.Tensor            # [B, n] solutions (device)
+    results: np.ndarray        # structured array, RESULT_DTYPE, host
+
+    @property
+    def num_iters(self):
+        return self.results["num_iters"]
+
+    @property
+    def stop_reason(self):
+        return self.results["stop_reason"]
+
+    @property
+    def final_cost(self):
+        return self.results["final_cost"]
+
+    def Succeeded(self):  # output.h:30
+        return self.results["stop_reason"] >= 0
+
+    def Converged(self):  # output.h:33-35
+        sr = self.results["stop_reason"]
+        return (sr >= 1) & (sr < 5)
+
+
+def _suf(dtype: torch.dtype) -> str:
+    if dtype == torch.float32:
+        return "f32"
+    if dtype == torch.float64:
+        return "f64"
+    raise TypeError(f"tinyopt_b200 computes in float32 or float64, got {dtype}")
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def to_tile32(a: torch.Tensor) -> torch.Tensor:
+    """[B, m, n] or [B, m] problem-major -> TILE32 [ceil(B/32), m, n, 32] (pure torch; host helper
+    for tests — the library re-tiles PROBLEM_MAJOR inputs itself on the device)."""
+    squeeze = a.dim() == 2
+    if squeeze:
+        a = a.unsqueeze(-1)
+    B, m, n = a.shape
+    nt = (B + 31) // 32
+    pad = torch.zeros((nt * 32, m, n), dtype=a.dtype, device=a.device)
+    pad[:B] = a
+    out = pad.view(nt, 32, m, n).permute(0, 2, 3, 1).contiguous()
+    return out.view(nt, m, 32) if squeeze else out
+
+
+def from_tile32(a: torch.Tensor, B: int) -> torch.Tensor:
+    """Inverse of to_tile32."""
+    if a.dim() == 3:
+        nt, m, _ = a.shape
+        return a.permute(0, 2, 1).reshape(nt * 32, m)[:B].contiguous()
+    nt, m, n, _ = a.shape
+    return a.permute(0, 3, 1, 2).reshape(nt * 32, m, n)[:B].contiguous()
+
+
+class Context:
+    """One tob200_ctx: one GPU, one stream.  Not thread-safe."""
+
+    def __init__(self, device: int | torch.device | None = None, stream: torch.cuda.Stream | None = None):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise TinyoptB200Error("no CUDA device: tinyopt_b200 has no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        h = C.c_void_p()
+        rc = self._lib.tob200_create(C.byref(h), self.device.index or 0, C.c_void_p(self.stream.cuda_stream))
+        if rc != 0:
+            raise TinyoptB200Error(f"tob200_create failed ({rc}): {self._lib.tob200_last_error(None).decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tob200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise TinyoptB200Error(f"{what} failed ({rc}): {self._lib.tob200_last_error(self._h).decode()}")
+
+    def sync(self):
+        self._ck(self._lib.tob200_sync(self._h), "tob200_sync")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.tob200_launch_count(self._h))
+
+    def last_elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        self._ck(self._lib.tob200_last_elapsed_ms(self._h, C.byref(ms)), "tob200_last_elapsed_ms")
+        return float(ms.value)
+
+    def kernel_family(self, dtype: torch.dtype, n: int) -> int:
+        return int(self._lib.tob200_kernel_family(0 if dtype == torch.float32 else 1, n))
+
+    # ---- layout -------------------------------------------------------------------------------
+    def retile(self, a: torch.Tensor) -> torch.Tensor:
+        """PROBLEM_MAJOR [B,m,n] / [B,m] -> TILE32 on the device (tob200_retile_*)."""
+        squeeze = a.dim() == 2
+        B, m = a.shape[0], a.shape[1]
+        n = 1 if squeeze else a.shape[2]
+        a = a.contiguous()
+        nt = (B + 31) // 32
+        out = torch.empty((nt, m, 32) if squeeze else (nt, m, n, 32), dtype=a.dtype, device=a.device)
+        fn = getattr(self._lib, f"tob200_retile_{_suf(a.dtype)}")
+        self._ck(fn(self._h, _p(a), B, m, n, _p(out)), "tob200_retile")
+        return out
+
+    # ---- a1+a3+a5+a6 ----------------------------------------------------------------------------
+    def build_solve(self, J: torch.Tensor, r: torch.Tensor, lam: torch.Tensor | None = None, *,
+                    B: int | None = None, layout: int = PROBLEM_MAJOR, want_H: bool = False, want_g: bool = False):
+        """One Build + Solve per problem from materialised residual blocks.
+
+        PROBLEM_MAJOR: J [B,m,n], r [B,m].  TILE32: J [nt,m,n,32], r [nt,m,32] and B given.
+        Returns dict(dx [B,n], cost [B] f64, status [B] i32, H [B,n,n]?, g [B,n]?).
+        """
+        if layout == PROBLEM_MAJOR:
+            B, m, n = J.shape
+        else:
+            _, m, n, _ = J.shape
+            assert B is not None
+        dt, dev = J.dtype, J.device
+        J = J.contiguous(); r = r.contiguous()
+        dx = torch.zeros((B, n), dtype=dt, device=dev)
+        cost = torch.zeros((B,), dtype=torch.float64, device=dev)
+        status = torch.zeros((B,), dtype=torch.int32, device=dev)
+        H = torch.zeros((B, n, n), dtype=dt, device=dev) if want_H else None
+        g = torch.zeros((B, n), dtype=dt, device=dev) if want_g else None
+        if lam is not None:
+            lam = lam.to(dtype=dt, device=dev).contiguous()
+        fn = getattr(self._lib, f"tob200_build_solve_{_suf(dt)}")
+        self._ck(fn(self._h, _p(J), _p(r), layout, B, m, n, _p(lam), _p(dx), _p(cost), _p(H), _p(g), _p(status)),
+                 "tob200_build_solve")
+        out = dict(dx=dx, cost=cost, status=status)
+        if want_H:
+            out["H"] = H
+        if want_g:
+            out["g"] = g
+        return out
+
+    # ---- a7-a10 ---------------------------------------------------------------------------------
+    def optimize_batch(self, A: torch.Tensor, y: torch.Tensor, x0: torch.Tensor, opt: Options | None = None, *,
+                       alpha: float = 0.1, layout: int = PROBLEM_MAJOR, results: torch.Tensor | None = None,
+                       sync: bool = True) -> Output:
+        """One tinyopt::Optimize() per problem of the polynomial family, device resident
+        (tob200_lm_run_*).  x0 [B,n] is copied; the returned Output holds the solutions."""
+        opt = opt if opt is not None else options()
+        B, n = x0.shape
+        m = A.shape[1]
+        dt, dev = A.dtype, A.device
+        x = x0.to(dtype=dt, device=dev).clone().contiguous()
+        if results is None:
+            results = torch.empty((B, C.sizeof(_lib.Result)), dtype=torch.uint8, device=dev)
+        fn = getattr(self._lib, f"tob200_lm_run_{_suf(dt)}")
+        ct = C.c_float if dt == torch.float32 else C.c_double
+        self._ck(fn(self._h, C.byref(opt), _p(A.contiguous()), _p(y.contiguous()), ct(alpha), layout, B, m, n,
+                    _p(x), _p(results)), "tob200_lm_run")
+        if not sync:
+            return Output(x=x, results=results)  # raw device buffer; caller decodes after sync
+        self.sync()
+        return Output(x=x, results=decode_results(results))
+
+    def optimize_batch_host(self, A: np.ndarray, y: np.ndarray, x: np.ndarray, opt: Options | None = None, *,
+                            alpha: float = 0.1, layout: int = PROBLEM_MAJOR, B: int | None = None,
+                            results: np.ndarray | None = None):
+        """Same through HOST buffers (numpy, ideally pinned): H2D + run + D2H inside
+        (tob200_lm_run_host_*).  x is updated in place; returns the results array."""
+        opt = opt if opt is not None else options()
+        if B is None:
+            B = x.shape[0]
+        n = x.shape[1]
+        m = A.shape[1]
+        if results is None:
+            results = np.zeros(B, RESULT_DTYPE)
+        suf = "f32" if A.dtype == np.float32 else "f64"
+        fn = getattr(self._lib, f"tob200_lm_run_host_{suf}")
+        ct = C.c_float if A.dtype == np.float32 else C.c_double
+        self._ck(fn(self._h, C.byref(opt), A.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), ct(alpha),
+                    layout, B, m, n, x.ctypes.data_as(C.c_void_p), results.ctypes.data_as(C.c_void_p)),
+                 "tob200_lm_run_host")
+        return results
+
+    # ---- synthetic family -----------------------------------------------------------------------
+    def synth_generate(self, B: int, m: int, n: int, dtype: torch.dtype, *, p0: int = 0, seed: int = 20261017,
+                       alpha: float = 0.1, sigma: float = 1e-2, layout: int = TILE32):
+        """A, y (in `layout`), xstar, x0 ([B,n]) generated on the device (tob200_synth_generate_*)."""
+        nt = (B + 31) // 32
+        dev = self.device
+        if layout == TILE32:
+            A = torch.empty((nt, m, n, 32), dtype=dtype, device=dev)
+            y = torch.empty((nt, m, 32), dtype=dtype, device=dev)
+        else:
+            A = torch.empty((B, m, n), dtype=dtype, device=dev)
+            y = torch.empty((B, m), dtype=dtype, device=dev)
+        xs = torch.empty((B, n), dtype=dtype, device=dev)
+        x0 = torch.empty((B, n), dtype=dtype, device=dev)
+        fn = getattr(self._lib, f"tob200_synth_generate_{_suf(dtype)}")
+        ct = C.c_float if dtype == torch.float32 else C.c_double
+        self._ck(fn(self._h, seed, p0, B, m, n, ct(alpha), ct(sigma), layout, _p(A), _p(y), _p(xs), _p(x0)),
+                 "tob200_synth_generate")
+        return A, y, xs, x0
+
+    def synth_eval(self, A: torch.Tensor, y: torch.Tensor, x: torch.Tensor, *, alpha: float = 0.1,
+                   layout: int = TILE32):
+        """Residual blocks r, J of the family at x, in `layout` (tob200_synth_eval_*)."""
+        B, n = x.shape
+        m = A.shape[1]
+        r = torch.empty_like(y)
+        J = torch.empty_like(A)
+        fn = getattr(self._lib, f"tob200_synth_eval_{_suf(A.dtype)}")
+        ct = C.c_float if A.dtype == torch.float32 else C.c_double
+        self._ck(fn(self._h, _p(A), _p(y), ct(alpha), layout, B, m, n, _p(x.contiguous()), _p(r), _p(J)),
+                 "tob200_synth_eval")
+        return r, J
+
+
+def decode_results(buf: torch.Tensor) -> np.ndarray:
+    """Device byte buffer of tob200_result[B] -> host structured array."""
+    return buf.cpu().numpy().view(RESULT_DTYPE).reshape(-1).copy()
+
+
+class BatchSolver:
+    """A batch of `Optimizer_<SolverLM>` whose state lives on the device; the caller evaluates the
+    residual blocks (its own lambda, AD, ...) at `x` and feeds them to `step`."""
+
+    def __init__(self, ctx: Context, B: int, n: int, dtype: torch.dtype, opt: Options | None = None):
+        self.ctx, self.B, self.n, self.dtype = ctx, B, n, dtype
+        self.opt = opt if opt is not None else options()
+        h = C.c_void_p()
+        ctx._ck(ctx._lib.tob200_solver_create(ctx._h, 0 if dtype == torch.float32 else 1, B, n,
+                                              C.byref(self.opt), C.byref(h)), "tob200_solver_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.tob200_solver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, x0: torch.Tensor):
+        x0 = x0.to(dtype=self.dtype, device=self.ctx.device).contiguous()
+        self.ctx._ck(self.ctx._lib.tob200_solver_reset(self._h, _p(x0)), "tob200_solver_reset")
+
+    def _wrap(self, ptr: int, shape, dtype):
+        """Zero-copy torch view of solver-owned device memory."""
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Holder(), device=self.ctx.device)
+
+    @property
+    def x(self) -> torch.Tensor:
+        """View of the solver's current x [B, n] (device memory owned by the solver)."""
+        return self._wrap(self.ctx._lib.tob200_solver_x(self._h), (self.B, self.n), self.dtype)
+
+    @property
+    def needs(self) -> torch.Tensor:
+        """[B] int32: 1 rebuild (J and r), 0 cost only (r), -1 finished."""
+        return self._wrap(self.ctx._lib.tob200_solver_needs(self._h), (self.B,), torch.int32)
+
+    def step(self, J: torch.Tensor, r: torch.Tensor, layout: int = PROBLEM_MAJOR):
+        m = r.shape[1]
+        fn = getattr(self.ctx._lib, f"tob200_solver_step_{_suf(self.dtype)}")
+        self.ctx._ck(fn(self._h, _p(J.contiguous()), _p(r.contiguous()), layout, m), "tob200_solver_step")
+
+    def num_active(self) -> int:
+        v = C.c_int64(0)
+        self.ctx._ck(self.ctx._lib.tob200_solver_num_active(self._h, C.byref(v)), "tob200_solver_num_active")
+        return int(v.value)
+
+    def results(self) -> np.ndarray:
+        buf = torch.empty((self.B, C.sizeof(_lib.Result)), dtype=torch.uint8, device=self.ctx.device)
+        self.ctx._ck(self.ctx._lib.tob200_solver_results(self._h, _p(buf)), "tob200_solver_results")
+        self.ctx.sync()
+        return decode_results(buf)
+
+    def final_hessian(self) -> torch.Tensor:
+        H = torch.empty((self.B, self.n, self.n), dtype=torch.float64, device=self.ctx.device)
+        self.ctx._ck(self.ctx._lib.tob200_solver_final_hessian(self._h, _p(H)), "tob200_solver_final_hessian")
+        return H

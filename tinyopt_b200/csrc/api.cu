@@ -1,0 +1,661 @@
+// api.cu — the C-ABI of include/tinyopt_b200.h: context, argument checking, kernel selection and
+// launch.  No CPU fallback anywhere: every compute entry point either launches a CUDA kernel or
+// returns an error.
+#include "../../include/tinyopt_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "internal.h"
+#include "tpp_inst.cuh"
+
+using namespace tob200;
+
+static thread_local std::string g_create_error;
+
+struct tob200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  std::string err;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch for PROBLEM_MAJOR -> TILE32 conversion and for the *_host entry points
+  void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::map<std::tuple<int, int, int, int, size_t>, int> occupancy;  // (dtype, n, kind, block, smem) -> CTAs/SM
+  // tuning knobs (env: TOB200_TPP_STAGE_BYTES, TOB200_TPP_WARPS, TOB200_TPP_CTAS_PER_SM)
+  int tpp_stage_bytes = 4096;
+  int tpp_warps = 4;
+  int tpp_ctas_per_sm = 0;  // 0: occupancy limit
+};
+
+namespace {
+
+int fail(tob200_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+int fail_cuda(tob200_ctx *ctx, cudaError_t e, const char *what) {
+  return fail(ctx, e == cudaErrorMemoryAllocation ? TOB200_ERR_NOMEM : TOB200_ERR_CUDA,
+              std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(expr)                                                 \
+  do {                                                           \
+    cudaError_t e__ = (expr);                                    \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #expr);   \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+int ensure_scratch(tob200_ctx *ctx, int slot, size_t bytes) {
+  if (ctx->scratch_bytes[slot] >= bytes) return TOB200_OK;
+  if (ctx->scratch[slot]) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(ctx->scratch[slot]));
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+  }
+  CK(cudaMalloc(&ctx->scratch[slot], bytes));
+  ctx->scratch_bytes[slot] = bytes;
+  return TOB200_OK;
+}
+
+template <typename T> constexpr int dtype_of();
+template <> constexpr int dtype_of<float>() { return TOB200_F32; }
+template <> constexpr int dtype_of<double>() { return TOB200_F64; }
+
+template <typename T>
+TppEntry tpp_entry_for(int n) {
+  if (sizeof(T) == 4) {
+    if (n >= 1 && n <= 4) return tpp_entry_f32_a;
+    if (n <= 8) return tpp_entry_f32_b;
+    if (n <= 10) return tpp_entry_f32_c;
+    if (n <= kTppMaxN_f32) return tpp_entry_f32_d;
+  } else {
+    if (n >= 1 && n <= 4) return tpp_entry_f64_a;
+    if (n <= 6) return tpp_entry_f64_b;
+    if (n <= kTppMaxN_f64) return tpp_entry_f64_c;
+  }
+  return nullptr;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// launch geometry of a thread-per-problem kernel
+template <typename T>
+int tpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, TppData<T> *d, TppLaunch *cfg) {
+  TppEntry entry = tpp_entry_for<T>(n);
+  if (!entry) return fail(ctx, TOB200_ERR_UNSUPPORTED, "no thread-per-problem kernel for this n");
+  const size_t row_bytes = (size_t)(n + 1) * kTile * sizeof(T);
+  int rows = (int)(ctx->tpp_stage_bytes / row_bytes);
+  if (rows < 1) rows = 1;
+  if (rows > m) rows = m > 0 ? m : 1;
+  const int warps = ctx->tpp_warps;
+  d->B = B;
+  d->ntiles = (B + kTile - 1) / kTile;
+  d->m = m;
+  d->rows = rows;
+  d->warp_smem = (uint32_t)tpp_warp_smem_bytes(n, rows, sizeof(T));
+  cfg->block = warps * 32;
+  cfg->smem = (size_t)d->warp_smem * warps;
+  cfg->stream = ctx->stream;
+  const auto key = std::make_tuple(dtype_of<T>(), n, kind, cfg->block, cfg->smem);
+  auto it = ctx->occupancy.find(key);
+  int per_sm = 0;
+  if (it == ctx->occupancy.end()) {
+    cudaError_t e = entry(kTppQuery, n, kind, nullptr, *cfg, &per_sm);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "occupancy query");
+    if (per_sm < 1) return fail(ctx, TOB200_ERR_CUDA, "kernel does not fit on an SM (shared memory / registers)");
+    ctx->occupancy[key] = per_sm;
+  } else {
+    per_sm = it->second;
+  }
+  if (ctx->tpp_ctas_per_sm > 0 && ctx->tpp_ctas_per_sm < per_sm) per_sm = ctx->tpp_ctas_per_sm;
+  int64_t grid = (int64_t)per_sm * ctx->num_sms;
+  const int64_t need = (d->ntiles + warps - 1) / warps;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  cfg->grid = (int)grid;
+  return TOB200_OK;
+}
+
+// PROBLEM_MAJOR inputs are re-tiled into context scratch (slots 0: J/A, 1: r/y)
+template <typename T>
+int to_tile32(tob200_ctx *ctx, int layout, int64_t B, int m, int n, const T **J, const T **r) {
+  if (layout == TOB200_LAYOUT_TILE32) return TOB200_OK;
+  if (layout != TOB200_LAYOUT_PROBLEM_MAJOR) return fail(ctx, TOB200_ERR_INVALID, "unknown layout");
+  const size_t ej = (size_t)tob200_tiled_elems(B, m, n), er = (size_t)tob200_tiled_elems(B, m, 1);
+  int rc;
+  if ((rc = ensure_scratch(ctx, 0, ej * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, 1, er * sizeof(T))) != TOB200_OK) return rc;
+  CK(launch_retile<T>(*J, B, m, n, (T *)ctx->scratch[0], ctx->stream));
+  CK(launch_retile<T>(*r, B, m, 1, (T *)ctx->scratch[1], ctx->stream));
+  ctx->launches += 2;
+  *J = (const T *)ctx->scratch[0];
+  *r = (const T *)ctx->scratch[1];
+  return TOB200_OK;
+}
+
+int check_options(tob200_ctx *ctx, const tob200_options *o) {
+  if (!o) return fail(ctx, TOB200_ERR_INVALID, "options is NULL");
+  if (o->solver_type != 0 && o->solver_type != 1)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "solver_type must be LevenbergMarquardt (0) or GaussNewton (1)");
+  if (!o->use_ldlt) return fail(ctx, TOB200_ERR_UNSUPPORTED, "hessian.use_ldlt = false is not implemented");
+  if (o->max_iters < 0 || o->max_iters > 65535) return fail(ctx, TOB200_ERR_INVALID, "max_iters out of range");
+  if (o->max_consec_failures < 0 || o->max_consec_failures > 255 || o->max_total_failures < 0 ||
+      o->max_total_failures > 255)
+    return fail(ctx, TOB200_ERR_INVALID, "failure limits are uint8 in tinyopt::Options");
+  return TOB200_OK;
+}
+
+template <typename T>
+int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_t B, int m, int n, const T *lambda,
+                     T *dx, double *cost, T *H_out, T *g_out, int32_t *status) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (B < 0 || m < 0 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 0, m >= 0, n >= 1");
+  if (B == 0) return TOB200_OK;
+  if (!J || !r || !dx || !cost || !status) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  if (!aligned16(J) || !aligned16(r)) return fail(ctx, TOB200_ERR_INVALID, "J and r must be 16-byte aligned");
+  DeviceGuard guard(ctx->device);
+  if (tob200_kernel_family(dtype_of<T>(), n) != 1)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "build_solve: n has no kernel yet for this dtype");
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = to_tile32<T>(ctx, layout, B, m, n, &J, &r);
+  if (rc != TOB200_OK) return rc;
+  TppBuildSolveParams<T> p;
+  TppLaunch cfg;
+  if ((rc = tpp_configure<T>(ctx, n, m, B, kTppBuildSolve, &p.d, &cfg)) != TOB200_OK) return rc;
+  p.d.J = J;
+  p.d.r = r;
+  p.lambda = lambda;
+  p.dx = dx;
+  p.cost = cost;
+  p.H_out = H_out;
+  p.g_out = g_out;
+  p.status = status;
+  CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppBuildSolve, &p, cfg, nullptr));
+  ctx->launches++;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  return TOB200_OK;
+}
+
+template <typename T>
+int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T *y, T alpha, int layout, int64_t B,
+                int m, int n, T *x, tob200_result *results, bool record_events = true) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  int rc = check_options(ctx, opt);
+  if (rc != TOB200_OK) return rc;
+  if (B < 0 || m < 0 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 0, m >= 0, n >= 1");
+  if (B == 0) return TOB200_OK;
+  if (!A || !y || !x || !results) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  if (!aligned16(A) || !aligned16(y)) return fail(ctx, TOB200_ERR_INVALID, "A and y must be 16-byte aligned");
+  DeviceGuard guard(ctx->device);
+  if (tob200_kernel_family(dtype_of<T>(), n) != 1)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n has no kernel yet for this dtype");
+  if (record_events) CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if ((rc = to_tile32<T>(ctx, layout, B, m, n, &A, &y)) != TOB200_OK) return rc;
+  TppRunParams<T> p;
+  TppLaunch cfg;
+  if ((rc = tpp_configure<T>(ctx, n, m, B, kTppRun, &p.d, &cfg)) != TOB200_OK) return rc;
+  p.d.J = A;
+  p.d.r = y;
+  p.opt = make_dev_options<T>(*opt);
+  p.alpha = alpha;
+  p.alpha3 = (T)3 * alpha;
+  p.x = x;
+  p.results = results;
+  CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppRun, &p, cfg, nullptr));
+  ctx->launches++;
+  if (record_events) CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  return TOB200_OK;
+}
+
+template <typename T>
+int lm_run_host_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T *y, T alpha, int layout,
+                     int64_t B, int m, int n, T *x, tob200_result *results) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (B < 0 || m < 0 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 0, m >= 0, n >= 1");
+  if (B == 0) return TOB200_OK;
+  if (!A || !y || !x || !results) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  DeviceGuard guard(ctx->device);
+  const bool tiled = layout == TOB200_LAYOUT_TILE32;
+  const size_t ea = tiled ? (size_t)tob200_tiled_elems(B, m, n) : (size_t)B * m * n;
+  const size_t ey = tiled ? (size_t)tob200_tiled_elems(B, m, 1) : (size_t)B * m;
+  int rc;
+  if ((rc = ensure_scratch(ctx, 2, ea * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, 3, ey * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, 4, (size_t)B * n * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, 5, (size_t)B * sizeof(tob200_result))) != TOB200_OK) return rc;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->scratch[2], A, ea * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->scratch[3], y, ey * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->scratch[4], x, (size_t)B * n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  rc = lm_run_impl<T>(ctx, opt, (const T *)ctx->scratch[2], (const T *)ctx->scratch[3], alpha, layout, B, m, n,
+                      (T *)ctx->scratch[4], (tob200_result *)ctx->scratch[5], false);
+  if (rc != TOB200_OK) return rc;
+  CK(cudaMemcpyAsync(x, ctx->scratch[4], (size_t)B * n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(results, ctx->scratch[5], (size_t)B * sizeof(tob200_result), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return TOB200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+struct tob200_solver {
+  tob200_ctx *ctx = nullptr;
+  int dtype = 0, n = 0;
+  int64_t B = 0;
+  tob200_options opt;
+  void *rec = nullptr, *x = nullptr, *last_dx = nullptr, *H = nullptr, *g = nullptr;
+  int32_t *needs = nullptr;
+  unsigned long long *n_active = nullptr;  // device
+  bool is_reset = false;
+};
+
+namespace {
+
+template <typename T>
+int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m, int reset) {
+  if (!s) return fail(nullptr, TOB200_ERR_INVALID, "solver is NULL");
+  tob200_ctx *ctx = s->ctx;
+  if (s->dtype != dtype_of<T>()) return fail(ctx, TOB200_ERR_INVALID, "solver dtype mismatch");
+  DeviceGuard guard(ctx->device);
+  const int n = s->n;
+  const int64_t B = s->B;
+  if (!reset) {
+    if (!s->is_reset) return fail(ctx, TOB200_ERR_INVALID, "tob200_solver_reset must be called first");
+    if (m < 0) return fail(ctx, TOB200_ERR_INVALID, "m < 0");
+    if (!J || !r) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+    if (!aligned16(J) || !aligned16(r)) return fail(ctx, TOB200_ERR_INVALID, "J and r must be 16-byte aligned");
+    int rc = to_tile32<T>(ctx, layout, B, m, n, &J, &r);
+    if (rc != TOB200_OK) return rc;
+  }
+  TppStepParams<T> p;
+  TppLaunch cfg;
+  int rc = tpp_configure<T>(ctx, n, reset ? 1 : m, B, kTppStep, &p.d, &cfg);
+  if (rc != TOB200_OK) return rc;
+  p.d.J = J;
+  p.d.r = r;
+  p.opt = make_dev_options<T>(s->opt);
+  p.rec = (StateRec<T> *)s->rec;
+  p.x = (T *)s->x;
+  p.last_dx = (T *)s->last_dx;
+  p.H = (T *)s->H;
+  p.g = (T *)s->g;
+  p.needs = s->needs;
+  p.n_active = s->n_active;
+  p.reset = reset;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemsetAsync(s->n_active, 0, sizeof(unsigned long long), ctx->stream));
+  CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppStep, &p, cfg, nullptr));
+  ctx->launches++;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  return TOB200_OK;
+}
+
+}  // namespace
+
+template <typename T>
+__global__ void results_kernel(const StateRec<T> *rec, int64_t B, tob200_result *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const StateRec<T> r = rec[i];
+  tob200_result o;
+  o.final_cost = r.final_cost;
+  o.final_rerr_dec = r.final_rerr_dec;
+  o.last_lambda = (double)r.lambda;
+  o.last_prev_lambda = (double)r.prev_lambda;
+  o.final_num_residuals = r.final_nres;
+  // a problem that is still running reports kNone, or kMaxIters semantics are applied by the loop
+  o.stop_reason = r.stop_reason;
+  o.num_iters = r.num_iters;
+  o.num_failures = r.num_failures;
+  o.num_consec_failures = r.num_consec_failures;
+  o.num_builds = r.num_builds;
+  out[i] = o;
+}
+
+// ================================================================================================
+extern "C" {
+
+int tob200_version(void) { return TOB200_VERSION; }
+
+void tob200_options_default(tob200_options *o) {  // optimizers/options.h defaults
+  if (!o) return;
+  o->solver_type = 0;
+  o->check_final_cost = 0;
+  o->use_step_quality_approx = 0;
+  o->grad_clipping = 0;
+  o->use_ldlt = 1;
+  o->H_is_full = 1;
+  o->check_min_H_diag = 0;
+  o->save_last = 1;
+  o->use_squared_norm = 1;
+  o->downscale_by_2 = 0;
+  o->normalize = 0;
+  o->max_iters = 50;
+  o->min_error = 1e-12f;
+  o->min_rerr_dec = 1e-10f;
+  o->min_step_norm2 = 1e-14f;
+  o->min_grad_norm2 = 1e-18f;
+  o->max_total_failures = 0;
+  o->max_consec_failures = 5;
+  o->damping_init = 1e-4f;
+  o->damping_min = 1e-9f;
+  o->damping_max = 1e9f;
+  o->good_factor = 1.0f / 3.0f;
+  o->bad_factor = 2.0f;
+}
+
+int64_t tob200_tiled_elems(int64_t B, int m, int n) {
+  if (B <= 0 || m <= 0 || n <= 0) return 0;
+  return ((B + kTile - 1) / kTile) * kTile * (int64_t)m * n;
+}
+
+int tob200_kernel_family(int dtype, int n) {
+  if (n < 1) return 0;
+  if (dtype == TOB200_F32) return n <= kTppMaxN_f32 ? 1 : 0;
+  if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : 0;
+  return 0;
+}
+
+int tob200_create(tob200_ctx **out, int device, void *stream) {
+  if (!out) return fail(nullptr, TOB200_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, TOB200_ERR_CUDA,
+                std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                    " (tinyopt_b200 has no CPU fallback)");
+  if (device < 0 || device >= count) return fail(nullptr, TOB200_ERR_INVALID, "device ordinal out of range");
+  tob200_ctx *ctx = new (std::nothrow) tob200_ctx();
+  if (!ctx) return fail(nullptr, TOB200_ERR_NOMEM, "host allocation failed");
+  ctx->device = device;
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete ctx;
+    return fail_cuda(nullptr, e, "cudaGetDeviceProperties");
+  }
+  if (prop.major < 10) {
+    delete ctx;
+    return fail(nullptr, TOB200_ERR_UNSUPPORTED, "tinyopt_b200 is built for sm_100a (Blackwell B200) only");
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      delete ctx;
+      return fail_cuda(nullptr, e, "cudaStreamCreate");
+    }
+    ctx->own_stream = true;
+  }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  ctx->tpp_stage_bytes = env_int("TOB200_TPP_STAGE_BYTES", ctx->tpp_stage_bytes);
+  ctx->tpp_warps = env_int("TOB200_TPP_WARPS", ctx->tpp_warps);
+  if (ctx->tpp_warps < 1 || ctx->tpp_warps > 32) ctx->tpp_warps = 4;
+  ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
+  *out = ctx;
+  return TOB200_OK;
+}
+
+int tob200_destroy(tob200_ctx *ctx) {
+  if (!ctx) return TOB200_OK;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return TOB200_OK;
+}
+
+int tob200_sync(tob200_ctx *ctx) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard guard(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return TOB200_OK;
+}
+
+const char *tob200_last_error(const tob200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int64_t tob200_launch_count(const tob200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tob200_last_elapsed_ms(tob200_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return fail(ctx, TOB200_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(ctx->device);
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return TOB200_OK;
+}
+
+#define RETILE(SUF, T)                                                                                  \
+  int tob200_retile_##SUF(tob200_ctx *ctx, const T *src, int64_t B, int m, int n, T *dst) {              \
+    if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");                                   \
+    if (B < 0 || m < 0 || n < 0) return fail(ctx, TOB200_ERR_INVALID, "negative size");                  \
+    if (B == 0 || m == 0 || n == 0) return TOB200_OK;                                                    \
+    if (!src || !dst) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");                               \
+    DeviceGuard guard(ctx->device);                                                                      \
+    CK(launch_retile<T>(src, B, m, n, dst, ctx->stream));                                                \
+    ctx->launches++;                                                                                     \
+    return TOB200_OK;                                                                                    \
+  }
+RETILE(f32, float)
+RETILE(f64, double)
+
+int tob200_build_solve_f32(tob200_ctx *ctx, const float *J, const float *r, int layout, int64_t B, int m, int n,
+                           const float *lambda, float *dx, double *cost, float *H_out, float *g_out,
+                           int32_t *status) {
+  return build_solve_impl<float>(ctx, J, r, layout, B, m, n, lambda, dx, cost, H_out, g_out, status);
+}
+int tob200_build_solve_f64(tob200_ctx *ctx, const double *J, const double *r, int layout, int64_t B, int m, int n,
+                           const double *lambda, double *dx, double *cost, double *H_out, double *g_out,
+                           int32_t *status) {
+  return build_solve_impl<double>(ctx, J, r, layout, B, m, n, lambda, dx, cost, H_out, g_out, status);
+}
+
+int tob200_lm_run_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y, float alpha,
+                      int layout, int64_t B, int m, int n, float *x, tob200_result *results) {
+  return lm_run_impl<float>(ctx, opt, A, y, alpha, layout, B, m, n, x, results);
+}
+int tob200_lm_run_f64(tob200_ctx *ctx, const tob200_options *opt, const double *A, const double *y, double alpha,
+                      int layout, int64_t B, int m, int n, double *x, tob200_result *results) {
+  return lm_run_impl<double>(ctx, opt, A, y, alpha, layout, B, m, n, x, results);
+}
+int tob200_lm_run_host_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y, float alpha,
+                           int layout, int64_t B, int m, int n, float *x, tob200_result *results) {
+  return lm_run_host_impl<float>(ctx, opt, A, y, alpha, layout, B, m, n, x, results);
+}
+int tob200_lm_run_host_f64(tob200_ctx *ctx, const tob200_options *opt, const double *A, const double *y,
+                           double alpha, int layout, int64_t B, int m, int n, double *x, tob200_result *results) {
+  return lm_run_host_impl<double>(ctx, opt, A, y, alpha, layout, B, m, n, x, results);
+}
+
+// ---- solver object -------------------------------------------------------------------------------
+int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob200_options *opt,
+                         tob200_solver **out) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (!out) return fail(ctx, TOB200_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = check_options(ctx, opt);
+  if (rc != TOB200_OK) return rc;
+  if (B < 1 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 1 and n >= 1");
+  if (tob200_kernel_family(dtype, n) != 1)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "solver: n has no kernel yet for this dtype");
+  DeviceGuard guard(ctx->device);
+  tob200_solver *s = new (std::nothrow) tob200_solver();
+  if (!s) return fail(ctx, TOB200_ERR_NOMEM, "host allocation failed");
+  s->ctx = ctx;
+  s->dtype = dtype;
+  s->n = n;
+  s->B = B;
+  s->opt = *opt;
+  const size_t elt = dtype == TOB200_F32 ? 4 : 8;
+  const size_t ntiles = (size_t)((B + kTile - 1) / kTile);
+  const size_t rec_bytes = dtype == TOB200_F32 ? sizeof(StateRec<float>) : sizeof(StateRec<double>);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void **p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  alloc(&s->rec, rec_bytes * B);
+  alloc(&s->x, elt * B * n);
+  alloc(&s->last_dx, elt * B * n);
+  alloc(&s->H, elt * ntiles * tri_count(n) * kTile);
+  alloc(&s->g, elt * ntiles * n * kTile);
+  alloc((void **)&s->needs, sizeof(int32_t) * B);
+  alloc((void **)&s->n_active, sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    tob200_solver_destroy(s);
+    return fail_cuda(ctx, e, "solver allocation");
+  }
+  *out = s;
+  return TOB200_OK;
+}
+
+int tob200_solver_destroy(tob200_solver *s) {
+  if (!s) return TOB200_OK;
+  DeviceGuard guard(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->rec);
+  cudaFree(s->x);
+  cudaFree(s->last_dx);
+  cudaFree(s->H);
+  cudaFree(s->g);
+  cudaFree(s->needs);
+  cudaFree(s->n_active);
+  delete s;
+  return TOB200_OK;
+}
+
+int tob200_solver_reset(tob200_solver *s, const void *x0) {
+  if (!s) return fail(nullptr, TOB200_ERR_INVALID, "solver is NULL");
+  tob200_ctx *ctx = s->ctx;
+  if (!x0) return fail(ctx, TOB200_ERR_INVALID, "x0 is NULL");
+  DeviceGuard guard(ctx->device);
+  const size_t elt = s->dtype == TOB200_F32 ? 4 : 8;
+  CK(cudaMemcpyAsync(s->x, x0, elt * s->B * s->n, cudaMemcpyDeviceToDevice, ctx->stream));
+  const size_t ntiles = (size_t)((s->B + kTile - 1) / kTile);
+  CK(cudaMemsetAsync(s->H, 0, elt * ntiles * tri_count(s->n) * kTile, ctx->stream));
+  CK(cudaMemsetAsync(s->g, 0, elt * ntiles * s->n * kTile, ctx->stream));
+  int rc = s->dtype == TOB200_F32 ? solver_step_impl<float>(s, nullptr, nullptr, 0, 0, 1)
+                                  : solver_step_impl<double>(s, nullptr, nullptr, 0, 0, 1);
+  if (rc == TOB200_OK) s->is_reset = true;
+  return rc;
+}
+
+void *tob200_solver_x(tob200_solver *s) { return s ? s->x : nullptr; }
+const int32_t *tob200_solver_needs(tob200_solver *s) { return s ? s->needs : nullptr; }
+
+int tob200_solver_step_f32(tob200_solver *s, const float *J, const float *r, int layout, int m) {
+  return solver_step_impl<float>(s, J, r, layout, m, 0);
+}
+int tob200_solver_step_f64(tob200_solver *s, const double *J, const double *r, int layout, int m) {
+  return solver_step_impl<double>(s, J, r, layout, m, 0);
+}
+
+int tob200_solver_num_active(tob200_solver *s, int64_t *n_active) {
+  if (!s || !n_active) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "NULL argument");
+  tob200_ctx *ctx = s->ctx;
+  DeviceGuard guard(ctx->device);
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, s->n_active, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n_active = (int64_t)v;
+  return TOB200_OK;
+}
+
+int tob200_solver_results(tob200_solver *s, tob200_result *results) {
+  if (!s || !results) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "NULL argument");
+  tob200_ctx *ctx = s->ctx;
+  DeviceGuard guard(ctx->device);
+  const unsigned grid = (unsigned)((s->B + 255) / 256);
+  if (s->dtype == TOB200_F32)
+    results_kernel<float><<<grid, 256, 0, ctx->stream>>>((const StateRec<float> *)s->rec, s->B, results);
+  else
+    results_kernel<double><<<grid, 256, 0, ctx->stream>>>((const StateRec<double> *)s->rec, s->B, results);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return TOB200_OK;
+}
+
+int tob200_solver_final_hessian(tob200_solver *s, double *H) {
+  if (!s || !H) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "NULL argument");
+  tob200_ctx *ctx = s->ctx;
+  DeviceGuard guard(ctx->device);
+  const unsigned grid = (unsigned)((s->B + 127) / 128);
+  if (s->dtype == TOB200_F32)
+    final_hessian_kernel<float><<<grid, 128, 0, ctx->stream>>>((const float *)s->H, (const StateRec<float> *)s->rec,
+                                                             s->opt.solver_type, s->B, s->n, H);
+  else
+    final_hessian_kernel<double><<<grid, 128, 0, ctx->stream>>>((const double *)s->H,
+                                                              (const StateRec<double> *)s->rec, s->opt.solver_type,
+                                                              s->B, s->n, H);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return TOB200_OK;
+}
+
+// ---- synthetic family ----------------------------------------------------------------------------
+#define SYNTH(SUF, T)                                                                                              \
+  int tob200_synth_generate_##SUF(tob200_ctx *ctx, uint64_t seed, int64_t p0, int64_t B, int m, int n, T alpha,     \
+                                  T sigma, int layout, T *A, T *y, T *xstar, T *x0) {                               \
+    if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");                                              \
+    if (B < 0 || m < 0 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 0, m >= 0, n >= 1");               \
+    if (layout != TOB200_LAYOUT_TILE32 && layout != TOB200_LAYOUT_PROBLEM_MAJOR)                                    \
+      return fail(ctx, TOB200_ERR_INVALID, "unknown layout");                                                       \
+    DeviceGuard guard(ctx->device);                                                                                 \
+    int launches = 0;                                                                                               \
+    CK(launch_synth_generate<T>(seed, p0, B, m, n, alpha, sigma, layout, A, y, xstar, x0, ctx->stream, &launches)); \
+    ctx->launches += launches;                                                                                      \
+    return TOB200_OK;                                                                                               \
+  }                                                                                                                 \
+  int tob200_synth_eval_##SUF(tob200_ctx *ctx, const T *A, const T *y, T alpha, int layout, int64_t B, int m,       \
+                              int n, const T *x, T *r, T *J) {                                                      \
+    if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");                                              \
+    if (B < 0 || m < 0 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 0, m >= 0, n >= 1");               \
+    if (!A || !y || !x) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");                                        \
+    if (layout != TOB200_LAYOUT_TILE32 && layout != TOB200_LAYOUT_PROBLEM_MAJOR)                                    \
+      return fail(ctx, TOB200_ERR_INVALID, "unknown layout");                                                       \
+    DeviceGuard guard(ctx->device);                                                                                 \
+    CK(launch_synth_eval<T>(A, y, alpha, layout, B, m, n, x, r, J, ctx->stream));                                   \
+    ctx->launches++;                                                                                                \
+    return TOB200_OK;                                                                                               \
+  }
+SYNTH(f32, float)
+SYNTH(f64, double)
+
+}  // extern "C"

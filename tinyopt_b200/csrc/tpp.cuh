@@ -1,0 +1,441 @@
+// tpp.cuh — "thread per problem" kernels for small n (n <= 12 float, n <= 8 double).
+//
+// Mapping: one warp owns one TILE32 tile (32 problems, lane l = problem 32*tile + l).  The rows of
+// the residual blocks are streamed HBM -> shared memory by TMA bulk copies (cp.async.bulk, one
+// contiguous copy per row chunk because TILE32 interleaves the 32 problems) through a warp-private
+// 4-stage mbarrier ring; every lane then reads its own column of the stage (stride-1 across lanes:
+// conflict-free) and accumulates its problem's cost, g = J^T r and the upper triangle of
+// H = J^T J in registers, rows in order i = 0..m-1, one fma per term (the canonical op sequence,
+// identical to the CPU oracle's).  Damping, the pivoted LDL^T, the solve and the whole LM state
+// machine then run per lane in registers (lm_state.cuh, ldlt_reg.cuh) — H never touches HBM.
+//
+// Reference path replaced: the product site (diff/optimize_autodiff.h:151-157), SolverLM::Build /
+// SolverGN::Solve (solvers/lm.h:60-120, solvers/gn.h:150-171), SolveLDLT (math.h:232-240),
+// Optimizer_::Step / OptimizeAcc (optimizers/optimizer.h:243-539).
+#pragma once
+
+#include "common.cuh"
+#include "lm_state.cuh"
+
+namespace tob200 {
+
+constexpr int kTppStages = 4;
+constexpr int kTppBarBytes = 128;  // kTppStages mbarriers, padded so the stages stay 128-B aligned
+
+// shared-memory layout of one warp: [mbarriers | stages | persistent H_ + grad_ (lane-interleaved)]
+__host__ __device__ inline size_t tpp_stage_bytes(int n, int rows, size_t elt) { return (size_t)rows * (n + 1) * kTile * elt; }
+__host__ __device__ inline size_t tpp_warp_smem_bytes(int n, int rows, size_t elt) {
+  size_t b = kTppBarBytes + kTppStages * tpp_stage_bytes(n, rows, elt) + (size_t)(tri_count(n) + n) * kTile * elt;
+  return (b + 127) & ~(size_t)127;
+}
+
+template <typename T>
+struct TppData {      // one batch of residual blocks in TILE32 layout
+  const T *J;         // [ntiles][m][n][32]  (A for the polynomial family)
+  const T *r;         // [ntiles][m][32]     (y for the polynomial family)
+  int64_t B;          // problems
+  int64_t ntiles;     // ceil(B / 32)
+  int m, rows;        // residuals per problem, rows per pipeline stage
+  uint32_t warp_smem; // bytes of shared memory per warp
+};
+
+template <typename T, int N>
+struct SmemHG {  // persistent H_ / grad_ of the 32 problems of a warp, lane-interleaved
+  T *base;
+  int lane;
+  __device__ __forceinline__ T ld_h(int i) const { return base[i * kTile + lane]; }
+  __device__ __forceinline__ void st_h(int i, T v) { base[i * kTile + lane] = v; }
+  __device__ __forceinline__ T ld_g(int j) const { return base[(tri_count(N) + j) * kTile + lane]; }
+  __device__ __forceinline__ void st_g(int j, T v) { base[(tri_count(N) + j) * kTile + lane] = v; }
+};
+
+template <typename T, int N>
+struct GlobalHG {  // same, in global memory (tile-interleaved) for the host-driven step kernel
+  T *h;            // [ntiles][NT][32] + lane offset applied
+  T *g;            // [ntiles][N][32]
+  __device__ __forceinline__ T ld_h(int i) const { return h[i * kTile]; }
+  __device__ __forceinline__ void st_h(int i, T v) { h[i * kTile] = v; }
+  __device__ __forceinline__ T ld_g(int j) const { return g[j * kTile]; }
+  __device__ __forceinline__ void st_g(int j, T v) { g[j * kTile] = v; }
+};
+
+// warp-private TMA ring
+template <typename T, int N>
+struct TppPipe {
+  uint64_t *bars;
+  unsigned char *stages;
+  uint32_t stage_bytes;
+  uint32_t count;  // chunks consumed so far by this warp (monotonic: gives stage and phase)
+
+  __device__ __forceinline__ void init(unsigned char *warp_smem, int rows, int lane) {
+    bars = reinterpret_cast<uint64_t *>(warp_smem);
+    stages = warp_smem + kTppBarBytes;
+    stage_bytes = (uint32_t)tpp_stage_bytes(N, rows, sizeof(T));
+    count = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < kTppStages; ++s) mbar_init(&bars[s], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ T *stage_ptr(uint32_t stage) const {
+    return reinterpret_cast<T *>(stages + (size_t)stage * stage_bytes);
+  }
+  // lane 0 only: fill `stage` with rows [row0, row0 + nrows) of `tile`
+  __device__ __forceinline__ void issue(const TppData<T> &d, int64_t tile, int row0, int nrows, uint32_t stage) {
+    const uint32_t bj = (uint32_t)nrows * N * kTile * sizeof(T);
+    const uint32_t br = (uint32_t)nrows * kTile * sizeof(T);
+    T *sj = stage_ptr(stage);
+    T *sr = sj + (size_t)d.rows * N * kTile;
+    mbar_expect_tx(&bars[stage], bj + br);
+    tma_bulk_g2s(sj, d.J + ((size_t)tile * d.m + row0) * N * kTile, bj, &bars[stage]);
+    tma_bulk_g2s(sr, d.r + ((size_t)tile * d.m + row0) * kTile, br, &bars[stage]);
+  }
+};
+
+// One streaming pass over the m rows of a tile.  kSynth: the stage holds A and y of the polynomial
+// family and the lane evaluates r_i = t (1 + alpha t^2) - y_i, J_i = (1 + 3 alpha t^2) a_i at its x
+// (SURVEY.md §8d); otherwise the stage holds J and r themselves.
+template <typename T, int N, bool kSynth>
+__device__ __forceinline__ void tpp_pass(TppPipe<T, N> &pipe, const TppData<T> &d, int64_t tile, int lane,
+                                         bool active, bool do_rebuild, const T (&x)[N], T alpha, T alpha3,
+                                         T (&hu)[tri_count(N)], T (&g)[N], T &cost) {
+  using O = Ops<T>;
+  constexpr int NT = tri_count(N);
+#pragma unroll
+  for (int i = 0; i < NT; ++i) hu[i] = (T)0;  // solvers/gn.h:77-81 clear()
+#pragma unroll
+  for (int j = 0; j < N; ++j) g[j] = (T)0;
+  cost = (T)0;
+
+  const int m = d.m, R = d.rows;
+  const int nchunks = (m + R - 1) / R;
+  const uint32_t c0 = pipe.count;
+  if (lane == 0) {
+    fence_proxy_async();
+    const int pre = nchunks < kTppStages ? nchunks : kTppStages;
+    for (int c = 0; c < pre; ++c) {
+      const int row0 = c * R;
+      pipe.issue(d, tile, row0, (m - row0 < R) ? (m - row0) : R, (c0 + c) % kTppStages);
+    }
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t stage = pipe.count % kTppStages;
+    mbar_wait(&pipe.bars[stage], (pipe.count / kTppStages) & 1u);
+    const int row0 = c * R;
+    const int nrows = (m - row0 < R) ? (m - row0) : R;
+    if (active) {
+      const T *sj = pipe.stage_ptr(stage) + lane;
+      const T *sr = pipe.stage_ptr(stage) + (size_t)R * N * kTile + lane;
+      for (int rr = 0; rr < nrows; ++rr) {
+        T a[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[j] = sj[(rr * N + j) * kTile];
+        const T yv = sr[rr * kTile];
+        T ri;
+        T sc = (T)1;
+        if (kSynth) {
+          T t = (T)0;
+#pragma unroll
+          for (int j = 0; j < N; ++j) t = O::fma(a[j], x[j], t);
+          const T t2 = O::mul(t, t);
+          ri = O::fma(t, O::fma(alpha, t2, (T)1), -yv);
+          sc = O::fma(alpha3, t2, (T)1);
+        } else {
+          ri = yv;
+        }
+        cost = O::fma(ri, ri, cost);
+        if (do_rebuild) {
+          if (kSynth) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) a[j] = O::mul(sc, a[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < N; ++j) g[j] = O::fma(a[j], ri, g[j]);
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+#pragma unroll
+            for (int k = j; k < N; ++k) hu[tri_index(N, j, k)] = O::fma(a[j], a[k], hu[tri_index(N, j, k)]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && c + kTppStages < nchunks) {
+      fence_proxy_async();
+      const int nrow0 = (c + kTppStages) * R;
+      pipe.issue(d, tile, nrow0, (m - nrow0 < R) ? (m - nrow0) : R, stage);
+    }
+    pipe.count++;
+  }
+}
+
+__device__ __forceinline__ unsigned char *tpp_warp_smem(unsigned char *smem, uint32_t warp_smem) {
+  return smem + (size_t)(threadIdx.x / 32) * warp_smem;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tob200_lm_run_*: the whole LM loop per problem, polynomial family evaluated on the fly
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct TppRunParams {
+  TppData<T> d;
+  DevOptions<T> opt;
+  T alpha, alpha3;
+  T *x;                    // [B][n] in/out
+  tob200_result *results;  // [B]
+};
+
+template <typename T, int N>
+__global__ void tpp_lm_run_kernel(const __grid_constant__ TppRunParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NT = tri_count(N);
+  const int lane = threadIdx.x & 31;
+  unsigned char *ws = tpp_warp_smem(smem, p.d.warp_smem);
+  TppPipe<T, N> pipe;
+  pipe.init(ws, p.d.rows, lane);
+  SmemHG<T, N> hg{reinterpret_cast<T *>(ws + kTppBarBytes + (size_t)kTppStages * pipe.stage_bytes), lane};
+
+  const int warps_per_cta = blockDim.x / 32;
+  const int64_t gw = (int64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32;
+  const int64_t nw = (int64_t)gridDim.x * warps_per_cta;
+  const bool is_lm = p.opt.solver_type == 0;
+
+  for (int64_t tile = gw; tile < p.d.ntiles; tile += nw) {
+    const int64_t pidx = tile * kTile + lane;
+    const bool valid = pidx < p.d.B;
+    LmState<T, N> s;
+    s.reset(p.opt);
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) s.x[j] = p.x[pidx * N + j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) s.x[j] = (T)0;
+      s.flags |= kFlagDone;
+    }
+    while (__any_sync(0xffffffffu, !s.done())) {
+      const bool active = !s.done();
+      const bool do_rebuild = !is_lm || s.rebuild();  // GN's Build always re-accumulates (gn.h:118-131)
+      T hu[NT], g[N], cost;
+      tpp_pass<T, N, true>(pipe, p.d, tile, lane, active, do_rebuild, s.x, p.alpha, p.alpha3, hu, g, cost);
+      if (active) lm_after_pass<T, N>(s, p.opt, do_rebuild, hu, g, cost, p.d.m, hg);
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) p.x[pidx * N + j] = s.x[j];
+      lm_write_result(s, &p.results[pidx]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tob200_build_solve_*: one Build + Solve from materialised J, r
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct TppBuildSolveParams {
+  TppData<T> d;
+  const T *lambda;  // [B] or nullptr
+  T *dx;            // [B][n]
+  double *cost;     // [B]
+  T *H_out;         // [B][n][n] or nullptr
+  T *g_out;         // [B][n] or nullptr
+  int32_t *status;  // [B]
+};
+
+template <typename T, int N>
+__global__ void tpp_build_solve_kernel(const __grid_constant__ TppBuildSolveParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NT = tri_count(N);
+  using L = LdltReg<T, N>;
+  const int lane = threadIdx.x & 31;
+  unsigned char *ws = tpp_warp_smem(smem, p.d.warp_smem);
+  TppPipe<T, N> pipe;
+  pipe.init(ws, p.d.rows, lane);
+
+  const int warps_per_cta = blockDim.x / 32;
+  const int64_t gw = (int64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32;
+  const int64_t nw = (int64_t)gridDim.x * warps_per_cta;
+
+  for (int64_t tile = gw; tile < p.d.ntiles; tile += nw) {
+    const int64_t pidx = tile * kTile + lane;
+    const bool valid = pidx < p.d.B;
+    T hu[NT], g[N], cost, x[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = (T)0;
+    tpp_pass<T, N, false>(pipe, p.d, tile, lane, valid, true, x, (T)0, (T)0, hu, g, cost);
+    if (valid) {
+      const T lam = p.lambda ? p.lambda[pidx] : (T)0;
+      if (lam > (T)0) {  // solvers/lm.h:108-117
+        const double sc = 1.0 + (double)lam;
+#pragma unroll
+        for (int j = 0; j < N; ++j) hu[tri_index(N, j, j)] = (T)((double)hu[tri_index(N, j, j)] * sc);
+      }
+      p.cost[pidx] = (double)cost;
+      if (p.g_out) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) p.g_out[pidx * N + j] = g[j];
+      }
+      if (p.H_out) {
+        T *Ho = p.H_out + pidx * N * N;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+          for (int k = j; k < N; ++k) {
+            Ho[j * N + k] = hu[tri_index(N, j, k)];
+            Ho[k * N + j] = hu[tri_index(N, j, k)];
+          }
+        }
+      }
+      int tr[N];
+      T dx[N];
+      const bool ok = L::factor(hu, tr);  // math.h:232-240
+      if (ok) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) dx[j] = -g[j];  // solvers/gn.h:155
+        L::solve(hu, tr, dx);
+#pragma unroll
+        for (int j = 0; j < N; ++j) p.dx[pidx * N + j] = dx[j];
+      }
+      p.status[pidx] = ok ? 0 : 1;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tob200_solver_step_*: one Optimizer_::Step + OptimizeAcc update, state in global memory
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct StateRec {  // per-problem scalars of LmState (x, last_dx, H_, grad_ live in their own arrays)
+  double final_cost, final_rerr_dec;
+  T lambda, prev_lambda, bad_factor;
+  int final_nres, stop_reason;
+  uint32_t flags;
+  int num_builds, iter;
+  uint16_t num_iters;
+  uint8_t num_failures, num_consec_failures;
+};
+
+template <typename T>
+struct TppStepParams {
+  TppData<T> d;
+  DevOptions<T> opt;
+  StateRec<T> *rec;  // [B]
+  T *x;              // [B][n]
+  T *last_dx;        // [B][n]
+  T *H;              // [ntiles][NT][32]
+  T *g;              // [ntiles][n][32]
+  int32_t *needs;    // [B]
+  unsigned long long *n_active;  // device counter, zeroed by the host before the launch
+  int reset;         // 1: initialise the state instead of stepping (x already holds x0)
+};
+
+template <typename T, int N>
+__device__ __forceinline__ void state_load(LmState<T, N> &s, const StateRec<T> &r) {
+  s.final_cost = r.final_cost; s.final_rerr_dec = r.final_rerr_dec;
+  s.lambda = r.lambda; s.prev_lambda = r.prev_lambda; s.bad_factor = r.bad_factor;
+  s.final_nres = r.final_nres; s.stop_reason = r.stop_reason; s.flags = r.flags;
+  s.num_builds = r.num_builds; s.iter = r.iter; s.num_iters = r.num_iters;
+  s.num_failures = r.num_failures; s.num_consec_failures = r.num_consec_failures;
+}
+template <typename T, int N>
+__device__ __forceinline__ void state_store(const LmState<T, N> &s, StateRec<T> &r) {
+  r.final_cost = s.final_cost; r.final_rerr_dec = s.final_rerr_dec;
+  r.lambda = s.lambda; r.prev_lambda = s.prev_lambda; r.bad_factor = s.bad_factor;
+  r.final_nres = s.final_nres; r.stop_reason = s.stop_reason; r.flags = s.flags;
+  r.num_builds = s.num_builds; r.iter = s.iter; r.num_iters = s.num_iters;
+  r.num_failures = s.num_failures; r.num_consec_failures = s.num_consec_failures;
+}
+
+template <typename T, int N>
+__global__ void tpp_step_kernel(const __grid_constant__ TppStepParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NT = tri_count(N);
+  const int lane = threadIdx.x & 31;
+  unsigned char *ws = tpp_warp_smem(smem, p.d.warp_smem);
+  TppPipe<T, N> pipe;
+  pipe.init(ws, p.d.rows, lane);
+
+  const int warps_per_cta = blockDim.x / 32;
+  const int64_t gw = (int64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32;
+  const int64_t nw = (int64_t)gridDim.x * warps_per_cta;
+  const bool is_lm = p.opt.solver_type == 0;
+  unsigned long long local_active = 0;
+
+  for (int64_t tile = gw; tile < p.d.ntiles; tile += nw) {
+    const int64_t pidx = tile * kTile + lane;
+    const bool valid = pidx < p.d.B;
+    LmState<T, N> s;
+    if (p.reset) {
+      if (valid) {
+        s.reset(p.opt);
+        state_store(s, p.rec[pidx]);
+#pragma unroll
+        for (int j = 0; j < N; ++j) p.last_dx[pidx * N + j] = (T)0;
+        p.needs[pidx] = 1;
+        local_active++;
+      }
+      continue;
+    }
+    if (valid) {
+      state_load(s, p.rec[pidx]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        s.x[j] = p.x[pidx * N + j];
+        s.last_dx[j] = p.last_dx[pidx * N + j];
+      }
+    } else {
+      s.reset(p.opt);
+      s.flags |= kFlagDone;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s.x[j] = (T)0;
+    }
+    if (!__any_sync(0xffffffffu, !s.done())) continue;  // whole tile finished: no traffic at all
+    const bool active = !s.done();
+    const bool do_rebuild = !is_lm || s.rebuild();
+    T hu[NT], g[N], cost;
+    tpp_pass<T, N, false>(pipe, p.d, tile, lane, active, do_rebuild, s.x, (T)0, (T)0, hu, g, cost);
+    if (active) {
+      GlobalHG<T, N> hg{p.H + (size_t)tile * NT * kTile + lane, p.g + (size_t)tile * N * kTile + lane};
+      lm_after_pass<T, N>(s, p.opt, do_rebuild, hu, g, cost, p.d.m, hg);
+      state_store(s, p.rec[pidx]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        p.x[pidx * N + j] = s.x[j];
+        p.last_dx[pidx * N + j] = s.last_dx[j];
+      }
+      p.needs[pidx] = s.done() ? -1 : (s.rebuild() || !is_lm ? 1 : 0);
+      if (!s.done()) local_active++;
+    }
+  }
+  // one atomic per warp
+  for (int off = 16; off > 0; off >>= 1) local_active += __shfl_xor_sync(0xffffffffu, local_active, off);
+  if (lane == 0 && local_active) atomicAdd(p.n_active, local_active);
+}
+
+// un-damped final Hessian (solvers/lm.h:157-171) from the step solver's persistent H_
+template <typename T>
+__global__ void final_hessian_kernel(const T *H, const StateRec<T> *rec, int solver_type, int64_t B, int n,
+                                     double *out) {
+  const int64_t pidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= B) return;
+  const int64_t tile = pidx / kTile;
+  const int lane = (int)(pidx % kTile);
+  const int nt = tri_count(n);
+  const T *h = H + (size_t)tile * nt * kTile + lane;
+  const T pl = rec[pidx].prev_lambda;
+  const bool undamp = solver_type == 0 && pl > (T)0;
+  const T sc = Ops<T>::add((T)1, pl);
+  double *o = out + (size_t)pidx * n * n;
+  for (int j = 0; j < n; ++j)
+    for (int k = j; k < n; ++k) {
+      T v = h[tri_index(n, j, k) * kTile];
+      if (j == k && undamp) v = Ops<T>::div(v, sc);
+      o[j * n + k] = (double)v;
+      o[k * n + j] = (double)v;
+    }
+}
+
+}  // namespace tob200

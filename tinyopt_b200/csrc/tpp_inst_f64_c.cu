@@ -1,0 +1,5 @@
+// thread-per-problem kernels, double, n = 7..8 (see tpp.cuh)
+#include "tpp_inst.cuh"
+namespace tob200 {
+TOB200_TPP_ENTRY_DEFINE(tpp_entry_f64_c, double, 7, 8)
+}
