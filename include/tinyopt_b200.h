@@ -111,7 +111,8 @@ typedef struct tob200_solver tob200_solver;
 
 /* ---- context ---------------------------------------------------------------------------------- */
 int tob200_version(void);
-/* device: CUDA ordinal.  stream: a cudaStream_t to run on, or NULL to let the context own one. */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (use cudaStreamLegacy / cudaStreamPerThread
+ * to name a default stream), or NULL to let the context create its own non-blocking stream. */
 int tob200_create(tob200_ctx **out, int device, void *stream);
 int tob200_destroy(tob200_ctx *ctx);
 int tob200_sync(tob200_ctx *ctx);

@@ -96,6 +96,17 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _layout_of(J: torch.Tensor, layout: int | None) -> int:
+    """TILE32 tensors are 4-D [tiles, m, n, 32], problem-major ones 3-D [B, m, n]."""
+    if layout is not None:
+        return layout
+    if J.dim() == 4 and J.shape[-1] == 32:
+        return TILE32
+    if J.dim() == 3:
+        return PROBLEM_MAJOR
+    raise ValueError(f"cannot infer the layout of a tensor of shape {tuple(J.shape)}")
+
+
 def to_tile32(a: torch.Tensor) -> torch.Tensor:
     """[B, m, n] or [B, m] problem-major -> TILE32 [ceil(B/32), m, n, 32] (pure torch; host helper
     for tests — the library re-tiles PROBLEM_MAJOR inputs itself on the device)."""
@@ -131,7 +142,11 @@ class Context:
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
         h = C.c_void_p()
-        rc = self._lib.tob200_create(C.byref(h), self.device.index or 0, C.c_void_p(self.stream.cuda_stream))
+        # torch's default stream has handle 0, which the C-ABI reads as "create your own stream":
+        # name the legacy default stream explicitly (cudaStreamLegacy == 0x1) so that the kernels are
+        # ordered with the torch ops that produce / consume their buffers
+        handle = self.stream.cuda_stream or 1
+        rc = self._lib.tob200_create(C.byref(h), self.device.index or 0, C.c_void_p(handle))
         if rc != 0:
             raise TinyoptB200Error(f"tob200_create failed ({rc}): {self._lib.tob200_last_error(None).decode()}")
         self._h = h
@@ -181,17 +196,19 @@ class Context:
 
     # ---- a1+a3+a5+a6 ----------------------------------------------------------------------------
     def build_solve(self, J: torch.Tensor, r: torch.Tensor, lam: torch.Tensor | None = None, *,
-                    B: int | None = None, layout: int = PROBLEM_MAJOR, want_H: bool = False, want_g: bool = False):
+                    B: int | None = None, layout: int | None = None, want_H: bool = False, want_g: bool = False):
         """One Build + Solve per problem from materialised residual blocks.
 
         PROBLEM_MAJOR: J [B,m,n], r [B,m].  TILE32: J [nt,m,n,32], r [nt,m,32] and B given.
         Returns dict(dx [B,n], cost [B] f64, status [B] i32, H [B,n,n]?, g [B,n]?).
         """
+        layout = _layout_of(J, layout)
         if layout == PROBLEM_MAJOR:
             B, m, n = J.shape
         else:
             _, m, n, _ = J.shape
-            assert B is not None
+            if B is None:
+                raise ValueError("TILE32 input needs B (the number of problems)")
         dt, dev = J.dtype, J.device
         J = J.contiguous(); r = r.contiguous()
         dx = torch.zeros((B, n), dtype=dt, device=dev)
@@ -213,11 +230,12 @@ class Context:
 
     # ---- a7-a10 ---------------------------------------------------------------------------------
     def optimize_batch(self, A: torch.Tensor, y: torch.Tensor, x0: torch.Tensor, opt: Options | None = None, *,
-                       alpha: float = 0.1, layout: int = PROBLEM_MAJOR, results: torch.Tensor | None = None,
+                       alpha: float = 0.1, layout: int | None = None, results: torch.Tensor | None = None,
                        sync: bool = True) -> Output:
         """One tinyopt::Optimize() per problem of the polynomial family, device resident
         (tob200_lm_run_*).  x0 [B,n] is copied; the returned Output holds the solutions."""
         opt = opt if opt is not None else options()
+        layout = _layout_of(A, layout)
         B, n = x0.shape
         m = A.shape[1]
         dt, dev = A.dtype, A.device
@@ -234,11 +252,13 @@ class Context:
         return Output(x=x, results=decode_results(results))
 
     def optimize_batch_host(self, A: np.ndarray, y: np.ndarray, x: np.ndarray, opt: Options | None = None, *,
-                            alpha: float = 0.1, layout: int = PROBLEM_MAJOR, B: int | None = None,
+                            alpha: float = 0.1, layout: int | None = None, B: int | None = None,
                             results: np.ndarray | None = None):
         """Same through HOST buffers (numpy, ideally pinned): H2D + run + D2H inside
         (tob200_lm_run_host_*).  x is updated in place; returns the results array."""
         opt = opt if opt is not None else options()
+        if layout is None:
+            layout = TILE32 if A.ndim == 4 else PROBLEM_MAJOR
         if B is None:
             B = x.shape[0]
         n = x.shape[1]
@@ -274,8 +294,9 @@ class Context:
         return A, y, xs, x0
 
     def synth_eval(self, A: torch.Tensor, y: torch.Tensor, x: torch.Tensor, *, alpha: float = 0.1,
-                   layout: int = TILE32):
+                   layout: int | None = None):
         """Residual blocks r, J of the family at x, in `layout` (tob200_synth_eval_*)."""
+        layout = _layout_of(A, layout)
         B, n = x.shape
         m = A.shape[1]
         r = torch.empty_like(y)
@@ -337,7 +358,8 @@ class BatchSolver:
         """[B] int32: 1 rebuild (J and r), 0 cost only (r), -1 finished."""
         return self._wrap(self.ctx._lib.tob200_solver_needs(self._h), (self.B,), torch.int32)
 
-    def step(self, J: torch.Tensor, r: torch.Tensor, layout: int = PROBLEM_MAJOR):
+    def step(self, J: torch.Tensor, r: torch.Tensor, layout: int | None = None):
+        layout = _layout_of(J, layout)
         m = r.shape[1]
         fn = getattr(self.ctx._lib, f"tob200_solver_step_{_suf(self.dtype)}")
         self.ctx._ck(fn(self._h, _p(J.contiguous()), _p(r.contiguous()), layout, m), "tob200_solver_step")

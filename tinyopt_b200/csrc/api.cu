@@ -33,10 +33,11 @@ struct tob200_ctx {
   void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::map<std::tuple<int, int, int, int, size_t>, int> occupancy;  // (dtype, n, kind, block, smem) -> CTAs/SM
-  // tuning knobs (env: TOB200_TPP_STAGE_BYTES, TOB200_TPP_WARPS, TOB200_TPP_CTAS_PER_SM)
-  int tpp_stage_bytes = 4096;
-  int tpp_warps = 4;
-  int tpp_ctas_per_sm = 0;  // 0: occupancy limit
+  // tuning knobs (env: TOB200_TPP_STAGE_BYTES, TOB200_TPP_STAGES, TOB200_TPP_CTAS_PER_SM)
+  int tpp_stage_bytes = 16384;  // upper bound of one pipeline stage
+  int tpp_stages = 2;  // measured best on B200 (tools/tune_tpp.py): few, large stages
+  int tpp_ctas_per_sm = 0;  // 0: what the kernel was compiled for (__launch_bounds__)
+  unsigned long long *tile_counter = nullptr;
 };
 
 namespace {
@@ -107,22 +108,42 @@ TppEntry tpp_entry_for(int n) {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// launch geometry of a thread-per-problem kernel
+template <typename T>
+int tpp_min_blocks_rt(int n) {  // tpp_min_blocks<T, N>() for a run-time n
+  if (sizeof(T) == 8) return n <= 2 ? 4 : (n <= 6 ? 3 : 2);
+  return n <= 6 ? 4 : (n <= 8 ? 3 : 2);
+}
+
+// launch geometry of a thread-per-problem kernel: pipeline shape from the shared-memory budget of
+// the occupancy the kernel was compiled for, persistent grid = resident CTAs, dynamic tile queue
 template <typename T>
 int tpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, TppData<T> *d, TppLaunch *cfg) {
   TppEntry entry = tpp_entry_for<T>(n);
   if (!entry) return fail(ctx, TOB200_ERR_UNSUPPORTED, "no thread-per-problem kernel for this n");
+  const int warps = kTppThreads / 32;
+  int minb = tpp_min_blocks_rt<T>(n);
+  if (ctx->tpp_ctas_per_sm > 0 && ctx->tpp_ctas_per_sm < minb) minb = ctx->tpp_ctas_per_sm;
   const size_t row_bytes = (size_t)(n + 1) * kTile * sizeof(T);
-  int rows = (int)(ctx->tpp_stage_bytes / row_bytes);
+  const size_t fixed = kTppBarBytes + (size_t)(tri_count(n) + n) * kTile * sizeof(T) + 128;
+  const size_t budget = (232448 - (size_t)minb * 1024) / ((size_t)minb * warps);
+  int stages = ctx->tpp_stages;
+  if (stages < 2) stages = 2;
+  if (stages > kTppMaxStages) stages = kTppMaxStages;
+  size_t avail = budget > fixed ? budget - fixed : 0;
+  int rows = (int)(avail / ((size_t)stages * row_bytes));
+  while (rows < 1 && stages > 2) rows = (int)(avail / ((size_t)(--stages) * row_bytes));
+  if (rows < 1) rows = 1;  // occupancy will drop below minb; the query below reports what fits
+  if ((size_t)rows * row_bytes > (size_t)ctx->tpp_stage_bytes) rows = (int)(ctx->tpp_stage_bytes / row_bytes);
   if (rows < 1) rows = 1;
   if (rows > m) rows = m > 0 ? m : 1;
-  const int warps = ctx->tpp_warps;
   d->B = B;
   d->ntiles = (B + kTile - 1) / kTile;
   d->m = m;
   d->rows = rows;
-  d->warp_smem = (uint32_t)tpp_warp_smem_bytes(n, rows, sizeof(T));
-  cfg->block = warps * 32;
+  d->stages = stages;
+  d->warp_smem = (uint32_t)tpp_warp_smem_bytes(n, rows, stages, sizeof(T));
+  d->tile_counter = ctx->tile_counter;
+  cfg->block = kTppThreads;
   cfg->smem = (size_t)d->warp_smem * warps;
   cfg->stream = ctx->stream;
   const auto key = std::make_tuple(dtype_of<T>(), n, kind, cfg->block, cfg->smem);
@@ -142,6 +163,9 @@ int tpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, TppData<T>
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   cfg->grid = (int)grid;
+  // the tile queue starts at 0 for every launch
+  cudaError_t e = cudaMemsetAsync(ctx->tile_counter, 0, sizeof(unsigned long long), ctx->stream);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMemsetAsync(tile_counter)");
   return TOB200_OK;
 }
 
@@ -424,9 +448,12 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   ctx->tpp_stage_bytes = env_int("TOB200_TPP_STAGE_BYTES", ctx->tpp_stage_bytes);
-  ctx->tpp_warps = env_int("TOB200_TPP_WARPS", ctx->tpp_warps);
-  if (ctx->tpp_warps < 1 || ctx->tpp_warps > 32) ctx->tpp_warps = 4;
+  ctx->tpp_stages = env_int("TOB200_TPP_STAGES", ctx->tpp_stages);
   ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
+  if ((e = cudaMalloc((void **)&ctx->tile_counter, sizeof(unsigned long long))) != cudaSuccess) {
+    tob200_destroy(ctx);
+    return fail_cuda(nullptr, e, "cudaMalloc(tile_counter)");
+  }
   *out = ctx;
   return TOB200_OK;
 }
@@ -437,6 +464,7 @@ int tob200_destroy(tob200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->tile_counter) cudaFree(ctx->tile_counter);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -6,7 +6,7 @@
 // largest-|diagonal| pivot (first maximum wins), sign tracking, failure only when a non-zero pivot
 // follows a zero pivot, pseudo-inverse of D in the solve.  Every loop is fully unrolled so that all
 // indices into the triangle are static (registers); the run-time pivot row is handled by
-// predicating the unrolled swap code on `p == pp`.
+// conditional selects over the unrolled swap pattern (`cswp`), never by a branch.
 #pragma once
 
 #include "common.cuh"
@@ -21,10 +21,13 @@ struct LdltReg {
   // element (i, j), j <= i, of the lower-triangular working matrix == upper (j, i) of H
   static __device__ __forceinline__ constexpr int idx(int i, int j) { return tri_index(N, j, i); }
 
-  static __device__ __forceinline__ void swp(T &a, T &b) {
-    const T t = a;
-    a = b;
-    b = t;
+  // conditional swap as two selects: the run-time pivot row never becomes a branch, so the lanes of
+  // a warp (32 different problems, 32 different pivots) do not diverge
+  static __device__ __forceinline__ void cswp(bool c, T &a, T &b) {
+    const T ta = c ? b : a;
+    const T tb = c ? a : b;
+    a = ta;
+    b = tb;
   }
 
   // In-place factorisation.  Returns true iff info()==Success && isPositive().
@@ -50,15 +53,14 @@ struct LdltReg {
       tr[k] = p;
 #pragma unroll
       for (int pp = k + 1; pp < N; ++pp) {
-        if (p == pp) {
+        const bool c = (p == pp);
 #pragma unroll
-          for (int j = 0; j < k; ++j) swp(w[idx(k, j)], w[idx(pp, j)]);
+        for (int j = 0; j < k; ++j) cswp(c, w[idx(k, j)], w[idx(pp, j)]);
 #pragma unroll
-          for (int i = pp + 1; i < N; ++i) swp(w[idx(i, k)], w[idx(i, pp)]);
-          swp(w[idx(k, k)], w[idx(pp, pp)]);
+        for (int i = pp + 1; i < N; ++i) cswp(c, w[idx(i, k)], w[idx(i, pp)]);
+        cswp(c, w[idx(k, k)], w[idx(pp, pp)]);
 #pragma unroll
-          for (int i = k + 1; i < pp; ++i) swp(w[idx(i, k)], w[idx(pp, i)]);
-        }
+        for (int i = k + 1; i < pp; ++i) cswp(c, w[idx(i, k)], w[idx(pp, i)]);
       }
       if (k > 0) {
         T temp[N];
@@ -115,8 +117,7 @@ struct LdltReg {
 #pragma unroll
       for (int k = 0; k < N; ++k) {
 #pragma unroll
-        for (int pp = k + 1; pp < N; ++pp)
-          if (tr[k] == pp) swp(y[k], y[pp]);
+        for (int pp = k + 1; pp < N; ++pp) cswp(tr[k] == pp, y[k], y[pp]);
       }
     }
 #pragma unroll
@@ -142,8 +143,7 @@ struct LdltReg {
 #pragma unroll
       for (int k = N - 1; k >= 0; --k) {
 #pragma unroll
-        for (int pp = k + 1; pp < N; ++pp)
-          if (tr[k] == pp) swp(y[k], y[pp]);
+        for (int pp = k + 1; pp < N; ++pp) cswp(tr[k] == pp, y[k], y[pp]);
       }
     }
   }

@@ -3,7 +3,7 @@
 // Mapping: one warp owns one TILE32 tile (32 problems, lane l = problem 32*tile + l).  The rows of
 // the residual blocks are streamed HBM -> shared memory by TMA bulk copies (cp.async.bulk, one
 // contiguous copy per row chunk because TILE32 interleaves the 32 problems) through a warp-private
-// 4-stage mbarrier ring; every lane then reads its own column of the stage (stride-1 across lanes:
+// multi-stage mbarrier ring; every lane then reads its own column of the stage (stride-1 across lanes:
 // conflict-free) and accumulates its problem's cost, g = J^T r and the upper triangle of
 // H = J^T J in registers, rows in order i = 0..m-1, one fma per term (the canonical op sequence,
 // identical to the CPU oracle's).  Damping, the pivoted LDL^T, the solve and the whole LM state
@@ -19,14 +19,23 @@
 
 namespace tob200 {
 
-constexpr int kTppStages = 4;
-constexpr int kTppBarBytes = 128;  // kTppStages mbarriers, padded so the stages stay 128-B aligned
+constexpr int kTppMaxStages = 8;
+constexpr int kTppBarBytes = 128;  // up to 8 mbarriers, padded so the stages stay 128-B aligned
+constexpr int kTppThreads = 128;   // 4 warps per CTA, each warp independent
 
 // shared-memory layout of one warp: [mbarriers | stages | persistent H_ + grad_ (lane-interleaved)]
 __host__ __device__ inline size_t tpp_stage_bytes(int n, int rows, size_t elt) { return (size_t)rows * (n + 1) * kTile * elt; }
-__host__ __device__ inline size_t tpp_warp_smem_bytes(int n, int rows, size_t elt) {
-  size_t b = kTppBarBytes + kTppStages * tpp_stage_bytes(n, rows, elt) + (size_t)(tri_count(n) + n) * kTile * elt;
+__host__ __device__ inline size_t tpp_warp_smem_bytes(int n, int rows, int stages, size_t elt) {
+  size_t b = kTppBarBytes + (size_t)stages * tpp_stage_bytes(n, rows, elt) + (size_t)(tri_count(n) + n) * kTile * elt;
   return (b + 127) & ~(size_t)127;
+}
+
+// Resident CTAs per SM each kernel is compiled for (__launch_bounds__): fixes the register budget
+// (65536 / (128 * k)).  Chosen from ptxas -v so that nothing spills.
+template <typename T, int N>
+__host__ __device__ constexpr int tpp_min_blocks() {
+  if (sizeof(T) == 8) return N <= 2 ? 4 : (N <= 6 ? 3 : 2);
+  return N <= 6 ? 4 : (N <= 8 ? 3 : 2);
 }
 
 template <typename T>
@@ -36,7 +45,9 @@ struct TppData {      // one batch of residual blocks in TILE32 layout
   int64_t B;          // problems
   int64_t ntiles;     // ceil(B / 32)
   int m, rows;        // residuals per problem, rows per pipeline stage
+  int stages;         // pipeline depth (2..kTppMaxStages)
   uint32_t warp_smem; // bytes of shared memory per warp
+  unsigned long long *tile_counter;  // dynamic tile scheduler, zeroed before the launch
 };
 
 template <typename T, int N>
@@ -65,38 +76,85 @@ struct TppPipe {
   uint64_t *bars;
   unsigned char *stages;
   uint32_t stage_bytes;
-  uint32_t count;  // chunks consumed so far by this warp (monotonic: gives stage and phase)
+  uint32_t r_off;    // element offset of the r / y rows inside a stage
+  uint32_t nstages;
+  uint32_t stage;    // next stage to consume
+  uint32_t phase;    // its mbarrier phase parity
 
-  __device__ __forceinline__ void init(unsigned char *warp_smem, int rows, int lane) {
+  __device__ __forceinline__ void init(unsigned char *warp_smem, int rows, int nst, int lane) {
     bars = reinterpret_cast<uint64_t *>(warp_smem);
     stages = warp_smem + kTppBarBytes;
     stage_bytes = (uint32_t)tpp_stage_bytes(N, rows, sizeof(T));
-    count = 0;
+    r_off = (uint32_t)rows * N * kTile;
+    nstages = (uint32_t)nst;
+    stage = 0;
+    phase = 0;
     if (lane == 0) {
-#pragma unroll
-      for (int s = 0; s < kTppStages; ++s) mbar_init(&bars[s], 1);
+      for (uint32_t s = 0; s < nstages; ++s) mbar_init(&bars[s], 1);
       mbar_fence_init();
     }
     __syncwarp();
   }
-  __device__ __forceinline__ T *stage_ptr(uint32_t stage) const {
-    return reinterpret_cast<T *>(stages + (size_t)stage * stage_bytes);
+  __device__ __forceinline__ T *stage_ptr(uint32_t st) const {
+    return reinterpret_cast<T *>(stages + (size_t)st * stage_bytes);
   }
-  // lane 0 only: fill `stage` with rows [row0, row0 + nrows) of `tile`
-  __device__ __forceinline__ void issue(const TppData<T> &d, int64_t tile, int row0, int nrows, uint32_t stage) {
-    const uint32_t bj = (uint32_t)nrows * N * kTile * sizeof(T);
-    const uint32_t br = (uint32_t)nrows * kTile * sizeof(T);
-    T *sj = stage_ptr(stage);
-    T *sr = sj + (size_t)d.rows * N * kTile;
-    mbar_expect_tx(&bars[stage], bj + br);
-    tma_bulk_g2s(sj, d.J + ((size_t)tile * d.m + row0) * N * kTile, bj, &bars[stage]);
-    tma_bulk_g2s(sr, d.r + ((size_t)tile * d.m + row0) * kTile, br, &bars[stage]);
+  __device__ __forceinline__ void advance() {
+    if (++stage == nstages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+  // lane 0 only: fill stage `st` with `nrows` rows starting at row `row0` of the tile whose J / r
+  // rows start at jt / rt
+  __device__ __forceinline__ void issue(const T *jt, const T *rt, int row0, int nrows, uint32_t st) {
+    const uint32_t bj = (uint32_t)nrows * (N * kTile * (uint32_t)sizeof(T));
+    const uint32_t br = (uint32_t)nrows * (kTile * (uint32_t)sizeof(T));
+    T *sj = stage_ptr(st);
+    mbar_expect_tx(&bars[st], bj + br);
+    tma_bulk_g2s(sj, jt + (uint32_t)row0 * (N * kTile), bj, &bars[st]);
+    tma_bulk_g2s(sj + r_off, rt + (uint32_t)row0 * kTile, br, &bars[st]);
   }
 };
 
-// One streaming pass over the m rows of a tile.  kSynth: the stage holds A and y of the polynomial
-// family and the lane evaluates r_i = t (1 + alpha t^2) - y_i, J_i = (1 + 3 alpha t^2) a_i at its x
-// (SURVEY.md §8d); otherwise the stage holds J and r themselves.
+// ---- the per-row arithmetic (canonical op sequence) -------------------------------
+// kSynth: (a, yv) are a row of A and y of the polynomial family; the lane evaluates
+// r_i = t (1 + alpha t^2) - y_i and J_i = (1 + 3 alpha t^2) a_i at its x.
+// Otherwise (a, yv) are the row of J and r themselves.
+template <typename T, int N, bool kSynth>
+__device__ __forceinline__ void tpp_row_residual(T (&a)[N], T yv, const T (&x)[N], T alpha, T alpha3, bool want_j,
+                                                 T &ri) {
+  using O = Ops<T>;
+  if (kSynth) {
+    T t = (T)0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) t = O::fma(a[j], x[j], t);
+    const T t2 = O::mul(t, t);
+    ri = O::fma(t, O::fma(alpha, t2, (T)1), -yv);
+    if (want_j) {
+      const T sc = O::fma(alpha3, t2, (T)1);
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[j] = O::mul(sc, a[j]);
+    }
+  } else {
+    ri = yv;
+  }
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void tpp_row_accumulate(const T (&a)[N], T ri, T (&hu)[tri_count(N)], T (&g)[N]) {
+  using O = Ops<T>;
+#pragma unroll
+  for (int j = 0; j < N; ++j) g[j] = O::fma(a[j], ri, g[j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+#pragma unroll
+    for (int k = j; k < N; ++k) hu[tri_index(N, j, k)] = O::fma(a[j], a[k], hu[tri_index(N, j, k)]);
+  }
+}
+
+// One streaming pass over the m rows of a tile: cost, and (do_rebuild) g and the upper triangle of H.
+// Rows are consumed two at a time so that the two dependent t-chains interleave (ILP); the
+// accumulation order into every sum is still row 0, 1, 2, ...
 template <typename T, int N, bool kSynth>
 __device__ __forceinline__ void tpp_pass(TppPipe<T, N> &pipe, const TppData<T> &d, int64_t tile, int lane,
                                          bool active, bool do_rebuild, const T (&x)[N], T alpha, T alpha3,
@@ -111,64 +169,78 @@ __device__ __forceinline__ void tpp_pass(TppPipe<T, N> &pipe, const TppData<T> &
 
   const int m = d.m, R = d.rows;
   const int nchunks = (m + R - 1) / R;
-  const uint32_t c0 = pipe.count;
+  const T *jt = d.J + (size_t)tile * m * (N * kTile);
+  const T *rt = d.r + (size_t)tile * m * kTile;
   if (lane == 0) {
     fence_proxy_async();
-    const int pre = nchunks < kTppStages ? nchunks : kTppStages;
+    const int pre = nchunks < (int)pipe.nstages ? nchunks : (int)pipe.nstages;
+    uint32_t st = pipe.stage;
     for (int c = 0; c < pre; ++c) {
       const int row0 = c * R;
-      pipe.issue(d, tile, row0, (m - row0 < R) ? (m - row0) : R, (c0 + c) % kTppStages);
+      pipe.issue(jt, rt, row0, (m - row0 < R) ? (m - row0) : R, st);
+      if (++st == pipe.nstages) st = 0;
     }
   }
   for (int c = 0; c < nchunks; ++c) {
-    const uint32_t stage = pipe.count % kTppStages;
-    mbar_wait(&pipe.bars[stage], (pipe.count / kTppStages) & 1u);
+    mbar_wait(&pipe.bars[pipe.stage], pipe.phase);
     const int row0 = c * R;
     const int nrows = (m - row0 < R) ? (m - row0) : R;
     if (active) {
-      const T *sj = pipe.stage_ptr(stage) + lane;
-      const T *sr = pipe.stage_ptr(stage) + (size_t)R * N * kTile + lane;
-      for (int rr = 0; rr < nrows; ++rr) {
-        T a[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) a[j] = sj[(rr * N + j) * kTile];
-        const T yv = sr[rr * kTile];
-        T ri;
-        T sc = (T)1;
-        if (kSynth) {
-          T t = (T)0;
-#pragma unroll
-          for (int j = 0; j < N; ++j) t = O::fma(a[j], x[j], t);
-          const T t2 = O::mul(t, t);
-          ri = O::fma(t, O::fma(alpha, t2, (T)1), -yv);
-          sc = O::fma(alpha3, t2, (T)1);
-        } else {
-          ri = yv;
-        }
-        cost = O::fma(ri, ri, cost);
-        if (do_rebuild) {
-          if (kSynth) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) a[j] = O::mul(sc, a[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < N; ++j) g[j] = O::fma(a[j], ri, g[j]);
+      const T *sj = pipe.stage_ptr(pipe.stage) + lane;
+      const T *sr = sj + pipe.r_off;
+      if (do_rebuild) {
+        int rr = 0;
+        for (; rr + 2 <= nrows; rr += 2) {
+          T a0[N], a1[N];
 #pragma unroll
           for (int j = 0; j < N; ++j) {
-#pragma unroll
-            for (int k = j; k < N; ++k) hu[tri_index(N, j, k)] = O::fma(a[j], a[k], hu[tri_index(N, j, k)]);
+            a0[j] = sj[(rr * N + j) * kTile];
+            a1[j] = sj[((rr + 1) * N + j) * kTile];
           }
+          const T y0 = sr[rr * kTile], y1 = sr[(rr + 1) * kTile];
+          T r0, r1;
+          tpp_row_residual<T, N, kSynth>(a0, y0, x, alpha, alpha3, true, r0);
+          tpp_row_residual<T, N, kSynth>(a1, y1, x, alpha, alpha3, true, r1);
+          cost = O::fma(r0, r0, cost);
+          cost = O::fma(r1, r1, cost);
+          tpp_row_accumulate<T, N>(a0, r0, hu, g);
+          tpp_row_accumulate<T, N>(a1, r1, hu, g);
+        }
+        if (rr < nrows) {
+          T a0[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) a0[j] = sj[(rr * N + j) * kTile];
+          T r0;
+          tpp_row_residual<T, N, kSynth>(a0, sr[rr * kTile], x, alpha, alpha3, true, r0);
+          cost = O::fma(r0, r0, cost);
+          tpp_row_accumulate<T, N>(a0, r0, hu, g);
+        }
+      } else {  // cost-only pass (solvers/gn.h:98-105 Evaluate)
+        for (int rr = 0; rr < nrows; ++rr) {
+          T a0[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) a0[j] = sj[(rr * N + j) * kTile];
+          T r0;
+          tpp_row_residual<T, N, kSynth>(a0, sr[rr * kTile], x, alpha, alpha3, false, r0);
+          cost = O::fma(r0, r0, cost);
         }
       }
     }
     __syncwarp();
-    if (lane == 0 && c + kTppStages < nchunks) {
+    if (lane == 0 && c + (int)pipe.nstages < nchunks) {
       fence_proxy_async();
-      const int nrow0 = (c + kTppStages) * R;
-      pipe.issue(d, tile, nrow0, (m - nrow0 < R) ? (m - nrow0) : R, stage);
+      const int nrow0 = (c + (int)pipe.nstages) * R;
+      pipe.issue(jt, rt, nrow0, (m - nrow0 < R) ? (m - nrow0) : R, pipe.stage);
     }
-    pipe.count++;
+    pipe.advance();
   }
+}
+
+// dynamic tile scheduler: one atomic per warp per tile, broadcast by shuffle
+__device__ __forceinline__ int64_t tpp_next_tile(unsigned long long *counter, int lane) {
+  unsigned long long t = 0;
+  if (lane == 0) t = atomicAdd(counter, 1ull);
+  return (int64_t)__shfl_sync(0xffffffffu, t, 0);
 }
 
 __device__ __forceinline__ unsigned char *tpp_warp_smem(unsigned char *smem, uint32_t warp_smem) {
@@ -188,21 +260,20 @@ struct TppRunParams {
 };
 
 template <typename T, int N>
-__global__ void tpp_lm_run_kernel(const __grid_constant__ TppRunParams<T> p) {
+__global__ void __launch_bounds__(kTppThreads, tpp_min_blocks<T, N>())
+    tpp_lm_run_kernel(const __grid_constant__ TppRunParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NT = tri_count(N);
   const int lane = threadIdx.x & 31;
   unsigned char *ws = tpp_warp_smem(smem, p.d.warp_smem);
   TppPipe<T, N> pipe;
-  pipe.init(ws, p.d.rows, lane);
-  SmemHG<T, N> hg{reinterpret_cast<T *>(ws + kTppBarBytes + (size_t)kTppStages * pipe.stage_bytes), lane};
+  pipe.init(ws, p.d.rows, p.d.stages, lane);
+  SmemHG<T, N> hg{reinterpret_cast<T *>(ws + kTppBarBytes + (size_t)pipe.nstages * pipe.stage_bytes), lane};
 
-  const int warps_per_cta = blockDim.x / 32;
-  const int64_t gw = (int64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32;
-  const int64_t nw = (int64_t)gridDim.x * warps_per_cta;
   const bool is_lm = p.opt.solver_type == 0;
 
-  for (int64_t tile = gw; tile < p.d.ntiles; tile += nw) {
+  for (int64_t tile = tpp_next_tile(p.d.tile_counter, lane); tile < p.d.ntiles;
+       tile = tpp_next_tile(p.d.tile_counter, lane)) {
     const int64_t pidx = tile * kTile + lane;
     const bool valid = pidx < p.d.B;
     LmState<T, N> s;
@@ -245,20 +316,19 @@ struct TppBuildSolveParams {
 };
 
 template <typename T, int N>
-__global__ void tpp_build_solve_kernel(const __grid_constant__ TppBuildSolveParams<T> p) {
+__global__ void __launch_bounds__(kTppThreads, tpp_min_blocks<T, N>())
+    tpp_build_solve_kernel(const __grid_constant__ TppBuildSolveParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NT = tri_count(N);
   using L = LdltReg<T, N>;
   const int lane = threadIdx.x & 31;
   unsigned char *ws = tpp_warp_smem(smem, p.d.warp_smem);
   TppPipe<T, N> pipe;
-  pipe.init(ws, p.d.rows, lane);
+  pipe.init(ws, p.d.rows, p.d.stages, lane);
 
-  const int warps_per_cta = blockDim.x / 32;
-  const int64_t gw = (int64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32;
-  const int64_t nw = (int64_t)gridDim.x * warps_per_cta;
 
-  for (int64_t tile = gw; tile < p.d.ntiles; tile += nw) {
+  for (int64_t tile = tpp_next_tile(p.d.tile_counter, lane); tile < p.d.ntiles;
+       tile = tpp_next_tile(p.d.tile_counter, lane)) {
     const int64_t pidx = tile * kTile + lane;
     const bool valid = pidx < p.d.B;
     T hu[NT], g[N], cost, x[N];
@@ -350,21 +420,20 @@ __device__ __forceinline__ void state_store(const LmState<T, N> &s, StateRec<T> 
 }
 
 template <typename T, int N>
-__global__ void tpp_step_kernel(const __grid_constant__ TppStepParams<T> p) {
+__global__ void __launch_bounds__(kTppThreads, tpp_min_blocks<T, N>())
+    tpp_step_kernel(const __grid_constant__ TppStepParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NT = tri_count(N);
   const int lane = threadIdx.x & 31;
   unsigned char *ws = tpp_warp_smem(smem, p.d.warp_smem);
   TppPipe<T, N> pipe;
-  pipe.init(ws, p.d.rows, lane);
+  pipe.init(ws, p.d.rows, p.d.stages, lane);
 
-  const int warps_per_cta = blockDim.x / 32;
-  const int64_t gw = (int64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32;
-  const int64_t nw = (int64_t)gridDim.x * warps_per_cta;
   const bool is_lm = p.opt.solver_type == 0;
   unsigned long long local_active = 0;
 
-  for (int64_t tile = gw; tile < p.d.ntiles; tile += nw) {
+  for (int64_t tile = tpp_next_tile(p.d.tile_counter, lane); tile < p.d.ntiles;
+       tile = tpp_next_tile(p.d.tile_counter, lane)) {
     const int64_t pidx = tile * kTile + lane;
     const bool valid = pidx < p.d.B;
     LmState<T, N> s;
