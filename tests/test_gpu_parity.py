@@ -292,3 +292,68 @@ def test_full_size_configs(ctx, dtype, B, m, n):
     # total work
     assert r["num_iters"].sum() == r["num_iters"].astype(np.int64).sum()
     assert 2 <= r["num_iters"].min() and r["num_iters"].max() <= 12
+
+
+# ---- warp-per-problem family (13 <= n <= 55, float; config C4 shape n = 50, m = 500) ---------------
+WPP_SHAPES = [(40, 500, 50), (33, 37, 13), (17, 64, 20), (9, 100, 27), (21, 96, 28), (12, 45, 32),
+              (10, 130, 40), (7, 33, 47), (6, 70, 55), (5, 7, 13), (3, 1, 29)]
+
+
+def test_wpp_kernel_family(ctx):
+    assert ctx.kernel_family(torch.float32, 12) == 1 and ctx.kernel_family(torch.float32, 13) == 2
+    assert ctx.kernel_family(torch.float32, 55) == 2 and ctx.kernel_family(torch.float32, 56) == 0
+    assert ctx.kernel_family(torch.float64, 9) == 0
+
+
+@pytest.mark.parametrize("B,m,n", WPP_SHAPES)
+def test_wpp_build_solve_parity(ctx, B, m, n):
+    import tinyopt_b200 as tb
+    dtype = np.float32
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=11)
+    r, J = O.synth_eval(A, y, x0)
+    lam = np.full(B, np.float32(1e-4), dtype)
+    lam[::3] = 0
+    dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+    for layout in (tb.PROBLEM_MAJOR, tb.TILE32):
+        Jd, rd = torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda()
+        if layout == tb.TILE32:
+            Jd, rd = tb.to_tile32(Jd), tb.to_tile32(rd)
+        out = ctx.build_solve(Jd, rd, torch.from_numpy(lam).cuda(), B=B, layout=layout, want_H=True, want_g=True)
+        ctx.sync()
+        assert np.array_equal(out["status"].cpu().numpy(), st), (B, m, n)
+        ok = st == 0
+        assert rel_err(out["dx"].cpu().numpy()[ok], dx[ok]) <= TOL[dtype], (B, m, n)
+        assert rel_err(out["cost"].cpu().numpy(), cost) <= TOL[dtype]
+        # same canonical op sequence as the oracle -> same bits
+        assert np.array_equal(out["cost"].cpu().numpy(), cost)
+        assert np.array_equal(out["g"].cpu().numpy(), g)
+        assert np.array_equal(out["H"].cpu().numpy(), H)
+        assert np.array_equal(out["dx"].cpu().numpy()[ok], dx[ok]), (B, m, n, layout)
+
+
+@pytest.mark.parametrize("B,m,n", [(300, 500, 50), (40, 64, 13), (33, 90, 27), (35, 100, 28), (20, 77, 40), (9, 131, 55)])
+def test_wpp_lm_run_parity(ctx, B, m, n):
+    """config C4 shape (n=50, m=500, float, float-tuned thresholds) and the family's corners;
+    m*n % 4 != 0 cases take the non-TMA loader."""
+    import tinyopt_b200 as tb
+    xo, ro, out = run_both(ctx, np.float32, B, m, n, layout=tb.PROBLEM_MAJOR)
+    assert_lm_parity(np.float32, xo, ro, out)
+    assert (ro["stop_reason"] > 0).all()
+
+
+@pytest.mark.parametrize("optkw", [dict(min_rerr_dec=1e-10, min_step_norm2=1e-14),  # tinyopt defaults: fp32 noise floor
+                                   dict(solver_type=1), dict(max_iters=2), dict(damping_init=10.0, max_consec_failures=2),
+                                   dict(check_min_H_diag=1e3), dict(grad_clipping=0.05)])
+def test_wpp_lm_run_option_variants(ctx, optkw):
+    import tinyopt_b200 as tb
+    xo, ro, out = run_both(ctx, np.float32, 96, 120, 30, layout=tb.PROBLEM_MAJOR, **optkw)
+    assert_lm_parity(np.float32, xo, ro, out)
+    if "min_rerr_dec" in optkw:
+        assert (out.results["num_builds"] < out.results["num_iters"]).any()  # cost-only passes happened
+
+
+def test_wpp_layouts_agree(ctx):
+    import tinyopt_b200 as tb
+    _, _, out_p = run_both(ctx, np.float32, 70, 60, 33, layout=tb.PROBLEM_MAJOR)
+    _, _, out_t = run_both(ctx, np.float32, 70, 60, 33, layout=tb.TILE32)
+    assert torch.equal(out_t.x, out_p.x) and np.array_equal(out_t.results, out_p.results)

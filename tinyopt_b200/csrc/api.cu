@@ -16,6 +16,7 @@
 
 #include "internal.h"
 #include "tpp_inst.cuh"
+#include "wpp_inst.cuh"
 
 using namespace tob200;
 
@@ -38,6 +39,7 @@ struct tob200_ctx {
   int tpp_stages = 2;  // measured best on B200 (tools/tune_tpp.py): few, large stages
   int tpp_ctas_per_sm = 0;  // 0: what the kernel was compiled for (__launch_bounds__)
   unsigned long long *tile_counter = nullptr;
+  int wpp_stages = 2;  // env TOB200_WPP_STAGES
 };
 
 namespace {
@@ -169,20 +171,86 @@ int tpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, TppData<T>
   return TOB200_OK;
 }
 
-// PROBLEM_MAJOR inputs are re-tiled into context scratch (slots 0: J/A, 1: r/y)
+// Each kernel family has a native layout (1: TILE32, 2: PROBLEM_MAJOR); inputs in the other layout
+// are converted on the device into context scratch (slots 0: J/A, 1: r/y)
 template <typename T>
-int to_tile32(tob200_ctx *ctx, int layout, int64_t B, int m, int n, const T **J, const T **r) {
-  if (layout == TOB200_LAYOUT_TILE32) return TOB200_OK;
-  if (layout != TOB200_LAYOUT_PROBLEM_MAJOR) return fail(ctx, TOB200_ERR_INVALID, "unknown layout");
+int to_native_layout(tob200_ctx *ctx, int family, int layout, int64_t B, int m, int n, const T **J, const T **r) {
+  if (layout != TOB200_LAYOUT_TILE32 && layout != TOB200_LAYOUT_PROBLEM_MAJOR)
+    return fail(ctx, TOB200_ERR_INVALID, "unknown layout");
+  const int native = family == 1 ? TOB200_LAYOUT_TILE32 : TOB200_LAYOUT_PROBLEM_MAJOR;
+  if (layout == native || B == 0 || m == 0) return TOB200_OK;
   const size_t ej = (size_t)tob200_tiled_elems(B, m, n), er = (size_t)tob200_tiled_elems(B, m, 1);
   int rc;
   if ((rc = ensure_scratch(ctx, 0, ej * sizeof(T))) != TOB200_OK) return rc;
   if ((rc = ensure_scratch(ctx, 1, er * sizeof(T))) != TOB200_OK) return rc;
-  CK(launch_retile<T>(*J, B, m, n, (T *)ctx->scratch[0], ctx->stream));
-  CK(launch_retile<T>(*r, B, m, 1, (T *)ctx->scratch[1], ctx->stream));
+  if (native == TOB200_LAYOUT_TILE32) {
+    CK(launch_retile<T>(*J, B, m, n, (T *)ctx->scratch[0], ctx->stream));
+    CK(launch_retile<T>(*r, B, m, 1, (T *)ctx->scratch[1], ctx->stream));
+  } else {
+    CK(launch_untile<T>(*J, B, m, n, (T *)ctx->scratch[0], ctx->stream));
+    CK(launch_untile<T>(*r, B, m, 1, (T *)ctx->scratch[1], ctx->stream));
+  }
   ctx->launches += 2;
   *J = (const T *)ctx->scratch[0];
   *r = (const T *)ctx->scratch[1];
+  return TOB200_OK;
+}
+
+// launch geometry of a warp-per-problem kernel (family 2, float only)
+typedef cudaError_t (*WppEntry)(int, int, int, const void *, const TppLaunch &, int *);
+inline WppEntry wpp_entry_for(int n) { return wpp_blk_for(n) == 4 ? wpp_entry_f32_blk4 : wpp_entry_f32_blk8; }
+
+template <typename T>
+int wpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, const T *A, const T *y, WppData<T> *d,
+                  TppLaunch *cfg) {
+  const int blk = wpp_blk_for(n), nb = wpp_nb_for(n), np = nb * blk;
+  const int warps = kWppThreads / 32;
+  int stages = ctx->wpp_stages;
+  if (stages < 1) stages = 1;
+  if (stages > kWppMaxStages) stages = kWppMaxStages;
+  d->A = A;
+  d->y = y;
+  d->B = B;
+  d->m = m;
+  d->n = n;
+  d->stages = stages;
+  d->L = wpp_smem_layout(n, np, stages);
+  // TMA bulk copies need 16-byte aligned sources and sizes for every chunk of every problem
+  d->use_tma = (aligned16(A) && aligned16(y) && ((int64_t)m * n) % 4 == 0 && m % 4 == 0) ? 1 : 0;
+  d->counter = ctx->tile_counter;
+  cfg->block = kWppThreads;
+  cfg->smem = (size_t)d->L.total * warps;
+  cfg->stream = ctx->stream;
+  const auto key = std::make_tuple(100 + blk, nb, kind, cfg->block, cfg->smem);
+  auto it = ctx->occupancy.find(key);
+  int per_sm = 0;
+  if (it == ctx->occupancy.end()) {
+    cudaError_t e = wpp_entry_for(n)(kTppQuery, nb, kind, nullptr, *cfg, &per_sm);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "occupancy query");
+    if (per_sm < 1) return fail(ctx, TOB200_ERR_CUDA, "kernel does not fit on an SM (shared memory / registers)");
+    ctx->occupancy[key] = per_sm;
+  } else {
+    per_sm = it->second;
+  }
+  int64_t grid = (int64_t)per_sm * ctx->num_sms;
+  const int64_t need = (B + warps - 1) / warps;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  cfg->grid = (int)grid;
+  int rc = ensure_scratch(ctx, 7, (size_t)grid * warps * np * wpp_ldw(np) * sizeof(T));
+  if (rc != TOB200_OK) return rc;
+  d->hpersist = (T *)ctx->scratch[7];
+  cudaError_t e = cudaMemsetAsync(ctx->tile_counter, 0, sizeof(unsigned long long), ctx->stream);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMemsetAsync(counter)");
+  return TOB200_OK;
+}
+
+// float-only family: the double instantiation exists only so that the templates below compile
+template <typename T>
+int wpp_launch(tob200_ctx *ctx, int n, int kind, const void *params, const TppLaunch &cfg) {
+  if (sizeof(T) != 4) return fail(ctx, TOB200_ERR_UNSUPPORTED, "warp-per-problem kernels are float only");
+  CK(wpp_entry_for(n)(kTppLaunch, wpp_nb_for(n), kind, params, cfg, nullptr));
+  ctx->launches++;
   return TOB200_OK;
 }
 
@@ -207,24 +275,36 @@ int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_
   if (!J || !r || !dx || !cost || !status) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
   if (!aligned16(J) || !aligned16(r)) return fail(ctx, TOB200_ERR_INVALID, "J and r must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
-  if (tob200_kernel_family(dtype_of<T>(), n) != 1)
-    return fail(ctx, TOB200_ERR_UNSUPPORTED, "build_solve: n has no kernel yet for this dtype");
+  const int family = tob200_kernel_family(dtype_of<T>(), n);
+  if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "build_solve: n has no kernel yet for this dtype");
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = to_tile32<T>(ctx, layout, B, m, n, &J, &r);
+  int rc = to_native_layout<T>(ctx, family, layout, B, m, n, &J, &r);
   if (rc != TOB200_OK) return rc;
-  TppBuildSolveParams<T> p;
   TppLaunch cfg;
-  if ((rc = tpp_configure<T>(ctx, n, m, B, kTppBuildSolve, &p.d, &cfg)) != TOB200_OK) return rc;
-  p.d.J = J;
-  p.d.r = r;
-  p.lambda = lambda;
-  p.dx = dx;
-  p.cost = cost;
-  p.H_out = H_out;
-  p.g_out = g_out;
-  p.status = status;
-  CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppBuildSolve, &p, cfg, nullptr));
-  ctx->launches++;
+  if (family == 1) {
+    TppBuildSolveParams<T> p;
+    if ((rc = tpp_configure<T>(ctx, n, m, B, kTppBuildSolve, &p.d, &cfg)) != TOB200_OK) return rc;
+    p.d.J = J;
+    p.d.r = r;
+    p.lambda = lambda;
+    p.dx = dx;
+    p.cost = cost;
+    p.H_out = H_out;
+    p.g_out = g_out;
+    p.status = status;
+    CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppBuildSolve, &p, cfg, nullptr));
+    ctx->launches++;
+  } else {
+    WppBuildSolveParams<T> p;
+    if ((rc = wpp_configure<T>(ctx, n, m, B, kWppBuildSolve, J, r, &p.d, &cfg)) != TOB200_OK) return rc;
+    p.lambda = lambda;
+    p.dx = dx;
+    p.cost = cost;
+    p.H_out = H_out;
+    p.g_out = g_out;
+    p.status = status;
+    if ((rc = wpp_launch<T>(ctx, n, kWppBuildSolve, &p, cfg)) != TOB200_OK) return rc;
+  }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   return TOB200_OK;
 }
@@ -240,22 +320,33 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
   if (!A || !y || !x || !results) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
   if (!aligned16(A) || !aligned16(y)) return fail(ctx, TOB200_ERR_INVALID, "A and y must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
-  if (tob200_kernel_family(dtype_of<T>(), n) != 1)
-    return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n has no kernel yet for this dtype");
+  const int family = tob200_kernel_family(dtype_of<T>(), n);
+  if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n has no kernel yet for this dtype");
   if (record_events) CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  if ((rc = to_tile32<T>(ctx, layout, B, m, n, &A, &y)) != TOB200_OK) return rc;
-  TppRunParams<T> p;
+  if ((rc = to_native_layout<T>(ctx, family, layout, B, m, n, &A, &y)) != TOB200_OK) return rc;
   TppLaunch cfg;
-  if ((rc = tpp_configure<T>(ctx, n, m, B, kTppRun, &p.d, &cfg)) != TOB200_OK) return rc;
-  p.d.J = A;
-  p.d.r = y;
-  p.opt = make_dev_options<T>(*opt);
-  p.alpha = alpha;
-  p.alpha3 = (T)3 * alpha;
-  p.x = x;
-  p.results = results;
-  CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppRun, &p, cfg, nullptr));
-  ctx->launches++;
+  if (family == 1) {
+    TppRunParams<T> p;
+    if ((rc = tpp_configure<T>(ctx, n, m, B, kTppRun, &p.d, &cfg)) != TOB200_OK) return rc;
+    p.d.J = A;
+    p.d.r = y;
+    p.opt = make_dev_options<T>(*opt);
+    p.alpha = alpha;
+    p.alpha3 = (T)3 * alpha;
+    p.x = x;
+    p.results = results;
+    CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppRun, &p, cfg, nullptr));
+    ctx->launches++;
+  } else {
+    WppRunParams<T> p;
+    if ((rc = wpp_configure<T>(ctx, n, m, B, kWppRun, A, y, &p.d, &cfg)) != TOB200_OK) return rc;
+    p.opt = make_dev_options<T>(*opt);
+    p.alpha = alpha;
+    p.alpha3 = (T)3 * alpha;
+    p.x = x;
+    p.results = results;
+    if ((rc = wpp_launch<T>(ctx, n, kWppRun, &p, cfg)) != TOB200_OK) return rc;
+  }
   if (record_events) CK(cudaEventRecord(ctx->ev1, ctx->stream));
   return TOB200_OK;
 }
@@ -320,7 +411,7 @@ int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m
     if (m < 0) return fail(ctx, TOB200_ERR_INVALID, "m < 0");
     if (!J || !r) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
     if (!aligned16(J) || !aligned16(r)) return fail(ctx, TOB200_ERR_INVALID, "J and r must be 16-byte aligned");
-    int rc = to_tile32<T>(ctx, layout, B, m, n, &J, &r);
+    int rc = to_native_layout<T>(ctx, 1, layout, B, m, n, &J, &r);
     if (rc != TOB200_OK) return rc;
   }
   TppStepParams<T> p;
@@ -407,7 +498,7 @@ int64_t tob200_tiled_elems(int64_t B, int m, int n) {
 
 int tob200_kernel_family(int dtype, int n) {
   if (n < 1) return 0;
-  if (dtype == TOB200_F32) return n <= kTppMaxN_f32 ? 1 : 0;
+  if (dtype == TOB200_F32) return n <= kTppMaxN_f32 ? 1 : (n <= kWppMaxN_f32 ? 2 : 0);
   if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : 0;
   return 0;
 }
@@ -450,6 +541,7 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->tpp_stage_bytes = env_int("TOB200_TPP_STAGE_BYTES", ctx->tpp_stage_bytes);
   ctx->tpp_stages = env_int("TOB200_TPP_STAGES", ctx->tpp_stages);
   ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
+  ctx->wpp_stages = env_int("TOB200_WPP_STAGES", ctx->wpp_stages);
   if ((e = cudaMalloc((void **)&ctx->tile_counter, sizeof(unsigned long long))) != cudaSuccess) {
     tob200_destroy(ctx);
     return fail_cuda(nullptr, e, "cudaMalloc(tile_counter)");

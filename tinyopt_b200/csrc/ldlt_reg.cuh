@@ -132,11 +132,12 @@ struct LdltReg {
       const T d = w[idx(i, i)];
       y[i] = (O::abs(d) > O::min_normal()) ? O::div(y[i], d) : (T)0;
     }
+    // L^T y = y, updates applied to y_i in the order j = N-1 .. i+1 (canonical order)
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
       T s = y[i];
 #pragma unroll
-      for (int j = i + 1; j < N; ++j) s = O::fma(-w[idx(j, i)], y[j], s);
+      for (int j = N - 1; j > i; --j) s = O::fma(-w[idx(j, i)], y[j], s);
       y[i] = s;
     }
     if (N > 1) {

@@ -70,22 +70,21 @@ enum : uint32_t {
   kFlagDone = 8u,            // the OptimizeAcc loop has exited for this problem
 };
 
-template <typename T, int N>
-struct LmState {
-  T x[N];
-  T last_dx[N];
+// Scalar part of one `Optimizer_<SolverLM<...>>` + its `Output` (what does not depend on n).
+template <typename T>
+struct LmScalars {
   T lambda, prev_lambda, bad_factor;  // solvers/lm.h:191-193
   double final_cost;                  // Output::final_cost.cost (output.h:122)
   double final_rerr_dec;              // output.h:123
   int final_nres;
   int stop_reason;
   uint32_t flags;
-  uint16_t num_iters;  // output.h:133
+  uint16_t num_iters;                         // output.h:133
   uint8_t num_failures, num_consec_failures;  // output.h:134-136 (uint8 wrap-around kept)
   int num_builds;
   int iter;  // OptimizeAcc's loop counter (== num_iters while running)
 
-  __device__ __forceinline__ void reset(const DevOptions<T> &o) {
+  __device__ __forceinline__ void reset_scalars(const DevOptions<T> &o) {
     lambda = o.damping_init;  // lm.h:46-52
     prev_lambda = (T)0;
     bad_factor = o.bad_factor;
@@ -99,11 +98,21 @@ struct LmState {
     num_consec_failures = 0;
     num_builds = 0;
     iter = 0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) last_dx[j] = (T)0;
   }
   __device__ __forceinline__ bool done() const { return flags & kFlagDone; }
   __device__ __forceinline__ bool rebuild() const { return flags & kFlagRebuild; }
+};
+
+// thread-per-problem state: scalars + x and last_dx in registers
+template <typename T, int N>
+struct LmState : LmScalars<T> {
+  T x[N];
+  T last_dx[N];
+  __device__ __forceinline__ void reset(const DevOptions<T> &o) {
+    this->reset_scalars(o);
+#pragma unroll
+    for (int j = 0; j < N; ++j) last_dx[j] = (T)0;
+  }
 };
 
 template <typename T>
@@ -112,8 +121,8 @@ __device__ __forceinline__ T clamp_t(T v, T lo, T hi) {  // std::clamp
 }
 
 // solvers/lm.h:123-137
-template <typename T, int N>
-__device__ __forceinline__ void lm_good_step(LmState<T, N> &s, const DevOptions<T> &o, T quality) {
+template <typename T>
+__device__ __forceinline__ void lm_good_step(LmScalars<T> &s, const DevOptions<T> &o, T quality) {
   if (o.solver_type != 0) return;  // base.h:52: no-op for Gauss-Newton
   T sc = o.good_factor;
   if (quality != (T)0) {
@@ -130,8 +139,8 @@ __device__ __forceinline__ void lm_good_step(LmState<T, N> &s, const DevOptions<
 }
 
 // solvers/lm.h:140-148 (FailedStep == BadStep)
-template <typename T, int N>
-__device__ __forceinline__ void lm_bad_step(LmState<T, N> &s, const DevOptions<T> &o) {
+template <typename T>
+__device__ __forceinline__ void lm_bad_step(LmScalars<T> &s, const DevOptions<T> &o) {
   if (o.solver_type != 0) return;
   const T sc = s.bad_factor;
   s.prev_lambda = s.lambda;
@@ -141,12 +150,155 @@ __device__ __forceinline__ void lm_bad_step(LmState<T, N> &s, const DevOptions<T
 
 __device__ __forceinline__ bool is_nan_or_inf(double v) { return isnan(v) || isinf(v); }
 
-// Everything after the data pass of one OptimizeAcc iteration.
+// ---- the storage-independent pieces of one OptimizeAcc iteration -------------------------------
+// They are shared by the thread-per-problem kernels (vectors in registers) and the warp-per-problem
+// kernels (vectors in shared memory), so both run the very same decision sequence.
+
+// NormalizeCost (base.h:41-45) + Cost::isValid (cost.h:83)
+template <typename T>
+__device__ __forceinline__ bool lm_normalize_cost(const DevOptions<T> &o, T cost_t, int nres, double &cost) {
+  cost = (double)cost_t;
+  if (!o.use_squared_norm) cost = sqrt(cost);
+  if (o.downscale_by_2) cost *= 0.5f;
+  if (o.normalize && nres > 0) cost /= nres;
+  return nres > 0 && cost != 1.7976931348623157e+308;
+}
+
+// optimizer.h:356-357
+template <typename T>
+__device__ __forceinline__ uint8_t lm_max_tries(const DevOptions<T> &o) {
+  return o.max_consec_failures > 0 ? (uint8_t)(o.max_consec_failures > 1 ? o.max_consec_failures : 1) : 255;
+}
+
+// Build's damping factor (lm.h:108-117): returns false when no damping applies
+template <typename T>
+__device__ __forceinline__ bool lm_damping_scale(const LmScalars<T> &s, const DevOptions<T> &o, bool pass_rebuilt,
+                                                 double &sc) {
+  if (o.solver_type != 0 || !(s.lambda > (T)0)) return false;
+  sc = pass_rebuilt ? 1.0 + (double)s.lambda : (1.0 + (double)s.lambda) / (1.0 + (double)s.prev_lambda);
+  return true;
+}
+
+enum LmFailureAction { kLmRetry = 0, kLmBreak = 1, kLmEarlyReturn = 2 };
+
+// One failed Build-or-Solve inside Step's retry loop (optimizer.h:370-392)
+template <typename T>
+__device__ __forceinline__ int lm_on_solver_failure(LmScalars<T> &s, const DevOptions<T> &o, double cost, int nres) {
+  s.num_consec_failures++;
+  s.num_failures++;
+  if (nres == 0) {  // :374-377
+    s.stop_reason = TOB200_STOP_SKIPPED;
+    return kLmEarlyReturn;
+  }
+  if (is_nan_or_inf(cost)) {  // :378-381
+    s.stop_reason = TOB200_STOP_SYSTEM_HAS_NAN_OR_INF;
+    return kLmEarlyReturn;
+  }
+  if (o.max_consec_failures > 0 && s.num_consec_failures >= o.max_consec_failures) {  // :382-386
+    if (s.final_cost < (double)Ops<T>::max_value()) s.stop_reason = TOB200_STOP_MAX_CONSEC_NO_DECR;
+    return kLmBreak;
+  }
+  lm_bad_step(s, o);  // FailedStep (:389)
+  return kLmRetry;
+}
+
+// The rest of Step once the retry loop is over (optimizer.h:395-538): NaN guards, accept / reject,
+// lambda schedule, failure counters, stop tests.  Returns through success / has_dx the pair Step
+// hands back to OptimizeAcc.
+template <typename T>
+__device__ __forceinline__ void lm_finish_step(LmScalars<T> &s, const DevOptions<T> &o, bool early_return,
+                                               bool solver_failed, double cost, int nres, double dx_norm2,
+                                               double grad_norm2, bool &success, bool &has_dx) {
+  using O = Ops<T>;
+  success = false;
+  has_dx = false;
+  const int iter = s.num_iters;
+  if (early_return) return;  // stop_reason already set; status = {false, nullopt}
+  if (solver_failed) {       // :396-399
+    s.stop_reason = TOB200_STOP_SOLVER_FAILED;
+    return;
+  }
+  const double err = cost;
+  if (is_nan_or_inf(err) || is_nan_or_inf(dx_norm2)) {  // :405-409, :416-425
+    s.stop_reason = TOB200_STOP_SYSTEM_HAS_NAN_OR_INF;
+    return;
+  }
+  const double derr = err - s.final_cost;  // :428
+  const bool is_good_step = derr < 0.0;    // :429
+  const double rel_derr = (s.final_cost > (double)O::float_eps() && s.final_cost < (double)O::max_value())
+                              ? (s.final_cost - err) / s.final_cost
+                              : 0.0;  // :431-434
+  if (is_good_step || iter == 0) {  // :441-446
+    if (iter > 0) lm_good_step(s, o, o.use_step_quality_approx ? (T)rel_derr : (T)0);
+    s.num_consec_failures = 0;
+    s.final_cost = cost;
+    s.final_nres = nres;
+    s.final_rerr_dec = rel_derr;
+  } else {  // :447-460
+    lm_bad_step(s, o);
+    s.num_failures++;
+    s.num_consec_failures++;
+    if (o.max_consec_failures > 0 && s.num_consec_failures >= o.max_consec_failures) {
+      s.stop_reason = TOB200_STOP_MAX_CONSEC_NO_DECR;
+      return;
+    }
+    if (o.max_total_failures > 0 && s.num_failures >= o.max_total_failures) {
+      s.stop_reason = TOB200_STOP_MAX_NO_DECR;
+      return;
+    }
+  }
+  // :518-528
+  if (o.min_error_f > 0 && err < o.min_error) s.stop_reason = TOB200_STOP_MIN_ERROR;
+  else if (o.min_rerr_dec_f > 0 && rel_derr > 0.0 && rel_derr < o.min_rerr_dec) s.stop_reason = TOB200_STOP_MIN_REL_ERROR;
+  else if (o.min_step_norm2_f > 0 && dx_norm2 < o.min_step_norm2) s.stop_reason = TOB200_STOP_MIN_DELTA_NORM;
+  else if (o.min_grad_norm2_f > 0 && grad_norm2 < o.min_grad_norm2) s.stop_reason = TOB200_STOP_MIN_GRAD_NORM;
+  success = is_good_step;  // :536-538
+  has_dx = true;
+}
+
+enum LmUpdateAction { kLmNoMove = 0, kLmApplyDx = 1, kLmRollBack = 2, kLmProbeDx = 3 };
+
+// OptimizeAcc's reaction to Step's result (optimizer.h:269-309, 320-321): which move to apply to x
+// (kLmApplyDx / kLmProbeDx: x += dx and last_dx = dx; kLmRollBack: x -= last_dx), the rebuild flag
+// of the next Build, the iteration counter and the loop exit.
+template <typename T>
+__device__ __forceinline__ int lm_update_action(LmScalars<T> &s, const DevOptions<T> &o, bool success, bool has_dx) {
+  const int max_iters = o.max_iters + 1 + (o.check_final_cost ? 1 : 0);  // :248-250
+  bool eval_only = false;
+  int action = kLmNoMove;
+  if (success) {  // :271-279
+    action = kLmApplyDx;
+    s.flags |= kFlagHasLastDx | kFlagLastWasSuccess;
+    if (o.check_final_cost && s.iter + 1 == max_iters) eval_only = true;
+  } else {  // :281-297
+    if (s.flags & kFlagHasLastDx) {
+      action = kLmRollBack;
+      s.flags &= ~kFlagHasLastDx;
+    } else if (has_dx) {
+      action = kLmProbeDx;
+      s.flags |= kFlagHasLastDx;
+    }
+    eval_only = !(s.flags & kFlagLastWasSuccess);
+    s.flags &= ~kFlagLastWasSuccess;
+  }
+  if (eval_only) s.flags &= ~kFlagRebuild;  // :299 solver_.Rebuild(!eval_only)
+  else s.flags |= kFlagRebuild;
+  s.num_iters++;  // :307
+  s.iter++;
+  if (s.stop_reason != TOB200_STOP_NONE) {
+    s.flags |= kFlagDone;  // :309
+  } else if (s.iter >= max_iters) {
+    s.stop_reason = TOB200_STOP_MAX_ITERS;  // :320-321
+    s.flags |= kFlagDone;
+  }
+  return action;
+}
+
+// ---- thread-per-problem: everything after the data pass of one OptimizeAcc iteration -----------
 //   pass_rebuilt : the pass accumulated H and g (true) or only the cost (false)
 //   hu, g        : undamped accumulated upper triangle / gradient (valid iff pass_rebuilt)
 //   cost_t       : sum r^2 accumulated in T, nres : number of residuals the pass saw
 //   hg           : persistent H_ / grad_ storage of the solver
-//   dx_out       : the solved step (valid when the function returns true == dx engaged)
 template <typename T, int N, class HG>
 __device__ __forceinline__ void lm_after_pass(LmState<T, N> &s, const DevOptions<T> &o,
                                               bool pass_rebuilt, T (&hu)[tri_count(N)], T (&g)[N],
@@ -154,17 +306,10 @@ __device__ __forceinline__ void lm_after_pass(LmState<T, N> &s, const DevOptions
   using O = Ops<T>;
   using L = LdltReg<T, N>;
   constexpr int NT = tri_count(N);
-  const bool is_lm = (o.solver_type == 0);
-  const int iter = s.num_iters;
 
-  // ---- Build, first attempt: cost_ = acc(...); NormalizeCost (base.h:41-45) ----
-  double cost = (double)cost_t;
-  if (!o.use_squared_norm) cost = sqrt(cost);
-  if (o.downscale_by_2) cost *= 0.5f;
-  if (o.normalize && nres > 0) cost /= nres;
-  const bool cost_valid = nres > 0 && cost != 1.7976931348623157e+308;  // cost.h:83
-
-  bool built_ok = cost_valid;
+  // ---- Build, first attempt: cost_ = acc(...); NormalizeCost ----
+  double cost;
+  bool built_ok = lm_normalize_cost(o, cost_t, nres, cost);
   T diag0[N];  // undamped diagonal, for the re-damping of a retry after a rebuild
   if (pass_rebuilt) {
     s.num_builds++;
@@ -198,16 +343,13 @@ __device__ __forceinline__ void lm_after_pass(LmState<T, N> &s, const DevOptions
   }
 
   // ---- solve-retry loop (optimizer.h:354-399) ----
-  bool solver_failed = true;
+  bool solver_failed = true, early_return = false;
   T dx[N];
   int tr[N];
-  const uint8_t max_tries =
-      o.max_consec_failures > 0 ? (uint8_t)(o.max_consec_failures > 1 ? o.max_consec_failures : 1) : 255;
-  int attempt = 0;
-  bool early_return = false;
-  for (; s.num_consec_failures <= max_tries; ++attempt) {
-    // Build's damping (lm.h:108-117).  A failed Build (invalid cost / diagonal check) returns
-    // before the damping, exactly like the early `return false`s of lm.h:72-76,85,102.
+  const uint8_t max_tries = lm_max_tries(o);
+  for (int attempt = 0; s.num_consec_failures <= max_tries; ++attempt) {
+    // A failed Build (invalid cost / diagonal check) returns before the damping, exactly like the
+    // early `return false`s of lm.h:72-76,85,102.
     if (built_ok) {
       // `hu` is factorised in place below, so a retry (and every cost-only pass) starts from the
       // persistent copy of H_ instead of keeping a second triangle alive in registers
@@ -215,16 +357,12 @@ __device__ __forceinline__ void lm_after_pass(LmState<T, N> &s, const DevOptions
 #pragma unroll
         for (int i = 0; i < NT; ++i) hu[i] = hg.ld_h(i);
       }
-      if (is_lm && s.lambda > (T)0) {
-        if (pass_rebuilt) {  // re-accumulating at the same x gives the same H: re-damp diag0
-          const double sc = 1.0 + (double)s.lambda;
+      double sc;
+      if (lm_damping_scale(s, o, pass_rebuilt, sc)) {
+        // re-accumulating at the same x gives the same H, so a retry re-damps the saved diagonal
 #pragma unroll
-          for (int j = 0; j < N; ++j) hu[tri_index(N, j, j)] = (T)((double)diag0[j] * sc);
-        } else {
-          const double sc = (1.0 + (double)s.lambda) / (1.0 + (double)s.prev_lambda);
-#pragma unroll
-          for (int j = 0; j < N; ++j) hu[tri_index(N, j, j)] = (T)((double)hu[tri_index(N, j, j)] * sc);
-        }
+        for (int j = 0; j < N; ++j)
+          hu[tri_index(N, j, j)] = (T)((double)(pass_rebuilt ? diag0[j] : hu[tri_index(N, j, j)]) * sc);
       } else if (pass_rebuilt) {
 #pragma unroll
         for (int j = 0; j < N; ++j) hu[tri_index(N, j, j)] = diag0[j];
@@ -246,124 +384,46 @@ __device__ __forceinline__ void lm_after_pass(LmState<T, N> &s, const DevOptions
       }
     }
     if (!solver_failed) break;
-    s.num_consec_failures++;
-    s.num_failures++;
-    if (nres == 0) {  // optimizer.h:374-377
-      s.stop_reason = TOB200_STOP_SKIPPED;
-      early_return = true;
-      break;
-    } else if (is_nan_or_inf(cost)) {  // :378-381
-      s.stop_reason = TOB200_STOP_SYSTEM_HAS_NAN_OR_INF;
-      early_return = true;
-      break;
-    } else if (o.max_consec_failures > 0 && s.num_consec_failures >= o.max_consec_failures) {  // :382-386
-      if (s.final_cost < (double)O::max_value()) s.stop_reason = TOB200_STOP_MAX_CONSEC_NO_DECR;
-      break;
-    }
-    lm_bad_step(s, o);  // FailedStep (:389)
+    const int act = lm_on_solver_failure(s, o, cost, nres);
+    if (act == kLmEarlyReturn) early_return = true;
+    if (act != kLmRetry) break;
     // the reference would retry forever when max_consec_failures == 0 and H never becomes
     // positive; give up after 100000 retries like the oracle does
     if (attempt >= 100000) break;
   }
 
-  bool success = false, has_dx = false;
-  if (early_return) {
-    // stop_reason already set; status = {false, nullopt}
-  } else if (solver_failed) {  // optimizer.h:396-399
-    s.stop_reason = TOB200_STOP_SOLVER_FAILED;
-  } else {
-    const double err = cost;
-    T dn = (T)0, gn = (T)0;
+  double dx_norm2 = 0.0, grad_norm2 = 0.0;
+  if (!solver_failed) {
+    T dn = (T)0;
 #pragma unroll
     for (int j = 0; j < N; ++j) dn = O::fma(dx[j], dx[j], dn);
-    const double dx_norm2 = (double)dn;  // optimizer.h:412
-    double grad_norm2 = 0.0;
+    dx_norm2 = (double)dn;  // optimizer.h:412
     if (o.min_grad_norm2_f > 0.0f) {  // :413-415
+      T gn = (T)0;
 #pragma unroll
       for (int j = 0; j < N; ++j) gn = O::fma(g[j], g[j], gn);
       grad_norm2 = (double)gn;
     }
-    if (is_nan_or_inf(err)) {  // :405-409
-      s.stop_reason = TOB200_STOP_SYSTEM_HAS_NAN_OR_INF;
-    } else if (is_nan_or_inf(dx_norm2)) {  // :416-425
-      s.stop_reason = TOB200_STOP_SYSTEM_HAS_NAN_OR_INF;
-    } else {
-      const double derr = err - s.final_cost;  // :428
-      const bool is_good_step = derr < 0.0;    // :429
-      const double rel_derr = (s.final_cost > (double)O::float_eps() && s.final_cost < (double)O::max_value())
-                                  ? (s.final_cost - err) / s.final_cost
-                                  : 0.0;  // :431-434
-      bool stop_now = false;
-      if (is_good_step || iter == 0) {  // :441-446
-        if (iter > 0) lm_good_step(s, o, o.use_step_quality_approx ? (T)rel_derr : (T)0);
-        s.num_consec_failures = 0;
-        s.final_cost = cost;
-        s.final_nres = nres;
-        s.final_rerr_dec = rel_derr;
-      } else {  // :447-460
-        lm_bad_step(s, o);
-        s.num_failures++;
-        s.num_consec_failures++;
-        if (o.max_consec_failures > 0 && s.num_consec_failures >= o.max_consec_failures) {
-          s.stop_reason = TOB200_STOP_MAX_CONSEC_NO_DECR;
-          stop_now = true;
-        } else if (o.max_total_failures > 0 && s.num_failures >= o.max_total_failures) {
-          s.stop_reason = TOB200_STOP_MAX_NO_DECR;
-          stop_now = true;
-        }
-      }
-      if (!stop_now) {  // :518-528
-        if (o.min_error_f > 0 && err < o.min_error) s.stop_reason = TOB200_STOP_MIN_ERROR;
-        else if (o.min_rerr_dec_f > 0 && rel_derr > 0.0 && rel_derr < o.min_rerr_dec) s.stop_reason = TOB200_STOP_MIN_REL_ERROR;
-        else if (o.min_step_norm2_f > 0 && dx_norm2 < o.min_step_norm2) s.stop_reason = TOB200_STOP_MIN_DELTA_NORM;
-        else if (o.min_grad_norm2_f > 0 && grad_norm2 < o.min_grad_norm2) s.stop_reason = TOB200_STOP_MIN_GRAD_NORM;
-        success = is_good_step;  // :536-538
-        has_dx = true;
-      }
-    }
   }
+  bool success, has_dx;
+  lm_finish_step(s, o, early_return, solver_failed, cost, nres, dx_norm2, grad_norm2, success, has_dx);
 
-  // ---- OptimizeAcc's update (optimizer.h:269-309) ----
-  int max_iters = o.max_iters + 1 + (o.check_final_cost ? 1 : 0);  // :248-250
-  bool eval_only = false;
-  if (success) {  // :271-279
+  // ---- OptimizeAcc's update (traits.h:162,184-190 PlusEq) ----
+  const int action = lm_update_action(s, o, success, has_dx);
+  if (action == kLmApplyDx || action == kLmProbeDx) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      s.x[j] = O::add(s.x[j], dx[j]);  // traits.h:162,184-190
+      s.x[j] = O::add(s.x[j], dx[j]);
       s.last_dx[j] = dx[j];
     }
-    s.flags |= kFlagHasLastDx | kFlagLastWasSuccess;
-    if (o.check_final_cost && s.iter + 1 == max_iters) eval_only = true;
-  } else {  // :281-297
-    if (s.flags & kFlagHasLastDx) {
+  } else if (action == kLmRollBack) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) s.x[j] = O::add(s.x[j], -s.last_dx[j]);
-      s.flags &= ~kFlagHasLastDx;
-    } else if (has_dx) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        s.x[j] = O::add(s.x[j], dx[j]);
-        s.last_dx[j] = dx[j];
-      }
-      s.flags |= kFlagHasLastDx;
-    }
-    eval_only = !(s.flags & kFlagLastWasSuccess);
-    s.flags &= ~kFlagLastWasSuccess;
-  }
-  if (eval_only) s.flags &= ~kFlagRebuild;  // :299 solver_.Rebuild(!eval_only)
-  else s.flags |= kFlagRebuild;
-  s.num_iters++;  // :307
-  s.iter++;
-  if (s.stop_reason != TOB200_STOP_NONE) {
-    s.flags |= kFlagDone;  // :309
-  } else if (s.iter >= max_iters) {
-    s.stop_reason = TOB200_STOP_MAX_ITERS;  // :320-321
-    s.flags |= kFlagDone;
+    for (int j = 0; j < N; ++j) s.x[j] = O::add(s.x[j], -s.last_dx[j]);
   }
 }
 
-template <typename T, int N>
-__device__ __forceinline__ void lm_write_result(const LmState<T, N> &s, tob200_result *r) {
+template <typename T>
+__device__ __forceinline__ void lm_write_result(const LmScalars<T> &s, tob200_result *r) {
   r->final_cost = s.final_cost;
   r->final_rerr_dec = s.final_rerr_dec;
   r->last_lambda = (double)s.lambda;

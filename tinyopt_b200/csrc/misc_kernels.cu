@@ -35,6 +35,33 @@ cudaError_t launch_retile(const T *src, int64_t B, int m, int n, T *dst, cudaStr
   return cudaGetLastError();
 }
 
+// ---- TILE32 -> PROBLEM_MAJOR (inverse) ----
+template <typename T>
+__global__ void untile_kernel(const T *__restrict__ src, int64_t B, int64_t mn, T *__restrict__ dst) {
+  __shared__ T tile[32][33];
+  const int64_t t = blockIdx.x;
+  const int64_t e0 = (int64_t)blockIdx.y * 32;
+  for (int el = threadIdx.y; el < 32; el += blockDim.y) {
+    const int64_t e = e0 + el;
+    tile[el][threadIdx.x] = e < mn ? src[(t * mn + e) * 32 + threadIdx.x] : (T)0;
+  }
+  __syncthreads();
+  for (int pl = threadIdx.y; pl < 32; pl += blockDim.y) {
+    const int64_t p = t * 32 + pl, e = e0 + threadIdx.x;
+    if (p < B && e < mn) dst[p * mn + e] = tile[threadIdx.x][pl];
+  }
+}
+
+template <typename T>
+cudaError_t launch_untile(const T *src, int64_t B, int m, int n, T *dst, cudaStream_t st) {
+  const int64_t mn = (int64_t)m * n;
+  if (B <= 0 || mn <= 0) return cudaSuccess;
+  const int64_t ntiles = (B + 31) / 32;
+  dim3 grid((unsigned)ntiles, (unsigned)((mn + 31) / 32)), block(32, 8);
+  untile_kernel<T><<<grid, block, 0, st>>>(src, B, mn, dst);
+  return cudaGetLastError();
+}
+
 // ---- counter RNG: splitmix64 finaliser of seed ^ (p * golden + k) ----
 __device__ __forceinline__ uint64_t hash64(uint64_t seed, uint64_t p, uint64_t k) {
   uint64_t z = seed ^ (p * 0x9E3779B97F4A7C15ull + k);
@@ -171,6 +198,7 @@ cudaError_t launch_synth_eval(const T *A, const T *y, T alpha, int layout, int64
 
 #define INST(T)                                                                                                   \
   template cudaError_t launch_retile<T>(const T *, int64_t, int, int, T *, cudaStream_t);                          \
+  template cudaError_t launch_untile<T>(const T *, int64_t, int, int, T *, cudaStream_t);                          \
   template cudaError_t launch_synth_generate<T>(uint64_t, int64_t, int64_t, int, int, T, T, int, T *, T *, T *, T *, \
                                                 cudaStream_t, int *);                                              \
   template cudaError_t launch_synth_eval<T>(const T *, const T *, T, int, int64_t, int, int, const T *, T *, T *,  \

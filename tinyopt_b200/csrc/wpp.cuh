@@ -1,0 +1,651 @@
+// wpp.cuh — "warp per problem" kernels for mid n (13 <= n <= 55, float): config C4 (n = 50).
+//
+// One warp owns one problem.  Rows of the residual block (PROBLEM_MAJOR: A[p][i][j], dense) are
+// streamed HBM -> shared memory in chunks of 32 rows by TMA bulk copies (one contiguous copy per
+// chunk) through a warp-private mbarrier ring.  Per chunk:
+//   phase 1 (lane = row): t_i = a_i . x as the canonical left-to-right fma chain, r_i, the scale
+//            (1 + 3 alpha t_i^2), and the AUGMENTED row [J_i | r_i] is written to a packed buffer
+//            whose pitch keeps 16-byte vector loads aligned and conflict-free;
+//   phase 2 (lane = 8x8 register block of the upper triangle of [J|r]^T [J|r]): per row two
+//            broadcast vector loads per operand and 64 fmas.  The augmented column gives
+//            g = J^T r and the corner gives cost = r^T r for free, and every accumulator still
+//            receives its terms in row order i = 0..m-1 — the same sequence as the CPU oracle.
+// Then the damped matrix is laid out in shared memory and factorised by the warp with the same
+// diagonal-pivoted LDL^T as ldlt_reg.cuh (left-looking, lane = row, sequential dots; column-
+// oriented substitutions whose per-element update order equals the oracle's), and the LM state
+// machine (lm_state.cuh) runs warp-uniformly.  The persistent copy of H_ that tinyopt keeps for
+// cost-only iterations (solvers/lm.h:96-117) is written to a per-warp global scratch only when the
+// coming step can actually be followed by one.
+//
+// Reference path replaced: diff/optimize_autodiff.h:151-157, solvers/lm.h:60-120,
+// solvers/gn.h:150-171, math.h:232-240, optimizers/optimizer.h:243-539.
+#pragma once
+
+#include "common.cuh"
+#include "lm_state.cuh"
+
+namespace tob200 {
+
+constexpr int kWppRows = 32;      // rows per chunk == lanes
+constexpr int kWppThreads = 128;  // 4 independent warps per CTA
+constexpr int kWppMaxStages = 4;
+
+// geometry: the (n+1) columns of [J|r] are cut into NB blocks of BLK columns (BLK = 4 for n <= 27,
+// 8 above), NP = NB*BLK padded columns, NB*(NB+1)/2 <= 28 upper-triangular blocks = busy lanes
+__host__ __device__ constexpr int wpp_blk_for(int n) { return n + 1 <= 28 ? 4 : 8; }
+__host__ __device__ constexpr int wpp_nb_for(int n) { return (n + 1 + wpp_blk_for(n) - 1) / wpp_blk_for(n); }
+__host__ __device__ constexpr int wpp_ldw(int np) { return np + 1; }  // odd pitch of the LDLT matrix
+// pitch of the packed [J|r] rows: multiple of 4 floats (16-byte loads) with pitch/4 odd
+// (conflict-free lane-per-row stores)
+__host__ __device__ constexpr int wpp_nps(int np) { return ((np / 4) & 1) ? np : np + 4; }
+
+struct WppSmem {  // byte offsets inside one warp's shared memory
+  uint32_t bars, xs, last_dx, g, dxs, temp, tr, stages, stage_bytes, jbuf, total;
+};
+__host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
+  WppSmem L;
+  const uint32_t np = (uint32_t)np_;
+  uint32_t o = 0;
+  L.bars = o; o += 64;
+  L.xs = o; o += np * 4;
+  L.last_dx = o; o += np * 4;
+  L.g = o; o += np * 4;
+  L.dxs = o; o += np * 4;
+  L.temp = o; o += np * 4;
+  L.tr = o; o += np * 4;
+  o = (o + 127u) & ~127u;
+  L.stages = o;
+  L.stage_bytes = ((uint32_t)kWppRows * (uint32_t)(n + 1) * 4u + 127u) & ~127u;  // A rows, then y
+  o += (uint32_t)stages * L.stage_bytes;
+  L.jbuf = o; o += (uint32_t)kWppRows * (uint32_t)wpp_nps(np_) * 4u;
+  // the LDLT working matrix aliases [stages .. jbuf end): make sure it fits
+  const uint32_t wbytes = np * (uint32_t)wpp_ldw(np_) * 4u;
+  if (o - L.stages < wbytes) o = L.stages + wbytes;
+  L.total = (o + 127u) & ~127u;
+  return L;
+}
+
+template <typename T>
+struct WppData {
+  const T *A;  // [B][m][n] dense (J for build_solve)
+  const T *y;  // [B][m]    (r for build_solve)
+  int64_t B;
+  int m, n;
+  int stages;
+  int use_tma;  // 1: every chunk is 16-byte aligned; 0: cooperative loads
+  WppSmem L;
+  unsigned long long *counter;  // dynamic problem queue, zeroed before the launch
+  T *hpersist;                  // [warps in grid][NP * LDW] persistent damped H_
+};
+
+// ---- warp-private chunk loader ---------------------------------------------------------------------
+template <typename T>
+struct WppPipe {
+  uint64_t *bars;
+  unsigned char *stages;
+  uint32_t stage_bytes, nstages, stage, phase;
+  int use_tma;
+
+  __device__ __forceinline__ void init(unsigned char *ws, const WppData<T> &d, int lane) {
+    bars = reinterpret_cast<uint64_t *>(ws + d.L.bars);
+    stages = ws + d.L.stages;
+    stage_bytes = d.L.stage_bytes;
+    nstages = (uint32_t)d.stages;
+    stage = 0;
+    phase = 0;
+    use_tma = d.use_tma;
+    if (lane == 0) {
+      for (uint32_t s = 0; s < nstages; ++s) mbar_init(&bars[s], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ T *stage_ptr(uint32_t st) const { return reinterpret_cast<T *>(stages + (size_t)st * stage_bytes); }
+  __device__ __forceinline__ void advance() {
+    if (++stage == nstages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+  // all lanes call; rows [row0, row0 + nrows) of the problem whose rows start at ap / yp
+  __device__ __forceinline__ void issue(const T *ap, const T *yp, int n, int row0, int nrows, uint32_t st, int lane) {
+    T *sa = stage_ptr(st);
+    T *sy = sa + (size_t)kWppRows * n;
+    if (use_tma) {
+      if (lane == 0) {
+        const uint32_t ba = (uint32_t)nrows * (uint32_t)n * 4u, by = (uint32_t)nrows * 4u;
+        mbar_expect_tx(&bars[st], ba + by);
+        tma_bulk_g2s(sa, ap + (size_t)row0 * n, ba, &bars[st]);
+        tma_bulk_g2s(sy, yp + row0, by, &bars[st]);
+      }
+    } else {  // unaligned shapes: plain coalesced loads, completed before anyone reads
+      const T *ga = ap + (size_t)row0 * n;
+      for (int e = lane; e < nrows * n; e += 32) sa[e] = ga[e];
+      for (int e = lane; e < nrows; e += 32) sy[e] = yp[row0 + e];
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    if (use_tma) mbar_wait(&bars[stage], phase);
+    else __syncwarp();
+  }
+};
+
+// ---- warp-cooperative pivoted LDL^T on W (lower triangle, pitch ldw), same semantics and the same
+// ---- per-element operation order as LdltReg / the CPU oracle ------------------------------------------
+template <typename T>
+__device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, int *tr, T *temp, int lane) {
+  using O = Ops<T>;
+#define WW(i, j) W[(i) * ldw + (j)]
+  if (n == 1) {
+    if (lane == 0) tr[0] = 0;
+    __syncwarp();
+    return !(WW(0, 0) < (T)0);
+  }
+  int sign = 0;
+  bool found_zero_pivot = false, ret = true;
+  for (int k = 0; k < n; ++k) {
+    // largest |diagonal|, first maximum wins, NaN never wins unless it sits at k
+    T best = (T)-1;
+    int bi = 0x7fffffff;
+    for (int i = k + lane; i < n; i += 32) {
+      const T v = O::abs(WW(i, i));
+      if (v > best) {
+        best = v;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    const T wkk = WW(k, k);
+    const int p = (wkk != wkk) ? k : bi;
+    if (lane == 0) tr[k] = p;
+    if (p != k) {
+      for (int j = lane; j < k; j += 32) { const T t = WW(k, j); WW(k, j) = WW(p, j); WW(p, j) = t; }
+      for (int i = p + 1 + lane; i < n; i += 32) { const T t = WW(i, k); WW(i, k) = WW(i, p); WW(i, p) = t; }
+      for (int i = k + 1 + lane; i < p; i += 32) { const T t = WW(i, k); WW(i, k) = WW(p, i); WW(p, i) = t; }
+      if (lane == 0) { const T t = WW(k, k); WW(k, k) = WW(p, p); WW(p, p) = t; }
+    }
+    __syncwarp();
+    if (k > 0) {
+      for (int j = lane; j < k; j += 32) temp[j] = O::mul(WW(j, j), WW(k, j));
+      __syncwarp();
+      for (int i = k + lane; i < n; i += 32) {  // row k itself gives A_kk -= A10 . temp
+        T s = (T)0;
+        for (int j = 0; j < k; ++j) s = O::fma(WW(i, j), temp[j], s);
+        WW(i, k) = O::sub(WW(i, k), s);
+      }
+      __syncwarp();
+    }
+    const T akk = WW(k, k);
+    const bool pivot_is_valid = O::abs(akk) > (T)0;
+    if (k == 0 && !pivot_is_valid) {
+      bool z = true;
+      for (int j = 0; j < n; ++j)
+        for (int i = j + 1 + lane; i < n; i += 32) z = z && (WW(i, j) == (T)0);
+      if (lane == 0)
+        for (int j = 0; j < n; ++j) tr[j] = j;
+      __syncwarp();
+      return __all_sync(0xffffffffu, z);
+    }
+    if (k < n - 1) {
+      if (pivot_is_valid) {
+        for (int i = k + 1 + lane; i < n; i += 32) WW(i, k) = O::div(WW(i, k), akk);
+      } else {
+        bool z = true;
+        for (int i = k + 1 + lane; i < n; i += 32) z = z && (WW(i, k) == (T)0);
+        ret = ret && __all_sync(0xffffffffu, z);
+      }
+    }
+    __syncwarp();
+    if (found_zero_pivot && pivot_is_valid) ret = false;
+    else if (!pivot_is_valid) found_zero_pivot = true;
+    if (sign == 1) { if (akk < (T)0) sign = 2; }
+    else if (sign == -1) { if (akk > (T)0) sign = 2; }
+    else if (sign == 0) { if (akk > (T)0) sign = 1; else if (akk < (T)0) sign = -1; }
+  }
+  return ret && (sign == 1 || sign == 0);
+#undef WW
+}
+
+// y (shared, n values) <- P^T L^-T D^+ L^-1 P y; n <= 64
+template <typename T>
+__device__ __forceinline__ void wpp_ldlt_solve(const T *W, int ldw, int n, const int *tr, T *y, int lane) {
+  using O = Ops<T>;
+#define WW(i, j) W[(i) * ldw + (j)]
+  if (lane == 0) {
+    for (int k = 0; k < n; ++k) {
+      const int p = tr[k];
+      if (p != k) { const T t = y[k]; y[k] = y[p]; y[p] = t; }
+    }
+  }
+  __syncwarp();
+  T y0 = lane < n ? y[lane] : (T)0, y1 = lane + 32 < n ? y[lane + 32] : (T)0;
+  // L y = y, column oriented: y_i takes its updates in the order j = 0 .. i-1
+  for (int j = 0; j < n; ++j) {
+    const T yj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
+    if (lane > j && lane < n) y0 = O::fma(-WW(lane, j), yj, y0);
+    if (lane + 32 > j && lane + 32 < n) y1 = O::fma(-WW(lane + 32, j), yj, y1);
+  }
+  if (lane < n) { const T d = WW(lane, lane); y0 = (O::abs(d) > O::min_normal()) ? O::div(y0, d) : (T)0; }
+  if (lane + 32 < n) { const T d = WW(lane + 32, lane + 32); y1 = (O::abs(d) > O::min_normal()) ? O::div(y1, d) : (T)0; }
+  // L^T y = y, column oriented from the last column: y_i takes its updates in the order j = n-1 .. i+1
+  for (int j = n - 1; j >= 0; --j) {
+    const T yj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
+    if (lane < j) y0 = O::fma(-WW(j, lane), yj, y0);
+    if (lane + 32 < j) y1 = O::fma(-WW(j, lane + 32), yj, y1);
+  }
+  if (lane < n) y[lane] = y0;
+  if (lane + 32 < n) y[lane + 32] = y1;
+  __syncwarp();
+  if (lane == 0) {
+    for (int k = n - 1; k >= 0; --k) {
+      const int p = tr[k];
+      if (p != k) { const T t = y[k]; y[k] = y[p]; y[p] = t; }
+    }
+  }
+  __syncwarp();
+#undef WW
+}
+
+// sequential (canonical) sum of squares of a shared vector, computed by lane 0, broadcast
+template <typename T>
+__device__ __forceinline__ T wpp_sqnorm(const T *v, int n, int lane) {
+  T s = (T)0;
+  if (lane == 0)
+    for (int j = 0; j < n; ++j) s = Ops<T>::fma(v[j], v[j], s);
+  return __shfl_sync(0xffffffffu, s, 0);
+}
+
+// ---- per-warp register block bookkeeping ---------------------------------------------------------------
+template <int NB>
+__device__ __forceinline__ void wpp_block_of_lane(int lane, int &bi, int &bj, bool &has_block) {
+  // upper-triangular blocks enumerated row by row: (0,0) (0,1) .. (0,NB-1) (1,1) ..
+  bi = 0;
+  bj = 0;
+  has_block = false;
+  int rem = lane;
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    const int len = NB - r;
+    if (!has_block) {
+      if (rem < len) {
+        bi = r;
+        bj = r + rem;
+        has_block = true;
+      } else {
+        rem -= len;
+      }
+    }
+  }
+}
+
+// One streaming pass over the rows of a problem: accumulates the register block of
+// [J|r]^T [J|r] (do_rebuild) or only the cost (cost-only pass: returns it in cost_only).
+template <typename T, int NB, int BLK, bool kSynth>
+__device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, unsigned char *ws, int64_t p, int lane,
+                                         bool do_rebuild, T alpha, T alpha3, int bi, int bj, bool has_block,
+                                         T (&acc)[BLK][BLK], T &cost_only) {
+  using O = Ops<T>;
+  constexpr int NP = NB * BLK, NPS = wpp_nps(NP);
+  const int m = d.m, n = d.n;
+  const T *xs = reinterpret_cast<const T *>(ws + d.L.xs);
+  T *jbuf = reinterpret_cast<T *>(ws + d.L.jbuf);
+#pragma unroll
+  for (int u = 0; u < BLK; ++u)
+#pragma unroll
+    for (int v = 0; v < BLK; ++v) acc[u][v] = (T)0;
+  cost_only = (T)0;
+
+  const int nchunks = (m + kWppRows - 1) / kWppRows;
+  const T *ap = d.A + (size_t)p * m * n;
+  const T *yp = d.y + (size_t)p * m;
+  {
+    if (lane == 0) fence_proxy_async();
+    const int pre = nchunks < (int)pipe.nstages ? nchunks : (int)pipe.nstages;
+    uint32_t st = pipe.stage;
+    for (int c = 0; c < pre; ++c) {
+      const int row0 = c * kWppRows;
+      pipe.issue(ap, yp, n, row0, (m - row0 < kWppRows) ? (m - row0) : kWppRows, st, lane);
+      if (++st == pipe.nstages) st = 0;
+    }
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    pipe.wait();
+    const int row0 = c * kWppRows;
+    const int nrows = (m - row0 < kWppRows) ? (m - row0) : kWppRows;
+    const T *sa = pipe.stage_ptr(pipe.stage);
+    const T *sy = sa + (size_t)kWppRows * n;
+    // ---- phase 1: lane = row ----
+    if (lane < nrows) {
+      const T *arow = sa + lane * n;
+      T *jrow = jbuf + lane * NPS;
+      T ri, sc = (T)1;
+      if (kSynth) {
+        T t = (T)0;
+        for (int j = 0; j < n; ++j) t = O::fma(arow[j], xs[j], t);
+        const T t2 = O::mul(t, t);
+        ri = O::fma(t, O::fma(alpha, t2, (T)1), -sy[lane]);
+        sc = O::fma(alpha3, t2, (T)1);
+      } else {
+        ri = sy[lane];
+      }
+      if (do_rebuild) {
+        if (kSynth) {
+          for (int j = 0; j < n; ++j) jrow[j] = O::mul(sc, arow[j]);
+        } else {
+          for (int j = 0; j < n; ++j) jrow[j] = arow[j];
+        }
+      }
+      jrow[n] = ri;
+    }
+    __syncwarp();
+    // the stage is free again: refill it with chunk c + nstages
+    if (c + (int)pipe.nstages < nchunks) {
+      if (lane == 0) fence_proxy_async();
+      const int nrow0 = (c + (int)pipe.nstages) * kWppRows;
+      pipe.issue(ap, yp, n, nrow0, (m - nrow0 < kWppRows) ? (m - nrow0) : kWppRows, pipe.stage, lane);
+    }
+    pipe.advance();
+    // ---- phase 2: lane = 8x8 block of the upper triangle ----
+    if (do_rebuild) {
+      if (has_block) {
+        const T *pa = jbuf + bi * BLK;
+        const T *pb = jbuf + bj * BLK;
+#pragma unroll 2
+        for (int i = 0; i < nrows; ++i) {
+          T a[BLK], b[BLK];
+#pragma unroll
+          for (int q = 0; q < BLK / 4; ++q) {
+            const float4 av = *reinterpret_cast<const float4 *>(pa + i * NPS + 4 * q);
+            const float4 bv = *reinterpret_cast<const float4 *>(pb + i * NPS + 4 * q);
+            a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
+            b[4 * q] = bv.x; b[4 * q + 1] = bv.y; b[4 * q + 2] = bv.z; b[4 * q + 3] = bv.w;
+          }
+#pragma unroll
+          for (int u = 0; u < BLK; ++u)
+#pragma unroll
+            for (int v = 0; v < BLK; ++v) acc[u][v] = O::fma(a[u], b[v], acc[u][v]);
+        }
+      }
+    } else if (lane == 0) {  // cost-only pass (solvers/gn.h:98-105): sum r_i^2 in row order
+      for (int i = 0; i < nrows; ++i) {
+        const T ri = jbuf[i * NPS + n];
+        cost_only = O::fma(ri, ri, cost_only);
+      }
+    }
+    __syncwarp();
+  }
+  cost_only = __shfl_sync(0xffffffffu, cost_only, 0);
+}
+
+// write the register blocks as the lower-triangular LDLT matrix W(i,j) = H(j,i), j <= i
+template <typename T, int NB, int BLK>
+__device__ __forceinline__ void wpp_store_blocks(T *W, int bi, int bj, bool has_block, const T (&acc)[BLK][BLK]) {
+  constexpr int LDW = wpp_ldw(NB * BLK);
+  if (!has_block) return;
+#pragma unroll
+  for (int u = 0; u < BLK; ++u)
+#pragma unroll
+    for (int v = 0; v < BLK; ++v) {
+      const int row = bi * BLK + u, col = bj * BLK + v;  // upper element (row, col)
+      if (row <= col) W[col * LDW + row] = acc[u][v];
+    }
+}
+
+// Everything after the data pass for one problem, warp-cooperative; mirrors lm_after_pass.
+template <typename T, int NB, int BLK>
+__device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions<T> &o, const WppData<T> &d,
+                                               unsigned char *ws, T *hp, bool pass_rebuilt, int bi, int bj,
+                                               bool has_block, const T (&acc)[BLK][BLK], T cost_only, int lane) {
+  using O = Ops<T>;
+  constexpr int LDW = wpp_ldw(NB * BLK);
+  const int n = d.n, nres = d.m;
+  T *W = reinterpret_cast<T *>(ws + d.L.stages);
+  T *xs = reinterpret_cast<T *>(ws + d.L.xs);
+  T *last_dx = reinterpret_cast<T *>(ws + d.L.last_dx);
+  T *g = reinterpret_cast<T *>(ws + d.L.g);
+  T *dxs = reinterpret_cast<T *>(ws + d.L.dxs);
+  T *temp = reinterpret_cast<T *>(ws + d.L.temp);
+  int *tr = reinterpret_cast<int *>(ws + d.L.tr);
+
+  T cost_t = cost_only;
+  if (pass_rebuilt) {
+    wpp_store_blocks<T, NB, BLK>(W, bi, bj, has_block, acc);
+    __syncwarp();
+    cost_t = W[n * LDW + n];                                    // r^T r
+    for (int j = lane; j < n; j += 32) g[j] = W[n * LDW + j];  // J^T r
+    __syncwarp();
+  }
+  double cost;
+  bool built_ok = lm_normalize_cost(o, cost_t, nres, cost);
+  if (pass_rebuilt) {
+    s.num_builds++;
+    if (built_ok) {
+      if (o.grad_clipping != (T)0) {  // base.h:30-38
+        for (int j = lane; j < n; j += 32) {
+          T v = g[j];
+          v = v < -o.grad_clipping ? -o.grad_clipping : v;
+          v = v > o.grad_clipping ? o.grad_clipping : v;
+          g[j] = v;
+        }
+        __syncwarp();
+      }
+      if (o.check_min_H_diag > (T)0) {  // lm.h:82-86
+        bool low = false;
+        for (int j = lane; j < n; j += 32) low = low || (O::abs(W[j * LDW + j]) < o.check_min_H_diag);
+        if (__any_sync(0xffffffffu, low)) built_ok = false;
+      }
+    }
+  }
+  // Will a cost-only iteration possibly follow this one?  Only then does H_ have to outlive the
+  // next pass (optimizer.h:295: eval_only = !last_was_success, after a step that did not succeed).
+  const bool may_need_stale_h =
+      !pass_rebuilt || (!(cost - s.final_cost < 0.0) && !(s.flags & kFlagLastWasSuccess));
+
+  bool solver_failed = true, early_return = false;
+  const uint8_t max_tries = lm_max_tries(o);
+  for (int attempt = 0; s.num_consec_failures <= max_tries; ++attempt) {
+    if (built_ok) {
+      if (pass_rebuilt) {
+        if (attempt > 0) {  // the factorisation destroyed W: lay the undamped blocks out again
+          wpp_store_blocks<T, NB, BLK>(W, bi, bj, has_block, acc);
+          __syncwarp();
+        }
+      } else {  // cost-only pass, or a retry of one: start from the persistent damped H_
+        for (int e = lane; e < n * LDW; e += 32) W[e] = hp[e];
+        __syncwarp();
+      }
+      double sc;
+      if (lm_damping_scale(s, o, pass_rebuilt, sc)) {  // lm.h:108-117
+        for (int j = lane; j < n; j += 32) W[j * LDW + j] = (T)((double)W[j * LDW + j] * sc);
+        __syncwarp();
+      }
+      if (may_need_stale_h) {  // publish H_ (damped)
+        if (pass_rebuilt) {
+          for (int e = lane; e < n * LDW; e += 32) hp[e] = W[e];
+        } else {
+          for (int j = lane; j < n; j += 32) hp[j * LDW + j] = W[j * LDW + j];
+        }
+      }
+      if (wpp_ldlt_factor<T>(W, LDW, n, tr, temp, lane)) {  // gn.h:150-156
+        for (int j = lane; j < n; j += 32) dxs[j] = -g[j];
+        __syncwarp();
+        wpp_ldlt_solve<T>(W, LDW, n, tr, dxs, lane);
+        solver_failed = false;
+      }
+    }
+    if (!solver_failed) break;
+    const int act = lm_on_solver_failure(s, o, cost, nres);
+    if (act == kLmEarlyReturn) early_return = true;
+    if (act != kLmRetry) break;
+    if (attempt >= 100000) break;
+  }
+
+  double dx_norm2 = 0.0, grad_norm2 = 0.0;
+  if (!solver_failed) {
+    dx_norm2 = (double)wpp_sqnorm<T>(dxs, n, lane);
+    if (o.min_grad_norm2_f > 0.0f) grad_norm2 = (double)wpp_sqnorm<T>(g, n, lane);
+  }
+  bool success, has_dx;
+  lm_finish_step(s, o, early_return, solver_failed, cost, nres, dx_norm2, grad_norm2, success, has_dx);
+  const int action = lm_update_action(s, o, success, has_dx);
+  if (action == kLmApplyDx || action == kLmProbeDx) {
+    for (int j = lane; j < n; j += 32) {
+      xs[j] = O::add(xs[j], dxs[j]);
+      last_dx[j] = dxs[j];
+    }
+  } else if (action == kLmRollBack) {
+    for (int j = lane; j < n; j += 32) xs[j] = O::add(xs[j], -last_dx[j]);
+  }
+  __syncwarp();
+}
+
+// columns [c0, c1) of all 32 packed rows <- 0 (the LDLT matrix aliases the packed buffer, so the
+// pad columns are cleared before every pass)
+template <typename T>
+__device__ __forceinline__ void wpp_zero_pad_columns(T *jbuf, int nps, int c0, int c1, int lane) {
+  const int w = c1 - c0;
+  for (int e = lane; e < kWppRows * w; e += 32) jbuf[(e / w) * nps + c0 + (e % w)] = (T)0;
+  __syncwarp();
+}
+
+__device__ __forceinline__ int64_t wpp_next(unsigned long long *counter, int lane) {
+  unsigned long long t = 0;
+  if (lane == 0) t = atomicAdd(counter, 1ull);
+  return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tob200_lm_run_* for mid n
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct WppRunParams {
+  WppData<T> d;
+  DevOptions<T> opt;
+  T alpha, alpha3;
+  T *x;                    // [B][n] in/out
+  tob200_result *results;  // [B]
+};
+
+template <typename T, int NB, int BLK>
+__global__ void __launch_bounds__(kWppThreads, 2) wpp_lm_run_kernel(const __grid_constant__ WppRunParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x / 32;
+  unsigned char *ws = smem + (size_t)wid * p.d.L.total;
+  const int n = p.d.n;
+  constexpr int NP = NB * BLK, NPS = wpp_nps(NP), LDW = wpp_ldw(NP);
+  WppPipe<T> pipe;
+  pipe.init(ws, p.d, lane);
+  T *xs = reinterpret_cast<T *>(ws + p.d.L.xs);
+  T *last_dx = reinterpret_cast<T *>(ws + p.d.L.last_dx);
+  T *jbuf = reinterpret_cast<T *>(ws + p.d.L.jbuf);
+  T *hp = p.d.hpersist + ((size_t)blockIdx.x * (kWppThreads / 32) + wid) * (NP * LDW);
+  int bi, bj;
+  bool has_block;
+  wpp_block_of_lane<NB>(lane, bi, bj, has_block);
+  const bool is_lm = p.opt.solver_type == 0;
+
+  for (int64_t pr = wpp_next(p.d.counter, lane); pr < p.d.B; pr = wpp_next(p.d.counter, lane)) {
+    // pad columns of the packed rows are zero and stay zero (the LDLT matrix aliases this buffer,
+    // so they are cleared again for every problem)
+    for (int j = lane; j < NP; j += 32) {
+      xs[j] = j < n ? p.x[pr * n + j] : (T)0;
+      last_dx[j] = (T)0;
+    }
+    LmScalars<T> s;
+    s.reset_scalars(p.opt);
+    __syncwarp();
+    while (!s.done()) {
+      wpp_zero_pad_columns<T>(jbuf, NPS, n + 1, NP, lane);
+      const bool do_rebuild = !is_lm || s.rebuild();
+      T acc[BLK][BLK], cost_only;
+      wpp_pass<T, NB, BLK, true>(pipe, p.d, ws, pr, lane, do_rebuild, p.alpha, p.alpha3, bi, bj, has_block, acc, cost_only);
+      wpp_after_pass<T, NB, BLK>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane);
+    }
+    for (int j = lane; j < n; j += 32) p.x[pr * n + j] = xs[j];
+    if (lane == 0) lm_write_result(s, &p.results[pr]);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tob200_build_solve_* for mid n
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct WppBuildSolveParams {
+  WppData<T> d;
+  const T *lambda;
+  T *dx;
+  double *cost;
+  T *H_out;
+  T *g_out;
+  int32_t *status;
+};
+
+template <typename T, int NB, int BLK>
+__global__ void __launch_bounds__(kWppThreads, 2) wpp_build_solve_kernel(const __grid_constant__ WppBuildSolveParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x / 32;
+  unsigned char *ws = smem + (size_t)wid * p.d.L.total;
+  const int n = p.d.n;
+  constexpr int NP = NB * BLK, NPS = wpp_nps(NP), LDW = wpp_ldw(NP);
+  WppPipe<T> pipe;
+  pipe.init(ws, p.d, lane);
+  T *W = reinterpret_cast<T *>(ws + p.d.L.stages);
+  T *g = reinterpret_cast<T *>(ws + p.d.L.g);
+  T *dxs = reinterpret_cast<T *>(ws + p.d.L.dxs);
+  T *temp = reinterpret_cast<T *>(ws + p.d.L.temp);
+  int *tr = reinterpret_cast<int *>(ws + p.d.L.tr);
+  T *jbuf = reinterpret_cast<T *>(ws + p.d.L.jbuf);
+  int bi, bj;
+  bool has_block;
+  wpp_block_of_lane<NB>(lane, bi, bj, has_block);
+
+  for (int64_t pr = wpp_next(p.d.counter, lane); pr < p.d.B; pr = wpp_next(p.d.counter, lane)) {
+    wpp_zero_pad_columns<T>(jbuf, NPS, n + 1, NP, lane);
+    T acc[BLK][BLK], cost_only;
+    wpp_pass<T, NB, BLK, false>(pipe, p.d, ws, pr, lane, true, (T)0, (T)0, bi, bj, has_block, acc, cost_only);
+    wpp_store_blocks<T, NB, BLK>(W, bi, bj, has_block, acc);
+    __syncwarp();
+    const T cost_t = W[n * LDW + n];
+    for (int j = lane; j < n; j += 32) g[j] = W[n * LDW + j];
+    __syncwarp();
+    const T lam = p.lambda ? p.lambda[pr] : (T)0;
+    if (lam > (T)0) {  // solvers/lm.h:108-117
+      const double sc = 1.0 + (double)lam;
+      for (int j = lane; j < n; j += 32) W[j * LDW + j] = (T)((double)W[j * LDW + j] * sc);
+      __syncwarp();
+    }
+    if (lane == 0) p.cost[pr] = (double)cost_t;
+    if (p.g_out)
+      for (int j = lane; j < n; j += 32) p.g_out[pr * n + j] = g[j];
+    if (p.H_out) {
+      T *Ho = p.H_out + (size_t)pr * n * n;
+      for (int e = lane; e < n * n; e += 32) {
+        const int r = e / n, c = e % n;
+        Ho[e] = r <= c ? W[c * LDW + r] : W[r * LDW + c];
+      }
+    }
+    __syncwarp();
+    const bool ok = wpp_ldlt_factor<T>(W, LDW, n, tr, temp, lane);  // math.h:232-240
+    if (ok) {
+      for (int j = lane; j < n; j += 32) dxs[j] = -g[j];  // solvers/gn.h:155
+      __syncwarp();
+      wpp_ldlt_solve<T>(W, LDW, n, tr, dxs, lane);
+      for (int j = lane; j < n; j += 32) p.dx[pr * n + j] = dxs[j];
+    }
+    if (lane == 0) p.status[pr] = ok ? 0 : 1;
+    __syncwarp();
+  }
+}
+
+}  // namespace tob200

@@ -1,0 +1,48 @@
+// wpp_inst.cuh — instantiation + launch plumbing for the warp-per-problem kernels (wpp.cuh).
+#pragma once
+
+#include "tpp_inst.cuh"  // TppLaunch, TppOp
+#include "wpp.cuh"
+
+namespace tob200 {
+
+enum WppKind { kWppRun = 0, kWppBuildSolve = 1 };
+
+template <typename T, int NB, int BLK>
+cudaError_t wpp_entry_one(int op, int kind, const void *params, const TppLaunch &cfg, int *out) {
+  const void *fn = nullptr;
+  switch (kind) {
+    case kWppRun: fn = (const void *)wpp_lm_run_kernel<T, NB, BLK>; break;
+    case kWppBuildSolve: fn = (const void *)wpp_build_solve_kernel<T, NB, BLK>; break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (op == kTppQuery) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, fn, cfg.block, cfg.smem);
+  }
+  void *args[] = {const_cast<void *>(params)};
+  return cudaLaunchKernel(fn, dim3(cfg.grid), dim3(cfg.block), args, cfg.smem, cfg.stream);
+}
+
+// one entry per block edge; nb = 4..7
+#define TOB200_WPP_ENTRY_DECL(name) \
+  cudaError_t name(int op, int nb, int kind, const void *params, const TppLaunch &cfg, int *out)
+#define TOB200_WPP_ENTRY_DEFINE(name, T, BLK)                                              \
+  TOB200_WPP_ENTRY_DECL(name) {                                                            \
+    switch (nb) {                                                                          \
+      case 4: return wpp_entry_one<T, 4, BLK>(op, kind, params, cfg, out);                 \
+      case 5: return wpp_entry_one<T, 5, BLK>(op, kind, params, cfg, out);                 \
+      case 6: return wpp_entry_one<T, 6, BLK>(op, kind, params, cfg, out);                 \
+      case 7: return wpp_entry_one<T, 7, BLK>(op, kind, params, cfg, out);                 \
+      default: return cudaErrorInvalidValue;                                               \
+    }                                                                                      \
+  }
+
+constexpr int kWppMinN_f32 = kTppMaxN_f32 + 1;  // 13
+constexpr int kWppMaxN_f32 = 55;                // n + 1 <= 7 * 8
+
+TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk4);  // n = 13..27
+TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk8);  // n = 28..55
+
+}  // namespace tob200
