@@ -29,6 +29,9 @@ FLOAT_OPTS = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)
 CONFIGS = {
     "C2": dict(B=100_000, m=30, n=6, dtype="f64", opts={}, desc="batch 100k problems, n=6 params, 30 residuals each, double"),
     "C3": dict(B=100_000, m=200, n=12, dtype="f32", opts=FLOAT_OPTS, desc="batch 100k problems, n=12 params, 200 residuals each, float"),
+    # C4 is the sharded config: 1M problems in total, split over the ranks (strong scaling)
+    "C4": dict(B=1_000_000, m=500, n=50, dtype="f32", opts=FLOAT_OPTS, strong=True,
+               desc="batch 1M problems, n=50 params, 500 residuals, float, sharded over the GPUs"),
 }
 SEED, ALPHA, SIGMA = 20261017, 0.1, 1e-2
 

@@ -39,7 +39,7 @@ struct tob200_ctx {
   int tpp_stages = 2;  // measured best on B200 (tools/tune_tpp.py): few, large stages
   int tpp_ctas_per_sm = 0;  // 0: what the kernel was compiled for (__launch_bounds__)
   unsigned long long *tile_counter = nullptr;
-  int wpp_stages = 2;  // env TOB200_WPP_STAGES
+  int wpp_stages = 1;  // env TOB200_WPP_STAGES (1: three CTAs per SM fit, measured best)
 };
 
 namespace {

@@ -40,7 +40,7 @@ __host__ __device__ constexpr int wpp_ldw(int np) { return np + 1; }  // odd pit
 __host__ __device__ constexpr int wpp_nps(int np) { return ((np / 4) & 1) ? np : np + 4; }
 
 struct WppSmem {  // byte offsets inside one warp's shared memory
-  uint32_t bars, xs, last_dx, g, dxs, temp, tr, stages, stage_bytes, jbuf, total;
+  uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, stages, stage_bytes, jbuf, total;
 };
 __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   WppSmem L;
@@ -52,7 +52,10 @@ __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   L.g = o; o += np * 4;
   L.dxs = o; o += np * 4;
   L.temp = o; o += np * 4;
-  L.tr = o; o += np * 4;
+  L.dg = o; o += np * 4;
+  L.dd = o; o += np * 4;
+  L.perm = o; o += np * 4;
+  L.inv = o; o += np * 4;
   o = (o + 127u) & ~127u;
   L.stages = o;
   L.stage_bytes = ((uint32_t)kWppRows * (uint32_t)(n + 1) * 4u + 127u) & ~127u;  // A rows, then y
@@ -130,68 +133,84 @@ struct WppPipe {
   }
 };
 
-// ---- warp-cooperative pivoted LDL^T on W (lower triangle, pitch ldw), same semantics and the same
-// ---- per-element operation order as LdltReg / the CPU oracle ------------------------------------------
+// ---- warp-cooperative pivoted LDL^T, same semantics and the same per-element operation order as
+// ---- LdltReg / the CPU oracle -----------------------------------------------------------------------
+// Eigen's unblocked LDLT is left-looking: step k only finishes column k, so the trailing diagonal it
+// searches for the next pivot is still the ORIGINAL (permuted) diagonal.  The whole pivot sequence is
+// therefore a function of the diagonal alone: it is computed first (in registers, one REDUX + two
+// ballots per step), the matrix is laid out already permuted, and the factorisation itself runs
+// without any search or swap.  P A P^T = L D L^T with the same P, the same L, the same bits.
+
+// pos2orig of the pivot order for the diagonal dd[0..n) (n <= 64); writes perm[pos] = orig and
+// inv[orig] = pos.  "First maximum wins" and NaN handling as in Eigen's maxCoeff visitor.
+__device__ __forceinline__ void wpp_pivot_order(const float *dd, int n, int *perm, int *inv, int lane) {
+  const int i0 = lane, i1 = lane + 32;
+  uint32_t k0 = 0, k1 = 0;  // 0: NaN (never wins), otherwise 1 + bits(|d|) (monotone in |d|)
+  if (i0 < n) { const float v = fabsf(dd[i0]); k0 = (v != v) ? 0u : __float_as_uint(v) + 1u; }
+  if (i1 < n) { const float v = fabsf(dd[i1]); k1 = (v != v) ? 0u : __float_as_uint(v) + 1u; }
+  int o0 = i0, o1 = i1;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t kk = __shfl_sync(0xffffffffu, k < 32 ? k0 : k1, k & 31);
+    int p = k;
+    if (kk != 0u) {  // a NaN sitting at k stays (nothing compares greater than it)
+      const bool e0 = i0 >= k && i0 < n, e1 = i1 >= k && i1 < n;
+      const uint32_t c0 = e0 ? k0 : 0u, c1 = e1 ? k1 : 0u;
+      const uint32_t m = __reduce_max_sync(0xffffffffu, c0 > c1 ? c0 : c1);
+      const uint32_t b0 = __ballot_sync(0xffffffffu, e0 && k0 == m);
+      const uint32_t b1 = __ballot_sync(0xffffffffu, e1 && k1 == m);
+      p = b0 ? (__ffs(b0) - 1) : (32 + __ffs(b1) - 1);
+    }
+    if (p != k) {  // swap the contents of positions k and p (warp-uniform branch)
+      const int ok = __shfl_sync(0xffffffffu, k < 32 ? o0 : o1, k & 31);
+      const int op = __shfl_sync(0xffffffffu, p < 32 ? o0 : o1, p & 31);
+      const uint32_t kp = __shfl_sync(0xffffffffu, p < 32 ? k0 : k1, p & 31);
+      if (i0 == k) { k0 = kp; o0 = op; }
+      if (i1 == k) { k1 = kp; o1 = op; }
+      if (i0 == p) { k0 = kk; o0 = ok; }
+      if (i1 == p) { k1 = kk; o1 = ok; }
+    }
+  }
+  if (i0 < n) { perm[i0] = o0; inv[o0] = i0; }
+  if (i1 < n) { perm[i1] = o1; inv[o1] = i1; }
+  __syncwarp();
+}
+
+// unpivoted left-looking LDL^T of the already permuted W (lower triangle, pitch ldw)
 template <typename T>
-__device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, int *tr, T *temp, int lane) {
+__device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, T *temp, int lane) {
   using O = Ops<T>;
 #define WW(i, j) W[(i) * ldw + (j)]
-  if (n == 1) {
-    if (lane == 0) tr[0] = 0;
-    __syncwarp();
-    return !(WW(0, 0) < (T)0);
-  }
+  if (n == 1) return !(WW(0, 0) < (T)0);
   int sign = 0;
   bool found_zero_pivot = false, ret = true;
   for (int k = 0; k < n; ++k) {
-    // largest |diagonal|, first maximum wins, NaN never wins unless it sits at k
-    T best = (T)-1;
-    int bi = 0x7fffffff;
-    for (int i = k + lane; i < n; i += 32) {
-      const T v = O::abs(WW(i, i));
-      if (v > best) {
-        best = v;
-        bi = i;
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const T ov = __shfl_xor_sync(0xffffffffu, best, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ov > best || (ov == best && oi < bi)) {
-        best = ov;
-        bi = oi;
-      }
-    }
-    const T wkk = WW(k, k);
-    const int p = (wkk != wkk) ? k : bi;
-    if (lane == 0) tr[k] = p;
-    if (p != k) {
-      for (int j = lane; j < k; j += 32) { const T t = WW(k, j); WW(k, j) = WW(p, j); WW(p, j) = t; }
-      for (int i = p + 1 + lane; i < n; i += 32) { const T t = WW(i, k); WW(i, k) = WW(i, p); WW(i, p) = t; }
-      for (int i = k + 1 + lane; i < p; i += 32) { const T t = WW(i, k); WW(i, k) = WW(p, i); WW(p, i) = t; }
-      if (lane == 0) { const T t = WW(k, k); WW(k, k) = WW(p, p); WW(p, p) = t; }
-    }
-    __syncwarp();
     if (k > 0) {
       for (int j = lane; j < k; j += 32) temp[j] = O::mul(WW(j, j), WW(k, j));
       __syncwarp();
-      for (int i = k + lane; i < n; i += 32) {  // row k itself gives A_kk -= A10 . temp
-        T s = (T)0;
-        for (int j = 0; j < k; ++j) s = O::fma(WW(i, j), temp[j], s);
-        WW(i, k) = O::sub(WW(i, k), s);
+      // rows k+lane and k+lane+32 together (row k itself gives A_kk -= A10 . temp)
+      const int r0 = k + lane, r1 = k + lane + 32;
+      if (r0 < n) {
+        const T *w0 = &WW(r0, 0);
+        const bool two = r1 < n;
+        const T *w1 = two ? &WW(r1, 0) : w0;
+        T s0 = (T)0, s1 = (T)0;
+#pragma unroll 4
+        for (int j = 0; j < k; ++j) {
+          const T t = temp[j];
+          s0 = O::fma(w0[j], t, s0);
+          s1 = O::fma(w1[j], t, s1);
+        }
+        WW(r0, k) = O::sub(WW(r0, k), s0);
+        if (two) WW(r1, k) = O::sub(WW(r1, k), s1);
       }
       __syncwarp();
     }
     const T akk = WW(k, k);
     const bool pivot_is_valid = O::abs(akk) > (T)0;
-    if (k == 0 && !pivot_is_valid) {
+    if (k == 0 && !pivot_is_valid) {  // the whole diagonal is zero (the pivot order is the identity)
       bool z = true;
       for (int j = 0; j < n; ++j)
         for (int i = j + 1 + lane; i < n; i += 32) z = z && (WW(i, j) == (T)0);
-      if (lane == 0)
-        for (int j = 0; j < n; ++j) tr[j] = j;
-      __syncwarp();
       return __all_sync(0xffffffffu, z);
     }
     if (k < n - 1) {
@@ -202,8 +221,8 @@ __device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, int *tr, T
         for (int i = k + 1 + lane; i < n; i += 32) z = z && (WW(i, k) == (T)0);
         ret = ret && __all_sync(0xffffffffu, z);
       }
+      __syncwarp();
     }
-    __syncwarp();
     if (found_zero_pivot && pivot_is_valid) ret = false;
     else if (!pivot_is_valid) found_zero_pivot = true;
     if (sign == 1) { if (akk < (T)0) sign = 2; }
@@ -214,19 +233,12 @@ __device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, int *tr, T
 #undef WW
 }
 
-// y (shared, n values) <- P^T L^-T D^+ L^-1 P y; n <= 64
+// x (shared, n values, original order) <- P^T L^-T D^+ L^-1 P b;  n <= 64
 template <typename T>
-__device__ __forceinline__ void wpp_ldlt_solve(const T *W, int ldw, int n, const int *tr, T *y, int lane) {
+__device__ __forceinline__ void wpp_ldlt_solve(const T *W, int ldw, int n, const int *perm, const T *b, T *x, int lane) {
   using O = Ops<T>;
 #define WW(i, j) W[(i) * ldw + (j)]
-  if (lane == 0) {
-    for (int k = 0; k < n; ++k) {
-      const int p = tr[k];
-      if (p != k) { const T t = y[k]; y[k] = y[p]; y[p] = t; }
-    }
-  }
-  __syncwarp();
-  T y0 = lane < n ? y[lane] : (T)0, y1 = lane + 32 < n ? y[lane + 32] : (T)0;
+  T y0 = lane < n ? b[perm[lane]] : (T)0, y1 = lane + 32 < n ? b[perm[lane + 32]] : (T)0;
   // L y = y, column oriented: y_i takes its updates in the order j = 0 .. i-1
   for (int j = 0; j < n; ++j) {
     const T yj = __shfl_sync(0xffffffffu, j < 32 ? y0 : y1, j & 31);
@@ -241,15 +253,9 @@ __device__ __forceinline__ void wpp_ldlt_solve(const T *W, int ldw, int n, const
     if (lane < j) y0 = O::fma(-WW(j, lane), yj, y0);
     if (lane + 32 < j) y1 = O::fma(-WW(j, lane + 32), yj, y1);
   }
-  if (lane < n) y[lane] = y0;
-  if (lane + 32 < n) y[lane + 32] = y1;
   __syncwarp();
-  if (lane == 0) {
-    for (int k = n - 1; k >= 0; --k) {
-      const int p = tr[k];
-      if (p != k) { const T t = y[k]; y[k] = y[p]; y[p] = t; }
-    }
-  }
+  if (lane < n) x[perm[lane]] = y0;
+  if (lane + 32 < n) x[perm[lane + 32]] = y1;
   __syncwarp();
 #undef WW
 }
@@ -258,8 +264,10 @@ __device__ __forceinline__ void wpp_ldlt_solve(const T *W, int ldw, int n, const
 template <typename T>
 __device__ __forceinline__ T wpp_sqnorm(const T *v, int n, int lane) {
   T s = (T)0;
-  if (lane == 0)
+  if (lane == 0) {
+#pragma unroll 8
     for (int j = 0; j < n; ++j) s = Ops<T>::fma(v[j], v[j], s);
+  }
   return __shfl_sync(0xffffffffu, s, 0);
 }
 
@@ -322,13 +330,14 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     const int nrows = (m - row0 < kWppRows) ? (m - row0) : kWppRows;
     const T *sa = pipe.stage_ptr(pipe.stage);
     const T *sy = sa + (size_t)kWppRows * n;
-    // ---- phase 1: lane = row ----
+    // ---- phase 1: lane = row: canonical t-chain, residual, then the packed row [sc * a | r] ----
     if (lane < nrows) {
       const T *arow = sa + lane * n;
       T *jrow = jbuf + lane * NPS;
       T ri, sc = (T)1;
       if (kSynth) {
         T t = (T)0;
+#pragma unroll 8
         for (int j = 0; j < n; ++j) t = O::fma(arow[j], xs[j], t);
         const T t2 = O::mul(t, t);
         ri = O::fma(t, O::fma(alpha, t2, (T)1), -sy[lane]);
@@ -336,14 +345,18 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       } else {
         ri = sy[lane];
       }
+      jrow[n] = ri;
       if (do_rebuild) {
-        if (kSynth) {
-          for (int j = 0; j < n; ++j) jrow[j] = O::mul(sc, arow[j]);
-        } else {
-          for (int j = 0; j < n; ++j) jrow[j] = arow[j];
+        // elementwise, so the column order is free: lane l starts at column l, which spreads the
+        // 32 rows (pitch n / NPS) over all banks for both the load and the store
+        int cc = lane < n ? lane : lane - n;  // n >= 13 and lane < 32, one wrap is enough... for n >= 16
+        while (cc >= n) cc -= n;
+#pragma unroll 8
+        for (int k = 0; k < n; ++k) {
+          jrow[cc] = kSynth ? O::mul(sc, arow[cc]) : arow[cc];
+          if (++cc == n) cc = 0;
         }
       }
-      jrow[n] = ri;
     }
     __syncwarp();
     // the stage is free again: refill it with chunk c + nstages
@@ -385,17 +398,54 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
   cost_only = __shfl_sync(0xffffffffu, cost_only, 0);
 }
 
-// write the register blocks as the lower-triangular LDLT matrix W(i,j) = H(j,i), j <= i
+// ---- moving the register blocks of [J|r]^T [J|r] out ---------------------------------------------------
+// g = J^T r (column n of the augmented matrix), cost = r^T r (its corner), undamped diagonal of H
 template <typename T, int NB, int BLK>
-__device__ __forceinline__ void wpp_store_blocks(T *W, int bi, int bj, bool has_block, const T (&acc)[BLK][BLK]) {
+__device__ __forceinline__ void wpp_extract(const T (&acc)[BLK][BLK], int bi, int bj, bool has_block, int n, T *g,
+                                            T *dg, T *cost_slot) {
+  if (!has_block) return;
+  const int vn = n - (NB - 1) * BLK;  // column n sits in the last block column
+#pragma unroll
+  for (int u = 0; u < BLK; ++u) {
+    const int row = bi * BLK + u;
+    if (bi == bj && row < n) dg[row] = acc[u][u];
+    if (bj == NB - 1) {
+#pragma unroll
+      for (int v = 0; v < BLK; ++v) {
+        if (v == vn) {
+          if (row < n) g[row] = acc[u][v];
+          else if (row == n) *cost_slot = acc[u][v];
+        }
+      }
+    }
+  }
+}
+
+// W <- P H P^T (lower triangle) with the damped diagonal dd; optionally the unpermuted damped H_ to
+// the persistent global copy hp (lower-triangular layout W(i,j) = H(j,i))
+template <typename T, int NB, int BLK>
+__device__ __forceinline__ void wpp_store_permuted(T *W, const T (&acc)[BLK][BLK], int bi, int bj, bool has_block,
+                                                   int n, const T *dd, const int *inv, T *hp) {
   constexpr int LDW = wpp_ldw(NB * BLK);
   if (!has_block) return;
+  int pr[BLK], pc[BLK];
+#pragma unroll
+  for (int u = 0; u < BLK; ++u) {
+    const int row = bi * BLK + u, col = bj * BLK + u;
+    pr[u] = row < n ? inv[row] : 0;
+    pc[u] = col < n ? inv[col] : 0;
+  }
 #pragma unroll
   for (int u = 0; u < BLK; ++u)
 #pragma unroll
     for (int v = 0; v < BLK; ++v) {
       const int row = bi * BLK + u, col = bj * BLK + v;  // upper element (row, col)
-      if (row <= col) W[col * LDW + row] = acc[u][v];
+      if (row <= col && col < n) {
+        const T val = row == col ? dd[row] : acc[u][v];
+        const int a = pr[u], b = pc[v];
+        W[(a > b ? a : b) * LDW + (a > b ? b : a)] = val;
+        if (hp) hp[col * LDW + row] = val;
+      }
     }
 }
 
@@ -413,14 +463,16 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
   T *g = reinterpret_cast<T *>(ws + d.L.g);
   T *dxs = reinterpret_cast<T *>(ws + d.L.dxs);
   T *temp = reinterpret_cast<T *>(ws + d.L.temp);
-  int *tr = reinterpret_cast<int *>(ws + d.L.tr);
+  T *dg = reinterpret_cast<T *>(ws + d.L.dg);
+  T *dd = reinterpret_cast<T *>(ws + d.L.dd);
+  int *perm = reinterpret_cast<int *>(ws + d.L.perm);
+  int *inv = reinterpret_cast<int *>(ws + d.L.inv);
 
   T cost_t = cost_only;
   if (pass_rebuilt) {
-    wpp_store_blocks<T, NB, BLK>(W, bi, bj, has_block, acc);
+    wpp_extract<T, NB, BLK>(acc, bi, bj, has_block, n, g, dg, temp);  // temp[0] <- r^T r
     __syncwarp();
-    cost_t = W[n * LDW + n];                                    // r^T r
-    for (int j = lane; j < n; j += 32) g[j] = W[n * LDW + j];  // J^T r
+    cost_t = temp[0];
     __syncwarp();
   }
   double cost;
@@ -439,7 +491,7 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
       }
       if (o.check_min_H_diag > (T)0) {  // lm.h:82-86
         bool low = false;
-        for (int j = lane; j < n; j += 32) low = low || (O::abs(W[j * LDW + j]) < o.check_min_H_diag);
+        for (int j = lane; j < n; j += 32) low = low || (O::abs(dg[j]) < o.check_min_H_diag);
         if (__any_sync(0xffffffffu, low)) built_ok = false;
       }
     }
@@ -453,31 +505,35 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
   const uint8_t max_tries = lm_max_tries(o);
   for (int attempt = 0; s.num_consec_failures <= max_tries; ++attempt) {
     if (built_ok) {
-      if (pass_rebuilt) {
-        if (attempt > 0) {  // the factorisation destroyed W: lay the undamped blocks out again
-          wpp_store_blocks<T, NB, BLK>(W, bi, bj, has_block, acc);
-          __syncwarp();
-        }
-      } else {  // cost-only pass, or a retry of one: start from the persistent damped H_
-        for (int e = lane; e < n * LDW; e += 32) W[e] = hp[e];
-        __syncwarp();
-      }
+      // damped diagonal of H_ (lm.h:108-117): from the undamped one after a rebuild (a retry
+      // re-accumulates the same H), cumulative on the stale H_ otherwise
       double sc;
-      if (lm_damping_scale(s, o, pass_rebuilt, sc)) {  // lm.h:108-117
-        for (int j = lane; j < n; j += 32) W[j * LDW + j] = (T)((double)W[j * LDW + j] * sc);
-        __syncwarp();
+      const bool damp = lm_damping_scale(s, o, pass_rebuilt, sc);
+      for (int j = lane; j < n; j += 32) {
+        const T base = pass_rebuilt ? dg[j] : hp[j * LDW + j];
+        dd[j] = damp ? (T)((double)base * sc) : base;
       }
-      if (may_need_stale_h) {  // publish H_ (damped)
-        if (pass_rebuilt) {
-          for (int e = lane; e < n * LDW; e += 32) hp[e] = W[e];
-        } else {
-          for (int j = lane; j < n; j += 32) hp[j * LDW + j] = W[j * LDW + j];
+      __syncwarp();
+      wpp_pivot_order(dd, n, perm, inv, lane);
+      if (pass_rebuilt) {
+        wpp_store_permuted<T, NB, BLK>(W, acc, bi, bj, has_block, n, dd, inv, may_need_stale_h ? hp : nullptr);
+      } else {  // cost-only pass, or a retry of one: lay the persistent H_ out, publish its new diagonal
+        for (int e = lane; e < n * LDW; e += 32) {
+          const int i = e / LDW, j = e - i * LDW;
+          if (j <= i) {
+            const T val = i == j ? dd[i] : hp[e];
+            const int a = inv[i], b = inv[j];
+            W[(a > b ? a : b) * LDW + (a > b ? b : a)] = val;
+          }
         }
-      }
-      if (wpp_ldlt_factor<T>(W, LDW, n, tr, temp, lane)) {  // gn.h:150-156
-        for (int j = lane; j < n; j += 32) dxs[j] = -g[j];
         __syncwarp();
-        wpp_ldlt_solve<T>(W, LDW, n, tr, dxs, lane);
+        for (int j = lane; j < n; j += 32) hp[j * LDW + j] = dd[j];
+      }
+      __syncwarp();
+      if (wpp_ldlt_factor<T>(W, LDW, n, temp, lane)) {  // gn.h:150-156
+        for (int j = lane; j < n; j += 32) temp[j] = -g[j];
+        __syncwarp();
+        wpp_ldlt_solve<T>(W, LDW, n, perm, temp, dxs, lane);
         solver_failed = false;
       }
     }
@@ -535,7 +591,7 @@ struct WppRunParams {
 };
 
 template <typename T, int NB, int BLK>
-__global__ void __launch_bounds__(kWppThreads, 2) wpp_lm_run_kernel(const __grid_constant__ WppRunParams<T> p) {
+__global__ void __launch_bounds__(kWppThreads, 3) wpp_lm_run_kernel(const __grid_constant__ WppRunParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x / 32;
@@ -604,7 +660,10 @@ __global__ void __launch_bounds__(kWppThreads, 2) wpp_build_solve_kernel(const _
   T *g = reinterpret_cast<T *>(ws + p.d.L.g);
   T *dxs = reinterpret_cast<T *>(ws + p.d.L.dxs);
   T *temp = reinterpret_cast<T *>(ws + p.d.L.temp);
-  int *tr = reinterpret_cast<int *>(ws + p.d.L.tr);
+  T *dg = reinterpret_cast<T *>(ws + p.d.L.dg);
+  T *dd = reinterpret_cast<T *>(ws + p.d.L.dd);
+  int *perm = reinterpret_cast<int *>(ws + p.d.L.perm);
+  int *inv = reinterpret_cast<int *>(ws + p.d.L.inv);
   T *jbuf = reinterpret_cast<T *>(ws + p.d.L.jbuf);
   int bi, bj;
   bool has_block;
@@ -614,33 +673,38 @@ __global__ void __launch_bounds__(kWppThreads, 2) wpp_build_solve_kernel(const _
     wpp_zero_pad_columns<T>(jbuf, NPS, n + 1, NP, lane);
     T acc[BLK][BLK], cost_only;
     wpp_pass<T, NB, BLK, false>(pipe, p.d, ws, pr, lane, true, (T)0, (T)0, bi, bj, has_block, acc, cost_only);
-    wpp_store_blocks<T, NB, BLK>(W, bi, bj, has_block, acc);
+    wpp_extract<T, NB, BLK>(acc, bi, bj, has_block, n, g, dg, temp);
     __syncwarp();
-    const T cost_t = W[n * LDW + n];
-    for (int j = lane; j < n; j += 32) g[j] = W[n * LDW + j];
-    __syncwarp();
+    const T cost_t = temp[0];
     const T lam = p.lambda ? p.lambda[pr] : (T)0;
-    if (lam > (T)0) {  // solvers/lm.h:108-117
-      const double sc = 1.0 + (double)lam;
-      for (int j = lane; j < n; j += 32) W[j * LDW + j] = (T)((double)W[j * LDW + j] * sc);
-      __syncwarp();
-    }
+    const double sc = 1.0 + (double)lam;  // solvers/lm.h:108-117
+    for (int j = lane; j < n; j += 32) dd[j] = lam > (T)0 ? (T)((double)dg[j] * sc) : dg[j];
+    __syncwarp();
     if (lane == 0) p.cost[pr] = (double)cost_t;
     if (p.g_out)
       for (int j = lane; j < n; j += 32) p.g_out[pr * n + j] = g[j];
-    if (p.H_out) {
+    if (p.H_out && has_block) {  // damped H_, full symmetric
       T *Ho = p.H_out + (size_t)pr * n * n;
-      for (int e = lane; e < n * n; e += 32) {
-        const int r = e / n, c = e % n;
-        Ho[e] = r <= c ? W[c * LDW + r] : W[r * LDW + c];
-      }
+#pragma unroll
+      for (int u = 0; u < BLK; ++u)
+#pragma unroll
+        for (int v = 0; v < BLK; ++v) {
+          const int row = bi * BLK + u, col = bj * BLK + v;
+          if (row <= col && col < n) {
+            const T val = row == col ? dd[row] : acc[u][v];
+            Ho[row * n + col] = val;
+            Ho[col * n + row] = val;
+          }
+        }
     }
+    wpp_pivot_order(dd, n, perm, inv, lane);
+    wpp_store_permuted<T, NB, BLK>(W, acc, bi, bj, has_block, n, dd, inv, nullptr);
     __syncwarp();
-    const bool ok = wpp_ldlt_factor<T>(W, LDW, n, tr, temp, lane);  // math.h:232-240
+    const bool ok = wpp_ldlt_factor<T>(W, LDW, n, temp, lane);  // math.h:232-240
     if (ok) {
-      for (int j = lane; j < n; j += 32) dxs[j] = -g[j];  // solvers/gn.h:155
+      for (int j = lane; j < n; j += 32) temp[j] = -g[j];  // solvers/gn.h:155
       __syncwarp();
-      wpp_ldlt_solve<T>(W, LDW, n, tr, dxs, lane);
+      wpp_ldlt_solve<T>(W, LDW, n, perm, temp, dxs, lane);
       for (int j = lane; j < n; j += 32) p.dx[pr * n + j] = dxs[j];
     }
     if (lane == 0) p.status[pr] = ok ? 0 : 1;

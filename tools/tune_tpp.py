@@ -15,17 +15,19 @@ name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 cfg = CONFIGS[name]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["B"]
 tdt = torch.float64 if cfg["dtype"] == "f64" else torch.float32
+family2 = cfg["n"] > 12
 grid_stages = [int(v) for v in os.environ.get("SWEEP_STAGES", "2,3,4").split(",")]
 grid_bytes = [int(v) for v in os.environ.get("SWEEP_BYTES", "2048,4096,8192,16384").split(",")]
 grid_ctas = [int(v) for v in os.environ.get("SWEEP_CTAS", "0").split(",")]
 data = None
 for st, sb, ct in itertools.product(grid_stages, grid_bytes, grid_ctas):
     os.environ["TOB200_TPP_STAGES"] = str(st)
+    os.environ["TOB200_WPP_STAGES"] = str(st)
     os.environ["TOB200_TPP_STAGE_BYTES"] = str(sb)
     os.environ["TOB200_TPP_CTAS_PER_SM"] = str(ct)
     ctx = tb.Context(0)
     if data is None:
-        data = ctx.synth_generate(B, cfg["m"], cfg["n"], tdt)
+        data = ctx.synth_generate(B, cfg["m"], cfg["n"], tdt, layout=tb.PROBLEM_MAJOR if family2 else tb.TILE32)
     A, y, xs, x0 = data
     opt = tb.options(**cfg["opts"])
     ms = []
