@@ -34,13 +34,15 @@ constexpr int kWppMaxStages = 4;
 // 8 above), NP = NB*BLK padded columns, NB*(NB+1)/2 <= 28 upper-triangular blocks = busy lanes
 __host__ __device__ constexpr int wpp_blk_for(int n) { return n + 1 <= 28 ? 4 : 8; }
 __host__ __device__ constexpr int wpp_nb_for(int n) { return (n + 1 + wpp_blk_for(n) - 1) / wpp_blk_for(n); }
-__host__ __device__ constexpr int wpp_ldw(int np) { return np + 1; }  // odd pitch of the LDLT matrix
+// pitch of the LDLT matrix: multiple of 4 floats with pitch/4 odd, so that a lane can read its own row
+// with aligned, conflict-free 16-byte loads in the dot products
+__host__ __device__ constexpr int wpp_ldw(int np) { return ((np / 4) & 1) ? np : np + 4; }
 // pitch of the packed [J|r] rows: multiple of 4 floats (16-byte loads) with pitch/4 odd
 // (conflict-free lane-per-row stores)
 __host__ __device__ constexpr int wpp_nps(int np) { return ((np / 4) & 1) ? np : np + 4; }
 
 struct WppSmem {  // byte offsets inside one warp's shared memory
-  uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, stages, stage_bytes, jbuf, total;
+  uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, scb, stages, stage_bytes, jbuf, total;
 };
 __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   WppSmem L;
@@ -56,6 +58,7 @@ __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   L.dd = o; o += np * 4;
   L.perm = o; o += np * 4;
   L.inv = o; o += np * 4;
+  L.scb = o; o += kWppRows * 4;
   o = (o + 127u) & ~127u;
   L.stages = o;
   L.stage_bytes = ((uint32_t)kWppRows * (uint32_t)(n + 1) * 4u + 127u) & ~127u;  // A rows, then y
@@ -187,15 +190,26 @@ __device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, T *temp, i
     if (k > 0) {
       for (int j = lane; j < k; j += 32) temp[j] = O::mul(WW(j, j), WW(k, j));
       __syncwarp();
-      // rows k+lane and k+lane+32 together (row k itself gives A_kk -= A10 . temp)
+      // rows k+lane and k+lane+32 together (row k itself gives A_kk -= A10 . temp); rows and temp
+      // are 16-byte aligned, so four terms per load, consumed in order
       const int r0 = k + lane, r1 = k + lane + 32;
       if (r0 < n) {
         const T *w0 = &WW(r0, 0);
         const bool two = r1 < n;
         const T *w1 = two ? &WW(r1, 0) : w0;
         T s0 = (T)0, s1 = (T)0;
-#pragma unroll 4
-        for (int j = 0; j < k; ++j) {
+        int j = 0;
+#pragma unroll 2
+        for (; j + 4 <= k; j += 4) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(temp + j);
+          const float4 a4 = *reinterpret_cast<const float4 *>(w0 + j);
+          const float4 b4 = *reinterpret_cast<const float4 *>(w1 + j);
+          s0 = O::fma(a4.x, t4.x, s0); s1 = O::fma(b4.x, t4.x, s1);
+          s0 = O::fma(a4.y, t4.y, s0); s1 = O::fma(b4.y, t4.y, s1);
+          s0 = O::fma(a4.z, t4.z, s0); s1 = O::fma(b4.z, t4.z, s1);
+          s0 = O::fma(a4.w, t4.w, s0); s1 = O::fma(b4.w, t4.w, s1);
+        }
+        for (; j < k; ++j) {
           const T t = temp[j];
           s0 = O::fma(w0[j], t, s0);
           s1 = O::fma(w1[j], t, s1);
@@ -305,6 +319,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
   const int m = d.m, n = d.n;
   const T *xs = reinterpret_cast<const T *>(ws + d.L.xs);
   T *jbuf = reinterpret_cast<T *>(ws + d.L.jbuf);
+  T *scb = reinterpret_cast<T *>(ws + d.L.scb);
 #pragma unroll
   for (int u = 0; u < BLK; ++u)
 #pragma unroll
@@ -330,32 +345,45 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     const int nrows = (m - row0 < kWppRows) ? (m - row0) : kWppRows;
     const T *sa = pipe.stage_ptr(pipe.stage);
     const T *sy = sa + (size_t)kWppRows * n;
-    // ---- phase 1: lane = row: canonical t-chain, residual, then the packed row [sc * a | r] ----
+    // ---- phase 1a: lane = row: canonical t-chain, residual r_i, Jacobian scale sc_i ----
     if (lane < nrows) {
       const T *arow = sa + lane * n;
-      T *jrow = jbuf + lane * NPS;
       T ri, sc = (T)1;
       if (kSynth) {
         T t = (T)0;
+        if ((n & 1) == 0) {  // even n: rows are 8-byte aligned, two columns per load
+          const float2 *a2 = reinterpret_cast<const float2 *>(arow);
+          const float2 *x2 = reinterpret_cast<const float2 *>(xs);
 #pragma unroll 8
-        for (int j = 0; j < n; ++j) t = O::fma(arow[j], xs[j], t);
+          for (int j = 0; j < n / 2; ++j) {
+            const float2 av = a2[j], xv = x2[j];
+            t = O::fma(av.x, xv.x, t);
+            t = O::fma(av.y, xv.y, t);
+          }
+        } else {
+#pragma unroll 8
+          for (int j = 0; j < n; ++j) t = O::fma(arow[j], xs[j], t);
+        }
         const T t2 = O::mul(t, t);
         ri = O::fma(t, O::fma(alpha, t2, (T)1), -sy[lane]);
         sc = O::fma(alpha3, t2, (T)1);
       } else {
         ri = sy[lane];
       }
-      jrow[n] = ri;
-      if (do_rebuild) {
-        // elementwise, so the column order is free: lane l starts at column l, which spreads the
-        // 32 rows (pitch n / NPS) over all banks for both the load and the store
-        int cc = lane < n ? lane : lane - n;  // n >= 13 and lane < 32, one wrap is enough... for n >= 16
-        while (cc >= n) cc -= n;
-#pragma unroll 8
-        for (int k = 0; k < n; ++k) {
-          jrow[cc] = kSynth ? O::mul(sc, arow[cc]) : arow[cc];
-          if (++cc == n) cc = 0;
-        }
+      scb[lane] = sc;
+      jbuf[lane * NPS + n] = ri;
+    }
+    __syncwarp();
+    // ---- phase 1b: lane = column: packed row i <- sc_i * a_i (rows independent: unrolled for ILP) ----
+    if (do_rebuild) {
+      const bool second = lane + 32 < n;
+#pragma unroll 4
+      for (int i = 0; i < nrows; ++i) {
+        const T sc = scb[i];
+        const T v0 = sa[i * n + lane];  // n >= 13 and chunk rows are contiguous: in bounds even if lane >= n
+        const T v1 = second ? sa[i * n + lane + 32] : (T)0;
+        if (lane < n) jbuf[i * NPS + lane] = kSynth ? O::mul(sc, v0) : v0;
+        if (second) jbuf[i * NPS + lane + 32] = kSynth ? O::mul(sc, v1) : v1;
       }
     }
     __syncwarp();
