@@ -161,11 +161,19 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     tdt = torch.float64 if cfg["dtype"] == "f64" else torch.float32
-    B, m, n = cfg["B"], cfg["m"], cfg["n"]  # per GPU: weak scaling over independent problems
+    m, n = cfg["m"], cfg["n"]
+    strong = bool(cfg.get("strong"))
+    from tinyopt_b200.shard import shard_range
+    if strong:   # a fixed total batch split over the ranks
+        lo, hi = shard_range(cfg["B"], rank, world)
+    else:        # the config's batch per GPU: weak scaling over independent problems
+        lo, hi = rank * cfg["B"], (rank + 1) * cfg["B"]
+    B = hi - lo
     ctx = tb.Context(local_rank)
     opt = tb.options(**cfg["opts"])
-    # rank g owns problems [g*B, (g+1)*B): generated in place from (seed, index), no scatter needed
-    A, y, xs, x0 = ctx.synth_generate(B, m, n, tdt, p0=rank * B, seed=SEED, alpha=ALPHA, sigma=SIGMA, layout=tb.TILE32)
+    layout = tb.TILE32 if ctx.kernel_family(tdt, n) == 1 else tb.PROBLEM_MAJOR  # the family's native layout
+    # rank g owns problems [lo, hi): generated in place from (seed, index), no scatter needed
+    A, y, xs, x0 = ctx.synth_generate(B, m, n, tdt, p0=lo, seed=SEED, alpha=ALPHA, sigma=SIGMA, layout=layout)
     res_buf = torch.empty((B, tba.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     x = torch.empty_like(x0)
 
@@ -174,7 +182,7 @@ def main():
 
     def step():
         x.copy_(x0)
-        ctx._ck(lm_run(ctx._h, ctypes.byref(opt), tba._p(A), tba._p(y), c_alpha, tb.TILE32, B, m, n, tba._p(x),
+        ctx._ck(lm_run(ctx._h, ctypes.byref(opt), tba._p(A), tba._p(y), c_alpha, layout, B, m, n, tba._p(x),
                        tba._p(res_buf)), "tob200_lm_run")
 
     for _ in range(args.warmup):
@@ -220,8 +228,9 @@ def main():
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
         # the one data-path collective: gather of the per-problem results (solutions stay sharded)
         from tinyopt_b200.shard import gather_rows
-        gathered = gather_rows(res_buf, B * world, rank, world)
-        assert gathered.shape[0] == B * world
+        Btot = cfg["B"] if strong else cfg["B"] * world
+        gathered = gather_rows(res_buf, Btot, rank, world)
+        assert gathered.shape[0] == Btot
     ms_total = float(t.item())
     iters_all = float(it.item())
     value = iters_all * args.steps / (ms_total * 1e-3)
@@ -234,13 +243,13 @@ def main():
         line = {
             "metric": "LM iterations/sec (batched dense NLLS)", "value": value, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg['desc']}", "B_per_gpu": B, "m": m, "n": n,
                        "options": "tinyopt defaults" + (" + float thresholds min_rerr_dec=1e-5 min_step_norm2=1e-9" if cfg["opts"] else ""),
                        "iters_per_problem": iters_rank / B, "parallelism": f"{world} x independent problem shards",
                        "l2": f"inputs {(A.numel() + y.numel()) * A.element_size() / 1e6:.0f} MB per step > 126 MB L2, no flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "tpp_lm_run_kernel", "kernel_ms": kernel_ms_avg,
+                         "traffic": None, "kernel": "tpp_lm_run_kernel" if layout == tb.TILE32 else "wpp_lm_run_kernel", "kernel_ms": kernel_ms_avg,
                          "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src},
             "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -256,7 +265,7 @@ def main():
 
         def e2e_step():
             xh.copy_(x0h)
-            ctx.optimize_batch_host(Ah.numpy(), yh.numpy(), xh.numpy(), opt, alpha=ALPHA, layout=tb.TILE32, B=B, results=rh_np)
+            ctx.optimize_batch_host(Ah.numpy(), yh.numpy(), xh.numpy(), opt, alpha=ALPHA, layout=layout, B=B, results=rh_np)
 
         for _ in range(2):
             e2e_step()

@@ -38,7 +38,12 @@ struct tob200_ctx {
   int tpp_stage_bytes = 16384;  // upper bound of one pipeline stage
   int tpp_stages = 2;  // measured best on B200 (tools/tune_tpp.py): few, large stages
   int tpp_ctas_per_sm = 0;  // 0: what the kernel was compiled for (__launch_bounds__)
-  unsigned long long *tile_counter = nullptr;
+  // work-queue counters: a zeroed ring, one fresh counter per launch (re-zeroed when exhausted), so
+  // that a launch costs no extra memset
+  static constexpr int kNumCounters = 4096;
+  unsigned long long *counters = nullptr;
+  int next_counter = 0;
+  unsigned long long *tile_counter = nullptr;  // the counter of the launch being configured
   int wpp_stages = 1;  // env TOB200_WPP_STAGES (1: three CTAs per SM fit, measured best)
 };
 
@@ -86,6 +91,16 @@ int ensure_scratch(tob200_ctx *ctx, int slot, size_t bytes) {
   }
   CK(cudaMalloc(&ctx->scratch[slot], bytes));
   ctx->scratch_bytes[slot] = bytes;
+  return TOB200_OK;
+}
+
+// hands out a zeroed work-queue counter for the next launch
+int next_counter(tob200_ctx *ctx) {
+  if (ctx->next_counter >= tob200_ctx::kNumCounters) {
+    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * tob200_ctx::kNumCounters, ctx->stream));
+    ctx->next_counter = 0;
+  }
+  ctx->tile_counter = ctx->counters + ctx->next_counter++;
   return TOB200_OK;
 }
 
@@ -165,9 +180,10 @@ int tpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, TppData<T>
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   cfg->grid = (int)grid;
-  // the tile queue starts at 0 for every launch
-  cudaError_t e = cudaMemsetAsync(ctx->tile_counter, 0, sizeof(unsigned long long), ctx->stream);
-  if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMemsetAsync(tile_counter)");
+  // the tile queue of this launch: a fresh zeroed counter
+  int rcq = next_counter(ctx);
+  if (rcq != TOB200_OK) return rcq;
+  d->tile_counter = ctx->tile_counter;
   return TOB200_OK;
 }
 
@@ -240,8 +256,8 @@ int wpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, const T *A
   int rc = ensure_scratch(ctx, 7, (size_t)grid * warps * np * wpp_ldw(np) * sizeof(T));
   if (rc != TOB200_OK) return rc;
   d->hpersist = (T *)ctx->scratch[7];
-  cudaError_t e = cudaMemsetAsync(ctx->tile_counter, 0, sizeof(unsigned long long), ctx->stream);
-  if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMemsetAsync(counter)");
+  if ((rc = next_counter(ctx)) != TOB200_OK) return rc;
+  d->counter = ctx->tile_counter;
   return TOB200_OK;
 }
 
@@ -542,10 +558,11 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->tpp_stages = env_int("TOB200_TPP_STAGES", ctx->tpp_stages);
   ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
   ctx->wpp_stages = env_int("TOB200_WPP_STAGES", ctx->wpp_stages);
-  if ((e = cudaMalloc((void **)&ctx->tile_counter, sizeof(unsigned long long))) != cudaSuccess) {
+  if ((e = cudaMalloc((void **)&ctx->counters, sizeof(unsigned long long) * tob200_ctx::kNumCounters)) != cudaSuccess) {
     tob200_destroy(ctx);
-    return fail_cuda(nullptr, e, "cudaMalloc(tile_counter)");
+    return fail_cuda(nullptr, e, "cudaMalloc(counters)");
   }
+  ctx->next_counter = tob200_ctx::kNumCounters;  // forces the first memset
   *out = ctx;
   return TOB200_OK;
 }
@@ -556,7 +573,7 @@ int tob200_destroy(tob200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
-  if (ctx->tile_counter) cudaFree(ctx->tile_counter);
+  if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
