@@ -92,6 +92,14 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bounded_sample(cfg, budget_bytes):
+    """Problems of the workload whose inputs fit `budget_bytes` (a multiple of 32, at least 1024,
+    never more than the config's batch): the bounded sample of the CPU and e2e legs."""
+    s = 8 if cfg["dtype"] == "f64" else 4
+    per = s * (cfg["m"] * cfg["n"] + cfg["m"] + 2 * cfg["n"])
+    return int(min(cfg["B"], max(1024, (budget_bytes // per) // 32 * 32)))
+
+
 def cpu_reference(cfg, sample_B, reps, nthreads=0):
     """The reference's CPU implementation of the path = the oracle port (Eigen is not in the image,
     so the reference itself cannot be compiled: DESIGN.md §3), OpenMP over problems."""
@@ -113,8 +121,8 @@ def run_reference(args, cfg, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_B = cfg["B"]
-    cpu_reference(cfg, sample_B, max(1, args.warmup))
+    sample_B = bounded_sample(cfg, 1 << 30)  # <= 1 GiB of inputs per step
+    cpu_reference(cfg, sample_B, max(1, min(args.warmup, 2)))
     iters, times, used = cpu_reference(cfg, sample_B, args.steps)
     total = sum(times)
     value = iters * args.steps / total
@@ -124,7 +132,7 @@ def run_reference(args, cfg, name):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
         "config": {"workload": f"{name}: {cfg['desc']}", "B": sample_B, "m": cfg["m"], "n": cfg["n"]},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": used, "kind": "port",
-                         "sample": f"the whole {name} batch ({sample_B} problems) per step, {args.steps} steps, OpenMP over problems"},
+                         "sample": f"{sample_B} of the {cfg['B']} problems of {name} per step, {args.steps} steps, OpenMP over problems"},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -256,16 +264,20 @@ def main():
 
     # e2e: the same solve through the C-ABI with HOST buffers (pinned), H2D + D2H inside
     if not args.no_e2e:
-        Ah = torch.empty(A.shape, dtype=tdt, pin_memory=True); Ah.copy_(A)
-        yh = torch.empty(y.shape, dtype=tdt, pin_memory=True); yh.copy_(y)
-        x0h = x0.cpu()
-        xh = torch.empty(x0.shape, dtype=tdt, pin_memory=True)
-        rh = torch.empty((B, tba.RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+        # bounded to <= 4 GiB of pinned host memory (the whole batch for C2 / C3)
+        Be = min(B, bounded_sample(cfg, 4 << 30))
+        tiles = (Be + 31) // 32
+        Asrc, ysrc = (A[:tiles], y[:tiles]) if layout == tb.TILE32 else (A[:Be], y[:Be])
+        Ah = torch.empty(Asrc.shape, dtype=tdt, pin_memory=True); Ah.copy_(Asrc)
+        yh = torch.empty(ysrc.shape, dtype=tdt, pin_memory=True); yh.copy_(ysrc)
+        x0h = x0[:Be].cpu()
+        xh = torch.empty(x0h.shape, dtype=tdt, pin_memory=True)
+        rh = torch.empty((Be, tba.RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
         rh_np = rh.numpy().view(tba.RESULT_DTYPE).reshape(-1)
 
         def e2e_step():
             xh.copy_(x0h)
-            ctx.optimize_batch_host(Ah.numpy(), yh.numpy(), xh.numpy(), opt, alpha=ALPHA, layout=layout, B=B, results=rh_np)
+            ctx.optimize_batch_host(Ah.numpy(), yh.numpy(), xh.numpy(), opt, alpha=ALPHA, layout=layout, B=Be, results=rh_np)
 
         for _ in range(2):
             e2e_step()
@@ -284,12 +296,13 @@ def main():
             line["e2e"] = {"value": iters_e2e * ksteps / float(te.item()), "unit": "iterations/s",
                            "h2d_bytes_per_step": int((Ah.numel() + yh.numel() + xh.numel()) * Ah.element_size()),
                            "d2h_bytes_per_step": int(xh.numel() * xh.element_size() + rh.numel()),
-                           "steps": ksteps, "api": "tob200_lm_run_host (pinned host buffers)"}
+                           "steps": ksteps, "problems_per_step": Be, "api": "tob200_lm_run_host (pinned host buffers)"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        iters, times, used = cpu_reference(cfg, B, 3)
+        Bc = min(B, bounded_sample(cfg, 1 << 30))
+        iters, times, used = cpu_reference(cfg, Bc, 3)
         line["cpu_baseline"] = {"value": iters * len(times) / sum(times), "unit": "iterations/s", "cores": used, "kind": "port",
-                                "sample": f"the whole {args.config} batch ({B} problems) x {len(times)} repetitions, oracle port, OpenMP over problems"}
+                                "sample": f"{Bc} of the {B} problems of {args.config} x {len(times)} repetitions, oracle port, OpenMP over problems"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
