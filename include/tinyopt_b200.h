@@ -126,6 +126,15 @@ int tob200_last_elapsed_ms(tob200_ctx *ctx, float *ms);
 
 void tob200_options_default(tob200_options *opt); /* == tinyopt::Options{} */
 
+/* ---- device memory for callers without the CUDA toolkit (the C++ adaptor include/tinyopt_b200.hpp,
+ * a cgo / JNI / ctypes binding): plain cudaMalloc / cudaFree / stream-ordered cudaMemcpyAsync on the
+ * context's device and stream.  tob200_copy_to_host returns once the bytes are in host memory;
+ * tob200_copy_to_device is asynchronous when `src` is pinned (keep `src` alive until tob200_sync). */
+int tob200_device_alloc(tob200_ctx *ctx, size_t bytes, void **out);
+int tob200_device_free(tob200_ctx *ctx, void *ptr);
+int tob200_copy_to_device(tob200_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
+int tob200_copy_to_host(tob200_ctx *ctx, void *dst_host, const void *src_device, size_t bytes);
+
 /* Elements (not bytes) of a TILE32 buffer: ceil(B/32)*32*m*n.  r / y buffers: n = 1. */
 int64_t tob200_tiled_elems(int64_t B, int m, int n);
 /* Which kernel family serves (dtype, n): 1 thread-per-problem registers (small n),

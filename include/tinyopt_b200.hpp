@@ -1,0 +1,341 @@
+// tinyopt_b200.hpp — header-only C++17 adaptor over the C-ABI (include/tinyopt_b200.h).
+//
+// This is the host side a tinyopt user / maintainer sees.  It mirrors the reference's interface
+// for the batched dense-NLLS path: same `Options` (include/tinyopt/optimizers/options.h:18-156,
+// numeric subset, same nesting and defaults), same `StopReason` (stop_reasons.h:14-43), same
+// `Output` fields (output.h:26-145), same accumulation contract — the user's residual callable is
+// unchanged, it is simply invoked once per problem.  No Eigen, no CUDA headers: device memory goes
+// through tob200_device_alloc / tob200_copy_to_*.  Link with -ltinyopt_b200.
+//
+//   tinyopt::b200::Context ctx(0);
+//   auto outs = tinyopt::b200::OptimizeBatch<double>(ctx, xs, B, n, m, residuals, options);
+//
+// `residuals(p, x, r, J)` fills r[m] and, when J != nullptr, the row-major m x n Jacobian
+// (J == nullptr is the reference's cost-only `acc(x, nullptr, H)` call, solvers/gn.h:98-105).
+// Errors: misuse throws std::invalid_argument (as tinyopt does, solvers/gn.h:51,66), CUDA / device
+// failures throw tinyopt::b200::Error; numerical failures are reported through StopReason.
+#pragma once
+
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tinyopt_b200.h"
+
+namespace tinyopt::b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+
+/// stop_reasons.h:14-43
+enum class StopReason : int {
+  kOutOfMemory = -4,
+  kSolverFailed = -3,
+  kSystemHasNaNOrInf = -2,
+  kSkipped = -1,
+  kNone = 0,
+  kMinError,
+  kMinRelError,
+  kMinDeltaNorm,
+  kMinGradNorm,
+  kMaxIters,
+  kMaxNoDecr,
+  kMaxConsecNoDecr,
+  kTimedOut,
+  kUserStopped
+};
+
+/// optimizers/options.h:18-156 (numeric subset; logging, callbacks and GD are host-only concerns)
+struct Options {
+  enum Solver { LevenbergMarquardt = 0, GaussNewton };
+  Solver solver_type = LevenbergMarquardt;
+  Options(Solver type = LevenbergMarquardt) : solver_type(type) {}
+  bool check_final_cost = false;
+  bool use_step_quality_approx = false;
+  float grad_clipping = 0;
+  struct Hessian {
+    bool use_ldlt = true;
+    bool H_is_full = true;
+    float check_min_H_diag = 0;
+    bool save_last = true;
+  } hessian;
+  struct CostScaling {
+    bool use_squared_norm = true;
+    bool downscale_by_2 = false;
+    bool normalize = false;
+  } cost;
+  uint16_t max_iters = 50;
+  float min_error = 1e-12f;
+  float min_rerr_dec = 1e-10f;
+  float min_step_norm2 = 1e-14f;
+  float min_grad_norm2 = 1e-18f;
+  uint8_t max_total_failures = 0;
+  uint8_t max_consec_failures = 5;
+  struct LM {
+    float damping_init = 1e-4f;
+    std::array<float, 2> damping_range{{1e-9f, 1e9f}};
+    float good_factor = 1.0f / 3.0f;
+    float bad_factor = 2.0f;
+  } lm;
+
+  tob200_options pod() const {
+    tob200_options o;
+    o.solver_type = (int)solver_type;
+    o.check_final_cost = check_final_cost;
+    o.use_step_quality_approx = use_step_quality_approx;
+    o.grad_clipping = grad_clipping;
+    o.use_ldlt = hessian.use_ldlt;
+    o.H_is_full = hessian.H_is_full;
+    o.check_min_H_diag = hessian.check_min_H_diag;
+    o.save_last = hessian.save_last;
+    o.use_squared_norm = cost.use_squared_norm;
+    o.downscale_by_2 = cost.downscale_by_2;
+    o.normalize = cost.normalize;
+    o.max_iters = max_iters;
+    o.min_error = min_error;
+    o.min_rerr_dec = min_rerr_dec;
+    o.min_step_norm2 = min_step_norm2;
+    o.min_grad_norm2 = min_grad_norm2;
+    o.max_total_failures = max_total_failures;
+    o.max_consec_failures = max_consec_failures;
+    o.damping_init = lm.damping_init;
+    o.damping_min = lm.damping_range[0];
+    o.damping_max = lm.damping_range[1];
+    o.good_factor = lm.good_factor;
+    o.bad_factor = lm.bad_factor;
+    return o;
+  }
+};
+
+/// cost.h:18-25
+struct Cost {
+  double cost = std::numeric_limits<double>::max();
+  int num_resisuals = 0;  // (sic) the reference's spelling
+};
+
+/// output.h:26-145, one per problem
+struct Output {
+  bool Succeeded() const { return stop_reason >= StopReason::kNone; }
+  bool Converged() const { return stop_reason >= StopReason::kMinError && stop_reason < StopReason::kMaxIters; }
+  Cost final_cost;
+  double final_rerr_dec = std::numeric_limits<double>::max();
+  StopReason stop_reason = StopReason::kNone;
+  uint16_t num_residuals = 0;
+  uint16_t num_iters = 0;
+  uint8_t num_failures = 0;
+  uint8_t num_consec_failures = 0;
+  std::vector<double> final_hessian;  ///< n*n row-major, un-damped (options.hessian.save_last), else empty
+  bool has_final_hessian() const { return !final_hessian.empty(); }
+};
+
+inline Output to_output(const tob200_result &r) {
+  Output o;
+  o.final_cost.cost = r.final_cost;
+  o.final_cost.num_resisuals = r.final_num_residuals;
+  o.final_rerr_dec = r.final_rerr_dec;
+  o.stop_reason = (StopReason)r.stop_reason;
+  o.num_residuals = (uint16_t)r.final_num_residuals;
+  o.num_iters = (uint16_t)r.num_iters;
+  o.num_failures = (uint8_t)r.num_failures;
+  o.num_consec_failures = (uint8_t)r.num_consec_failures;
+  return o;
+}
+
+template <typename Scalar>
+struct scalar_traits;
+template <>
+struct scalar_traits<float> {
+  static constexpr int dtype = TOB200_F32;
+};
+template <>
+struct scalar_traits<double> {
+  static constexpr int dtype = TOB200_F64;
+};
+
+/// One GPU, one stream.  Not thread-safe; distinct contexts are independent (like distinct
+/// `Optimizer_` instances in the reference).
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    const int rc = tob200_create(&ctx_, device, nullptr);
+    if (rc != TOB200_OK) throw Error(rc, std::string("tob200_create: ") + tob200_last_error(nullptr));
+  }
+  ~Context() { tob200_destroy(ctx_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  tob200_ctx *get() const { return ctx_; }
+  void check(int rc, const char *what) const {
+    if (rc == TOB200_OK) return;
+    const std::string msg = std::string(what) + ": " + tob200_last_error(ctx_);
+    if (rc == TOB200_ERR_INVALID) throw std::invalid_argument(msg);
+    throw Error(rc, msg);
+  }
+  void sync() const { check(tob200_sync(ctx_), "tob200_sync"); }
+
+ private:
+  tob200_ctx *ctx_ = nullptr;
+};
+
+/// RAII device buffer of `count` elements
+template <typename T>
+class DeviceBuffer {
+ public:
+  DeviceBuffer(const Context &ctx, size_t count) : ctx_(ctx), count_(count) {
+    ctx_.check(tob200_device_alloc(ctx_.get(), count * sizeof(T), &ptr_), "tob200_device_alloc");
+  }
+  ~DeviceBuffer() { tob200_device_free(ctx_.get(), ptr_); }
+  DeviceBuffer(const DeviceBuffer &) = delete;
+  DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+  T *data() const { return static_cast<T *>(ptr_); }
+  size_t size() const { return count_; }
+  void upload(const T *src, size_t count) const {
+    ctx_.check(tob200_copy_to_device(ctx_.get(), ptr_, src, count * sizeof(T)), "tob200_copy_to_device");
+  }
+  void download(T *dst, size_t count) const {
+    ctx_.check(tob200_copy_to_host(ctx_.get(), dst, ptr_, count * sizeof(T)), "tob200_copy_to_host");
+  }
+
+ private:
+  const Context &ctx_;
+  void *ptr_ = nullptr;
+  size_t count_;
+};
+
+namespace detail {
+inline int build_solve(tob200_ctx *c, const float *J, const float *r, int64_t B, int m, int n, const float *lam, float *dx,
+                       double *cost, float *H, float *g, int32_t *st) {
+  return tob200_build_solve_f32(c, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, lam, dx, cost, H, g, st);
+}
+inline int build_solve(tob200_ctx *c, const double *J, const double *r, int64_t B, int m, int n, const double *lam,
+                       double *dx, double *cost, double *H, double *g, int32_t *st) {
+  return tob200_build_solve_f64(c, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, lam, dx, cost, H, g, st);
+}
+inline int solver_step(tob200_solver *s, const float *J, const float *r, int m) {
+  return tob200_solver_step_f32(s, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, m);
+}
+inline int solver_step(tob200_solver *s, const double *J, const double *r, int m) {
+  return tob200_solver_step_f64(s, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, m);
+}
+inline int lm_run_host(tob200_ctx *c, const tob200_options *o, const float *A, const float *y, float alpha, int64_t B,
+                       int m, int n, float *x, tob200_result *res) {
+  return tob200_lm_run_host_f32(c, o, A, y, alpha, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, x, res);
+}
+inline int lm_run_host(tob200_ctx *c, const tob200_options *o, const double *A, const double *y, double alpha,
+                       int64_t B, int m, int n, double *x, tob200_result *res) {
+  return tob200_lm_run_host_f64(c, o, A, y, alpha, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, x, res);
+}
+}  // namespace detail
+
+/// A batch of `SolverLM` (solvers/lm.h:22) behind the `SolverType` seam of `Optimizer_`
+/// (optimizers/optimizer.h:34-43): one Build (JᵀJ, Jᵀr, cost, damping) + Solve (LDLT) per problem
+/// from host residual blocks.  J: [B][m][n] row-major, r: [B][m], lambda: [B] or nullptr
+/// (Gauss-Newton).  Returns per-problem status (0 ok, 1 = SolveLDLT rejected: std::nullopt in the
+/// reference).
+template <typename Scalar>
+std::vector<int32_t> BuildSolve(const Context &ctx, const Scalar *J, const Scalar *r, int64_t B, int m, int n,
+                                const Scalar *lambda, Scalar *dx, double *cost) {
+  if (B < 0 || m < 0 || n < 1) throw std::invalid_argument("BuildSolve: need B >= 0, m >= 0, n >= 1");
+  std::vector<int32_t> status((size_t)B, 0);
+  if (B == 0) return status;
+  DeviceBuffer<Scalar> dJ(ctx, (size_t)B * m * n), dr(ctx, (size_t)B * m), ddx(ctx, (size_t)B * n);
+  DeviceBuffer<Scalar> dl(ctx, lambda ? (size_t)B : 0);
+  DeviceBuffer<double> dc(ctx, (size_t)B);
+  DeviceBuffer<int32_t> ds(ctx, (size_t)B);
+  dJ.upload(J, dJ.size());
+  dr.upload(r, dr.size());
+  if (lambda) dl.upload(lambda, (size_t)B);
+  std::vector<Scalar> zero((size_t)B * n, (Scalar)0);
+  ddx.upload(zero.data(), zero.size());
+  ctx.check(detail::build_solve(ctx.get(), dJ.data(), dr.data(), B, m, n, lambda ? dl.data() : nullptr, ddx.data(),
+                                dc.data(), nullptr, nullptr, ds.data()),
+            "tob200_build_solve");
+  ddx.download(dx, (size_t)B * n);
+  dc.download(cost, (size_t)B);
+  ds.download(status.data(), (size_t)B);
+  return status;
+}
+
+/// `tinyopt::Optimize(x, residuals, options)` (optimize.h:17-77) for a batch of B independent
+/// problems with n parameters and m residuals each.  xs: [B][n], updated in place.
+/// `residuals(p, x, r, J)`: evaluate problem p at x; fill r[m]; fill J (m x n row-major) unless
+/// J == nullptr.  The LM state (x, lambda, H_, grad_, counters) lives on the device; each round
+/// trip evaluates the still-running problems on the host and runs one Optimizer_::Step +
+/// OptimizeAcc update for all of them (optimizers/optimizer.h:266-309).
+template <typename Scalar, typename Residuals>
+std::vector<Output> OptimizeBatch(const Context &ctx, Scalar *xs, int64_t B, int n, int m, Residuals &&residuals,
+                                  const Options &options = Options()) {
+  if (B < 0 || n < 1 || m < 0) throw std::invalid_argument("OptimizeBatch: need B >= 0, n >= 1, m >= 0");
+  std::vector<Output> outs((size_t)B);
+  if (B == 0) return outs;
+  const tob200_options pod = options.pod();
+  tob200_solver *solver = nullptr;
+  ctx.check(tob200_solver_create(ctx.get(), scalar_traits<Scalar>::dtype, B, n, &pod, &solver), "tob200_solver_create");
+  struct Guard {
+    tob200_solver *s;
+    ~Guard() { tob200_solver_destroy(s); }
+  } guard{solver};
+  {
+    DeviceBuffer<Scalar> x0(ctx, (size_t)B * n);
+    x0.upload(xs, (size_t)B * n);
+    ctx.check(tob200_solver_reset(solver, x0.data()), "tob200_solver_reset");
+    ctx.sync();
+  }
+  const size_t mm = (size_t)(m > 0 ? m : 1);
+  std::vector<Scalar> J((size_t)B * mm * n, (Scalar)0), r((size_t)B * mm, (Scalar)0), x((size_t)B * n);
+  std::vector<int32_t> needs((size_t)B);
+  DeviceBuffer<Scalar> dJ(ctx, J.size()), dr(ctx, r.size());
+  int64_t active = B;
+  while (active > 0) {
+    ctx.check(tob200_copy_to_host(ctx.get(), x.data(), tob200_solver_x(solver), x.size() * sizeof(Scalar)), "copy x");
+    ctx.check(tob200_copy_to_host(ctx.get(), needs.data(), tob200_solver_needs(solver), needs.size() * sizeof(int32_t)),
+              "copy needs");
+    for (int64_t p = 0; p < B; ++p) {
+      if (needs[(size_t)p] < 0) continue;  // finished
+      residuals((size_t)p, (const Scalar *)&x[(size_t)p * n], &r[(size_t)p * mm],
+                needs[(size_t)p] ? &J[(size_t)p * mm * n] : (Scalar *)nullptr);
+    }
+    dJ.upload(J.data(), J.size());
+    dr.upload(r.data(), r.size());
+    ctx.check(detail::solver_step(solver, dJ.data(), dr.data(), m), "tob200_solver_step");
+    ctx.check(tob200_solver_num_active(solver, &active), "tob200_solver_num_active");
+  }
+  DeviceBuffer<tob200_result> dres(ctx, (size_t)B);
+  ctx.check(tob200_solver_results(solver, dres.data()), "tob200_solver_results");
+  std::vector<tob200_result> res((size_t)B);
+  dres.download(res.data(), (size_t)B);
+  ctx.check(tob200_copy_to_host(ctx.get(), xs, tob200_solver_x(solver), (size_t)B * n * sizeof(Scalar)), "copy x");
+  std::vector<double> H;
+  if (options.hessian.save_last) {  // optimizer.h:313-316
+    DeviceBuffer<double> dH(ctx, (size_t)B * n * n);
+    ctx.check(tob200_solver_final_hessian(solver, dH.data()), "tob200_solver_final_hessian");
+    H.resize((size_t)B * n * n);
+    dH.download(H.data(), H.size());
+  }
+  for (int64_t p = 0; p < B; ++p) {
+    outs[(size_t)p] = to_output(res[(size_t)p]);
+    if (!H.empty()) outs[(size_t)p].final_hessian.assign(H.begin() + (size_t)p * n * n, H.begin() + (size_t)(p + 1) * n * n);
+  }
+  return outs;
+}
+
+/// The device-resident loop for the polynomial residual family r_i = t_i + alpha t_i^3 - y_i,
+/// t = A x (tob200_lm_run_host_*): A [B][m][n], y [B][m], xs [B][n] in/out, all host memory.
+template <typename Scalar>
+std::vector<Output> OptimizePolynomialBatch(const Context &ctx, const Scalar *A, const Scalar *y, Scalar alpha,
+                                            Scalar *xs, int64_t B, int m, int n, const Options &options = Options()) {
+  std::vector<tob200_result> res((size_t)(B > 0 ? B : 0));
+  const tob200_options pod = options.pod();
+  ctx.check(detail::lm_run_host(ctx.get(), &pod, A, y, alpha, B, m, n, xs, res.data()), "tob200_lm_run_host");
+  std::vector<Output> outs;
+  outs.reserve(res.size());
+  for (const auto &r : res) outs.push_back(to_output(r));
+  return outs;
+}
+
+}  // namespace tinyopt::b200

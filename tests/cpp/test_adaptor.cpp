@@ -1,0 +1,221 @@
+// C++ adaptor test (tinyopt_b200.hpp over the C-ABI).  Reads like the reference's own tests:
+// tests/sqrt2.cpp, tests/solvers.cpp:25-45, tests/circle.cpp, tests/basic.cpp:41-54.
+// Exit code 0 = all checks passed, 3 = no CUDA device (the library has no CPU fallback), 1 = failure.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "tinyopt_b200.hpp"
+
+using namespace tinyopt::b200;
+
+static int g_failures = 0;
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);  \
+      ++g_failures;                                                        \
+    }                                                                      \
+  } while (0)
+
+// tests/sqrt2.cpp: r = x*x - 2, J = 2x, from several x0
+static void test_sqrt2(const Context &ctx) {
+  const int64_t B = 96;
+  std::vector<double> xs(B);
+  for (int64_t p = 0; p < B; ++p) xs[p] = (p % 3 == 0) ? 1.0 : (p % 3 == 1 ? -0.3 : 3.2);
+  xs[5] = 0.5 + 0.01 * 5;
+  auto residuals = [](size_t, const double *x, double *r, double *J) {
+    r[0] = x[0] * x[0] - 2.0;
+    if (J) J[0] = 2.0 * x[0];
+  };
+  Options options;
+  auto outs = OptimizeBatch<double>(ctx, xs.data(), B, 1, 1, residuals, options);
+  for (int64_t p = 0; p < B; ++p) {
+    CHECK(outs[p].Succeeded());
+    CHECK(outs[p].Converged());
+    CHECK(std::fabs(std::fabs(xs[p]) - std::sqrt(2.0)) < 1e-5);
+    CHECK(outs[p].has_final_hessian() && outs[p].final_hessian[0] > 0);
+  }
+  // SURVEY.md §8(c) golden vector: x0 = 1, default Options -> 5 Steps, kMinError
+  CHECK(outs[0].num_iters == 5);
+  CHECK(outs[0].stop_reason == StopReason::kMinError);
+  std::printf("sqrt2: x[0]=%.16g iters=%d stop=%d\n", xs[0], (int)outs[0].num_iters, (int)outs[0].stop_reason);
+}
+
+// tests/basic.cpp:41-54: r = x - 2, H = 1 -> kMinDeltaNorm within 2..5 iterations (float and double)
+template <typename T>
+static void test_basic() {
+  Context ctx(0);
+  const int64_t B = 40;
+  std::vector<T> xs(B, (T)1);
+  auto residuals = [](size_t, const T *x, T *r, T *J) {
+    r[0] = x[0] - (T)2;
+    if (J) J[0] = (T)1;
+  };
+  Options options;
+  options.cost.use_squared_norm = false;  // Cost(|r|): the reference's lambda returns the norm
+  auto outs = OptimizeBatch<T>(ctx, xs.data(), B, 1, 1, residuals, options);
+  for (int64_t p = 0; p < B; ++p) {
+    CHECK(outs[p].Succeeded());
+    CHECK(outs[p].num_iters >= 2 && outs[p].num_iters <= 5);
+    CHECK(outs[p].final_cost.cost < 1e-5);
+    CHECK(std::fabs((double)xs[p] - 2.0) < 1e-5);
+  }
+  std::printf("basic<%s>: x=%.9g iters=%d stop=%d\n", sizeof(T) == 4 ? "float" : "double", (double)xs[0],
+              (int)outs[0].num_iters, (int)outs[0].stop_reason);
+}
+
+// tests/solvers.cpp:25-45: one Build + Solve on r = x - y from x = 0 gives dx ~= y
+static void test_build_solve(const Context &ctx) {
+  const int64_t B = 50;
+  const int n = 2, m = 2;
+  std::vector<double> J(B * m * n, 0.0), r(B * m), lam(B, 1e-4), dx(B * n), cost(B);
+  for (int64_t p = 0; p < B; ++p) {
+    J[p * 4 + 0] = 1.0;
+    J[p * 4 + 3] = 1.0;
+    r[p * 2 + 0] = -(4.0 + p);  // r = x - y at x = 0
+    r[p * 2 + 1] = -(5.0 + p);
+  }
+  auto st = BuildSolve<double>(ctx, J.data(), r.data(), B, m, n, lam.data(), dx.data(), cost.data());
+  for (int64_t p = 0; p < B; ++p) {
+    CHECK(st[p] == 0);
+    CHECK(std::fabs(dx[p * 2] - (4.0 + p)) < 1e-2 && std::fabs(dx[p * 2 + 1] - (5.0 + p)) < 1e-2);
+    CHECK(std::fabs(cost[p] - ((4.0 + p) * (4.0 + p) + (5.0 + p) * (5.0 + p))) < 1e-9);
+  }
+  std::printf("build_solve: dx[0]=(%.6f, %.6f)\n", dx[0], dx[1]);
+}
+
+// tests/circle.cpp: fit centre + radius to 10 noisy points per problem
+static void test_circle(const Context &ctx) {
+  const int64_t B = 200;
+  const int n = 3, m = 10;
+  std::vector<double> pts(B * m * 2), xs(B * n), truth(B * n);
+  uint64_t s = 12345;
+  auto rnd = [&]() {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    return (double)(s >> 11) / 9007199254740992.0;
+  };
+  for (int64_t p = 0; p < B; ++p) {
+    const double cx = 2 * rnd() - 1, cy = 2 * rnd() - 1, rad = 1 + rnd();
+    truth[p * 3] = cx; truth[p * 3 + 1] = cy; truth[p * 3 + 2] = rad;
+    for (int i = 0; i < m; ++i) {
+      const double a = 2 * M_PI * (i + rnd() * 0.5) / m;
+      pts[(p * m + i) * 2] = cx + rad * std::cos(a);
+      pts[(p * m + i) * 2 + 1] = cy + rad * std::sin(a);
+    }
+    xs[p * 3] = cx + 0.2; xs[p * 3 + 1] = cy - 0.1; xs[p * 3 + 2] = rad * 1.2;
+  }
+  auto residuals = [&](size_t p, const double *x, double *r, double *J) {
+    for (int i = 0; i < m; ++i) {
+      const double dx = pts[(p * m + i) * 2] - x[0], dy = pts[(p * m + i) * 2 + 1] - x[1];
+      const double d = std::sqrt(dx * dx + dy * dy);
+      r[i] = d - x[2];
+      if (J) {
+        J[i * 3] = -dx / d;
+        J[i * 3 + 1] = -dy / d;
+        J[i * 3 + 2] = -1.0;
+      }
+    }
+  };
+  auto outs = OptimizeBatch<double>(ctx, xs.data(), B, n, m, residuals);
+  for (int64_t p = 0; p < B; ++p) {
+    CHECK(outs[p].Succeeded());
+    for (int j = 0; j < 3; ++j) CHECK(std::fabs(xs[p * 3 + j] - truth[p * 3 + j]) < 1e-5);
+  }
+  std::printf("circle: iters[0]=%d stop[0]=%d\n", (int)outs[0].num_iters, (int)outs[0].stop_reason);
+}
+
+// The polynomial family through the host-driven solver (user lambda on the host, canonical fma
+// order) must equal the fused device-resident loop bit for bit, iteration counts included.
+template <typename T>
+static void test_family_equivalence(const Context &ctx, int n, int m) {
+  const int64_t B = 70;
+  const T alpha = (T)0.1;
+  std::vector<T> A(B * m * n), y(B * m), x1(B * n), x2;
+  uint64_t s = 99;
+  auto rnd = [&]() {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    return (T)((double)(s >> 11) / 9007199254740992.0 * 2 - 1);
+  };
+  std::vector<T> xt(n);
+  for (int64_t p = 0; p < B; ++p) {
+    for (int j = 0; j < n; ++j) xt[j] = rnd();
+    for (int i = 0; i < m; ++i) {
+      T t = 0;
+      for (int j = 0; j < n; ++j) {
+        A[(p * m + i) * n + j] = rnd() / std::sqrt((T)n);
+        t = std::fma(A[(p * m + i) * n + j], xt[j], t);
+      }
+      y[p * m + i] = t + alpha * t * t * t + (T)0.01 * rnd();
+    }
+    for (int j = 0; j < n; ++j) x1[p * n + j] = xt[j] + (T)0.3 * rnd();
+  }
+  x2 = x1;
+  Options options;
+  if (sizeof(T) == 4) {
+    options.min_rerr_dec = 1e-5f;
+    options.min_step_norm2 = 1e-9f;
+  }
+  options.hessian.save_last = false;
+  auto residuals = [&](size_t p, const T *x, T *r, T *J) {
+    for (int i = 0; i < m; ++i) {
+      const T *a = &A[(p * m + i) * n];
+      T t = 0;
+      for (int j = 0; j < n; ++j) t = std::fma(a[j], x[j], t);
+      const T t2 = t * t;
+      r[i] = std::fma(t, std::fma(alpha, t2, (T)1), -y[p * m + i]);
+      if (J) {
+        const T sc = std::fma((T)3 * alpha, t2, (T)1);
+        for (int j = 0; j < n; ++j) J[i * n + j] = sc * a[j];
+      }
+    }
+  };
+  auto o1 = OptimizeBatch<T>(ctx, x1.data(), B, n, m, residuals, options);
+  auto o2 = OptimizePolynomialBatch<T>(ctx, A.data(), y.data(), alpha, x2.data(), B, m, n, options);
+  int total = 0;
+  for (int64_t p = 0; p < B; ++p) {
+    CHECK(o1[p].num_iters == o2[p].num_iters);
+    CHECK(o1[p].stop_reason == o2[p].stop_reason);
+    CHECK(o1[p].final_cost.cost == o2[p].final_cost.cost);
+    total += o1[p].num_iters;
+  }
+  CHECK(std::memcmp(x1.data(), x2.data(), x1.size() * sizeof(T)) == 0);
+  std::printf("family<%s> n=%d m=%d: total iters=%d, host-driven == device-resident\n",
+              sizeof(T) == 4 ? "float" : "double", n, m, total);
+}
+
+static void test_misuse(const Context &ctx) {
+  bool threw = false;
+  try {
+    std::vector<double> x(4);
+    OptimizeBatch<double>(ctx, x.data(), 4, 0, 1, [](size_t, const double *, double *, double *) {});
+  } catch (const std::invalid_argument &) {
+    threw = true;
+  }
+  CHECK(threw);
+}
+
+int main() {
+  try {
+    Context ctx(0);
+    test_sqrt2(ctx);
+    test_basic<double>();
+    test_basic<float>();
+    test_build_solve(ctx);
+    test_circle(ctx);
+    test_family_equivalence<double>(ctx, 6, 30);
+    test_family_equivalence<float>(ctx, 12, 40);
+    test_misuse(ctx);
+  } catch (const Error &e) {
+    std::printf("tinyopt::b200::Error (%d): %s\n", e.code, e.what());
+    return e.code == TOB200_ERR_CUDA ? 3 : 1;
+  }
+  if (g_failures) {
+    std::printf("%d check(s) failed\n", g_failures);
+    return 1;
+  }
+  std::printf("all C++ adaptor checks passed\n");
+  return 0;
+}

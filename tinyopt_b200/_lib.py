@@ -53,6 +53,10 @@ SYMBOLS = {
     "tob200_launch_count": (_i64, [_vp]),
     "tob200_last_elapsed_ms": (_i, [_vp, C.POINTER(_f)]),
     "tob200_options_default": (None, [_PO]),
+    "tob200_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "tob200_device_free": (_i, [_vp, _vp]),
+    "tob200_copy_to_device": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "tob200_copy_to_host": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "tob200_tiled_elems": (_i64, [_i64, _i, _i]),
     "tob200_kernel_family": (_i, [_i, _i]),
     "tob200_retile_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp]),

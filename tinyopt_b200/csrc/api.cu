@@ -600,6 +600,43 @@ int tob200_last_elapsed_ms(tob200_ctx *ctx, float *ms) {
   return TOB200_OK;
 }
 
+int tob200_device_alloc(tob200_ctx *ctx, size_t bytes, void **out) {
+  if (!ctx || !out) return fail(ctx, TOB200_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (bytes == 0) return TOB200_OK;
+  DeviceGuard guard(ctx->device);
+  CK(cudaMalloc(out, bytes));
+  return TOB200_OK;
+}
+
+int tob200_device_free(tob200_ctx *ctx, void *ptr) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (!ptr) return TOB200_OK;
+  DeviceGuard guard(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(ptr));
+  return TOB200_OK;
+}
+
+int tob200_copy_to_device(tob200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (bytes == 0) return TOB200_OK;
+  if (!dst || !src) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  DeviceGuard guard(ctx->device);
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return TOB200_OK;
+}
+
+int tob200_copy_to_host(tob200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (bytes == 0) return TOB200_OK;
+  if (!dst || !src) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  DeviceGuard guard(ctx->device);
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return TOB200_OK;
+}
+
 #define RETILE(SUF, T)                                                                                  \
   int tob200_retile_##SUF(tob200_ctx *ctx, const T *src, int64_t B, int m, int n, T *dst) {              \
     if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");                                   \
