@@ -138,7 +138,8 @@ int tob200_copy_to_host(tob200_ctx *ctx, void *dst_host, const void *src_device,
 /* Elements (not bytes) of a TILE32 buffer: ceil(B/32)*32*m*n.  r / y buffers: n = 1. */
 int64_t tob200_tiled_elems(int64_t B, int m, int n);
 /* Which kernel family serves (dtype, n): 1 thread-per-problem registers (small n),
- * 2 warp-per-problem shared-memory tiles (mid n), 0 none. */
+ * 2 warp-per-problem shared-memory tiles (mid n), 3 tensor-core J^T J + blocked LDLT (large n,
+ * n % 4 == 0), 0 none. */
 int tob200_kernel_family(int dtype, int n);
 
 /* ---- layout ----------------------------------------------------------------------------------- */
@@ -160,6 +161,24 @@ int tob200_build_solve_f32(tob200_ctx *ctx, const float *J, const float *r, int 
 int tob200_build_solve_f64(tob200_ctx *ctx, const double *J, const double *r, int layout,
                            int64_t B, int m, int n, const double *lambda, double *dx, double *cost,
                            double *H_out, double *g_out, int32_t *status);
+
+/* ---- a1 alone: the product site H = J^T diag(s^2) J on the tensor cores (tcgen05, 3xTF32) --------
+ * Replaces `H = J.transpose() * J` (diff/optimize_autodiff.h:156, diff/num_diff.h:297) for
+ * 4 <= n <= 512, n % 4 == 0 (float).  J: [B][m][n] problem-major; row_scale: [B][m] or NULL
+ * (J_i = s_i a_i: the polynomial family's Jacobian from A);  H: [B][n][n] full symmetric. */
+int tob200_jtj_f32(tob200_ctx *ctx, const float *J, const float *row_scale, int64_t B, int m, int n,
+                   float *H);
+
+/* ---- a6 alone: tinyopt::SolveLDLT(A, b) (math.h:232-240) == Eigen LDLT<_, Upper> + solve ----------
+ * A: [B][n][n] row-major, only the upper triangle is read; b, x: [B][n]; status: [B], 0 ok,
+ * 1 rejected (info() != Success or not positive; x untouched).  1 <= n <= 512 (float).  Blocked
+ * left-looking factorisation with the oracle's operation order: bit-exact for the same A. */
+int tob200_solve_ldlt_f32(tob200_ctx *ctx, const float *A, const float *b, int64_t B, int n, float *x,
+                          int32_t *status);
+
+/* Device time (ms, CUDA events) the last large-n call (n > 55) spent in one kernel class:
+ * phase 0 residual/gradient pass, 1 tensor-core J^T J, 2 factor + solve + LM step. */
+int tob200_last_phase_ms(tob200_ctx *ctx, int phase, float *ms, int *launches);
 
 /* ---- a7-a10: the whole LM loop, device resident, for the polynomial residual family ------------
  * r_i(x) = t_i + alpha t_i^3 - y_i, t = A x.  One call == one tinyopt::Optimize()

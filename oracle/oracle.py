@@ -46,7 +46,7 @@ class Result(C.Structure):
         ("final_num_residuals", C.c_int32), ("stop_reason", C.c_int32), ("num_iters", C.c_int32),
         ("num_failures", C.c_int32), ("num_consec_failures", C.c_int32),
         ("history_len", C.c_int32), ("last_lambda", C.c_double), ("last_prev_lambda", C.c_double),
-        ("min_margin", C.c_double),
+        ("min_margin", C.c_double), ("sign_margin", C.c_double), ("thr_margin", C.c_double),
     ]
 
 
@@ -54,7 +54,8 @@ RESULT_DTYPE = np.dtype([
     ("final_cost", "f8"), ("final_rerr_dec", "f8"), ("final_num_residuals", "i4"),
     ("stop_reason", "i4"), ("num_iters", "i4"), ("num_failures", "i4"),
     ("num_consec_failures", "i4"), ("history_len", "i4"), ("last_lambda", "f8"),
-    ("last_prev_lambda", "f8"), ("min_margin", "f8")], align=True)
+    ("last_prev_lambda", "f8"), ("min_margin", "f8"), ("sign_margin", "f8"),
+    ("thr_margin", "f8")], align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 
 

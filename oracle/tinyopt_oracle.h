@@ -93,6 +93,8 @@ typedef struct too_result {
   double last_prev_lambda;    /* SolverLM::prev_lambda_ at exit */
   double min_margin;          /* smallest relative distance of any branch decision from its
                                  threshold (diagnostic: how fragile the iteration count is) */
+  double sign_margin;         /* ... of the accept/reject decisions only: min |derr| / |err| */
+  double thr_margin;          /* ... of the stop-threshold decisions only: min |v - thr| / thr */
 } too_result;
 
 /* Optional per-iteration trace (caller allocates `cap` entries of each non-NULL array). */

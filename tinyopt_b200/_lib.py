@@ -63,6 +63,9 @@ SYMBOLS = {
     "tob200_retile_f64": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "tob200_build_solve_f32": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tob200_build_solve_f64": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tob200_jtj_f32": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "tob200_solve_ldlt_f32": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "tob200_last_phase_ms": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_i)]),
     "tob200_lm_run_f32": (_i, [_vp, _PO, _vp, _vp, _f, _i, _i64, _i, _i, _vp, _vp]),
     "tob200_lm_run_f64": (_i, [_vp, _PO, _vp, _vp, _d, _i, _i64, _i, _i, _vp, _vp]),
     "tob200_lm_run_host_f32": (_i, [_vp, _PO, _vp, _vp, _f, _i, _i64, _i, _i, _vp, _vp]),

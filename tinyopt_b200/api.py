@@ -228,6 +228,30 @@ class Context:
             out["g"] = g
         return out
 
+    # ---- a1 / a6 alone (the reference's secondary seams) ------------------------------------------
+    def jtj(self, J: torch.Tensor, row_scale: torch.Tensor | None = None) -> torch.Tensor:
+        """H = Jᵀ diag(s²) J on the tensor cores (tob200_jtj_f32).  J [B,m,n] float32."""
+        B, m, n = J.shape
+        H = torch.empty((B, n, n), dtype=torch.float32, device=J.device)
+        rs = None if row_scale is None else row_scale.to(dtype=torch.float32, device=J.device).contiguous()
+        self._ck(self._lib.tob200_jtj_f32(self._h, _p(J.contiguous()), _p(rs), B, m, n, _p(H)), "tob200_jtj_f32")
+        return H
+
+    def solve_ldlt(self, A: torch.Tensor, b: torch.Tensor):
+        """tinyopt::SolveLDLT(A, b) per problem (tob200_solve_ldlt_f32).  Returns (x [B,n], status [B])."""
+        B, n, _ = A.shape
+        x = torch.zeros((B, n), dtype=torch.float32, device=A.device)
+        status = torch.zeros((B,), dtype=torch.int32, device=A.device)
+        self._ck(self._lib.tob200_solve_ldlt_f32(self._h, _p(A.contiguous()), _p(b.contiguous()), B, n, _p(x), _p(status)),
+                 "tob200_solve_ldlt_f32")
+        return x, status
+
+    def last_phase_ms(self, phase: int):
+        """(ms, launches) the last large-n call spent in phase 0 eval / 1 JᵀJ / 2 solve."""
+        ms, cnt = C.c_float(0), C.c_int(0)
+        self._ck(self._lib.tob200_last_phase_ms(self._h, phase, C.byref(ms), C.byref(cnt)), "tob200_last_phase_ms")
+        return float(ms.value), int(cnt.value)
+
     # ---- a7-a10 ---------------------------------------------------------------------------------
     def optimize_batch(self, A: torch.Tensor, y: torch.Tensor, x0: torch.Tensor, opt: Options | None = None, *,
                        alpha: float = 0.1, layout: int | None = None, results: torch.Tensor | None = None,

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "lg_params.h"
 #include "tpp_inst.cuh"
 #include "wpp_inst.cuh"
 
@@ -31,8 +32,10 @@ struct tob200_ctx {
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // scratch for PROBLEM_MAJOR -> TILE32 conversion and for the *_host entry points
-  void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // (slots 0-1 layout conversion, 2-5 host entry points, 7 warp-per-problem H_, 8-19 large-n family)
+  static constexpr int kScratchSlots = 24;
+  void *scratch[kScratchSlots] = {};
+  size_t scratch_bytes[kScratchSlots] = {};
   std::map<std::tuple<int, int, int, int, size_t>, int> occupancy;  // (dtype, n, kind, block, smem) -> CTAs/SM
   // tuning knobs (env: TOB200_TPP_STAGE_BYTES, TOB200_TPP_STAGES, TOB200_TPP_CTAS_PER_SM)
   int tpp_stage_bytes = 16384;  // upper bound of one pipeline stage
@@ -45,6 +48,13 @@ struct tob200_ctx {
   int next_counter = 0;
   unsigned long long *tile_counter = nullptr;  // the counter of the launch being configured
   int wpp_stages = 1;  // env TOB200_WPP_STAGES (1: three CTAs per SM fit, measured best)
+  // large-n family: 3 = 3xTF32 (hi*hi + hi*lo + lo*hi, FP32-level accuracy), 1 = plain TF32
+  int lg_tf32_terms = 3;  // env TOB200_LG_TF32_TERMS
+  // device time of the last large-n call by phase (0 eval, 1 syrk, 2 solve): CUDA event pairs
+  static constexpr int kMaxPhaseEvents = 3 * 80;
+  std::vector<cudaEvent_t> phase_ev;  // 2 events per (iteration, phase)
+  int phase_used = 0;
+  int phase_kind[kMaxPhaseEvents] = {};
 };
 
 namespace {
@@ -270,6 +280,180 @@ int wpp_launch(tob200_ctx *ctx, int n, int kind, const void *params, const TppLa
   return TOB200_OK;
 }
 
+
+// ---- large-n family (lg.cuh): host-orchestrated eval -> syrk -> solve per LM iteration ------------
+enum LgSlot { kLgH = 8, kLgHd, kLgG, kLgCost, kLgScale, kLgRec, kLgLastDx, kLgW, kLgActive, kLgDg };
+
+int lg_phase_begin(tob200_ctx *ctx, int kind) {
+  if (ctx->phase_used + 2 > tob200_ctx::kMaxPhaseEvents * 2) return -1;
+  while ((int)ctx->phase_ev.size() < ctx->phase_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    ctx->phase_ev.push_back(e);
+  }
+  ctx->phase_kind[ctx->phase_used / 2] = kind;
+  cudaEventRecord(ctx->phase_ev[ctx->phase_used], ctx->stream);
+  return ctx->phase_used;
+}
+void lg_phase_end(tob200_ctx *ctx, int slot) {
+  if (slot < 0) return;
+  cudaEventRecord(ctx->phase_ev[slot + 1], ctx->stream);
+  ctx->phase_used = slot + 2;
+}
+
+struct LgBuffers {
+  float *H, *hd, *g, *dg, *cost, *scale, *W, *last_dx;
+  LmScalars<float> *rec;
+  unsigned long long *n_active;
+  int np, solve_grid;
+};
+
+int lg_prepare(tob200_ctx *ctx, int64_t B, int m, int n, bool need_state, bool need_scale, LgBuffers *b) {
+  const int np = lg_np(n);
+  b->np = np;
+  b->solve_grid = (int)(B < ctx->num_sms ? B : ctx->num_sms);
+  int rc;
+  if ((rc = ensure_scratch(ctx, kLgH, (size_t)B * np * np * 4)) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kLgHd, (size_t)B * np * 4)) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kLgG, (size_t)B * n * 4)) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kLgDg, (size_t)B * n * 4)) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kLgCost, (size_t)B * 4)) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kLgW, (size_t)b->solve_grid * np * np * 4)) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kLgActive, 64)) != TOB200_OK) return rc;
+  if (need_scale && (rc = ensure_scratch(ctx, kLgScale, (size_t)B * (m > 0 ? m : 1) * 4)) != TOB200_OK) return rc;
+  if (need_state) {
+    if ((rc = ensure_scratch(ctx, kLgRec, (size_t)B * sizeof(LmScalars<float>))) != TOB200_OK) return rc;
+    if ((rc = ensure_scratch(ctx, kLgLastDx, (size_t)B * n * 4)) != TOB200_OK) return rc;
+  }
+  b->H = (float *)ctx->scratch[kLgH];
+  b->hd = (float *)ctx->scratch[kLgHd];
+  b->g = (float *)ctx->scratch[kLgG];
+  b->dg = (float *)ctx->scratch[kLgDg];
+  b->cost = (float *)ctx->scratch[kLgCost];
+  b->scale = (float *)ctx->scratch[kLgScale];
+  b->W = (float *)ctx->scratch[kLgW];
+  b->rec = (LmScalars<float> *)ctx->scratch[kLgRec];
+  b->last_dx = (float *)ctx->scratch[kLgLastDx];
+  b->n_active = (unsigned long long *)ctx->scratch[kLgActive];
+  return TOB200_OK;
+}
+
+LgSyrkParams lg_syrk_params(tob200_ctx *ctx, const LgBuffers &b, const float *A, const float *scale,
+                            const LmScalars<float> *rec, int64_t B, int m, int n, int is_lm) {
+  LgSyrkParams sp;
+  sp.A = A;
+  sp.scale = scale;
+  sp.rec = rec;
+  sp.H = b.H;
+  sp.B = B;
+  sp.m = m;
+  sp.n = n;
+  sp.np = b.np;
+  sp.nstrips = (b.np + 127) / 128;
+  sp.stages = lg_syrk_stages(b.np);
+  sp.terms = ctx->lg_tf32_terms;
+  sp.is_lm = is_lm;
+  sp.half_bytes = lg_syrk_half_bytes(b.np);
+  return sp;
+}
+
+// the whole LM loop for 56 <= n <= 512 (float): three kernels per iteration over the active problems
+int lg_lm_run(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y, float alpha, int64_t B, int m,
+              int n, float *x, tob200_result *results) {
+  LgBuffers b;
+  int rc = lg_prepare(ctx, B, m, n, true, true, &b);
+  if (rc != TOB200_OK) return rc;
+  const DevOptions<float> dopt = make_dev_options<float>(*opt);
+  const int is_lm = opt->solver_type == 0;
+  ctx->phase_used = 0;
+  CK(launch_lg_init(b.rec, dopt, b.last_dx, B, n, ctx->stream));
+  ctx->launches++;
+  LgEvalParams ep;
+  ep.A = A; ep.y = y; ep.x = x; ep.rec = b.rec; ep.scale_in = nullptr; ep.scale = b.scale; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost;
+  ep.B = B; ep.m = m; ep.n = n; ep.synth = 1; ep.is_lm = is_lm; ep.alpha = alpha; ep.alpha3 = 3.f * alpha;
+  const LgSyrkParams sp = lg_syrk_params(ctx, b, A, b.scale, b.rec, B, m, n, is_lm);
+  LgSolveParams vp;
+  vp.H = b.H; vp.dg = b.dg; vp.hd = b.hd; vp.g = b.g; vp.cost = b.cost; vp.W = b.W; vp.B = B; vp.n = n; vp.np = b.np; vp.nres = m;
+  vp.mode = 0; vp.opt = dopt; vp.rec = b.rec; vp.x = x; vp.last_dx = b.last_dx; vp.results = results;
+  vp.n_active = b.n_active; vp.lambda = nullptr; vp.b = nullptr; vp.dx = nullptr; vp.cost_out = nullptr; vp.status = nullptr;
+  const int max_passes = opt->max_iters + 1 + (opt->check_final_cost ? 1 : 0);  // optimizer.h:248-250
+  for (int pass = 0; pass < max_passes; ++pass) {
+    int ev = lg_phase_begin(ctx, 0);
+    if (m > 0) {
+      CK(launch_lg_eval(ep, ctx->num_sms, ctx->stream));
+      ctx->launches++;
+    } else {
+      CK(cudaMemsetAsync(b.cost, 0, (size_t)B * 4, ctx->stream));
+      CK(cudaMemsetAsync(b.g, 0, (size_t)B * n * 4, ctx->stream));
+      CK(cudaMemsetAsync(b.dg, 0, (size_t)B * n * 4, ctx->stream));
+    }
+    lg_phase_end(ctx, ev);
+    ev = lg_phase_begin(ctx, 1);
+    if (m > 0) {
+      CK(launch_lg_syrk(sp, ctx->num_sms, ctx->stream));
+      ctx->launches++;
+    } else {
+      CK(cudaMemsetAsync(b.H, 0, (size_t)B * b.np * b.np * 4, ctx->stream));
+    }
+    lg_phase_end(ctx, ev);
+    ev = lg_phase_begin(ctx, 2);
+    CK(cudaMemsetAsync(b.n_active, 0, sizeof(unsigned long long), ctx->stream));
+    CK(launch_lg_solve(vp, b.solve_grid, ctx->stream));
+    ctx->launches++;
+    lg_phase_end(ctx, ev);
+    unsigned long long active = 0;
+    CK(cudaMemcpyAsync(&active, b.n_active, sizeof(active), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (active == 0) break;
+  }
+  return TOB200_OK;
+}
+
+// one Build + Solve from materialised J, r for 56 <= n <= 512 (float)
+int lg_build_solve(tob200_ctx *ctx, const float *J, const float *r, int64_t B, int m, int n, const float *lambda,
+                   float *dx, double *cost, float *H_out, float *g_out, int32_t *status) {
+  LgBuffers b;
+  int rc = lg_prepare(ctx, B, m, n, false, false, &b);
+  if (rc != TOB200_OK) return rc;
+  ctx->phase_used = 0;
+  LgEvalParams ep;
+  ep.A = J; ep.y = r; ep.x = nullptr; ep.rec = nullptr; ep.scale_in = nullptr; ep.scale = nullptr; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost;
+  ep.B = B; ep.m = m; ep.n = n; ep.synth = 0; ep.is_lm = 1; ep.alpha = 0.f; ep.alpha3 = 0.f;
+  int ev = lg_phase_begin(ctx, 0);
+  if (m > 0) {
+    CK(launch_lg_eval(ep, ctx->num_sms, ctx->stream));
+    ctx->launches++;
+  } else {
+    CK(cudaMemsetAsync(b.cost, 0, (size_t)B * 4, ctx->stream));
+    CK(cudaMemsetAsync(b.g, 0, (size_t)B * n * 4, ctx->stream));
+    CK(cudaMemsetAsync(b.dg, 0, (size_t)B * n * 4, ctx->stream));
+  }
+  lg_phase_end(ctx, ev);
+  ev = lg_phase_begin(ctx, 1);
+  if (m > 0) {
+    const LgSyrkParams sp = lg_syrk_params(ctx, b, J, nullptr, nullptr, B, m, n, 1);
+    CK(launch_lg_syrk(sp, ctx->num_sms, ctx->stream));
+    ctx->launches++;
+  } else {
+    CK(cudaMemsetAsync(b.H, 0, (size_t)B * b.np * b.np * 4, ctx->stream));
+  }
+  lg_phase_end(ctx, ev);
+  if (H_out) {
+    CK(launch_lg_export_h(b.H, b.dg, lambda, B, n, b.np, H_out, ctx->stream));
+    ctx->launches++;
+  }
+  if (g_out) CK(cudaMemcpyAsync(g_out, b.g, (size_t)B * n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  LgSolveParams vp;
+  vp.H = b.H; vp.dg = b.dg; vp.hd = nullptr; vp.g = b.g; vp.cost = b.cost; vp.W = b.W; vp.B = B; vp.n = n; vp.np = b.np; vp.nres = m;
+  vp.mode = 1; vp.opt = DevOptions<float>(); vp.rec = nullptr; vp.x = nullptr; vp.last_dx = nullptr; vp.results = nullptr;
+  vp.n_active = nullptr; vp.lambda = lambda; vp.b = nullptr; vp.dx = dx; vp.cost_out = cost; vp.status = status;
+  ev = lg_phase_begin(ctx, 2);
+  CK(launch_lg_solve(vp, b.solve_grid, ctx->stream));
+  ctx->launches++;
+  lg_phase_end(ctx, ev);
+  return TOB200_OK;
+}
+
 int check_options(tob200_ctx *ctx, const tob200_options *o) {
   if (!o) return fail(ctx, TOB200_ERR_INVALID, "options is NULL");
   if (o->solver_type != 0 && o->solver_type != 1)
@@ -310,6 +494,11 @@ int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_
     p.status = status;
     CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppBuildSolve, &p, cfg, nullptr));
     ctx->launches++;
+  } else if (family == 3) {
+    if (sizeof(T) != 4) return fail(ctx, TOB200_ERR_UNSUPPORTED, "large-n kernels are float only");
+    if ((rc = lg_build_solve(ctx, (const float *)J, (const float *)r, B, m, n, (const float *)lambda, (float *)dx, cost,
+                             (float *)H_out, (float *)g_out, status)) != TOB200_OK)
+      return rc;
   } else {
     WppBuildSolveParams<T> p;
     if ((rc = wpp_configure<T>(ctx, n, m, B, kWppBuildSolve, J, r, &p.d, &cfg)) != TOB200_OK) return rc;
@@ -353,6 +542,11 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     p.results = results;
     CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppRun, &p, cfg, nullptr));
     ctx->launches++;
+  } else if (family == 3) {
+    if (sizeof(T) != 4) return fail(ctx, TOB200_ERR_UNSUPPORTED, "large-n kernels are float only");
+    if ((rc = lg_lm_run(ctx, opt, (const float *)A, (const float *)y, (float)alpha, B, m, n, (float *)x, results)) !=
+        TOB200_OK)
+      return rc;
   } else {
     WppRunParams<T> p;
     if ((rc = wpp_configure<T>(ctx, n, m, B, kWppRun, A, y, &p.d, &cfg)) != TOB200_OK) return rc;
@@ -514,7 +708,11 @@ int64_t tob200_tiled_elems(int64_t B, int m, int n) {
 
 int tob200_kernel_family(int dtype, int n) {
   if (n < 1) return 0;
-  if (dtype == TOB200_F32) return n <= kTppMaxN_f32 ? 1 : (n <= kWppMaxN_f32 ? 2 : 0);
+  if (dtype == TOB200_F32) {
+    if (n <= kTppMaxN_f32) return 1;
+    if (n <= kWppMaxN_f32) return 2;
+    return (n <= kLgMaxN && n % 4 == 0) ? 3 : 0;  // rows must stay 16-byte aligned for the bulk copies
+  }
   if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : 0;
   return 0;
 }
@@ -558,6 +756,7 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->tpp_stages = env_int("TOB200_TPP_STAGES", ctx->tpp_stages);
   ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
   ctx->wpp_stages = env_int("TOB200_WPP_STAGES", ctx->wpp_stages);
+  ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
   if ((e = cudaMalloc((void **)&ctx->counters, sizeof(unsigned long long) * tob200_ctx::kNumCounters)) != cudaSuccess) {
     tob200_destroy(ctx);
     return fail_cuda(nullptr, e, "cudaMalloc(counters)");
@@ -571,8 +770,9 @@ int tob200_destroy(tob200_ctx *ctx) {
   if (!ctx) return TOB200_OK;
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < tob200_ctx::kScratchSlots; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  for (cudaEvent_t e : ctx->phase_ev) cudaEventDestroy(e);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -660,6 +860,87 @@ int tob200_build_solve_f64(tob200_ctx *ctx, const double *J, const double *r, in
                            const double *lambda, double *dx, double *cost, double *H_out, double *g_out,
                            int32_t *status) {
   return build_solve_impl<double>(ctx, J, r, layout, B, m, n, lambda, dx, cost, H_out, g_out, status);
+}
+
+int tob200_jtj_f32(tob200_ctx *ctx, const float *J, const float *row_scale, int64_t B, int m, int n, float *H) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (B < 0 || m < 0 || n < 4 || n > kLgMaxN || n % 4) return fail(ctx, TOB200_ERR_INVALID, "need 4 <= n <= 512, n % 4 == 0");
+  if (B == 0) return TOB200_OK;
+  if (!J || !H) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  if (!aligned16(J)) return fail(ctx, TOB200_ERR_INVALID, "J must be 16-byte aligned");
+  DeviceGuard guard(ctx->device);
+  LgBuffers b;
+  int rc = lg_prepare(ctx, B, m, n, false, false, &b);
+  if (rc != TOB200_OK) return rc;
+  ctx->phase_used = 0;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  int ev = lg_phase_begin(ctx, 1);
+  if (m > 0) {
+    const LgSyrkParams sp = lg_syrk_params(ctx, b, J, row_scale, nullptr, B, m, n, 1);
+    CK(launch_lg_syrk(sp, ctx->num_sms, ctx->stream));
+  } else {
+    CK(cudaMemsetAsync(b.H, 0, (size_t)B * b.np * b.np * 4, ctx->stream));
+  }
+  lg_phase_end(ctx, ev);
+  // the diagonal in FP32 (lg.cuh: the tensor core truncates its long same-sign sums)
+  const float *dg = nullptr;
+  if (m > 0) {
+    LgEvalParams ep;
+    ep.A = J; ep.y = nullptr; ep.x = nullptr; ep.rec = nullptr; ep.scale_in = row_scale; ep.scale = nullptr; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost;
+    ep.B = B; ep.m = m; ep.n = n; ep.synth = 0; ep.is_lm = 1; ep.alpha = 0.f; ep.alpha3 = 0.f;
+    ev = lg_phase_begin(ctx, 0);
+    CK(launch_lg_eval(ep, ctx->num_sms, ctx->stream));
+    lg_phase_end(ctx, ev);
+    ctx->launches++;
+    dg = b.dg;
+  }
+  CK(launch_lg_export_h(b.H, dg, nullptr, B, n, b.np, H, ctx->stream));
+  ctx->launches += 2;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  return TOB200_OK;
+}
+
+int tob200_solve_ldlt_f32(tob200_ctx *ctx, const float *A, const float *bvec, int64_t B, int n, float *x,
+                          int32_t *status) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (B < 0 || n < 1 || n > kLgMaxN) return fail(ctx, TOB200_ERR_INVALID, "need 1 <= n <= 512");
+  if (B == 0) return TOB200_OK;
+  if (!A || !bvec || !x || !status) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  DeviceGuard guard(ctx->device);
+  LgBuffers b;
+  int rc = lg_prepare(ctx, B, 0, n, false, false, &b);
+  if (rc != TOB200_OK) return rc;
+  ctx->phase_used = 0;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(launch_lg_import_h(A, B, n, b.np, b.H, ctx->stream));
+  LgSolveParams vp;
+  vp.H = b.H; vp.dg = nullptr; vp.hd = nullptr; vp.g = nullptr; vp.cost = nullptr; vp.W = b.W; vp.B = B; vp.n = n; vp.np = b.np; vp.nres = 0;
+  vp.mode = 2; vp.opt = DevOptions<float>(); vp.rec = nullptr; vp.x = nullptr; vp.last_dx = nullptr; vp.results = nullptr;
+  vp.n_active = nullptr; vp.lambda = nullptr; vp.b = bvec; vp.dx = x; vp.cost_out = nullptr; vp.status = status;
+  int ev = lg_phase_begin(ctx, 2);
+  CK(launch_lg_solve(vp, b.solve_grid, ctx->stream));
+  lg_phase_end(ctx, ev);
+  ctx->launches += 2;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  return TOB200_OK;
+}
+
+int tob200_last_phase_ms(tob200_ctx *ctx, int phase, float *ms, int *launches) {
+  if (!ctx || !ms) return fail(ctx, TOB200_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  float total = 0.f;
+  int count = 0;
+  for (int i = 0; i + 1 < ctx->phase_used; i += 2) {
+    if (ctx->phase_kind[i / 2] != phase) continue;
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, ctx->phase_ev[i], ctx->phase_ev[i + 1]));
+    total += t;
+    ++count;
+  }
+  *ms = total;
+  if (launches) *launches = count;
+  return TOB200_OK;
 }
 
 int tob200_lm_run_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y, float alpha,

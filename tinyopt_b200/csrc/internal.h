@@ -19,3 +19,21 @@ cudaError_t launch_synth_eval(const T *A, const T *y, T alpha, int layout, int64
                               T *J, cudaStream_t st);
 
 }  // namespace tob200
+
+// lg_kernels.cu (large-n family; parameter structs in lg.cuh / lg_solve.cuh)
+namespace tob200 {
+template <typename T> struct LmScalars;
+template <typename T> struct DevOptions;
+struct LgEvalParams;
+struct LgSyrkParams;
+struct LgSolveParams;
+cudaError_t launch_lg_init(LmScalars<float> *rec, const DevOptions<float> &opt, float *last_dx, int64_t B, int n,
+                           cudaStream_t st);
+cudaError_t launch_lg_export_h(const float *H, const float *dg, const float *lambda, int64_t B, int n, int np, float *out,
+                               cudaStream_t st);
+cudaError_t launch_lg_import_h(const float *in, int64_t B, int n, int np, float *H, cudaStream_t st);
+cudaError_t launch_lg_eval(const LgEvalParams &p, int num_sms, cudaStream_t st);
+cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st);
+cudaError_t launch_lg_solve(const LgSolveParams &p, int grid, cudaStream_t st);
+int lg_syrk_stages(int np);
+}  // namespace tob200

@@ -1,0 +1,400 @@
+// lg.cuh — "large n" kernels (56 <= n <= 512, float): config C5 (n = 512, m = 4096).
+//
+// At this size H = J^T J is a true dense contraction (2 m n^2 flop per problem, 128-256 flop/B), so
+// it runs on the 5th-generation tensor cores; everything else stays FP32 CUDA-core work.  One LM
+// iteration of the batch is three kernels over the still-running problems (host-orchestrated, the
+// per-problem state lives in HBM; a whole-batch iteration is tens of milliseconds, so launch latency
+// is irrelevant here):
+//
+//   lg_eval_kernel   t = A x, r, cost, the Jacobian row scale s_i = 1 + 3 alpha t_i^2 and
+//                    g = J^T r.  One CTA per problem, rows streamed by TMA bulk copies
+//                    (cp.async.bulk, 16-row chunks of 32 KB through a 3-stage mbarrier ring).  HBM bound.
+//   lg_syrk_kernel   H = A^T diag(s^2) A on tcgen05: warp-specialised, one CTA per (problem, 128-row
+//                    strip of H); producer warps load rows of A, scale them by s_i, split every value
+//                    into TF32 hi + lo parts and store both, transposed, into the K-major UMMA
+//                    core-matrix layout; one thread issues tcgen05.mma.kind::tf32 (hi*hi + hi*lo + lo*hi: "3xTF32",
+//                    FP32-level accuracy) into a 128 x (n - 128 r) FP32 accumulator in TMEM — only the
+//                    blocks on or above the diagonal are computed; four epilogue warps drain TMEM with
+//                    tcgen05.ld and write the strip of H.  Tensor-pipe bound.
+//   lg_solve_kernel  damping, Eigen's pivot order, P H P^T, blocked left-looking LDL^T (32-column
+//                    panels, thread per row, every dot product a left-to-right fma chain: the same
+//                    operation sequence as the CPU oracle's unblocked factorisation, so the solver is
+//                    bit-exact for a given H), blocked substitutions, then the LM state machine of
+//                    lm_state.cuh and the x update.  One CTA per problem.
+//
+// Reference path replaced: diff/optimize_autodiff.h:151-157, solvers/lm.h:60-120,
+// solvers/gn.h:150-171, math.h:232-240, optimizers/optimizer.h:243-539.
+#pragma once
+
+#include "common.cuh"
+#include "lg_params.h"
+#include "lm_state.cuh"
+
+namespace tob200 {
+
+
+// ================================================================================================
+// lg_eval_kernel
+// ================================================================================================
+
+__global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid_constant__ LgEvalParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.n, m = p.m;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  float *xs = reinterpret_cast<float *>(smem + 64);
+  float *wbuf = xs + lg_np(n);
+  float *sbuf = wbuf + 16;
+  float *cbuf = sbuf + 16;
+  float *stages = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(cbuf + 16) + 127) & ~(uintptr_t)127);
+  const uint32_t stage_elems = (uint32_t)kLgEvalRows * n;
+  if (tid == 0) {
+    for (int s = 0; s < kLgEvalStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t it = 0;  // chunks consumed so far (ring position / parity)
+  const int nchunks = (m + kLgEvalRows - 1) / kLgEvalRows;
+
+  for (int64_t pr = blockIdx.x; pr < p.B; pr += gridDim.x) {
+    bool rebuild = true;
+    if (p.rec) {
+      const uint32_t fl = p.rec[pr].flags;
+      if (fl & kFlagDone) continue;
+      rebuild = !p.is_lm || (fl & kFlagRebuild);
+    }
+    const float *Ap = p.A + (size_t)pr * m * n;
+    const float *yp = p.y + (size_t)pr * m;
+    if (p.synth)
+      for (int j = tid; j < n; j += kLgEvalThreads) xs[j] = p.x[(size_t)pr * n + j];
+    __syncthreads();  // xs ready; every thread is past the previous problem's stages
+    auto issue = [&](int c, uint32_t st) {
+      const int row0 = c * kLgEvalRows;
+      const int nrows = (m - row0 < kLgEvalRows) ? (m - row0) : kLgEvalRows;
+      const uint32_t bytes = (uint32_t)nrows * (uint32_t)n * 4u;
+      mbar_expect_tx(&bars[st], bytes);
+      tma_bulk_g2s(stages + (size_t)st * stage_elems, Ap + (size_t)row0 * n, bytes, &bars[st]);
+    };
+    if (tid == 0) {
+      fence_proxy_async();
+      for (int c = 0; c < kLgEvalStages && c < nchunks; ++c) issue(c, (it + c) % kLgEvalStages);
+    }
+    float gacc = 0.f;   // thread j < n: g_j, rows in order
+    float dacc = 0.f;   // thread j < n: (J^T J)_jj, rows in order
+    float cacc = 0.f;   // lane 0 of warp w: sum of r_i^2 over its rows
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const uint32_t st = it % kLgEvalStages, ph = (it / kLgEvalStages) & 1u;
+      mbar_wait(&bars[st], ph);
+      const float *sa = stages + (size_t)st * stage_elems;
+      const int row = c * kLgEvalRows + warp;
+      // ---- warp = row: t_i, r_i, s_i ----
+      if (row < m) {
+        float ri, sc = 1.f;
+        if (p.synth) {
+          const float *arow = sa + warp * n;
+          float t = 0.f;
+          for (int j = lane * 4; j < n; j += 128) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(arow + j);
+            const float4 x4 = *reinterpret_cast<const float4 *>(xs + j);
+            t = __fmaf_rn(a4.x, x4.x, t);
+            t = __fmaf_rn(a4.y, x4.y, t);
+            t = __fmaf_rn(a4.z, x4.z, t);
+            t = __fmaf_rn(a4.w, x4.w, t);
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, off));
+          const float t2 = __fmul_rn(t, t);
+          ri = __fmaf_rn(t, __fmaf_rn(p.alpha, t2, 1.f), -yp[row]);
+          sc = __fmaf_rn(p.alpha3, t2, 1.f);
+        } else {
+          ri = p.y ? yp[row] : 0.f;
+          if (p.scale_in) sc = p.scale_in[(size_t)pr * m + row];
+        }
+        if (lane == 0) {
+          cacc = __fmaf_rn(ri, ri, cacc);
+          wbuf[warp] = __fmul_rn(sc, ri);
+          sbuf[warp] = sc;
+          if (p.synth && rebuild) p.scale[(size_t)pr * m + row] = sc;
+        }
+      } else if (lane == 0) {
+        wbuf[warp] = 0.f;
+        sbuf[warp] = 0.f;
+      }
+      __syncthreads();
+      // ---- thread = column: g_j += sum_i (s_i r_i) a_ij, rows in order ----
+      if (rebuild && tid < n) {
+        const int nrows = (m - c * kLgEvalRows < kLgEvalRows) ? (m - c * kLgEvalRows) : kLgEvalRows;
+#pragma unroll 4
+        for (int i = 0; i < nrows; ++i) {
+          const float a = sa[i * n + tid];
+          gacc = __fmaf_rn(a, wbuf[i], gacc);
+          const float jv = __fmul_rn(sbuf[i], a);
+          dacc = __fmaf_rn(jv, jv, dacc);
+        }
+      }
+      __syncthreads();  // the stage and wbuf are free again
+      if (tid == 0 && c + kLgEvalStages < nchunks) {
+        fence_proxy_async();
+        issue(c + kLgEvalStages, st);
+      }
+    }
+    if (rebuild && tid < n) {
+      p.g[(size_t)pr * n + tid] = gacc;
+      if (p.dg) p.dg[(size_t)pr * n + tid] = dacc;
+    }
+    if (lane == 0) cbuf[warp] = cacc;
+    __syncthreads();
+    if (tid == 0) {
+      float cs = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLgEvalRows; ++w) cs = __fadd_rn(cs, cbuf[w]);
+      p.cost[pr] = cs;
+    }
+  }
+}
+
+// ================================================================================================
+// lg_syrk_kernel (tcgen05 / TMEM)
+// ================================================================================================
+
+// ---- tcgen05 wrappers ----
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle.  Canonical layout (16-byte units):
+// ((8, n), 2) : ((1, SBO), LBO) — a core matrix is 8 MN rows x 16 bytes (4 tf32 of K), rows 16 bytes
+// apart; SBO = byte distance between 8-row groups along MN, LBO = between the two 4-element K chunks
+// of one K = 8 instruction.  (Probed on the B200 with tools/tc_probe.cu: MN-major tf32 operands
+// produce no output, K-major ones are exact.)
+__device__ __forceinline__ uint64_t tc_desc_k_major(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  return d;         // layout type 0: no swizzle
+}
+// round-to-nearest TF32 (low 13 mantissa bits cleared): hi part of the 3xTF32 split; lo = v - hi is
+// then exact and of either sign, so the hardware's truncation of lo does not bias the products
+__device__ __forceinline__ float tc_round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
+__device__ __forceinline__ uint32_t tc_idesc_tf32(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool lg_skip(const LgSyrkParams &p, int64_t pr) {
+  if (!p.rec) return false;
+  const uint32_t fl = p.rec[pr].flags;
+  if (fl & kFlagDone) return true;
+  return p.is_lm && !(fl & kFlagRebuild);
+}
+
+__global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid_constant__ LgSyrkParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // stages 1024-byte aligned (swizzle atoms), barriers behind them
+  unsigned char *stages = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = 2u * p.half_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)p.stages * stage_bytes);
+  uint64_t *full = bars, *empty = bars + kLgMaxStages, *tmem_full = bars + 2 * kLgMaxStages, *tmem_empty = tmem_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], kLgProdWarps);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kLgEpiWarps);
+    mbar_fence_init();
+  }
+  if (warp == 0) {  // the whole TMEM of this SM: 128 lanes x 512 FP32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t total = (int64_t)p.nstrips * p.B;  // strip-major: the widest strips first
+  const int m = p.m, n = p.n, np = p.np;
+  const int ksteps = (m + kLgStageK - 1) / kLgStageK;
+
+  if (warp > kLgMmaWarp) {
+    // ===================== producers =====================
+    // A stage is the K-major image of 8 rows x ncs columns of diag(s) A: operand row = column j of A,
+    // K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 4) of columns
+    // [128 cg, 128 cg + 128) (cg = w % 4): lane l owns columns l, l + 32, l + 64, l + 96 of that group
+    // (coalesced 128-byte global loads per row; conflict-free 16-byte shared stores, one per column).
+    const int w = warp - (kLgMmaWarp + 1);
+    const int kc = w >> 2, cg = w & 3;
+    uint32_t it = 0;
+    for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
+      const int r = (int)(idx / p.B);
+      const int64_t pr = idx % p.B;
+      if (lg_skip(p, pr)) continue;
+      const int c0 = 128 * r;
+      const int ncs = (np - c0 < 128) ? 128 : (np - c0);  // columns staged (the A operand needs 128)
+      const uint32_t lbo = (uint32_t)ncs * 16u;
+      const bool busy = 128 * cg < ncs;
+      const float *Ap = p.A + (size_t)pr * m * n;
+      const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
+      float nxt[4][4], nsc[4];  // register prefetch of the next stage: [q][t] = column l + 32 q, row t
+      auto load_rows = [&](int row0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int row = row0 + t;
+          nsc[t] = (row < m) ? (sp ? sp[row] : 1.f) : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = c0 + 128 * cg + lane + 32 * q;
+            nxt[q][t] = (busy && row < m && col < n) ? Ap[(size_t)row * n + col] : 0.f;
+          }
+        }
+      };
+      load_rows(4 * kc);
+      for (int ks = 0; ks < ksteps; ++ks, ++it) {
+        float cur[4][4], sc[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          sc[t] = nsc[t];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cur[q][t] = nxt[q][t];
+        }
+        if (ks + 1 < ksteps) load_rows((ks + 1) * kLgStageK + 4 * kc);
+        const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        unsigned char *sb = stages + (size_t)st * stage_bytes;
+        if (busy) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int rr = 128 * cg + lane + 32 * q;  // operand row (column of A relative to c0)
+            if (rr >= ncs) continue;                  // ncs is a multiple of 32: uniform per q
+            float v[4], hi[4], lo[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              v[t] = __fmul_rn(cur[q][t], sc[t]);
+              hi[t] = (p.terms == 3) ? tc_round_tf32(v[t]) : v[t];
+              lo[t] = __fsub_rn(v[t], hi[t]);
+            }
+            const uint32_t off = (uint32_t)kc * lbo + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
+            *reinterpret_cast<float4 *>(sb + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            if (p.terms == 3) *reinterpret_cast<float4 *>(sb + p.half_bytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[st]);
+      }
+    }
+  } else if (warp == kLgMmaWarp) {
+    // ===================== MMA issuer: one thread =====================
+    uint32_t it = 0, item = 0;
+    for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
+      const int r = (int)(idx / p.B);
+      const int64_t pr = idx % p.B;
+      if (lg_skip(p, pr)) continue;
+      const int nb = np - 128 * r;  // accumulator columns of this strip
+      const int ncs = nb < 128 ? 128 : nb;
+      if (lane == 0) {
+        mbar_wait(tmem_empty, (item & 1u) ^ 1u);  // the epilogue has drained the previous strip
+        tc_fence_after();
+      }
+      __syncwarp();
+      for (int ks = 0; ks < ksteps; ++ks, ++it) {
+        const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
+        if (lane == 0) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(stages + (size_t)st * stage_bytes);
+          const uint32_t lbo = (uint32_t)ncs * 16u;  // K chunk 1 follows all the core matrices of chunk 0
+          const uint64_t a_hi = tc_desc_k_major(sb, lbo, 128u);
+          const uint64_t a_lo = tc_desc_k_major(sb + p.half_bytes, lbo, 128u);
+          for (int n0 = 0; n0 < nb; n0 += 256) {
+            const int N = (nb - n0 < 256) ? (nb - n0) : 256;
+            const uint32_t idesc = tc_idesc_tf32(N);
+            const uint64_t b_hi = tc_desc_k_major(sb + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
+            const uint32_t d = tmem_base + (uint32_t)n0;
+            tc_mma_tf32(d, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+            if (p.terms == 3) {
+              const uint64_t b_lo = tc_desc_k_major(sb + p.half_bytes + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
+              tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+              tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+            }
+          }
+          tc_commit(&empty[st]);  // arrives when the MMAs above have read the stage
+          if (ks == ksteps - 1) tc_commit(tmem_full);
+        }
+        __syncwarp();
+      }
+      ++item;
+    }
+  } else {
+    // ===================== epilogue: warp w drains TMEM lanes [32 w, 32 w + 32) =====================
+    uint32_t item = 0;
+    for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
+      const int r = (int)(idx / p.B);
+      const int64_t pr = idx % p.B;
+      if (lg_skip(p, pr)) continue;
+      const int c0 = 128 * r, nb = np - c0;
+      mbar_wait(tmem_full, item & 1u);
+      tc_fence_after();
+      const int row = c0 + 32 * warp + lane;
+      float *hrow = p.H + ((size_t)pr * np + row) * np + c0;
+      for (int cb = 0; cb < nb; cb += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)cb, v);
+        tc_wait_ld();
+        if (row < np) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4 *>(hrow + cb + 4 * q) =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                            __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+      ++item;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+}  // namespace tob200

@@ -1,0 +1,115 @@
+// lg_params.h — parameter blocks and launch geometry of the large-n family (kernels: lg.cuh,
+// lg_solve.cuh; launchers: lg_kernels.cu; orchestration: api.cu).
+#pragma once
+
+#include "lm_state.cuh"
+
+namespace tob200 {
+
+constexpr int kLgMinN = 56;
+constexpr int kLgMaxN = 512;
+__host__ __device__ constexpr int lg_np(int n) { return (n + 31) / 32 * 32; }  // padded order (pitch of H, W)
+
+constexpr int kLgEvalThreads = 512;
+constexpr int kLgEvalRows = 16;  // rows per TMA chunk == warps per CTA
+constexpr int kLgEvalStages = 3;
+
+struct LgEvalParams {
+  const float *A;   // [B][m][n] (J when synth == 0)
+  const float *y;   // [B][m]    (r when synth == 0)
+  const float *x;   // [B][n]    (unused when synth == 0)
+  const LmScalars<float> *rec;  // per-problem state or nullptr (nullptr: every problem, full pass)
+  const float *scale_in;  // [B][m] row scale of a materialised J (synth == 0), or nullptr
+  float *scale;     // [B][m] out: s_i (only written when synth && the pass rebuilds)
+  float *g;         // [B][n] out (rebuild passes)
+  float *dg;        // [B][n] out (rebuild passes): diag(J^T J) in FP32, rows in order (the tensor core
+                    // accumulates with truncation, which biases the long same-sign sums of the diagonal)
+  float *cost;      // [B] out: sum r_i^2
+  int64_t B;
+  int m, n;
+  int synth;        // 1: polynomial family evaluated from A, y, x; 0: materialised J, r
+  int is_lm;
+  float alpha, alpha3;
+};
+
+__host__ __device__ inline size_t lg_eval_smem_bytes(int n) {
+  // [bars 64 | x n | w 16 | s 16 | cost 16 | stages * 16 rows * n]
+  return 64 + (size_t)lg_np(n) * 4 + 3 * 64 + (size_t)kLgEvalStages * kLgEvalRows * n * 4 + 128;
+}
+
+constexpr int kLgEpiWarps = 4;    // warps 0..3: TMEM lane quadrant == warp id
+constexpr int kLgMmaWarp = 4;     // warp 4: lane 0 issues every tcgen05.mma
+constexpr int kLgProdWarps = 8;   // warps 5..12: one K row of a stage each
+constexpr int kLgSyrkThreads = (kLgEpiWarps + 1 + kLgProdWarps) * 32;
+constexpr int kLgStageK = 8;      // K extent of one tf32 tcgen05.mma == rows per stage
+constexpr int kLgMaxStages = 8;
+
+struct LgSyrkParams {
+  const float *A;      // [B][m][n]
+  const float *scale;  // [B][m] row scale, or nullptr (materialised J)
+  const LmScalars<float> *rec;  // nullptr: every problem
+  float *H;            // [B][np][np]: strip r writes rows [128 r, 128 r + 128), columns >= 128 r
+  int64_t B;
+  int m, n, np, nstrips;
+  int stages;          // ring depth
+  int terms;           // 3: hi*hi + hi*lo + lo*hi; 1: plain TF32
+  int is_lm;
+  uint32_t half_bytes; // bytes of the hi (== lo) part of a stage: max(128, np) / 32 KB
+};
+
+__host__ __device__ inline uint32_t lg_syrk_half_bytes(int np) { return (uint32_t)((np < 128 ? 128 : np) / 32) * 1024u; }
+__host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages) {
+  return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np) + 256;
+}
+
+constexpr int kLgSolveThreads = 512;
+constexpr int kLgPanel = 32;
+
+struct LgSolveParams {
+  // ---- per problem inputs ----
+  float *H;            // [B][np][np] upper triangle (row <= col), undamped diagonal after a rebuild
+  const float *dg;     // [B][n] FP32 diagonal of the last rebuild (lg_eval), or nullptr: use H's own
+  float *hd;           // [B][np] persistent damped diagonal of H_ (solvers/lm.h keeps H_ damped)
+  float *g;            // [B][n] grad_
+  const float *cost;   // [B] sum r^2 of the pass
+  float *W;            // [grid][np][np] factor workspace (lower, permuted)
+  int64_t B;
+  int n, np, nres;
+  int mode;            // 0: LM loop step (rec/x/last_dx/results), 1: one Build+Solve (lambda/dx/status), 2: plain SolveLDLT(H, b)
+  // ---- mode 0 ----
+  DevOptions<float> opt;
+  LmScalars<float> *rec;
+  float *x, *last_dx;
+  tob200_result *results;
+  unsigned long long *n_active;
+  // ---- mode 1 / 2 ----
+  const float *lambda;  // [B] or nullptr
+  const float *b;       // mode 2: right-hand sides [B][n]
+  float *dx;            // [B][n]
+  double *cost_out;     // [B] (mode 1)
+  int32_t *status;      // [B]
+};
+
+struct LgSolveSmem {
+  // offsets in floats
+  int dd, dsm, ysm, rhs, perm, inv, temp, tt, tile, misc, total;
+};
+__host__ __device__ inline LgSolveSmem lg_solve_smem(int np) {
+  LgSolveSmem L;
+  const int vl = kLgMaxN;  // vectors are sized for the largest n: the pivot sort pads to a power of two
+  int o = 0;
+  L.dd = o; o += vl;
+  L.dsm = o; o += vl;
+  L.ysm = o; o += vl;
+  L.rhs = o; o += vl;
+  L.perm = o; o += vl;
+  L.inv = o; o += vl;
+  L.temp = o; o += 2 * kLgPanel;
+  L.tt = o; o += kLgPanel * kLgPanel;
+  L.tile = o; o += np * (kLgPanel + 1);
+  L.misc = o; o += 32;
+  L.total = o;
+  return L;
+}
+
+}  // namespace tob200
