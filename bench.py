@@ -32,6 +32,9 @@ CONFIGS = {
     # C4 is the sharded config: 1M problems in total, split over the ranks (strong scaling)
     "C4": dict(B=1_000_000, m=500, n=50, dtype="f32", opts=FLOAT_OPTS, strong=True,
                desc="batch 1M problems, n=50 params, 500 residuals, float, sharded over the GPUs"),
+    # C5: the tensor-core config (tcgen05 3xTF32 JᵀJ + blocked LDLT), 4k problems in total
+    "C5": dict(B=4096, m=4096, n=512, dtype="f32", opts=FLOAT_OPTS, strong=True,
+               desc="batch 4k problems, n=512 params, 4096 residuals, float, tensor-core JᵀJ tile, sharded over the GPUs"),
 }
 SEED, ALPHA, SIGMA = 20261017, 0.1, 1e-2
 
@@ -93,11 +96,27 @@ def measured_peak():
 
 
 def bounded_sample(cfg, budget_bytes):
-    """Problems of the workload whose inputs fit `budget_bytes` (a multiple of 32, at least 1024,
+    """Problems of the workload whose inputs fit `budget_bytes` (a multiple of 32, at least 32,
     never more than the config's batch): the bounded sample of the CPU and e2e legs."""
     s = 8 if cfg["dtype"] == "f64" else 4
     per = s * (cfg["m"] * cfg["n"] + cfg["m"] + 2 * cfg["n"])
-    return int(min(cfg["B"], max(1024, (budget_bytes // per) // 32 * 32)))
+    return int(min(cfg["B"], max(32, (budget_bytes // per) // 32 * 32)))
+
+
+def measured_tensor_peak():
+    """TF32 dense peak: MEASURED_PEAKS.json has bf16 only; TF32 runs at half the bf16 rate on B200
+    (tcgen05 K per instruction is 32 bytes for every dtype), so bf16 / 2 — said so in peak_source."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]) / 2, "measured bf16 burst / 2 (MEASURED_PEAKS.json bf16_tflops; no TF32 figure there)"
+    except Exception:
+        return 1590.0 / 2, "fallback bf16 1.59 PFLOP/s / 2 (B200_PROFILING.md)"
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the bench size, from
+# the committed `ncu --set full` captures (profiles/r1_*_ncu_full_summary.txt); None where no capture at
+# the bench size exists (C4's capture ran 16384 of the 1M problems)
+NCU_TRAFFIC = {"C2": 244.811520e6 + 11.034112e6, "C3": 3.177813e9 + 13.342976e6, "C4": None}
 
 
 def cpu_reference(cfg, sample_B, reps, nthreads=0):
@@ -107,7 +126,8 @@ def cpu_reference(cfg, sample_B, reps, nthreads=0):
     dt = np.float64 if cfg["dtype"] == "f64" else np.float32
     A, y, xs, x0 = O.synth_generate(sample_B, cfg["m"], cfg["n"], dt, seed=SEED, alpha=ALPHA, sigma=SIGMA)
     opt = O.default_options(**cfg["opts"])
-    O.synth_lm_run(A[:2048], y[:2048], x0[:2048], opt, alpha=ALPHA, nthreads=nthreads)  # warm-up
+    w = min(2048, max(16, sample_B // 4))
+    O.synth_lm_run(A[:w], y[:w], x0[:w], opt, alpha=ALPHA, nthreads=nthreads)  # warm-up
     times, iters, used = [], 0, 1
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -222,11 +242,17 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # per-launch duration of the dominant kernel, CUDA events on the launching stream, live
-    kms = []
-    for _ in range(min(args.steps, 10)):
+    family = ctx.kernel_family(tdt, n)
+    kms, tensor_ms, tensor_launches = [], [], 0
+    for _ in range(min(args.steps, 10 if family != 3 else 2)):
         x.copy_(x0)
         step()
-        kms.append(ctx.last_elapsed_ms())
+        if family == 3:   # multi-kernel pipeline: the tensor-core JᵀJ launches of this solve, summed
+            t_ms, tensor_launches = ctx.last_phase_ms(1)
+            tensor_ms.append(t_ms)
+            kms.append(sum(ctx.last_phase_ms(k)[0] for k in range(3)))
+        else:
+            kms.append(ctx.last_elapsed_ms())
     kernel_ms_avg = float(np.mean(kms))
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -248,6 +274,20 @@ def main():
         peak, peak_src = measured_peak()
         abytes = algorithmic_bytes(cfg, results)
         achieved = abytes / (kernel_ms_avg * 1e-3) / 1e9
+        if family == 3:
+            # dominant kernel = lg_syrk_kernel (tcgen05): algorithmic flops m*n*(n+1) per rebuilt problem
+            builds = int(results["num_builds"].astype(np.int64).sum())
+            aflops = builds * m * n * (n + 1)
+            t_ms = float(np.mean(tensor_ms))
+            tpeak, tsrc = measured_tensor_peak()
+            roof = {"bound": "tensor", "achieved": aflops / (t_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                    "traffic": None, "kernel": "lg_syrk_kernel", "kernel_ms": t_ms / max(1, tensor_launches),
+                    "launches_per_step": tensor_launches, "algorithmic_flops_per_step": aflops, "peak_source": tsrc,
+                    "mode": "3xTF32 (3 MMAs per product term, FP32-level accuracy): the hardware executes 3x the algorithmic flops, "
+                            "and 10 of 16 128x128 blocks for the n(n+1)/2 algorithmic triangle",
+                    "pipeline_ms": {k: ctx.last_phase_ms(i)[0] for i, k in enumerate(("eval", "jtj", "solve"))},
+                    "hbm_GBps_whole_pipeline": achieved}
+            roof["frac"] = roof["achieved"] / roof["peak"]
         line = {
             "metric": "LM iterations/sec (batched dense NLLS)", "value": value, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -256,9 +296,10 @@ def main():
                        "options": "tinyopt defaults" + (" + float thresholds min_rerr_dec=1e-5 min_step_norm2=1e-9" if cfg["opts"] else ""),
                        "iters_per_problem": iters_rank / B, "parallelism": f"{world} x independent problem shards",
                        "l2": f"inputs {(A.numel() + y.numel()) * A.element_size() / 1e6:.0f} MB per step > 126 MB L2, no flush"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "tpp_lm_run_kernel" if layout == tb.TILE32 else "wpp_lm_run_kernel", "kernel_ms": kernel_ms_avg,
-                         "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src},
+            "roofline": roof if family == 3 else
+                        {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC.get(args.config), "kernel": "tpp_lm_run_kernel" if family == 1 else "wpp_lm_run_kernel",
+                         "kernel_ms": kernel_ms_avg, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src},
             "gpu_launches": int(launches), "clocks": clocks,
         }
 

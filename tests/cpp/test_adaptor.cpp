@@ -30,7 +30,9 @@ static void test_sqrt2(const Context &ctx) {
     r[0] = x[0] * x[0] - 2.0;
     if (J) J[0] = 2.0 * x[0];
   };
-  Options options;
+  Options options;  // tests/sqrt2.cpp:22-28
+  options.max_iters = 20;
+  options.max_consec_failures = 0;
   auto outs = OptimizeBatch<double>(ctx, xs.data(), B, 1, 1, residuals, options);
   for (int64_t p = 0; p < B; ++p) {
     CHECK(outs[p].Succeeded());
@@ -38,9 +40,15 @@ static void test_sqrt2(const Context &ctx) {
     CHECK(std::fabs(std::fabs(xs[p]) - std::sqrt(2.0)) < 1e-5);
     CHECK(outs[p].has_final_hessian() && outs[p].final_hessian[0] > 0);
   }
-  // SURVEY.md §8(c) golden vector: x0 = 1, default Options -> 5 Steps, kMinError
+  // SURVEY.md §8(c) golden vector: x0 = 1 -> 5 Steps, kMinError (the same under default Options)
   CHECK(outs[0].num_iters == 5);
   CHECK(outs[0].stop_reason == StopReason::kMinError);
+  {  // default Options: x0 = -0.3 overshoots and gives up after 5 consecutive failures, as in the reference
+    std::vector<double> x1 = {1.0, -0.3};
+    auto o2 = OptimizeBatch<double>(ctx, x1.data(), 2, 1, 1, residuals, Options());
+    CHECK(o2[0].num_iters == 5 && o2[0].stop_reason == StopReason::kMinError);
+    CHECK(o2[1].stop_reason == StopReason::kMaxConsecNoDecr);
+  }
   std::printf("sqrt2: x[0]=%.16g iters=%d stop=%d\n", xs[0], (int)outs[0].num_iters, (int)outs[0].stop_reason);
 }
 

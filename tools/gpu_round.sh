@@ -14,7 +14,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1
 echo "pytest rc=$?" | tee -a $out/pytest_gpu_$tag.log
 tail -3 $out/pytest_gpu_$tag.log
 
-for c in C2 C3 C4; do
+for c in ${CONFIGS:-C2 C3 C4 C5}; do
   timeout 600 python bench.py --config $c --steps 10 --warmup 3 > $out/bench_${c}_$tag.json 2> $out/bench_${c}_$tag.err
   echo "bench $c rc=$?"; cat $out/bench_${c}_$tag.json
 done
