@@ -311,7 +311,7 @@ struct LgBuffers {
 int lg_prepare(tob200_ctx *ctx, int64_t B, int m, int n, bool need_state, bool need_scale, LgBuffers *b) {
   const int np = lg_np(n);
   b->np = np;
-  b->solve_grid = (int)(B < ctx->num_sms ? B : ctx->num_sms);
+  b->solve_grid = (int)(B < ctx->num_sms ? B : ctx->num_sms);  // lg_solve_kernel: 1 CTA per SM (128 registers)
   int rc;
   if ((rc = ensure_scratch(ctx, kLgH, (size_t)B * np * np * 4)) != TOB200_OK) return rc;
   if ((rc = ensure_scratch(ctx, kLgHd, (size_t)B * np * 4)) != TOB200_OK) return rc;

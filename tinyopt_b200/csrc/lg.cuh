@@ -256,12 +256,13 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   if (warp > kLgMmaWarp) {
     // ===================== producers =====================
     // A stage is the K-major image of 8 rows x ncs columns of diag(s) A: operand row = column j of A,
-    // K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 4) of columns
-    // [128 cg, 128 cg + 128) (cg = w % 4): lane l owns columns l, l + 32, l + 64, l + 96 of that group
-    // (coalesced 128-byte global loads per row; conflict-free 16-byte shared stores, one per column).
+    // K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 8) of columns
+    // [128 cg + 64 qh, + 64) (cg = (w / 2) % 4, qh = w % 2): lane l owns columns l and l + 32 of that
+    // range (coalesced 128-byte global loads per row; conflict-free 16-byte shared stores, one per
+    // column).  Sixteen warps keep enough loads in flight and enough issue slots for the transform.
     const int w = warp - (kLgMmaWarp + 1);
-    const int kc = w >> 2, cg = w & 3;
-    uint32_t it = 0;
+    const int kc = w >> 3, cg = (w >> 1) & 3, qh = w & 1;
+    uint32_t st = 0, ph = 0;  // ring position and its phase parity
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       const int r = (int)(idx / p.B);
       const int64_t pr = idx % p.B;
@@ -269,44 +270,36 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       const int c0 = 128 * r;
       const int ncs = (np - c0 < 128) ? 128 : (np - c0);  // columns staged (the A operand needs 128)
       const uint32_t lbo = (uint32_t)ncs * 16u;
-      const bool busy = 128 * cg < ncs;
-      const float *Ap = p.A + (size_t)pr * m * n;
+      const int rr0 = 128 * cg + 64 * qh + lane;          // my operand rows: rr0, rr0 + 32
+      const bool busy0 = rr0 < ncs, busy1 = rr0 + 32 < ncs;  // ncs is a multiple of 32: warp uniform
+      const float *Ap = p.A + (size_t)pr * m * n + c0 + rr0;
+      const bool cok0 = busy0 && c0 + rr0 < n, cok1 = busy1 && c0 + rr0 + 32 < n;
       const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
-      float nxt[4][4], nsc[4];  // register prefetch of the next stage: [q][t] = column l + 32 q, row t
-      auto load_rows = [&](int row0) {
+      // register prefetch three stages deep ([q][t] = column rr0 + 32 q, row t): the loads of stage
+      // ks + 3 are issued as soon as stage ks has been written, so ~48 KB per SM are in flight
+      float buf0[2][4], buf1[2][4], buf2[2][4], sc0[4], sc1[4], sc2[4];
+      auto load_rows = [&](float (&b)[2][4], float (&bs)[4], int ks) {
+        const int row0 = ks * kLgStageK + 4 * kc;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int row = row0 + t;
-          nsc[t] = (row < m) ? (sp ? sp[row] : 1.f) : 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int col = c0 + 128 * cg + lane + 32 * q;
-            nxt[q][t] = (busy && row < m && col < n) ? Ap[(size_t)row * n + col] : 0.f;
-          }
+          const bool rok = ks < ksteps && row < m;
+          bs[t] = rok ? (sp ? sp[row] : 1.f) : 0.f;
+          b[0][t] = (cok0 && rok) ? Ap[(size_t)row * n] : 0.f;
+          b[1][t] = (cok1 && rok) ? Ap[(size_t)row * n + 32] : 0.f;
         }
       };
-      load_rows(4 * kc);
-      for (int ks = 0; ks < ksteps; ++ks, ++it) {
-        float cur[4][4], sc[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          sc[t] = nsc[t];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) cur[q][t] = nxt[q][t];
-        }
-        if (ks + 1 < ksteps) load_rows((ks + 1) * kLgStageK + 4 * kc);
-        const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
+      auto put_stage = [&](const float (&b)[2][4], const float (&bs)[4]) {
         mbar_wait(&empty[st], ph ^ 1u);
         unsigned char *sb = stages + (size_t)st * stage_bytes;
-        if (busy) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int rr = 128 * cg + lane + 32 * q;  // operand row (column of A relative to c0)
-            if (rr >= ncs) continue;                  // ncs is a multiple of 32: uniform per q
+        for (int q = 0; q < 2; ++q) {
+          if (q == 0 ? busy0 : busy1) {
+            const int rr = rr0 + 32 * q;  // operand row (column of A relative to c0)
             float v[4], hi[4], lo[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              v[t] = __fmul_rn(cur[q][t], sc[t]);
+              v[t] = __fmul_rn(b[q][t], bs[t]);
               hi[t] = (p.terms == 3) ? tc_round_tf32(v[t]) : v[t];
               lo[t] = __fsub_rn(v[t], hi[t]);
             }
@@ -318,11 +311,27 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[st]);
+        if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
+      };
+      load_rows(buf0, sc0, 0);
+      load_rows(buf1, sc1, 1);
+      load_rows(buf2, sc2, 2);
+      for (int ks = 0; ks < ksteps; ks += 3) {
+        put_stage(buf0, sc0);
+        load_rows(buf0, sc0, ks + 3);
+        if (ks + 1 < ksteps) {
+          put_stage(buf1, sc1);
+          load_rows(buf1, sc1, ks + 4);
+        }
+        if (ks + 2 < ksteps) {
+          put_stage(buf2, sc2);
+          load_rows(buf2, sc2, ks + 5);
+        }
       }
     }
   } else if (warp == kLgMmaWarp) {
     // ===================== MMA issuer: one thread =====================
-    uint32_t it = 0, item = 0;
+    uint32_t st = 0, ph = 0, item = 0;
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       const int r = (int)(idx / p.B);
       const int64_t pr = idx % p.B;
@@ -334,8 +343,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         tc_fence_after();
       }
       __syncwarp();
-      for (int ks = 0; ks < ksteps; ++ks, ++it) {
-        const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
+      for (int ks = 0; ks < ksteps; ++ks) {
         if (lane == 0) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
@@ -359,6 +367,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
           if (ks == ksteps - 1) tc_commit(tmem_full);
         }
         __syncwarp();
+        if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
       }
       ++item;
     }

@@ -39,7 +39,7 @@ __host__ __device__ inline size_t lg_eval_smem_bytes(int n) {
 
 constexpr int kLgEpiWarps = 4;    // warps 0..3: TMEM lane quadrant == warp id
 constexpr int kLgMmaWarp = 4;     // warp 4: lane 0 issues every tcgen05.mma
-constexpr int kLgProdWarps = 8;   // warps 5..12: one K row of a stage each
+constexpr int kLgProdWarps = 16;  // warps 5..20: 4 K rows x 64 columns of a stage each
 constexpr int kLgSyrkThreads = (kLgEpiWarps + 1 + kLgProdWarps) * 32;
 constexpr int kLgStageK = 8;      // K extent of one tf32 tcgen05.mma == rows per stage
 constexpr int kLgMaxStages = 8;
@@ -63,7 +63,8 @@ __host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages) {
 }
 
 constexpr int kLgSolveThreads = 512;
-constexpr int kLgPanel = 32;
+constexpr int kLgPanel = 32;  // factorisation panel width (16 / 2 CTAs per SM was measured slower: more tiles, more barriers)
+constexpr int kLgBlk = 32;    // substitution block == warp
 
 struct LgSolveParams {
   // ---- per problem inputs ----
@@ -92,7 +93,7 @@ struct LgSolveParams {
 
 struct LgSolveSmem {
   // offsets in floats
-  int dd, dsm, ysm, rhs, perm, inv, temp, tt, tile, misc, total;
+  int dd, dsm, ysm, rhs, perm, inv, tt, tile, misc, total;
 };
 __host__ __device__ inline LgSolveSmem lg_solve_smem(int np) {
   LgSolveSmem L;
@@ -104,9 +105,11 @@ __host__ __device__ inline LgSolveSmem lg_solve_smem(int np) {
   L.rhs = o; o += vl;
   L.perm = o; o += vl;
   L.inv = o; o += vl;
-  L.temp = o; o += 2 * kLgPanel;
   L.tt = o; o += kLgPanel * kLgPanel;
-  L.tile = o; o += np * (kLgPanel + 1);
+  {  // double-buffered W tile; also the 16 per-warp 32 x 33 transpose tiles of lg_mirror_upper
+    const int a = 2 * np * (kLgPanel + 1), b = (kLgSolveThreads / 32) * 32 * 33;
+    L.tile = o; o += a > b ? a : b;
+  }
   L.misc = o; o += 32;
   L.total = o;
   return L;

@@ -15,10 +15,22 @@
 //    descending j backward).
 #pragma once
 
+#include <cstdio>
+
 #include "lg.cuh"
 
 namespace tob200 {
 
+// optional per-phase cycle counters of block 0 (build with -DTOB200_LG_TIMING; printed at kernel end)
+#ifdef TOB200_LG_TIMING
+__device__ long long g_lg_tm[32];
+__device__ long long g_lg_t0;
+#define LG_T0() do { if (threadIdx.x == 0 && blockIdx.x == 0) g_lg_t0 = clock64(); } while (0)
+#define LG_T(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t = clock64(); g_lg_tm[k] += t - g_lg_t0; g_lg_t0 = t; } } while (0)
+#else
+#define LG_T0()
+#define LG_T(k)
+#endif
 
 // monotone key of |d| for the pivot search: 0 for NaN (never greater than anything)
 __device__ __forceinline__ uint32_t lg_key(float d) {
@@ -27,13 +39,15 @@ __device__ __forceinline__ uint32_t lg_key(float d) {
 }
 
 // Pivot order of Eigen's LDLT for the diagonal dd[0..n): perm[pos] = original index, inv[orig] = pos.
-// Distinct keys: descending sort (bitonic, CTA wide).  Ties or NaNs: exact sequential simulation of
-// "first maximum wins + swap" by one thread (rare).
-__device__ void lg_pivot_order(const float *dd, int n, int np, int *perm, int *inv, float *scratch_keys, int *flag) {
+// Eigen picks, at step k, the FIRST largest |d| among positions k..n-1 and swaps it to position k.
+// With distinct keys that is a descending sort (bitonic, CTA wide).  With ties (or NaNs) the winner
+// among equal keys depends on where earlier swaps have moved them, so the swaps are replayed exactly
+// by one thread — in O(n + sum of squared tie-group sizes): the sorted order says which key value is
+// due at step k, only the members of that tie group are compared by current position.
+__device__ void lg_pivot_order(const float *dd, int n, int np, int *perm, int *inv, float *scratch_keys, int *spare, int *flag) {
   const int tid = threadIdx.x;
-  uint32_t *keys = reinterpret_cast<uint32_t *>(scratch_keys);  // np entries
-  // sort size: next power of two >= n (<= 512 == blockDim)
-  int sz = 1;
+  uint32_t *keys = reinterpret_cast<uint32_t *>(scratch_keys);  // kLgMaxN entries
+  int sz = 1;  // sort size: next power of two >= n (<= 512 == blockDim)
   while (sz < n) sz <<= 1;
   if (tid < sz) {
     keys[tid] = tid < n ? lg_key(dd[tid]) : 0u;
@@ -58,44 +72,122 @@ __device__ void lg_pivot_order(const float *dd, int n, int np, int *perm, int *i
       __syncthreads();
     }
   }
-  // ties among real entries, or a NaN (key 0 inside the first n) -> exact path
+  LG_T(10);
+  // ties among real entries, or a NaN (key 0 inside the first n) -> exact replay
   if (tid < n) {
     const bool tie = (tid + 1 < n && keys[tid] == keys[tid + 1]) || keys[tid] == 0u;
     if (tie) *flag = 1;
   }
   __syncthreads();
+  LG_T(11);
+#ifdef TOB200_LG_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    g_lg_tm[20] += *flag;
+    if (*flag && g_lg_tm[21] < 3) {
+      g_lg_tm[21]++;
+      int shown = 0;
+      for (int i = 0; i + 1 < n && shown < 4; ++i)
+        if (keys[i] == keys[i + 1] || keys[i] == 0u) { printf("tie at sorted %d: keys %u %u orig %d %d dd %g %g\n", i, keys[i], keys[i + 1], perm[i], perm[i + 1], dd[perm[i]], dd[perm[i + 1]]); ++shown; }
+    }
+  }
+#endif
   if (*flag) {
+    // srt = the sorted originals (moved to spare scratch), perm is rebuilt as at[pos] (element now at
+    // that position), inv as pos[orig]; keys stay sorted and delimit the tie groups
+    int *srt = spare;
+    if (tid < n) srt[tid] = perm[tid];
+    __syncthreads();
+    if (tid < n) { perm[tid] = tid; inv[tid] = tid; }
+    __syncthreads();
     if (tid == 0) {
-      for (int i = 0; i < n; ++i) { keys[i] = lg_key(dd[i]); perm[i] = i; }
-      for (int k = 0; k < n; ++k) {
-        int pbest = k;
-        uint32_t best = keys[k];
-        if (best != 0u) {  // a NaN at k stays: nothing compares greater
-          for (int i = k + 1; i < n; ++i)
-            if (keys[i] > best) { best = keys[i]; pbest = i; }
+      if (keys[n - 1] == 0u) {
+        // a NaN on the diagonal: replay Eigen's search literally (a NaN sitting at position k stays,
+        // elsewhere it never wins); the factorisation fails anyway, speed is irrelevant
+        for (int k = 0; k < n; ++k) {
+          int pbest = k;
+          uint32_t best = lg_key(dd[perm[k]]);
+          if (best != 0u)
+            for (int i = k + 1; i < n; ++i) {
+              const uint32_t kv = lg_key(dd[perm[i]]);
+              if (kv > best) { best = kv; pbest = i; }
+            }
+          const int ek = perm[k]; perm[k] = perm[pbest]; perm[pbest] = ek;
         }
-        if (pbest != k) {
-          const uint32_t tk = keys[k]; keys[k] = keys[pbest]; keys[pbest] = tk;
-          const int tp = perm[k]; perm[k] = perm[pbest]; perm[pbest] = tp;
+        for (int k = 0; k < n; ++k) inv[perm[k]] = k;
+      } else {
+        uint32_t prev = 0u, cur = keys[0];
+        for (int k = 0; k < n; ++k) {
+          const uint32_t next = (k + 1 < n) ? keys[k + 1] : 0u;
+          int e;
+          if (cur != prev && cur != next) {
+            e = srt[k];  // singleton: the k-th largest key
+          } else {       // tie group: the untaken member that currently sits first
+            int gs = k;
+            while (gs > 0 && keys[gs - 1] == cur) --gs;
+            e = -1;
+            int best_pos = n, slot = gs;
+            for (int i = gs; i < n && keys[i] == cur; ++i) {
+              const int o = srt[i];
+              if (o >= 0 && inv[o] < best_pos) { best_pos = inv[o]; e = o; slot = i; }
+            }
+            srt[slot] = -1;
+          }
+          const int pp = inv[e], f = perm[k];  // swap the contents of positions k and pp
+          perm[k] = e; perm[pp] = f;
+          inv[e] = k; inv[f] = pp;
+          prev = cur; cur = next;
         }
       }
     }
     __syncthreads();
+  } else {
+    if (tid < n) inv[perm[tid]] = tid;
+    __syncthreads();
   }
-  if (tid < n) inv[perm[tid]] = tid;
-  __syncthreads();
+  LG_T(12);
+}
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): the W tiles of phase 1 are double buffered
+__device__ __forceinline__ void lg_cp_async4(float *dst, const float *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void lg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Packed FP32 pairs: Blackwell's FFMA2 (fma.rn.f32x2) does two IEEE fused multiply-adds per issue slot
+// — same roundings as two scalar fmas, half the instructions in the FMA-issue-bound loops below.
+__device__ __forceinline__ void lg_ffma2(unsigned long long &acc, float w, float b0, float b1) {
+  unsigned long long a, b;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float lg_lo(unsigned long long v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float lg_hi(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ unsigned long long lg_pack(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
 
 // Blocked left-looking LDL^T of the permuted lower matrix W (pitch np) in global memory; D is left on
 // the diagonal of W and in dsm.  Returns info()==Success && isPositive() (uniform across the CTA).
+//
+// Panel kb (32 columns), thread = row kb + tid:
+//   phase 1   S_ic = sum_{j < kb} L_ij (D_j L_{kb+c,j}), j ascending: W tiles [rows x 32 j] stream through
+//             a double-buffered shared tile (cp.async), T[j][c] = D_j L_{kb+c,j} is formed once per tile,
+//             32 accumulators per thread.
+//   phase 2a  the 32 x 32 diagonal block, by warp 0 alone, right-looking in registers: after column jj
+//             is final every lane folds it into its pending sums S_r[c] (c > jj) — each S_r[c] still
+//             receives its terms in ascending jj, i.e. the oracle's order — with T2[c][jj] = D_jj L_{c,jj}
+//             exchanged by shuffles and left in shared memory for
+//   phase 2b  the rows below the block: same recurrence, no further synchronisation.
 __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolveSmem &L) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float *dsm = sm + L.dsm;
-  float *temp = sm + L.temp;  // [2][32]
-  float *tt = sm + L.tt;      // [32 j][32 c]
-  float *tile = sm + L.tile;  // [rows][33]
+  float *tt = sm + L.tt;      // [32 j][32 c]: T of phase 1, then T2 of phase 2
+  float *tile0 = sm + L.tile;  // 2 x [rows][33]
+  const int tile_elems = np * (kLgPanel + 1);
   int *misc = reinterpret_cast<int *>(sm + L.misc);  // 0: sign, 1: found_zero_pivot, 2: ret, 3: nonzero-below flag
-  float *piv = sm + L.misc + 8;                       // pivot broadcast [2]
   if (n == 1) {
     const float a = W[0];
     if (tid == 0) dsm[0] = a;
@@ -110,8 +202,18 @@ __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolve
     const int i = kb + tid;  // my row
     const bool active = tid < nrows;
     float areg[kLgPanel], S[kLgPanel];
+    unsigned long long S2[kLgPanel / 2];  // phase-1 accumulators, packed pairs (S[2 q], S[2 q + 1])
 #pragma unroll
-    for (int c = 0; c < kLgPanel; ++c) { areg[c] = 0.f; S[c] = 0.f; }
+    for (int c = 0; c < kLgPanel; ++c) areg[c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < kLgPanel / 2; ++q) S2[q] = 0ull;
+    auto issue_tile = [&](int jc, float *tile) {
+      constexpr int rpw = 32 / kLgPanel;  // rows per warp instruction
+      for (int rr = warp * rpw + lane / kLgPanel; rr < nrows; rr += (kLgSolveThreads / 32) * rpw)
+        lg_cp_async4(tile + rr * (kLgPanel + 1) + lane % kLgPanel, W + (size_t)(kb + rr) * np + jc + lane % kLgPanel);
+      lg_cp_async_commit();
+    };
+    if (kb > 0) issue_tile(0, tile0);
     if (active) {
       const float4 *wr = reinterpret_cast<const float4 *>(W + (size_t)i * np + kb);
 #pragma unroll
@@ -120,14 +222,15 @@ __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolve
         areg[4 * q] = v.x; areg[4 * q + 1] = v.y; areg[4 * q + 2] = v.z; areg[4 * q + 3] = v.w;
       }
     }
-    // ---- phase 1: S_ic = sum_{j < kb} W_ij (D_j W_{kb+c, j}), j ascending ----
-    for (int jc = 0; jc < kb; jc += kLgPanel) {
-      __syncthreads();  // previous tile / tt fully consumed
-      for (int rr = warp; rr < nrows; rr += kLgSolveThreads / 32)
-        tile[rr * (kLgPanel + 1) + lane] = W[(size_t)(kb + rr) * np + jc + lane];
-      __syncthreads();
+    LG_T(13);
+    // ---- phase 1 ----
+    for (int jc = 0, tb = 0; jc < kb; jc += kLgPanel, tb ^= 1) {
+      float *tile = tile0 + tb * tile_elems;
+      lg_cp_async_wait<0>();
+      __syncthreads();  // the tile has landed for everybody; the other buffer and tt are fully consumed
+      if (jc + kLgPanel < kb) issue_tile(jc + kLgPanel, tile0 + (tb ^ 1) * tile_elems);  // overlaps the FMAs below
       for (int e = tid; e < kLgPanel * kLgPanel; e += kLgSolveThreads) {
-        const int j = e >> 5, c = e & 31;
+        const int j = e / kLgPanel, c = e % kLgPanel;
         tt[j * kLgPanel + c] = (c < pw) ? __fmul_rn(dsm[jc + j], tile[c * (kLgPanel + 1) + j]) : 0.f;
       }
       __syncthreads();
@@ -140,55 +243,74 @@ __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolve
 #pragma unroll
           for (int q = 0; q < kLgPanel / 4; ++q) {
             const float4 tv = t4[q];
-            S[4 * q] = __fmaf_rn(w, tv.x, S[4 * q]);
-            S[4 * q + 1] = __fmaf_rn(w, tv.y, S[4 * q + 1]);
-            S[4 * q + 2] = __fmaf_rn(w, tv.z, S[4 * q + 2]);
-            S[4 * q + 3] = __fmaf_rn(w, tv.w, S[4 * q + 3]);
+            lg_ffma2(S2[2 * q], w, tv.x, tv.y);
+            lg_ffma2(S2[2 * q + 1], w, tv.z, tv.w);
           }
         }
       }
     }
-    __syncthreads();
-    // ---- phase 2: the panel, column by column (k = kb + c) ----
+    __syncthreads();  // tt is free
 #pragma unroll
-    for (int c = 0; c < kLgPanel; ++c) {
-      if (c < pw) {  // uniform
-        float *tb = temp + (c & 1) * kLgPanel;
-        if (tid == c) {  // the diagonal row finishes its own chain and publishes temp, pivot
-          float s = S[c];
+    for (int q = 0; q < kLgPanel / 2; ++q) { S[2 * q] = lg_lo(S2[q]); S[2 * q + 1] = lg_hi(S2[q]); }
+    LG_T(14);
+    // ---- phase 2a: diagonal block (lanes < kLgPanel) and the rows of warp 0 below it, warp 0 ----
+    if (warp == 0) {
+      int sign = misc[0], fzp = misc[1], ret = misc[2], bad = 0;
 #pragma unroll
-          for (int jj = 0; jj < c; ++jj) {
-            const float tv = __fmul_rn(dsm[kb + jj], areg[jj]);
-            tb[jj] = tv;
-            s = __fmaf_rn(areg[jj], tv, s);
-          }
-          const float akk = __fsub_rn(areg[c], s);
-          areg[c] = akk;
-          dsm[kb + c] = akk;
-          piv[c & 1] = akk;
-          // sign / zero-pivot bookkeeping (Eigen LDLT: m_sign, found_zero_pivot, ret)
+      for (int jj = 0; jj < kLgPanel; ++jj) {
+        if (jj < pw) {  // uniform
+          const float d = __fsub_rn(areg[jj], S[jj]);
+          const float akk = __shfl_sync(0xffffffffu, d, jj);
           const bool valid = fabsf(akk) > 0.f;
-          if (misc[1] && valid) misc[2] = 0;
-          else if (!valid) misc[1] = 1;
-          int sign = misc[0];
+          float tm = 0.f;
+          if (lane == jj) {
+            areg[jj] = akk;
+            dsm[kb + jj] = akk;
+          } else if (lane > jj) {
+            float v = d;
+            if (valid) v = __fdiv_rn(d, akk);
+            else if (v != 0.f && active) bad = 1;  // a zero pivot with a non-zero column below it
+            areg[jj] = v;
+            tm = __fmul_rn(akk, v);  // T2[lane][jj] = D_jj L_{lane,jj}
+          }
+          if (lane < kLgPanel) tt[jj * kLgPanel + lane] = tm;
+          // Eigen LDLT bookkeeping (identical in every lane: akk is uniform)
+          if (fzp && valid) ret = 0;
+          else if (!valid) fzp = 1;
           if (sign == 1) { if (akk < 0.f) sign = 2; }
           else if (sign == -1) { if (akk > 0.f) sign = 2; }
           else if (sign == 0) { if (akk > 0.f) sign = 1; else if (akk < 0.f) sign = -1; }
-          misc[0] = sign;
-        }
-        __syncthreads();
-        if (active && tid > c) {
-          const float akk = piv[c & 1];
-          float s = S[c];
 #pragma unroll
-          for (int jj = 0; jj < c; ++jj) s = __fmaf_rn(areg[jj], tb[jj], s);
-          float v = __fsub_rn(areg[c], s);
+          for (int c = jj + 1; c < kLgPanel; ++c) {
+            // no "lane >= c" guard: S[c] of a row above column c is never read
+            S[c] = __fmaf_rn(areg[jj], __shfl_sync(0xffffffffu, tm, c), S[c]);
+          }
+        }
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      if (lane == 0) {
+        misc[0] = sign; misc[1] = fzp; misc[2] = ret;
+        if (bad) misc[3] = 1;
+      }
+    }
+    __syncthreads();
+    LG_T(15);
+    // ---- phase 2b: the rows below the block ----
+    if (active && tid >= 32) {
+#pragma unroll
+      for (int jj = 0; jj < kLgPanel; ++jj) {
+        if (jj < pw) {
+          const float akk = dsm[kb + jj];
+          float v = __fsub_rn(areg[jj], S[jj]);
           if (fabsf(akk) > 0.f) v = __fdiv_rn(v, akk);
-          else if (v != 0.f) misc[3] = 1;  // a zero pivot with a non-zero column below it
-          areg[c] = v;
+          else if (v != 0.f) misc[3] = 1;
+          areg[jj] = v;
+#pragma unroll
+          for (int c = jj + 1; c < kLgPanel; ++c) S[c] = __fmaf_rn(v, tt[jj * kLgPanel + c], S[c]);
         }
       }
     }
+    LG_T(16);
     // ---- write the panel back (L below the diagonal, D on it) ----
     if (active) {
       float4 *wr = reinterpret_cast<float4 *>(W + (size_t)i * np + kb);
@@ -196,6 +318,7 @@ __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolve
       for (int q = 0; q < kLgPanel / 4; ++q) wr[q] = make_float4(areg[4 * q], areg[4 * q + 1], areg[4 * q + 2], areg[4 * q + 3]);
     }
     __syncthreads();
+    LG_T(17);
   }
   const bool ok = misc[2] && !misc[3] && (misc[0] == 1 || misc[0] == 0);
   __syncthreads();
@@ -212,33 +335,33 @@ __device__ void lg_ldlt_solve(const float *W, int n, int np, const int *perm, co
   const bool active = i < n;
   float yv = active ? b[perm[i]] : 0.f;
   // forward: y_i takes its updates in the order j = 0 .. i-1
-  for (int jb = 0; jb < n; jb += kLgPanel) {
+  for (int jb = 0; jb < n; jb += kLgBlk) {
     // diagonal block rows are exactly the lanes of warp jb / 32
     if ((tid >> 5) == (jb >> 5)) {
-      float lrow[kLgPanel];
+      float lrow[kLgBlk];
       if (active) {
         const float4 *wr = reinterpret_cast<const float4 *>(W + (size_t)i * np + jb);
 #pragma unroll
-        for (int q = 0; q < kLgPanel / 4; ++q) {
+        for (int q = 0; q < kLgBlk / 4; ++q) {
           const float4 v = wr[q];
           lrow[4 * q] = v.x; lrow[4 * q + 1] = v.y; lrow[4 * q + 2] = v.z; lrow[4 * q + 3] = v.w;
         }
       } else {
 #pragma unroll
-        for (int q = 0; q < kLgPanel; ++q) lrow[q] = 0.f;
+        for (int q = 0; q < kLgBlk; ++q) lrow[q] = 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < kLgPanel; ++j) {
+      for (int j = 0; j < kLgBlk; ++j) {
         const float yj = __shfl_sync(0xffffffffu, yv, j);
         if (lane > j && active) yv = __fmaf_rn(-lrow[j], yj, yv);
       }
       ysm[i] = yv;  // i < jb + 32 <= np
     }
     __syncthreads();
-    if (active && i >= jb + kLgPanel) {
+    if (active && i >= jb + kLgBlk) {
       const float4 *wr = reinterpret_cast<const float4 *>(W + (size_t)i * np + jb);
 #pragma unroll
-      for (int q = 0; q < kLgPanel / 4; ++q) {
+      for (int q = 0; q < kLgBlk / 4; ++q) {
         const float4 v = wr[q];
         const int j0 = jb + 4 * q;
         if (j0 < n) yv = __fmaf_rn(-v.x, ysm[j0], yv);
@@ -248,6 +371,7 @@ __device__ void lg_ldlt_solve(const float *W, int n, int np, const int *perm, co
       }
     }
   }
+  LG_T(18);
   // D^+ (pseudo-inverse with tolerance min())
   if (active) {
     const float d = dsm[i];
@@ -255,11 +379,11 @@ __device__ void lg_ldlt_solve(const float *W, int n, int np, const int *perm, co
   }
   __syncthreads();
   // backward: y_i takes its updates in the order j = n-1 .. i+1
-  const int last = ((n - 1) / kLgPanel) * kLgPanel;
-  for (int jb = last; jb >= 0; jb -= kLgPanel) {
+  const int last = ((n - 1) / kLgBlk) * kLgBlk;
+  for (int jb = last; jb >= 0; jb -= kLgBlk) {
     if ((tid >> 5) == (jb >> 5)) {
 #pragma unroll
-      for (int j = kLgPanel - 1; j >= 0; --j) {
+      for (int j = kLgBlk - 1; j >= 0; --j) {
         const float yj = __shfl_sync(0xffffffffu, yv, j);
         if (lane < j && jb + j < n) yv = __fmaf_rn(-W[(size_t)(jb + j) * np + i], yj, yv);
       }
@@ -267,12 +391,13 @@ __device__ void lg_ldlt_solve(const float *W, int n, int np, const int *perm, co
     }
     __syncthreads();
     if (i < jb) {
-      const int jend = (n - jb < kLgPanel) ? (n - jb) : kLgPanel;
+      const int jend = (n - jb < kLgBlk) ? (n - jb) : kLgBlk;
       for (int j = jend - 1; j >= 0; --j) yv = __fmaf_rn(-W[(size_t)(jb + j) * np + i], ysm[jb + j], yv);
     }
   }
   if (active) xout[perm[i]] = yv;
   __syncthreads();
+  LG_T(19);
 }
 
 // deterministic CTA-wide sum of v[0..n) squared (fixed tree)
@@ -290,6 +415,27 @@ __device__ float lg_sqnorm(const float *v, int n, float *red) {
   return t;
 }
 
+// lower triangle of H <- transpose of the upper one (32 x 32 tiles through per-warp shared tiles)
+__device__ void lg_mirror_upper(float *H, int n, int np, float *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *t = scratch + warp * (32 * 33);
+  const int nb = (n + 31) / 32;
+  const int ntiles = nb * (nb + 1) / 2;
+  for (int e = warp; e < ntiles; e += kLgSolveThreads / 32) {
+    int bi = 0, rem = e;  // tile (bi, bj), bi <= bj, enumerated row by row
+    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+    const int bj = bi + rem;
+    for (int r = 0; r < 32; ++r) t[r * 33 + lane] = H[(size_t)(32 * bi + r) * np + 32 * bj + lane];
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+      // element (32 bj + r, 32 bi + lane) <- (32 bi + lane, 32 bj + r); diagonal tiles: strictly lower part only
+      if (bi != bj || lane < r) H[(size_t)(32 * bj + r) * np + 32 * bi + lane] = t[lane * 33 + r];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __grid_constant__ LgSolveParams p) {
   extern __shared__ __align__(16) float sm[];
   const LgSolveSmem L = lg_solve_smem(p.np);
@@ -303,7 +449,15 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
   __shared__ double sh_cost;
   unsigned long long local_active = 0;
 
+#ifdef TOB200_LG_TIMING
+  int lg_cnt = 0;
+  if (tid == 0 && blockIdx.x == 0) for (int i = 0; i < 32; ++i) g_lg_tm[i] = 0;
+#endif
   for (int64_t pr = blockIdx.x; pr < p.B; pr += gridDim.x) {
+    LG_T0();
+#ifdef TOB200_LG_TIMING
+    ++lg_cnt;
+#endif
     float *Hp = p.H + (size_t)pr * np * np;
     float *hd = p.hd ? p.hd + (size_t)pr * np : nullptr;
     float *gp = p.g ? p.g + (size_t)pr * n : nullptr;
@@ -347,6 +501,7 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
     __syncthreads();
 
     bool solver_failed = true, early_return = false;
+    bool mirrored = (p.mode == 0) && !pass_rebuilt;  // a stale H_ was mirrored when it was built
     const uint8_t max_tries = p.mode == 0 ? lm_max_tries(p.opt) : 0;
     for (int attempt = 0;; ++attempt) {
       if (p.mode == 0 && !(s.num_consec_failures <= max_tries)) break;
@@ -363,14 +518,22 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
         }
         __syncthreads();
         if (hd && tid < n) hd[tid] = dd[tid];  // H_ keeps the damped diagonal
-        lg_pivot_order(dd, n, np, perm, inv, ysm, &sh_flag);
-        // W <- P H P^T, lower triangle: W(a, b) = H(min(i,j), max(i,j)), i = perm[a], j = perm[b]
+        LG_T(0);
+        lg_pivot_order(dd, n, np, perm, inv, ysm, reinterpret_cast<int *>(sm + L.dsm), &sh_flag);
+        LG_T(1);
+        // H is made fully symmetric in place once per rebuild (the upper triangle is the canonical
+        // one), so that a row of P H P^T is a gather from ONE row of H: W(a, b) = H(perm[a], perm[b])
+        if (!mirrored) {
+          lg_mirror_upper(Hp, n, np, sm + L.tile);
+          mirrored = true;
+        }
+        LG_T(2);
         for (int a = tid >> 5; a < n; a += kLgSolveThreads / 32) {
           const int ia = perm[a];
+          const float *hrow = Hp + (size_t)ia * np;
           for (int b = tid & 31; b <= a; b += 32) {
             const int jb = perm[b];
-            const float v = (ia == jb) ? dd[ia] : (ia < jb ? Hp[(size_t)ia * np + jb] : Hp[(size_t)jb * np + ia]);
-            W[(size_t)a * np + b] = v;
+            W[(size_t)a * np + b] = (ia == jb) ? dd[ia] : hrow[jb];
           }
         }
         __syncthreads();
@@ -384,10 +547,13 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
           if (tid < n) (sm + L.dsm)[tid] = 0.f;
           __syncthreads();
         } else {
+          LG_T(3);
           ok = lg_ldlt_factor(W, n, np, sm, L);
+          LG_T(4);
         }
         if (ok) {
           lg_ldlt_solve(W, n, np, perm, rhs, dd, sm, L);  // dd is dead once W is laid out: dx goes there
+          LG_T(5);
           solver_failed = false;
         }
       }
@@ -440,6 +606,13 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
       else local_active++;
     }
   }
+#ifdef TOB200_LG_TIMING
+  if (tid == 0 && blockIdx.x == 0)
+    printf("lg_solve block 0: %d problems; kcycles/problem: pre %lld pivot %lld (sort %lld tiechk %lld walk %lld) mirror %lld gatherW %lld factor %lld (load %lld ph1 %lld ph2a %lld ph2b %lld wb %lld) solve %lld (fwd %lld bwd %lld) tie-path taken %lld\n", lg_cnt,
+           g_lg_tm[0] / lg_cnt / 1000, g_lg_tm[1] / lg_cnt / 1000, g_lg_tm[10] / lg_cnt / 1000, g_lg_tm[11] / lg_cnt / 1000, g_lg_tm[12] / lg_cnt / 1000,
+           g_lg_tm[2] / lg_cnt / 1000, g_lg_tm[3] / lg_cnt / 1000, g_lg_tm[4] / lg_cnt / 1000, g_lg_tm[13] / lg_cnt / 1000, g_lg_tm[14] / lg_cnt / 1000,
+           g_lg_tm[15] / lg_cnt / 1000, g_lg_tm[16] / lg_cnt / 1000, g_lg_tm[17] / lg_cnt / 1000, g_lg_tm[5] / lg_cnt / 1000, g_lg_tm[18] / lg_cnt / 1000, g_lg_tm[19] / lg_cnt / 1000, g_lg_tm[20]);
+#endif
   if (tid == 0 && local_active && p.n_active) atomicAdd(p.n_active, local_active);
 }
 
