@@ -37,6 +37,14 @@ template <> struct Ops<double> {
   static __device__ __forceinline__ double float_eps() { return (double)1e-7f; }  // math.h:298-301
 };
 
+// acc (two packed floats) <- fma(a, (b0, b1), acc): Blackwell FFMA2, one issue slot for two IEEE fmas
+__device__ __forceinline__ void ffma2_bcast(unsigned long long &acc, float a, float b0, float b1) {
+  unsigned long long av, bv;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(av), "l"(bv));
+}
+
 // packed upper triangle of an N x N symmetric matrix, row-major: (j,k), j <= k
 __host__ __device__ constexpr int tri_count(int n) { return n * (n + 1) / 2; }
 __host__ __device__ constexpr int tri_index(int n, int j, int k) { return j * n - j * (j - 1) / 2 + (k - j); }

@@ -320,10 +320,13 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
   const T *xs = reinterpret_cast<const T *>(ws + d.L.xs);
   T *jbuf = reinterpret_cast<T *>(ws + d.L.jbuf);
   T *scb = reinterpret_cast<T *>(ws + d.L.scb);
+  // accumulators as packed FP32 pairs (acc[u][2 h], acc[u][2 h + 1]): FFMA2 (fma.rn.f32x2) does two
+  // IEEE fused multiply-adds per issue slot, same roundings as two scalar fmas
+  unsigned long long acc2[BLK][BLK / 2];
 #pragma unroll
   for (int u = 0; u < BLK; ++u)
 #pragma unroll
-    for (int v = 0; v < BLK; ++v) acc[u][v] = (T)0;
+    for (int h = 0; h < BLK / 2; ++h) acc2[u][h] = 0ull;
   cost_only = (T)0;
 
   const int nchunks = (m + kWppRows - 1) / kWppRows;
@@ -412,7 +415,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
 #pragma unroll
           for (int u = 0; u < BLK; ++u)
 #pragma unroll
-            for (int v = 0; v < BLK; ++v) acc[u][v] = O::fma(a[u], b[v], acc[u][v]);
+            for (int h = 0; h < BLK / 2; ++h) ffma2_bcast(acc2[u][h], a[u], b[2 * h], b[2 * h + 1]);
         }
       }
     } else if (lane == 0) {  // cost-only pass (solvers/gn.h:98-105): sum r_i^2 in row order
@@ -424,6 +427,13 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     __syncwarp();
   }
   cost_only = __shfl_sync(0xffffffffu, cost_only, 0);
+#pragma unroll
+  for (int u = 0; u < BLK; ++u)
+#pragma unroll
+    for (int h = 0; h < BLK / 2; ++h) {
+      acc[u][2 * h] = __uint_as_float((uint32_t)acc2[u][h]);
+      acc[u][2 * h + 1] = __uint_as_float((uint32_t)(acc2[u][h] >> 32));
+    }
 }
 
 // ---- moving the register blocks of [J|r]^T [J|r] out ---------------------------------------------------
