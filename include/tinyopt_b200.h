@@ -176,6 +176,20 @@ int tob200_jtj_f32(tob200_ctx *ctx, const float *J, const float *row_scale, int6
 int tob200_solve_ldlt_f32(tob200_ctx *ctx, const float *A, const float *b, int64_t B, int n, float *x,
                           int32_t *status);
 
+/* ---- SURVEY.md §8(f) rank 2, the step after the path: tinyopt::InvCov(H) (math.h:44-57 DenseInvCov:
+ * `H.selfadjointView<Upper>().ldlt()` then `chol.solve(Identity)`) and MaxStdDev (solvers/lm.h:176-187,
+ * solvers/gn.h:177: sqrt of the largest coefficient of InvCov(H)) for a batch, through the same
+ * diagonal-pivoted LDL^T as the solve of the path.
+ *   H       : [B][n][n] row-major, only the upper triangle is read
+ *   cov     : [B][n][n] out (untouched where status != 0), or NULL
+ *   max_std : [B] out (0 where status != 0, as the reference returns), or NULL
+ *   status  : [B]: 0 ok, 1 rejected (info() != Success or not positive: the reference's nullopt)
+ * n <= 64 (float, double; bit-exact with the oracle) or 64 < n <= 512 (float). */
+int tob200_inv_cov_f32(tob200_ctx *ctx, const float *H, int64_t B, int n, float *cov, float *max_std,
+                       int32_t *status);
+int tob200_inv_cov_f64(tob200_ctx *ctx, const double *H, int64_t B, int n, double *cov, double *max_std,
+                       int32_t *status);
+
 /* Device time (ms, CUDA events) the last large-n call (n > 55) spent in one kernel class:
  * phase 0 residual/gradient pass, 1 tensor-core J^T J, 2 factor + solve + LM step. */
 int tob200_last_phase_ms(tob200_ctx *ctx, int phase, float *ms, int *launches);
@@ -224,6 +238,11 @@ int tob200_solver_num_active(tob200_solver *s, int64_t *n_active);
 int tob200_solver_results(tob200_solver *s, tob200_result *results);
 /* Final un-damped Hessian (solvers/lm.h:157-171 Hessian()) as doubles, [B][n][n] device. */
 int tob200_solver_final_hessian(tob200_solver *s, double *H);
+/* Output::Covariance() (output.h:81-103) / SolverLM::Covariance() (solvers/lm.h:173): InvCov of the
+ * un-damped final Hessian, in double as the reference computes it.  cov: [B][n][n] device or NULL;
+ * max_std: [B] or NULL; status: [B] (1 where the reference returns nullopt).  `rescaled` is a host-side
+ * scalar (final_cost^2 / (num_residuals - n)): see the C++ / Python adaptors. */
+int tob200_solver_covariance(tob200_solver *s, double *cov, double *max_std, int32_t *status);
 
 /* ---- synthetic problem family, generated on the device (bit-identical to the CPU oracle's) ----
  * Any output may be NULL.  A, y in `layout`; xstar, x0: [B][n]. */

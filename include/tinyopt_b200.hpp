@@ -22,6 +22,7 @@
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "tinyopt_b200.h"
@@ -322,6 +323,42 @@ std::vector<Output> OptimizeBatch(const Context &ctx, Scalar *xs, int64_t B, int
     if (!H.empty()) outs[(size_t)p].final_hessian.assign(H.begin() + (size_t)p * n * n, H.begin() + (size_t)(p + 1) * n * n);
   }
   return outs;
+}
+
+/// Output::Covariance(rescaled) (output.h:81-103) for a batch: InvCov (math.h:44-57) of every
+/// final_hessian through tob200_inv_cov_f64.  Entry p is the n*n row-major covariance, or empty where
+/// the reference returns nullopt (no final Hessian, or the LDLT rejects it).  `rescaled` multiplies by
+/// final_cost^2 / (num_residuals - n) when num_residuals > n, as the reference does.
+inline std::vector<std::vector<double>> CovarianceBatch(const Context &ctx, const std::vector<Output> &outs, int n,
+                                                        bool rescaled = false) {
+  const int64_t B = (int64_t)outs.size();
+  std::vector<std::vector<double>> covs((size_t)B);
+  if (B == 0 || n < 1) return covs;
+  const size_t nn = (size_t)n * n;
+  std::vector<double> H((size_t)B * nn, 0.0);
+  for (int64_t p = 0; p < B; ++p) {
+    if (outs[(size_t)p].final_hessian.size() == nn)
+      std::copy(outs[(size_t)p].final_hessian.begin(), outs[(size_t)p].final_hessian.end(), H.begin() + (size_t)p * nn);
+    else
+      for (int i = 0; i < n; ++i) H[(size_t)p * nn + (size_t)i * n + i] = -1.0;  // rejected: not positive
+  }
+  DeviceBuffer<double> dH(ctx, H.size()), dC(ctx, H.size());
+  DeviceBuffer<int32_t> dS(ctx, (size_t)B);
+  dH.upload(H.data(), H.size());
+  ctx.check(tob200_inv_cov_f64(ctx.get(), dH.data(), B, n, dC.data(), nullptr, dS.data()), "tob200_inv_cov_f64");
+  std::vector<int32_t> st((size_t)B);
+  dC.download(H.data(), H.size());
+  dS.download(st.data(), st.size());
+  for (int64_t p = 0; p < B; ++p) {
+    const Output &o = outs[(size_t)p];
+    if (st[(size_t)p] != 0 || o.final_hessian.size() != nn) continue;
+    covs[(size_t)p].assign(H.begin() + (size_t)p * nn, H.begin() + (size_t)(p + 1) * nn);
+    if (rescaled && (int)o.num_residuals > n) {
+      const double f = o.final_cost.cost * o.final_cost.cost / (double)((int)o.num_residuals - n);
+      for (double &v : covs[(size_t)p]) v *= f;
+    }
+  }
+  return covs;
 }
 
 /// The device-resident loop for the polynomial residual family r_i = t_i + alpha t_i^3 - y_i,

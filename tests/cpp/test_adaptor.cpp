@@ -25,7 +25,6 @@ static void test_sqrt2(const Context &ctx) {
   const int64_t B = 96;
   std::vector<double> xs(B);
   for (int64_t p = 0; p < B; ++p) xs[p] = (p % 3 == 0) ? 1.0 : (p % 3 == 1 ? -0.3 : 3.2);
-  xs[5] = 0.5 + 0.01 * 5;
   auto residuals = [](size_t, const double *x, double *r, double *J) {
     r[0] = x[0] * x[0] - 2.0;
     if (J) J[0] = 2.0 * x[0];
@@ -194,6 +193,34 @@ static void test_family_equivalence(const Context &ctx, int n, int m) {
               sizeof(T) == 4 ? "float" : "double", n, m, total);
 }
 
+// tests/cov.cpp:66-91: whitened prior L^T (x - y); Output::Covariance() == the prior covariance
+static void test_covariance(const Context &ctx) {
+  const double Cy[4] = {10.0, 2.0, 2.0, 4.0};
+  // L^T of inv(Cy) = [[a, b], [0, c]] with inv(Cy) = 1/36 * [[4, -2], [-2, 10]]
+  const double i00 = 4.0 / 36.0, i01 = -2.0 / 36.0, i11 = 10.0 / 36.0;
+  const double l00 = std::sqrt(i00), l10 = i01 / l00, l11 = std::sqrt(i11 - l10 * l10);
+  const double Lt[4] = {l00, l10, 0.0, l11};  // L^T, row-major
+  const double y[2] = {0.5, -1.2};
+  const int64_t B = 4;
+  std::vector<double> xs((size_t)B * 2, 0.0);
+  auto residuals = [&](size_t, const double *x, double *r, double *J) {
+    const double d0 = x[0] - y[0], d1 = x[1] - y[1];
+    r[0] = Lt[0] * d0 + Lt[1] * d1;
+    r[1] = Lt[2] * d0 + Lt[3] * d1;
+    if (J) { J[0] = Lt[0]; J[1] = Lt[1]; J[2] = Lt[2]; J[3] = Lt[3]; }
+  };
+  auto outs = OptimizeBatch<double>(ctx, xs.data(), B, 2, 2, residuals, Options());
+  auto covs = CovarianceBatch(ctx, outs, 2);
+  for (int64_t p = 0; p < B; ++p) {
+    CHECK(outs[p].Converged());
+    CHECK(covs[p].size() == 4);
+    if (covs[p].size() == 4)
+      for (int e = 0; e < 4; ++e) CHECK(std::fabs(covs[p][e] - Cy[e]) < 1e-5);
+    CHECK(std::fabs(xs[2 * p] - y[0]) < 1e-6 && std::fabs(xs[2 * p + 1] - y[1]) < 1e-6);
+  }
+  std::printf("covariance: cov[0]=(%.6f, %.6f; %.6f, %.6f)\n", covs[0][0], covs[0][1], covs[0][2], covs[0][3]);
+}
+
 static void test_misuse(const Context &ctx) {
   bool threw = false;
   try {
@@ -213,6 +240,7 @@ int main() {
     test_basic<float>();
     test_build_solve(ctx);
     test_circle(ctx);
+    test_covariance(ctx);
     test_family_equivalence<double>(ctx, 6, 30);
     test_family_equivalence<float>(ctx, 12, 40);
     test_misuse(ctx);

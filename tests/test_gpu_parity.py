@@ -248,8 +248,8 @@ def test_lm_run_no_residuals_and_errors(ctx):
     assert (r["stop_reason"] == tb.StopReason.kSkipped).all() and (r["num_iters"] == 1).all()
     assert torch.equal(x0, torch.ones_like(x0))
     with pytest.raises(tb.TinyoptB200Error):
-        ctx.optimize_batch(torch.zeros((1, 4, 500, 32), device="cuda"), torch.zeros((1, 4, 32), device="cuda"),
-                           torch.zeros((3, 500), device="cuda"))
+        ctx.optimize_batch(torch.zeros((1, 4, 600, 32), device="cuda"), torch.zeros((1, 4, 32), device="cuda"),
+                           torch.zeros((3, 600), device="cuda"))   # n > 512: no kernel family
 
 
 # ---- BASELINE.json config sizes: exact on a slice, properties on the whole batch -------------------

@@ -65,6 +65,8 @@ SYMBOLS = {
     "tob200_build_solve_f64": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tob200_jtj_f32": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
     "tob200_solve_ldlt_f32": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "tob200_inv_cov_f32": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "tob200_inv_cov_f64": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "tob200_last_phase_ms": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_i)]),
     "tob200_lm_run_f32": (_i, [_vp, _PO, _vp, _vp, _f, _i, _i64, _i, _i, _vp, _vp]),
     "tob200_lm_run_f64": (_i, [_vp, _PO, _vp, _vp, _d, _i, _i64, _i, _i, _vp, _vp]),
@@ -80,6 +82,7 @@ SYMBOLS = {
     "tob200_solver_num_active": (_i, [_vp, C.POINTER(_i64)]),
     "tob200_solver_results": (_i, [_vp, _vp]),
     "tob200_solver_final_hessian": (_i, [_vp, _vp]),
+    "tob200_solver_covariance": (_i, [_vp, _vp, _vp, _vp]),
     "tob200_synth_generate_f32": (_i, [_vp, _u64, _i64, _i64, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
     "tob200_synth_generate_f64": (_i, [_vp, _u64, _i64, _i64, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
     "tob200_synth_eval_f32": (_i, [_vp, _vp, _vp, _f, _i, _i64, _i, _i, _vp, _vp, _vp]),

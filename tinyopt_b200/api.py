@@ -246,6 +246,20 @@ class Context:
                  "tob200_solve_ldlt_f32")
         return x, status
 
+    def inv_cov(self, H: torch.Tensor, want_cov: bool = True, want_max_std: bool = True):
+        """tinyopt::InvCov(H) and MaxStdDev per problem (tob200_inv_cov_*; math.h:44-57,
+        solvers/lm.h:176-187).  H [B,n,n] float32 / float64, only the upper triangle is read.
+        Returns (cov [B,n,n] or None, max_std [B] or None, status [B]: 1 where the reference gives nullopt)."""
+        B, n, _ = H.shape
+        suf = "f64" if H.dtype == torch.float64 else "f32"
+        cov = torch.zeros_like(H) if want_cov else None
+        ms = torch.zeros((B,), dtype=H.dtype, device=H.device) if want_max_std else None
+        status = torch.zeros((B,), dtype=torch.int32, device=H.device)
+        fn = getattr(self._lib, f"tob200_inv_cov_{suf}")
+        self._ck(fn(self._h, _p(H.contiguous()), B, n, _p(cov) if cov is not None else None,
+                    _p(ms) if ms is not None else None, _p(status)), f"tob200_inv_cov_{suf}")
+        return cov, ms, status
+
     def last_phase_ms(self, phase: int):
         """(ms, launches) the last large-n call spent in phase 0 eval / 1 JᵀJ / 2 solve."""
         ms, cnt = C.c_float(0), C.c_int(0)
@@ -403,3 +417,27 @@ class BatchSolver:
         H = torch.empty((self.B, self.n, self.n), dtype=torch.float64, device=self.ctx.device)
         self.ctx._ck(self.ctx._lib.tob200_solver_final_hessian(self._h, _p(H)), "tob200_solver_final_hessian")
         return H
+
+    def covariance(self, rescaled: bool = False):
+        """Output::Covariance(rescaled) (output.h:81-103): InvCov of the un-damped final Hessian in
+        double; `rescaled` multiplies by final_cost^2 / (num_residuals - n) when num_residuals > n.
+        Returns (cov [B,n,n] float64, status [B]: 1 where the reference returns nullopt)."""
+        cov = torch.zeros((self.B, self.n, self.n), dtype=torch.float64, device=self.ctx.device)
+        status = torch.zeros((self.B,), dtype=torch.int32, device=self.ctx.device)
+        self.ctx._ck(self.ctx._lib.tob200_solver_covariance(self._h, _p(cov), None, _p(status)),
+                     "tob200_solver_covariance")
+        if rescaled:
+            res = self.results()
+            fc = torch.from_numpy(res["final_cost"].astype("float64")).to(cov.device)
+            nr = torch.from_numpy(res["final_num_residuals"].astype("float64")).to(cov.device)
+            f = torch.where(nr > self.n, fc * fc / (nr - self.n).clamp(min=1.0), torch.ones_like(fc))
+            cov = cov * f[:, None, None]
+        return cov, status
+
+    def max_std_dev(self) -> torch.Tensor:
+        """SolverLM::MaxStdDev(use_damped=false) (solvers/lm.h:176-187) per problem; 0 where InvCov fails."""
+        ms = torch.zeros((self.B,), dtype=torch.float64, device=self.ctx.device)
+        status = torch.zeros((self.B,), dtype=torch.int32, device=self.ctx.device)
+        self.ctx._ck(self.ctx._lib.tob200_solver_covariance(self._h, None, _p(ms), _p(status)),
+                     "tob200_solver_covariance")
+        return ms

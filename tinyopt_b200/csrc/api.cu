@@ -48,6 +48,11 @@ struct tob200_ctx {
   int next_counter = 0;
   unsigned long long *tile_counter = nullptr;  // the counter of the launch being configured
   int wpp_stages = 1;  // env TOB200_WPP_STAGES (1: three CTAs per SM fit, measured best)
+  // *_host entry points: upload / solve / download pipeline over chunks of the batch
+  static constexpr int kMaxChunks = 16;
+  int host_chunks = 4;  // env TOB200_HOST_CHUNKS
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_run[kMaxChunks] = {}, ev_side = nullptr;
   // large-n family: 3 = 3xTF32 (hi*hi + hi*lo + lo*hi, FP32-level accuracy), 1 = plain TF32
   int lg_tf32_terms = 3;  // env TOB200_LG_TF32_TERMS
   // device time of the last large-n call by phase (0 eval, 1 syrk, 2 solve): CUDA event pairs
@@ -375,7 +380,7 @@ int lg_lm_run(tob200_ctx *ctx, const tob200_options *opt, const float *A, const 
   LgSolveParams vp;
   vp.H = b.H; vp.dg = b.dg; vp.hd = b.hd; vp.g = b.g; vp.cost = b.cost; vp.W = b.W; vp.B = B; vp.n = n; vp.np = b.np; vp.nres = m;
   vp.mode = 0; vp.opt = dopt; vp.rec = b.rec; vp.x = x; vp.last_dx = b.last_dx; vp.results = results;
-  vp.n_active = b.n_active; vp.lambda = nullptr; vp.b = nullptr; vp.dx = nullptr; vp.cost_out = nullptr; vp.status = nullptr;
+  vp.n_active = b.n_active; vp.lambda = nullptr; vp.b = nullptr; vp.dx = nullptr; vp.cost_out = nullptr; vp.status = nullptr; vp.max_std = nullptr;
   const int max_passes = opt->max_iters + 1 + (opt->check_final_cost ? 1 : 0);  // optimizer.h:248-250
   for (int pass = 0; pass < max_passes; ++pass) {
     int ev = lg_phase_begin(ctx, 0);
@@ -446,7 +451,7 @@ int lg_build_solve(tob200_ctx *ctx, const float *J, const float *r, int64_t B, i
   LgSolveParams vp;
   vp.H = b.H; vp.dg = b.dg; vp.hd = nullptr; vp.g = b.g; vp.cost = b.cost; vp.W = b.W; vp.B = B; vp.n = n; vp.np = b.np; vp.nres = m;
   vp.mode = 1; vp.opt = DevOptions<float>(); vp.rec = nullptr; vp.x = nullptr; vp.last_dx = nullptr; vp.results = nullptr;
-  vp.n_active = nullptr; vp.lambda = lambda; vp.b = nullptr; vp.dx = dx; vp.cost_out = cost; vp.status = status;
+  vp.n_active = nullptr; vp.lambda = lambda; vp.b = nullptr; vp.dx = dx; vp.cost_out = cost; vp.status = status; vp.max_std = nullptr;
   ev = lg_phase_begin(ctx, 2);
   CK(launch_lg_solve(vp, b.solve_grid, ctx->stream));
   ctx->launches++;
@@ -577,16 +582,66 @@ int lm_run_host_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, con
   if ((rc = ensure_scratch(ctx, 3, ey * sizeof(T))) != TOB200_OK) return rc;
   if ((rc = ensure_scratch(ctx, 4, (size_t)B * n * sizeof(T))) != TOB200_OK) return rc;
   if ((rc = ensure_scratch(ctx, 5, (size_t)B * sizeof(tob200_result))) != TOB200_OK) return rc;
+  // Chunked three-stage pipeline (problems are independent): every host->device copy is queued up
+  // front on its own stream, the solve of chunk c starts when its inputs have landed and overlaps the
+  // upload of chunk c + 1, and its results go back on a third stream while the next chunk runs (PCIe is
+  // full duplex).  Chunks are tile aligned; small inputs go in one piece.
+  if (!ctx->h2d_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int c = 0; c < tob200_ctx::kMaxChunks; ++c) {
+      CK(cudaEventCreateWithFlags(&ctx->ev_h2d[c], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ctx->ev_run[c], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
+  }
+  int nch = (ea * sizeof(T) >= ((size_t)32 << 20)) ? ctx->host_chunks : 1;
+  if (nch > tob200_ctx::kMaxChunks) nch = tob200_ctx::kMaxChunks;
+  if (nch < 1) nch = 1;
+  const int64_t per = ((B + nch - 1) / nch + 31) / 32 * 32;
+  T *dA = (T *)ctx->scratch[2], *dy = (T *)ctx->scratch[3], *dx = (T *)ctx->scratch[4];
+  tob200_result *dres = (tob200_result *)ctx->scratch[5];
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->scratch[2], A, ea * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->scratch[3], y, ey * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->scratch[4], x, (size_t)B * n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-  rc = lm_run_impl<T>(ctx, opt, (const T *)ctx->scratch[2], (const T *)ctx->scratch[3], alpha, layout, B, m, n,
-                      (T *)ctx->scratch[4], (tob200_result *)ctx->scratch[5], false);
-  if (rc != TOB200_OK) return rc;
-  CK(cudaMemcpyAsync(x, ctx->scratch[4], (size_t)B * n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(results, ctx->scratch[5], (size_t)B * sizeof(tob200_result), cudaMemcpyDeviceToHost,
-                     ctx->stream));
+  // the scratch buffers may still be read by earlier work on the compute stream
+  CK(cudaEventRecord(ctx->ev_side, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_side, 0));
+  CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_side, 0));
+  int used = 0;
+  for (int c = 0; c < nch; ++c, ++used) {
+    const int64_t p0 = (int64_t)c * per;
+    const int64_t pb = (B - p0 < per) ? (B - p0) : per;
+    if (pb <= 0) break;
+    const size_t oa = tiled ? (size_t)(p0 / 32) * m * n * 32 : (size_t)p0 * m * n;
+    const size_t oy = tiled ? (size_t)(p0 / 32) * m * 32 : (size_t)p0 * m;
+    const size_t ca = tiled ? (size_t)tob200_tiled_elems(pb, m, n) : (size_t)pb * m * n;
+    const size_t cy = tiled ? (size_t)tob200_tiled_elems(pb, m, 1) : (size_t)pb * m;
+    CK(cudaMemcpyAsync(dA + oa, A + oa, ca * sizeof(T), cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CK(cudaMemcpyAsync(dy + oy, y + oy, cy * sizeof(T), cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CK(cudaMemcpyAsync(dx + (size_t)p0 * n, x + (size_t)p0 * n, (size_t)pb * n * sizeof(T), cudaMemcpyHostToDevice,
+                       ctx->h2d_stream));
+    CK(cudaEventRecord(ctx->ev_h2d[c], ctx->h2d_stream));
+  }
+  for (int c = 0; c < used; ++c) {
+    const int64_t p0 = (int64_t)c * per;
+    const int64_t pb = (B - p0 < per) ? (B - p0) : per;
+    const size_t oa = tiled ? (size_t)(p0 / 32) * m * n * 32 : (size_t)p0 * m * n;
+    const size_t oy = tiled ? (size_t)(p0 / 32) * m * 32 : (size_t)p0 * m;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[c], 0));
+    rc = lm_run_impl<T>(ctx, opt, dA + oa, dy + oy, alpha, layout, pb, m, n, dx + (size_t)p0 * n, dres + p0, false);
+    if (rc != TOB200_OK) {
+      cudaStreamSynchronize(ctx->h2d_stream);
+      cudaStreamSynchronize(ctx->d2h_stream);
+      return rc;
+    }
+    CK(cudaEventRecord(ctx->ev_run[c], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_run[c], 0));
+    CK(cudaMemcpyAsync(x + (size_t)p0 * n, dx + (size_t)p0 * n, (size_t)pb * n * sizeof(T), cudaMemcpyDeviceToHost,
+                       ctx->d2h_stream));
+    CK(cudaMemcpyAsync(results + p0, dres + p0, (size_t)pb * sizeof(tob200_result), cudaMemcpyDeviceToHost,
+                       ctx->d2h_stream));
+  }
+  CK(cudaEventRecord(ctx->ev_side, ctx->d2h_stream));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return TOB200_OK;
@@ -668,6 +723,44 @@ __global__ void results_kernel(const StateRec<T> *rec, int64_t B, tob200_result 
   o.num_builds = r.num_builds;
   out[i] = o;
 }
+
+// ---- InvCov / MaxStdDev from the same factorisation -------------------------
+namespace {
+template <typename T>
+int inv_cov_impl(tob200_ctx *ctx, const T *H, int64_t B, int n, T *cov, T *max_std, int32_t *status) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  if (B < 0 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 0, n >= 1");
+  if (B == 0) return TOB200_OK;
+  if (!H || !status || (!cov && !max_std)) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  DeviceGuard guard(ctx->device);
+  if (n <= 64) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_cov_warp<T>(H, B, n, cov, max_std, status, ctx->num_sms, ctx->stream));
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    return TOB200_OK;
+  }
+  if (sizeof(T) != 4 || n > kLgMaxN)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "InvCov: n <= 64 (float, double) or n <= 512 (float)");
+  LgBuffers b;
+  int rc = lg_prepare(ctx, B, 0, n, false, false, &b);
+  if (rc != TOB200_OK) return rc;
+  ctx->phase_used = 0;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(launch_lg_import_h((const float *)H, B, n, b.np, b.H, ctx->stream));
+  LgSolveParams vp;
+  vp.H = b.H; vp.dg = nullptr; vp.hd = nullptr; vp.g = nullptr; vp.cost = nullptr; vp.W = b.W; vp.B = B; vp.n = n; vp.np = b.np; vp.nres = 0;
+  vp.mode = 3; vp.opt = DevOptions<float>(); vp.rec = nullptr; vp.x = nullptr; vp.last_dx = nullptr; vp.results = nullptr;
+  vp.n_active = nullptr; vp.lambda = nullptr; vp.b = nullptr; vp.dx = (float *)cov; vp.cost_out = nullptr; vp.status = status;
+  vp.max_std = (float *)max_std;
+  int ev = lg_phase_begin(ctx, 2);
+  CK(launch_lg_solve(vp, b.solve_grid, ctx->stream));
+  lg_phase_end(ctx, ev);
+  ctx->launches += 2;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  return TOB200_OK;
+}
+}  // namespace
 
 // ================================================================================================
 extern "C" {
@@ -757,6 +850,7 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
   ctx->wpp_stages = env_int("TOB200_WPP_STAGES", ctx->wpp_stages);
   ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
+  ctx->host_chunks = env_int("TOB200_HOST_CHUNKS", ctx->host_chunks);
   if ((e = cudaMalloc((void **)&ctx->counters, sizeof(unsigned long long) * tob200_ctx::kNumCounters)) != cudaSuccess) {
     tob200_destroy(ctx);
     return fail_cuda(nullptr, e, "cudaMalloc(counters)");
@@ -774,6 +868,15 @@ int tob200_destroy(tob200_ctx *ctx) {
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   for (cudaEvent_t e : ctx->phase_ev) cudaEventDestroy(e);
   if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->h2d_stream) {
+    cudaStreamDestroy(ctx->h2d_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+    for (int c = 0; c < tob200_ctx::kMaxChunks; ++c) {
+      if (ctx->ev_h2d[c]) cudaEventDestroy(ctx->ev_h2d[c]);
+      if (ctx->ev_run[c]) cudaEventDestroy(ctx->ev_run[c]);
+    }
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -916,13 +1019,21 @@ int tob200_solve_ldlt_f32(tob200_ctx *ctx, const float *A, const float *bvec, in
   LgSolveParams vp;
   vp.H = b.H; vp.dg = nullptr; vp.hd = nullptr; vp.g = nullptr; vp.cost = nullptr; vp.W = b.W; vp.B = B; vp.n = n; vp.np = b.np; vp.nres = 0;
   vp.mode = 2; vp.opt = DevOptions<float>(); vp.rec = nullptr; vp.x = nullptr; vp.last_dx = nullptr; vp.results = nullptr;
-  vp.n_active = nullptr; vp.lambda = nullptr; vp.b = bvec; vp.dx = x; vp.cost_out = nullptr; vp.status = status;
+  vp.n_active = nullptr; vp.lambda = nullptr; vp.b = bvec; vp.dx = x; vp.cost_out = nullptr; vp.status = status; vp.max_std = nullptr;
   int ev = lg_phase_begin(ctx, 2);
   CK(launch_lg_solve(vp, b.solve_grid, ctx->stream));
   lg_phase_end(ctx, ev);
   ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   return TOB200_OK;
+}
+
+int tob200_inv_cov_f32(tob200_ctx *ctx, const float *H, int64_t B, int n, float *cov, float *max_std, int32_t *status) {
+  return inv_cov_impl<float>(ctx, H, B, n, cov, max_std, status);
+}
+int tob200_inv_cov_f64(tob200_ctx *ctx, const double *H, int64_t B, int n, double *cov, double *max_std,
+                       int32_t *status) {
+  return inv_cov_impl<double>(ctx, H, B, n, cov, max_std, status);
 }
 
 int tob200_last_phase_ms(tob200_ctx *ctx, int phase, float *ms, int *launches) {
@@ -1082,6 +1193,16 @@ int tob200_solver_final_hessian(tob200_solver *s, double *H) {
   CK(cudaGetLastError());
   ctx->launches++;
   return TOB200_OK;
+}
+
+int tob200_solver_covariance(tob200_solver *s, double *cov, double *max_std, int32_t *status) {
+  if (!s || !status || (!cov && !max_std)) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "NULL argument");
+  tob200_ctx *ctx = s->ctx;
+  DeviceGuard guard(ctx->device);
+  int rc = ensure_scratch(ctx, 20, (size_t)s->B * s->n * s->n * sizeof(double));
+  if (rc != TOB200_OK) return rc;
+  if ((rc = tob200_solver_final_hessian(s, (double *)ctx->scratch[20])) != TOB200_OK) return rc;
+  return inv_cov_impl<double>(ctx, (const double *)ctx->scratch[20], s->B, s->n, cov, max_std, status);
 }
 
 // ---- synthetic family ----------------------------------------------------------------------------

@@ -212,6 +212,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// explicit shared-space accesses (the stage pointers go through an integer round-trip for alignment, so
+// the compiler would otherwise emit generic LD / ST, which are tracked like global accesses)
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ bool lg_skip(const LgSyrkParams &p, int64_t pr) {
@@ -227,9 +237,11 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   // stages 1024-byte aligned (swizzle atoms), barriers behind them
   unsigned char *stages = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = 2u * p.half_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)p.stages * stage_bytes);
+  float *raw = reinterpret_cast<float *>(stages + (size_t)p.stages * stage_bytes);  // kLgRawStages x half_bytes
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(raw) + (size_t)kLgRawStages * p.half_bytes);
   uint64_t *full = bars, *empty = bars + kLgMaxStages, *tmem_full = bars + 2 * kLgMaxStages, *tmem_empty = tmem_full + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+  uint64_t *raw_full = tmem_empty + 1, *raw_empty = raw_full + kLgRawStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kLgRawStages);
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -238,6 +250,10 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, kLgEpiWarps);
+    for (int s = 0; s < kLgRawStages; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], kLgProdWarps);
+    }
     mbar_fence_init();
   }
   if (warp == 0) {  // the whole TMEM of this SM: 128 lanes x 512 FP32 columns
@@ -249,49 +265,108 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t total = (int64_t)p.nstrips * p.B;  // strip-major: the widest strips first
+  // Work unit = (problem, pair of strips {h, nstrips - 1 - h}): both units of a problem cost the same
+  // (strip r has nstrips - r blocks) and are taken by neighbouring CTAs at the same time, so the
+  // second reader of a row of A hits L2 (strip-major order re-read A from HBM 2.5 times at n = 512).
+  const int upp = (p.nstrips + 1) / 2;  // units per problem
+  const int64_t total = (int64_t)upp * p.B;
+  // odd strip counts leave one lighter unit: rotate which CTA gets it from round to round
+  const bool rotate = (gridDim.x % upp) == 0;
+  auto unit_of = [&](int64_t idx, int64_t &pr, int &h) {
+    pr = idx / upp;
+    h = (int)(idx % upp);
+    if (rotate) h = (int)((h + (idx - blockIdx.x) / gridDim.x) % upp);
+  };
   const int m = p.m, n = p.n, np = p.np;
   const int ksteps = (m + kLgStageK - 1) / kLgStageK;
 
-  if (warp > kLgMmaWarp) {
+  if (warp == kLgLoadWarp) {
+    // ===================== loader: one thread streams raw rows of A with TMA bulk copies =====================
+    // A raw stage holds the 8 rows of one K step, columns [c0, c0 + ncs) of the strip (pitch ncs
+    // floats; one contiguous copy per row).  Pad columns >= n and rows >= m are simply not copied: the
+    // producers select 0 for them.
+    if (lane == 0) {
+      uint32_t rs = 0, rph = 0;
+      for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
+        int64_t pr; int h;
+        unit_of(idx, pr, h);
+        if (lg_skip(p, pr)) continue;
+        for (int half = 0; half < 2; ++half) {
+          const int r = half == 0 ? h : p.nstrips - 1 - h;
+          if (half == 1 && r == h) break;
+          const int c0 = 128 * r;
+          const int ncs = (np - c0 < 128) ? 128 : (np - c0);
+          const int ccnt = (n - c0 < ncs) ? (n - c0) : ncs;  // real columns (> 0: c0 <= np - 32 < n)
+          const uint32_t row_bytes = (uint32_t)ccnt * 4u;
+          const float *Ap = p.A + (size_t)pr * m * n + c0;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&raw_empty[rs], rph ^ 1u);
+            fence_proxy_async();  // the producers' generic reads of this stage precede the async writes
+            const int row0 = ks * kLgStageK;
+            const int rows = (m - row0 < kLgStageK) ? (m - row0) : kLgStageK;
+            float *dst = raw + (size_t)rs * (p.half_bytes / 4);
+            mbar_expect_tx(&raw_full[rs], (uint32_t)rows * row_bytes);
+            for (int t = 0; t < rows; ++t)
+              tma_bulk_g2s(dst + (size_t)t * ncs, Ap + (size_t)(row0 + t) * n, row_bytes, &raw_full[rs]);
+            if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp > kLgLoadWarp) {
     // ===================== producers =====================
-    // A stage is the K-major image of 8 rows x ncs columns of diag(s) A: operand row = column j of A,
-    // K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 8) of columns
+    // An operand stage is the K-major image of 8 rows x ncs columns of diag(s) A: operand row = column j
+    // of A, K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 8) of columns
     // [128 cg + 64 qh, + 64) (cg = (w / 2) % 4, qh = w % 2): lane l owns columns l and l + 32 of that
-    // range (coalesced 128-byte global loads per row; conflict-free 16-byte shared stores, one per
-    // column).  Sixteen warps keep enough loads in flight and enough issue slots for the transform.
-    const int w = warp - (kLgMmaWarp + 1);
+    // range — conflict-free 4-byte reads of the raw stage (lane = consecutive column), scaled by s_i, split
+    // into TF32 hi + lo, conflict-free 16-byte stores (one per column and part).
+    const int w = warp - (kLgLoadWarp + 1);
     const int kc = w >> 3, cg = (w >> 1) & 3, qh = w & 1;
-    uint32_t st = 0, ph = 0;  // ring position and its phase parity
+    uint32_t st = 0, ph = 0;    // operand ring position and its phase parity
+    uint32_t rs = 0, rph = 0;   // raw ring
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
-      const int r = (int)(idx / p.B);
-      const int64_t pr = idx % p.B;
+      int64_t pr; int h;
+      unit_of(idx, pr, h);
       if (lg_skip(p, pr)) continue;
+     for (int half = 0; half < 2; ++half) {
+      const int r = half == 0 ? h : p.nstrips - 1 - h;
+      if (half == 1 && r == h) break;
       const int c0 = 128 * r;
       const int ncs = (np - c0 < 128) ? 128 : (np - c0);  // columns staged (the A operand needs 128)
       const uint32_t lbo = (uint32_t)ncs * 16u;
       const int rr0 = 128 * cg + 64 * qh + lane;          // my operand rows: rr0, rr0 + 32
       const bool busy0 = rr0 < ncs, busy1 = rr0 + 32 < ncs;  // ncs is a multiple of 32: warp uniform
-      const float *Ap = p.A + (size_t)pr * m * n + c0 + rr0;
       const bool cok0 = busy0 && c0 + rr0 < n, cok1 = busy1 && c0 + rr0 + 32 < n;
       const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
-      // register prefetch three stages deep ([q][t] = column rr0 + 32 q, row t): the loads of stage
-      // ks + 3 are issued as soon as stage ks has been written, so ~48 KB per SM are in flight
-      float buf0[2][4], buf1[2][4], buf2[2][4], sc0[4], sc1[4], sc2[4];
-      auto load_rows = [&](float (&b)[2][4], float (&bs)[4], int ks) {
+      // row scales: lane l keeps s of row 32 g + l for the group g of four K steps being consumed and
+      // for the next one (one coalesced load per 32 rows, a whole group ahead of its use); the four
+      // values a K step needs are shuffled out of it
+      auto load_scale_group = [&](int g) {
+        const int row = 32 * g + lane;
+        return (row < m) ? (sp ? sp[row] : 1.f) : 0.f;
+      };
+      float sg_cur = load_scale_group(0), sg_next = load_scale_group(1);
+      const uint32_t raw_u32 = smem_u32(raw), stages_u32 = smem_u32(stages);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        if ((ks & 3) == 0 && ks > 0) {
+          sg_cur = sg_next;
+          sg_next = load_scale_group((ks >> 2) + 1);
+        }
+        float sc[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) sc[t] = __shfl_sync(0xffffffffu, sg_cur, 8 * (ks & 3) + 4 * kc + t);
+        mbar_wait(&raw_full[rs], rph);
+        const uint32_t rsrc = raw_u32 + rs * p.half_bytes + (uint32_t)((4 * kc) * ncs + rr0) * 4u;
         const int row0 = ks * kLgStageK + 4 * kc;
+        float b0[4], b1[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int row = row0 + t;
-          const bool rok = ks < ksteps && row < m;
-          bs[t] = rok ? (sp ? sp[row] : 1.f) : 0.f;
-          b[0][t] = (cok0 && rok) ? Ap[(size_t)row * n] : 0.f;
-          b[1][t] = (cok1 && rok) ? Ap[(size_t)row * n + 32] : 0.f;
+          const bool rok = row0 + t < m;
+          b0[t] = (cok0 && rok) ? lds_f32(rsrc + (uint32_t)(t * ncs) * 4u) : 0.f;
+          b1[t] = (cok1 && rok) ? lds_f32(rsrc + (uint32_t)(t * ncs + 32) * 4u) : 0.f;
         }
-      };
-      auto put_stage = [&](const float (&b)[2][4], const float (&bs)[4]) {
         mbar_wait(&empty[st], ph ^ 1u);
-        unsigned char *sb = stages + (size_t)st * stage_bytes;
+        const uint32_t sb = stages_u32 + st * stage_bytes;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (q == 0 ? busy0 : busy1) {
@@ -299,43 +374,36 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
             float v[4], hi[4], lo[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              v[t] = __fmul_rn(b[q][t], bs[t]);
+              v[t] = __fmul_rn(q == 0 ? b0[t] : b1[t], sc[t]);
               hi[t] = (p.terms == 3) ? tc_round_tf32(v[t]) : v[t];
               lo[t] = __fsub_rn(v[t], hi[t]);
             }
             const uint32_t off = (uint32_t)kc * lbo + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
-            *reinterpret_cast<float4 *>(sb + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            if (p.terms == 3) *reinterpret_cast<float4 *>(sb + p.half_bytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            sts_v4(sb + off, hi[0], hi[1], hi[2], hi[3]);
+            if (p.terms == 3) sts_v4(sb + p.half_bytes + off, lo[0], lo[1], lo[2], lo[3]);
           }
         }
         fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[st]);
+        if (lane == 0) {
+          mbar_arrive(&full[st]);
+          mbar_arrive(&raw_empty[rs]);
+        }
         if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
-      };
-      load_rows(buf0, sc0, 0);
-      load_rows(buf1, sc1, 1);
-      load_rows(buf2, sc2, 2);
-      for (int ks = 0; ks < ksteps; ks += 3) {
-        put_stage(buf0, sc0);
-        load_rows(buf0, sc0, ks + 3);
-        if (ks + 1 < ksteps) {
-          put_stage(buf1, sc1);
-          load_rows(buf1, sc1, ks + 4);
-        }
-        if (ks + 2 < ksteps) {
-          put_stage(buf2, sc2);
-          load_rows(buf2, sc2, ks + 5);
-        }
+        if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
       }
+     }
     }
   } else if (warp == kLgMmaWarp) {
     // ===================== MMA issuer: one thread =====================
     uint32_t st = 0, ph = 0, item = 0;
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
-      const int r = (int)(idx / p.B);
-      const int64_t pr = idx % p.B;
+      int64_t pr; int h;
+      unit_of(idx, pr, h);
       if (lg_skip(p, pr)) continue;
+     for (int half = 0; half < 2; ++half) {
+      const int r = half == 0 ? h : p.nstrips - 1 - h;
+      if (half == 1 && r == h) break;
       const int nb = np - 128 * r;  // accumulator columns of this strip
       const int ncs = nb < 128 ? 128 : nb;
       if (lane == 0) {
@@ -370,14 +438,18 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
       }
       ++item;
+     }
     }
   } else {
     // ===================== epilogue: warp w drains TMEM lanes [32 w, 32 w + 32) =====================
     uint32_t item = 0;
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
-      const int r = (int)(idx / p.B);
-      const int64_t pr = idx % p.B;
+      int64_t pr; int h;
+      unit_of(idx, pr, h);
       if (lg_skip(p, pr)) continue;
+     for (int half = 0; half < 2; ++half) {
+      const int r = half == 0 ? h : p.nstrips - 1 - h;
+      if (half == 1 && r == h) break;
       const int c0 = 128 * r, nb = np - c0;
       mbar_wait(tmem_full, item & 1u);
       tc_fence_after();
@@ -399,6 +471,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
       ++item;
+     }
     }
   }
   tc_fence_before();

@@ -80,7 +80,7 @@ cudaError_t launch_lg_eval(const LgEvalParams &p, int num_sms, cudaStream_t st) 
 
 int lg_syrk_stages(int np) {
   const size_t stage = 2 * (size_t)lg_syrk_half_bytes(np);
-  int s = (int)((200 * 1024) / stage);
+  int s = (int)((200 * 1024 - (size_t)kLgRawStages * lg_syrk_half_bytes(np)) / stage);
   if (s > kLgMaxStages) s = kLgMaxStages;
   if (s < 2) s = 2;
   return s;
@@ -95,7 +95,7 @@ cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st) 
     configured = smem;
   }
   int64_t grid = num_sms;  // one CTA per SM: each owns the SM's whole TMEM
-  const int64_t total = (int64_t)p.nstrips * p.B;
+  const int64_t total = (int64_t)((p.nstrips + 1) / 2) * p.B;  // work units: strip pairs
   if (grid > total) grid = total;
   lg_syrk_kernel<<<(unsigned)grid, kLgSyrkThreads, smem, st>>>(p);
   return cudaGetLastError();

@@ -39,8 +39,10 @@ __host__ __device__ inline size_t lg_eval_smem_bytes(int n) {
 
 constexpr int kLgEpiWarps = 4;    // warps 0..3: TMEM lane quadrant == warp id
 constexpr int kLgMmaWarp = 4;     // warp 4: lane 0 issues every tcgen05.mma
-constexpr int kLgProdWarps = 16;  // warps 5..20: 4 K rows x 64 columns of a stage each
-constexpr int kLgSyrkThreads = (kLgEpiWarps + 1 + kLgProdWarps) * 32;
+constexpr int kLgLoadWarp = 5;    // warp 5: lane 0 streams raw rows of A into the raw ring (TMA bulk copies)
+constexpr int kLgProdWarps = 16;  // warps 6..21: 4 K rows x 64 columns of a stage each
+constexpr int kLgRawStages = 4;   // raw ring depth (one K step = 8 rows each)
+constexpr int kLgSyrkThreads = (kLgEpiWarps + 2 + kLgProdWarps) * 32;
 constexpr int kLgStageK = 8;      // K extent of one tf32 tcgen05.mma == rows per stage
 constexpr int kLgMaxStages = 8;
 
@@ -59,7 +61,8 @@ struct LgSyrkParams {
 
 __host__ __device__ inline uint32_t lg_syrk_half_bytes(int np) { return (uint32_t)((np < 128 ? 128 : np) / 32) * 1024u; }
 __host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages) {
-  return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np) + 256;
+  // [1 KB alignment slack | operand stages (hi + lo) | raw stages | barriers]
+  return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np) + (size_t)kLgRawStages * lg_syrk_half_bytes(np) + 512;
 }
 
 constexpr int kLgSolveThreads = 512;
@@ -76,7 +79,8 @@ struct LgSolveParams {
   float *W;            // [grid][np][np] factor workspace (lower, permuted)
   int64_t B;
   int n, np, nres;
-  int mode;            // 0: LM loop step (rec/x/last_dx/results), 1: one Build+Solve (lambda/dx/status), 2: plain SolveLDLT(H, b)
+  int mode;            // 0: LM loop step (rec/x/last_dx/results), 1: one Build+Solve (lambda/dx/status), 2: plain SolveLDLT(H, b),
+                       // 3: InvCov(H) (dx = [B][n][n] inverse or nullptr, max_std, status)
   // ---- mode 0 ----
   DevOptions<float> opt;
   LmScalars<float> *rec;
@@ -86,7 +90,8 @@ struct LgSolveParams {
   // ---- mode 1 / 2 ----
   const float *lambda;  // [B] or nullptr
   const float *b;       // mode 2: right-hand sides [B][n]
-  float *dx;            // [B][n]
+  float *dx;            // [B][n]  (mode 3: [B][n][n])
+  float *max_std;       // mode 3: [B] sqrt(max coefficient of the inverse), or nullptr
   double *cost_out;     // [B] (mode 1)
   int32_t *status;      // [B]
 };

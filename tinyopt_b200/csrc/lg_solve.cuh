@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
       }
     }
     // right-hand side: -grad (gn.h:155), or b
-    if (tid < n) rhs[tid] = (p.mode == 2) ? p.b[(size_t)pr * n + tid] : -gp[tid];
+    if (tid < n) rhs[tid] = (p.mode == 2) ? p.b[(size_t)pr * n + tid] : (p.mode == 3 ? 0.f : -gp[tid]);
     __syncthreads();
 
     bool solver_failed = true, early_return = false;
@@ -551,7 +551,36 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
           ok = lg_ldlt_factor(W, n, np, sm, L);
           LG_T(4);
         }
-        if (ok) {
+        if (ok && p.mode == 3) {
+          // InvCov (math.h:44-57): chol.solve(Identity), one unit vector at a time through the factor
+          float best = -3.402823466e+38f;
+          for (int c = 0; c < n; ++c) {
+            if (tid < n) rhs[tid] = (tid == c) ? 1.f : 0.f;
+            __syncthreads();
+            lg_ldlt_solve(W, n, np, perm, rhs, dd, sm, L);
+            if (tid < n) {
+              const float v = dd[tid];
+              if (p.dx) p.dx[((size_t)pr * n + tid) * n + c] = v;
+              best = v > best ? v : best;
+            }
+            __syncthreads();
+          }
+          if (p.max_std) {  // MaxStdDev (solvers/lm.h:176-187): sqrt of the largest coefficient
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              const float o = __shfl_xor_sync(0xffffffffu, best, off);
+              best = o > best ? o : best;
+            }
+            if ((tid & 31) == 0) ysm[tid >> 5] = best;
+            __syncthreads();
+            if (tid == 0) {
+              for (int w = 1; w < kLgSolveThreads / 32; ++w) best = ysm[w] > best ? ysm[w] : best;
+              p.max_std[pr] = sqrtf(best);
+            }
+            __syncthreads();
+          }
+          solver_failed = false;
+        } else if (ok) {
           lg_ldlt_solve(W, n, np, perm, rhs, dd, sm, L);  // dd is dead once W is laid out: dx goes there
           LG_T(5);
           solver_failed = false;
@@ -568,9 +597,10 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
     }
     const float *dxs = dd;  // the solution, original order
     if (p.mode != 0) {
-      if (!solver_failed && tid < n) p.dx[(size_t)pr * n + tid] = dxs[tid];
+      if (!solver_failed && tid < n && p.mode != 3) p.dx[(size_t)pr * n + tid] = dxs[tid];
       if (tid == 0) {
         p.status[pr] = solver_failed ? 1 : 0;
+        if (p.mode == 3 && solver_failed && p.max_std) p.max_std[pr] = 0.f;
         if (p.mode == 1 && p.cost_out) p.cost_out[pr] = (double)p.cost[pr];
       }
       continue;

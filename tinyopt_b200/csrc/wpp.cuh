@@ -42,7 +42,7 @@ __host__ __device__ constexpr int wpp_ldw(int np) { return ((np / 4) & 1) ? np :
 __host__ __device__ constexpr int wpp_nps(int np) { return ((np / 4) & 1) ? np : np + 4; }
 
 struct WppSmem {  // byte offsets inside one warp's shared memory
-  uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, scb, stages, stage_bytes, jbuf, total;
+  uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, stages, stage_bytes, jbuf, total;
 };
 __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   WppSmem L;
@@ -58,7 +58,6 @@ __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   L.dd = o; o += np * 4;
   L.perm = o; o += np * 4;
   L.inv = o; o += np * 4;
-  L.scb = o; o += kWppRows * 4;
   o = (o + 127u) & ~127u;
   L.stages = o;
   L.stage_bytes = ((uint32_t)kWppRows * (uint32_t)(n + 1) * 4u + 127u) & ~127u;  // A rows, then y
@@ -151,6 +150,26 @@ __device__ __forceinline__ void wpp_pivot_order(const float *dd, int n, int *per
   uint32_t k0 = 0, k1 = 0;  // 0: NaN (never wins), otherwise 1 + bits(|d|) (monotone in |d|)
   if (i0 < n) { const float v = fabsf(dd[i0]); k0 = (v != v) ? 0u : __float_as_uint(v) + 1u; }
   if (i1 < n) { const float v = fabsf(dd[i1]); k1 = (v != v) ? 0u : __float_as_uint(v) + 1u; }
+  // Fast path: with distinct keys (no ties, no NaN) "the first largest of the rest goes to k" is the
+  // descending sort, so position = rank = number of larger keys (dd is in shared memory: broadcast
+  // loads).  Ties make the winner depend on where earlier swaps moved the candidates: replay below.
+  {
+    int gt0 = 0, gt1 = 0, eq0 = 0, eq1 = 0;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float v = fabsf(dd[j]);
+      const uint32_t kj = (v != v) ? 0u : __float_as_uint(v) + 1u;
+      gt0 += kj > k0; eq0 += kj == k0;
+      gt1 += kj > k1; eq1 += kj == k1;
+    }
+    const bool amb = (i0 < n && (eq0 != 1 || k0 == 0u)) || (i1 < n && (eq1 != 1 || k1 == 0u));
+    if (!__any_sync(0xffffffffu, amb)) {
+      if (i0 < n) { perm[gt0] = i0; inv[i0] = gt0; }
+      if (i1 < n) { perm[gt1] = i1; inv[i1] = gt1; }
+      __syncwarp();
+      return;
+    }
+  }
   int o0 = i0, o1 = i1;
   for (int k = 0; k < n; ++k) {
     const uint32_t kk = __shfl_sync(0xffffffffu, k < 32 ? k0 : k1, k & 31);
@@ -319,7 +338,6 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
   const int m = d.m, n = d.n;
   const T *xs = reinterpret_cast<const T *>(ws + d.L.xs);
   T *jbuf = reinterpret_cast<T *>(ws + d.L.jbuf);
-  T *scb = reinterpret_cast<T *>(ws + d.L.scb);
   // accumulators as packed FP32 pairs (acc[u][2 h], acc[u][2 h + 1]): FFMA2 (fma.rn.f32x2) does two
   // IEEE fused multiply-adds per issue slot, same roundings as two scalar fmas
   unsigned long long acc2[BLK][BLK / 2];
@@ -348,7 +366,9 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     const int nrows = (m - row0 < kWppRows) ? (m - row0) : kWppRows;
     const T *sa = pipe.stage_ptr(pipe.stage);
     const T *sy = sa + (size_t)kWppRows * n;
-    // ---- phase 1a: lane = row: canonical t-chain, residual r_i, Jacobian scale sc_i ----
+    // ---- phase 1 (lane = row): canonical t-chain, residual r_i, Jacobian scale sc_i, then the
+    // ---- augmented packed row [sc_i a_i | r_i | 0 ..] written with 16-byte stores (pitch / 4 odd:
+    // ---- conflict free); the pad columns are rewritten for every row, so they never go stale ----
     if (lane < nrows) {
       const T *arow = sa + lane * n;
       T ri, sc = (T)1;
@@ -373,20 +393,37 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       } else {
         ri = sy[lane];
       }
-      scb[lane] = sc;
-      jbuf[lane * NPS + n] = ri;
-    }
-    __syncwarp();
-    // ---- phase 1b: lane = column: packed row i <- sc_i * a_i (rows independent: unrolled for ILP) ----
-    if (do_rebuild) {
-      const bool second = lane + 32 < n;
-#pragma unroll 4
-      for (int i = 0; i < nrows; ++i) {
-        const T sc = scb[i];
-        const T v0 = sa[i * n + lane];  // n >= 13 and chunk rows are contiguous: in bounds even if lane >= n
-        const T v1 = second ? sa[i * n + lane + 32] : (T)0;
-        if (lane < n) jbuf[i * NPS + lane] = kSynth ? O::mul(sc, v0) : v0;
-        if (second) jbuf[i * NPS + lane + 32] = kSynth ? O::mul(sc, v1) : v1;
+      if (do_rebuild) {
+        float4 *jrow = reinterpret_cast<float4 *>(jbuf + lane * NPS);
+        if ((n & 1) == 0) {
+          const float2 *a2 = reinterpret_cast<const float2 *>(arow);
+          const int h = n / 2;  // pairs (2 q, 2 q + 1) hold J for q < h, (r_i, 0) for q == h, zeros after
+#pragma unroll 7
+          for (int q4 = 0; q4 < NP / 4; ++q4) {
+            float2 lo = make_float2((T)0, (T)0), hi = lo;
+            const int q0 = 2 * q4, q1 = 2 * q4 + 1;
+            if (q0 < h) { lo = a2[q0]; if (kSynth) { lo.x = O::mul(sc, lo.x); lo.y = O::mul(sc, lo.y); } }
+            else if (q0 == h) lo.x = ri;
+            if (q1 < h) { hi = a2[q1]; if (kSynth) { hi.x = O::mul(sc, hi.x); hi.y = O::mul(sc, hi.y); } }
+            else if (q1 == h) hi.x = ri;
+            jrow[q4] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+        } else {
+#pragma unroll 7
+          for (int q4 = 0; q4 < NP / 4; ++q4) {
+            T v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * q4 + e;
+              v[e] = (T)0;
+              if (j < n) v[e] = kSynth ? O::mul(sc, arow[j]) : arow[j];
+              else if (j == n) v[e] = ri;
+            }
+            jrow[q4] = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      } else {
+        jbuf[lane * NPS + n] = ri;
       }
     }
     __syncwarp();
@@ -601,15 +638,6 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
   __syncwarp();
 }
 
-// columns [c0, c1) of all 32 packed rows <- 0 (the LDLT matrix aliases the packed buffer, so the
-// pad columns are cleared before every pass)
-template <typename T>
-__device__ __forceinline__ void wpp_zero_pad_columns(T *jbuf, int nps, int c0, int c1, int lane) {
-  const int w = c1 - c0;
-  for (int e = lane; e < kWppRows * w; e += 32) jbuf[(e / w) * nps + c0 + (e % w)] = (T)0;
-  __syncwarp();
-}
-
 __device__ __forceinline__ int64_t wpp_next(unsigned long long *counter, int lane) {
   unsigned long long t = 0;
   if (lane == 0) t = atomicAdd(counter, 1ull);
@@ -648,8 +676,6 @@ __global__ void __launch_bounds__(kWppThreads, 3) wpp_lm_run_kernel(const __grid
   const bool is_lm = p.opt.solver_type == 0;
 
   for (int64_t pr = wpp_next(p.d.counter, lane); pr < p.d.B; pr = wpp_next(p.d.counter, lane)) {
-    // pad columns of the packed rows are zero and stay zero (the LDLT matrix aliases this buffer,
-    // so they are cleared again for every problem)
     for (int j = lane; j < NP; j += 32) {
       xs[j] = j < n ? p.x[pr * n + j] : (T)0;
       last_dx[j] = (T)0;
@@ -658,7 +684,6 @@ __global__ void __launch_bounds__(kWppThreads, 3) wpp_lm_run_kernel(const __grid
     s.reset_scalars(p.opt);
     __syncwarp();
     while (!s.done()) {
-      wpp_zero_pad_columns<T>(jbuf, NPS, n + 1, NP, lane);
       const bool do_rebuild = !is_lm || s.rebuild();
       T acc[BLK][BLK], cost_only;
       wpp_pass<T, NB, BLK, true>(pipe, p.d, ws, pr, lane, do_rebuild, p.alpha, p.alpha3, bi, bj, has_block, acc, cost_only);
@@ -708,7 +733,6 @@ __global__ void __launch_bounds__(kWppThreads, 2) wpp_build_solve_kernel(const _
   wpp_block_of_lane<NB>(lane, bi, bj, has_block);
 
   for (int64_t pr = wpp_next(p.d.counter, lane); pr < p.d.B; pr = wpp_next(p.d.counter, lane)) {
-    wpp_zero_pad_columns<T>(jbuf, NPS, n + 1, NP, lane);
     T acc[BLK][BLK], cost_only;
     wpp_pass<T, NB, BLK, false>(pipe, p.d, ws, pr, lane, true, (T)0, (T)0, bi, bj, has_block, acc, cost_only);
     wpp_extract<T, NB, BLK>(acc, bi, bj, has_block, n, g, dg, temp);

@@ -17,4 +17,8 @@ ctx = tb.Context(0)
 A, y, xs, x0 = ctx.synth_generate(B, cfg["m"], cfg["n"], tdt, layout=tb.PROBLEM_MAJOR if cfg["n"] > 12 else tb.TILE32)
 for _ in range(reps):
     out = ctx.optimize_batch(A, y, x0, tb.options(**cfg["opts"]))
-print(name, B, "iters", int(out.results["num_iters"].sum()), "kernel ms", ctx.last_elapsed_ms())
+iters = int(out.results["num_iters"].sum())
+ms = ctx.last_elapsed_ms()
+print(name, B, "iters", iters, "kernel ms", ms, "Mit/s", iters / ms / 1e3)
+if ctx.kernel_family(tdt, cfg["n"]) == 3:
+    print("  phases (ms, launches): eval", ctx.last_phase_ms(0), "jtj", ctx.last_phase_ms(1), "solve", ctx.last_phase_ms(2))
