@@ -1,0 +1,221 @@
+// tests/cuda/test_device_functor.cu — SURVEY.md §8(f) rank 1: the user's residual functor evaluated on
+// the device (include/tinyopt_b200_device.cuh).  Checks, on the GPU:
+//   1. tests/sqrt2.cpp / README.md:77-95 through a Jet functor: x0 = 1 -> 5 Steps, kMinError,
+//      x = 1.4142135623730951 (SURVEY §8c golden vector), and the reference's other two starts;
+//   2. the polynomial family of SURVEY §8(d) written as a user functor with its own Jacobian rows in the
+//      canonical op sequence == tob200_lm_run_* (which the parity suite pins to the CPU oracle) bit for
+//      bit: x, num_iters, stop_reason, final_cost — double n = 6 and float n = 12;
+//   3. the same family through automatic differentiation (Jets): same iteration counts and x within
+//      1e-10 (double) / 1e-4 (float) relative (the Jet derivative rounds differently from the closed form).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "tinyopt_b200_device.cuh"
+
+namespace dev = tinyopt::b200::device;
+
+static int g_failures = 0;
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);  \
+      ++g_failures;                                                        \
+    }                                                                      \
+  } while (0)
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      std::printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      std::exit(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? 3 : 2);  \
+    }                                                                                     \
+  } while (0)
+
+// ---- 1. sqrt2 ----------------------------------------------------------------------------------
+struct Sqrt2 {
+  template <typename S>
+  __device__ void operator()(int64_t, const S (&x)[1], dev::Emit<double, 1> &emit) const {
+    emit(x[0] * x[0] - 2.0);
+  }
+};
+
+static void test_sqrt2() {
+  const int64_t B = 3;
+  const double x0[B] = {1.0, (double)-0.3f, (double)3.2f};
+  double *dx;
+  tob200_result *dres;
+  CU(cudaMalloc(&dx, sizeof(x0)));
+  CU(cudaMalloc(&dres, B * sizeof(tob200_result)));
+  CU(cudaMemcpy(dx, x0, sizeof(x0), cudaMemcpyHostToDevice));
+  tob200_options opt;
+  tob200_options_default(&opt);
+  opt.max_iters = 20;            // tests/sqrt2.cpp:22-28
+  opt.max_consec_failures = 0;
+  CU(dev::OptimizeBatchAutoDiff<1>(Sqrt2{}, dx, B, opt, dres));
+  CU(cudaDeviceSynchronize());
+  double x[B];
+  tob200_result res[B];
+  CU(cudaMemcpy(x, dx, sizeof(x), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(res, dres, sizeof(res), cudaMemcpyDeviceToHost));
+  for (int p = 0; p < B; ++p) {
+    CHECK(res[p].stop_reason >= TOB200_STOP_MIN_ERROR && res[p].stop_reason < TOB200_STOP_MAX_ITERS);
+    CHECK(std::fabs(std::fabs(x[p]) - std::sqrt(2.0)) < 1e-5);
+  }
+  CHECK(res[0].num_iters == 5 && res[0].stop_reason == TOB200_STOP_MIN_ERROR);
+  CHECK(x[0] == 1.4142135623730951);
+  std::printf("sqrt2 (Jet functor): x[0]=%.16g iters=%d stop=%d\n", x[0], res[0].num_iters, res[0].stop_reason);
+  cudaFree(dx);
+  cudaFree(dres);
+}
+
+// ---- 2./3. the polynomial family as a user functor ------------------------------------------------
+// r_i = t + alpha t^3 - y_i, t = a_i . x; A [B][m][n], y [B][m] problem-major in HBM
+template <typename T, int N>
+struct PolyManual {  // own Jacobian rows, canonical op sequence
+  const T *A, *y;
+  int m;
+  T alpha, alpha3;
+  __device__ void operator()(int64_t p, const T (&x)[N], dev::Emit<T, N> &emit, bool want_j) const {
+    using O = tob200::Ops<T>;
+    const T *Ap = A + (size_t)p * m * N, *yp = y + (size_t)p * m;
+    for (int i = 0; i < m; ++i) {
+      T a[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[j] = Ap[(size_t)i * N + j];
+      T t = (T)0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) t = O::fma(a[j], x[j], t);
+      const T t2 = O::mul(t, t);
+      const T r = O::fma(t, O::fma(alpha, t2, (T)1), -yp[i]);
+      if (want_j) {
+        const T sc = O::fma(alpha3, t2, (T)1);
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[j] = O::mul(sc, a[j]);
+        emit(r, a);
+      } else {
+        emit(r);
+      }
+    }
+  }
+};
+template <typename T, int N>
+struct PolyAuto {  // templated on the scalar: Jets on rebuild passes, plain T on cost-only ones
+  const T *A, *y;
+  int m;
+  T alpha;
+  template <typename S>
+  __device__ void operator()(int64_t p, const S (&x)[N], dev::Emit<T, N> &emit) const {
+    const T *Ap = A + (size_t)p * m * N, *yp = y + (size_t)p * m;
+    for (int i = 0; i < m; ++i) {
+      S t = x[0] * Ap[(size_t)i * N];
+#pragma unroll
+      for (int j = 1; j < N; ++j) t = t + x[j] * Ap[(size_t)i * N + j];
+      emit(t + alpha * (t * t * t) - yp[i]);
+    }
+  }
+};
+
+static int synth(tob200_ctx *c, int64_t B, int m, int n, double *A, double *y, double *xs, double *x0) {
+  return tob200_synth_generate_f64(c, 20261017ull, 0, B, m, n, 0.1, 1e-2, TOB200_LAYOUT_PROBLEM_MAJOR, A, y, xs, x0);
+}
+static int synth(tob200_ctx *c, int64_t B, int m, int n, float *A, float *y, float *xs, float *x0) {
+  return tob200_synth_generate_f32(c, 20261017ull, 0, B, m, n, 0.1f, 1e-2f, TOB200_LAYOUT_PROBLEM_MAJOR, A, y, xs, x0);
+}
+static int lm_run(tob200_ctx *c, const tob200_options *o, const double *A, const double *y, int64_t B, int m, int n,
+                  double *x, tob200_result *r) {
+  return tob200_lm_run_f64(c, o, A, y, 0.1, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, x, r);
+}
+static int lm_run(tob200_ctx *c, const tob200_options *o, const float *A, const float *y, int64_t B, int m, int n,
+                  float *x, tob200_result *r) {
+  return tob200_lm_run_f32(c, o, A, y, 0.1f, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, x, r);
+}
+
+template <typename T, int N>
+static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
+  T *A, *y, *xs, *x0, *xa, *xb, *xc;
+  tob200_result *ra, *rb, *rc;
+  CU(cudaMalloc(&A, (size_t)B * m * N * sizeof(T)));
+  CU(cudaMalloc(&y, (size_t)B * m * sizeof(T)));
+  for (T **q : {&xs, &x0, &xa, &xb, &xc}) CU(cudaMalloc(q, (size_t)B * N * sizeof(T)));
+  for (tob200_result **q : {&ra, &rb, &rc}) CU(cudaMalloc(q, (size_t)B * sizeof(tob200_result)));
+  CHECK(synth(ctx, B, m, N, A, y, xs, x0) == TOB200_OK);
+  CHECK(tob200_sync(ctx) == TOB200_OK);  // the library runs on its own non-blocking stream
+  tob200_options opt;
+  tob200_options_default(&opt);
+  if (sizeof(T) == 4) { opt.min_rerr_dec = 1e-5f; opt.min_step_norm2 = 1e-9f; }  // SURVEY §8d float options
+  for (T *q : {xa, xb, xc}) CU(cudaMemcpyAsync(q, x0, (size_t)B * N * sizeof(T), cudaMemcpyDeviceToDevice, nullptr));
+  CU(cudaDeviceSynchronize());
+  CHECK(lm_run(ctx, &opt, A, y, B, m, N, xa, ra) == TOB200_OK);  // the library's own kernels (oracle-pinned)
+  CHECK(tob200_sync(ctx) == TOB200_OK);
+  PolyManual<T, N> fm{A, y, m, (T)0.1, (T)3 * (T)0.1};
+  CU((dev::OptimizeBatchManual<N>(fm, xb, B, opt, rb)));
+  PolyAuto<T, N> fa{A, y, m, (T)0.1};
+  CU((dev::OptimizeBatchAutoDiff<N>(fa, xc, B, opt, rc)));
+  CU(cudaDeviceSynchronize());
+  std::vector<T> ha((size_t)B * N), hb(ha.size()), hc(ha.size());
+  std::vector<tob200_result> qa((size_t)B), qb(qa.size()), qc(qa.size());
+  CU(cudaMemcpy(ha.data(), xa, ha.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hb.data(), xb, hb.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hc.data(), xc, hc.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(qa.data(), ra, qa.size() * sizeof(tob200_result), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(qb.data(), rb, qb.size() * sizeof(tob200_result), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(qc.data(), rc, qc.size() * sizeof(tob200_result), cudaMemcpyDeviceToHost));
+  // manual functor == library kernels, bit for bit
+  CHECK(std::memcmp(ha.data(), hb.data(), ha.size() * sizeof(T)) == 0);
+  int64_t iters = 0, same_iters_ad = 0;
+  double worst = 0.0, xmax = 0.0;
+  for (int64_t p = 0; p < B; ++p) {
+    if (!(qa[p].num_iters == qb[p].num_iters && qa[p].stop_reason == qb[p].stop_reason &&
+          qa[p].final_cost == qb[p].final_cost && qa[p].num_builds == qb[p].num_builds &&
+          qa[p].last_lambda == qb[p].last_lambda)) {
+      CHECK(!"manual functor result differs from tob200_lm_run");
+      std::printf("  p=%lld lm_run: iters=%d stop=%d builds=%d cost=%.9g x0=%.9g | manual: iters=%d stop=%d builds=%d cost=%.9g "
+                  "x0=%.9g | jets: iters=%d stop=%d cost=%.9g x0=%.9g\n", (long long)p, qa[p].num_iters, qa[p].stop_reason,
+                  qa[p].num_builds, qa[p].final_cost, (double)ha[p * N], qb[p].num_iters, qb[p].stop_reason,
+                  qb[p].num_builds, qb[p].final_cost, (double)hb[p * N], qc[p].num_iters, qc[p].stop_reason,
+                  qc[p].final_cost, (double)hc[p * N]);
+      break;
+    }
+    iters += qa[p].num_iters;
+    same_iters_ad += qa[p].num_iters == qc[p].num_iters && qa[p].stop_reason == qc[p].stop_reason;
+    for (int j = 0; j < N; ++j) {
+      worst = std::fmax(worst, std::fabs((double)ha[p * N + j] - (double)hc[p * N + j]));
+      xmax = std::fmax(xmax, std::fabs((double)ha[p * N + j]));
+    }
+  }
+  // Jets: same decisions on (nearly) every problem — a threshold may flip where a test lands within
+  // rounding of it — and the same solution to the north star's tolerance
+  CHECK(same_iters_ad >= B - B / 200);
+  CHECK(worst / xmax <= tol);
+  std::printf("family<%s> n=%d m=%d B=%lld: iters=%lld manual functor == lm_run bit for bit; Jets: %lld/%lld same "
+              "iteration count + stop reason, max rel dx %.2e\n",
+              sizeof(T) == 8 ? "double" : "float", N, m, (long long)B, (long long)iters, (long long)same_iters_ad,
+              (long long)B, worst / xmax);
+  for (T *q : {A, y, xs, x0, xa, xb, xc}) cudaFree(q);
+  for (tob200_result *q : {ra, rb, rc}) cudaFree(q);
+}
+
+int main() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    std::printf("no CUDA device: the device functor path has no CPU fallback\n");
+    return 3;
+  }
+  tob200_ctx *ctx = nullptr;
+  if (tob200_create(&ctx, 0, nullptr) != TOB200_OK) {
+    std::printf("tob200_create failed: %s\n", tob200_last_error(nullptr));
+    return 3;
+  }
+  test_sqrt2();
+  test_family<double, 6>(ctx, 4096, 30, 1e-10);
+  test_family<float, 12>(ctx, 4096, 200, 1e-4);
+  tob200_destroy(ctx);
+  if (g_failures) {
+    std::printf("%d check(s) failed\n", g_failures);
+    return 1;
+  }
+  std::printf("all device functor checks passed\n");
+  return 0;
+}

@@ -358,6 +358,7 @@ LgSyrkParams lg_syrk_params(tob200_ctx *ctx, const LgBuffers &b, const float *A,
   sp.stages = lg_syrk_stages(b.np);
   sp.terms = ctx->lg_tf32_terms;
   sp.is_lm = is_lm;
+  sp.debug = env_int("TOB200_LG_DEBUG", 0);
   sp.half_bytes = lg_syrk_half_bytes(b.np);
   return sp;
 }

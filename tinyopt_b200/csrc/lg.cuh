@@ -222,6 +222,9 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
 __device__ __forceinline__ void sts_v4(uint32_t saddr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2(const void *gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ bool lg_skip(const LgSyrkParams &p, int64_t pr) {
@@ -285,43 +288,59 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     // A raw stage holds the 8 rows of one K step, columns [c0, c0 + ncs) of the strip (pitch ncs
     // floats; one contiguous copy per row).  Pad columns >= n and rows >= m are simply not copied: the
     // producers select 0 for them.
-    if (lane == 0) {
-      uint32_t rs = 0, rph = 0;
-      for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
-        int64_t pr; int h;
-        unit_of(idx, pr, h);
-        if (lg_skip(p, pr)) continue;
-        for (int half = 0; half < 2; ++half) {
-          const int r = half == 0 ? h : p.nstrips - 1 - h;
-          if (half == 1 && r == h) break;
-          const int c0 = 128 * r;
-          const int ncs = (np - c0 < 128) ? 128 : (np - c0);
-          const int ccnt = (n - c0 < ncs) ? (n - c0) : ncs;  // real columns (> 0: c0 <= np - 32 < n)
-          const uint32_t row_bytes = (uint32_t)ccnt * 4u;
-          const float *Ap = p.A + (size_t)pr * m * n + c0;
-          for (int ks = 0; ks < ksteps; ++ks) {
+    // lane 0 owns the barrier; lanes 0..15 each issue one row copy (one instruction for the whole stage),
+    // lanes 16..31 prefetch the rows of the stage after the ring into L2
+    uint32_t rs = 0, rph = 0;
+    for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
+      int64_t pr; int h;
+      unit_of(idx, pr, h);
+      if (lg_skip(p, pr)) continue;
+      for (int half = 0; half < 2; ++half) {
+        const int r = half == 0 ? h : p.nstrips - 1 - h;
+        if (half == 1 && r == h) break;
+        const int c0 = 128 * r;
+        const int ncs = (np - c0 < 128) ? 128 : (np - c0);
+        const int ccnt = (n - c0 < ncs) ? (n - c0) : ncs;  // real columns (> 0: c0 <= np - 32 < n)
+        const uint32_t row_bytes = (uint32_t)ccnt * 4u;
+        const float *Ap = p.A + (size_t)pr * m * n + c0;
+        // L2 prefetch runs kLgPrefetchStages stages ahead of the copies (no shared memory needed): with two
+        // raw stages alone only ~40 KB per SM would be in flight, far below what HBM latency needs
+        for (int d = kLgRawStages; d < kLgRawStages + kLgPrefetchStages; ++d) {
+          const int prow = d * kLgStageK + (lane & 15);
+          if (lane >= 16 && prow < m) tma_prefetch_l2(Ap + (size_t)prow * n, row_bytes);
+        }
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int row0 = ks * kLgStageK;
+          const int rows = (m - row0 < kLgStageK) ? (m - row0) : kLgStageK;
+          if (lane == 0) {
             mbar_wait(&raw_empty[rs], rph ^ 1u);
             fence_proxy_async();  // the producers' generic reads of this stage precede the async writes
-            const int row0 = ks * kLgStageK;
-            const int rows = (m - row0 < kLgStageK) ? (m - row0) : kLgStageK;
-            float *dst = raw + (size_t)rs * (p.half_bytes / 4);
-            mbar_expect_tx(&raw_full[rs], (uint32_t)rows * row_bytes);
-            for (int t = 0; t < rows; ++t)
-              tma_bulk_g2s(dst + (size_t)t * ncs, Ap + (size_t)(row0 + t) * n, row_bytes, &raw_full[rs]);
-            if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
+            if (p.debug & 4) mbar_arrive(&raw_full[rs]);  // timing experiment: no copies
+            else mbar_expect_tx(&raw_full[rs], (uint32_t)rows * row_bytes);
           }
+          __syncwarp();
+          if (!(p.debug & 4)) {
+            float *dst = raw + (size_t)rs * (p.half_bytes / 4);
+            if (lane < rows) {
+              tma_bulk_g2s(dst + (size_t)lane * ncs, Ap + (size_t)(row0 + lane) * n, row_bytes, &raw_full[rs]);
+            } else if (lane >= 16) {
+              const int prow = row0 + (kLgRawStages + kLgPrefetchStages) * kLgStageK + (lane - 16);
+              if (prow < m) tma_prefetch_l2(Ap + (size_t)prow * n, row_bytes);
+            }
+          }
+          if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
         }
       }
     }
   } else if (warp > kLgLoadWarp) {
     // ===================== producers =====================
-    // An operand stage is the K-major image of 8 rows x ncs columns of diag(s) A: operand row = column j
-    // of A, K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 8) of columns
-    // [128 cg + 64 qh, + 64) (cg = (w / 2) % 4, qh = w % 2): lane l owns columns l and l + 32 of that
-    // range — conflict-free 4-byte reads of the raw stage (lane = consecutive column), scaled by s_i, split
-    // into TF32 hi + lo, conflict-free 16-byte stores (one per column and part).
+    // An operand stage is the K-major image of 16 rows x ncs columns of diag(s) A (two MMA K steps):
+    // operand row = column j of A, K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 4) of
+    // columns [128 cg, + 128) (cg = w % 4): lane l owns columns l + 32 q, q = 0..3, of that range —
+    // conflict-free 4-byte reads of the raw stage (lane = consecutive column), scaled by s_i, split into
+    // TF32 hi + lo, conflict-free 16-byte stores (one per column and part).
     const int w = warp - (kLgLoadWarp + 1);
-    const int kc = w >> 3, cg = (w >> 1) & 3, qh = w & 1;
+    const int kc = w >> 2, cg = w & 3;  // K chunk (rows 4 kc .. 4 kc + 3 of the stage), column group of 128
     uint32_t st = 0, ph = 0;    // operand ring position and its phase parity
     uint32_t rs = 0, rph = 0;   // raw ring
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
@@ -334,11 +353,9 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       const int c0 = 128 * r;
       const int ncs = (np - c0 < 128) ? 128 : (np - c0);  // columns staged (the A operand needs 128)
       const uint32_t lbo = (uint32_t)ncs * 16u;
-      const int rr0 = 128 * cg + 64 * qh + lane;          // my operand rows: rr0, rr0 + 32
-      const bool busy0 = rr0 < ncs, busy1 = rr0 + 32 < ncs;  // ncs is a multiple of 32: warp uniform
-      const bool cok0 = busy0 && c0 + rr0 < n, cok1 = busy1 && c0 + rr0 + 32 < n;
+      const int rr0 = 128 * cg + lane;  // my operand rows: rr0 + 32 q, q = 0..3
       const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
-      // row scales: lane l keeps s of row 32 g + l for the group g of four K steps being consumed and
+      // row scales: lane l keeps s of row 32 g + l for the group g of two stages being consumed and
       // for the next one (one coalesced load per 32 rows, a whole group ahead of its use); the four
       // values a K step needs are shuffled out of it
       auto load_scale_group = [&](int g) {
@@ -348,33 +365,49 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       float sg_cur = load_scale_group(0), sg_next = load_scale_group(1);
       const uint32_t raw_u32 = smem_u32(raw), stages_u32 = smem_u32(stages);
       for (int ks = 0; ks < ksteps; ++ks) {
-        if ((ks & 3) == 0 && ks > 0) {
+        if ((ks & 1) == 0 && ks > 0) {
           sg_cur = sg_next;
-          sg_next = load_scale_group((ks >> 2) + 1);
+          sg_next = load_scale_group((ks >> 1) + 1);
         }
         float sc[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) sc[t] = __shfl_sync(0xffffffffu, sg_cur, 8 * (ks & 3) + 4 * kc + t);
+        for (int t = 0; t < 4; ++t) sc[t] = __shfl_sync(0xffffffffu, sg_cur, kLgStageK * (ks & 1) + 4 * kc + t);
         mbar_wait(&raw_full[rs], rph);
         const uint32_t rsrc = raw_u32 + rs * p.half_bytes + (uint32_t)((4 * kc) * ncs + rr0) * 4u;
         const int row0 = ks * kLgStageK + 4 * kc;
-        float b0[4], b1[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const bool rok = row0 + t < m;
-          b0[t] = (cok0 && rok) ? lds_f32(rsrc + (uint32_t)(t * ncs) * 4u) : 0.f;
-          b1[t] = (cok1 && rok) ? lds_f32(rsrc + (uint32_t)(t * ncs + 32) * 4u) : 0.f;
+        if (p.debug & 2) {  // timing experiment: barrier protocol only
+          mbar_wait(&empty[st], ph ^ 1u);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&full[st]);
+            mbar_arrive(&raw_empty[rs]);
+          }
+          if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
+          if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
+          continue;
         }
+        float bv[4][4];  // [q][t]: column rr0 + 32 q, row 4 kc + t
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int rr = rr0 + 32 * q;
+          const bool cok = rr < ncs && c0 + rr < n;  // rr < ncs is warp uniform (ncs is a multiple of 32)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            bv[q][t] = (cok && row0 + t < m) ? lds_f32(rsrc + (uint32_t)(t * ncs + 32 * q) * 4u) : 0.f;
+        }
+        // the raw stage is consumed once the values are in registers: release it before the transform
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
         mbar_wait(&empty[st], ph ^ 1u);
         const uint32_t sb = stages_u32 + st * stage_bytes;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q == 0 ? busy0 : busy1) {
-            const int rr = rr0 + 32 * q;  // operand row (column of A relative to c0)
+        for (int q = 0; q < 4; ++q) {
+          const int rr = rr0 + 32 * q;  // operand row (column of A relative to c0)
+          if (rr < ncs) {
             float v[4], hi[4], lo[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              v[t] = __fmul_rn(q == 0 ? b0[t] : b1[t], sc[t]);
+              v[t] = __fmul_rn(bv[q][t], sc[t]);
               hi[t] = (p.terms == 3) ? tc_round_tf32(v[t]) : v[t];
               lo[t] = __fsub_rn(v[t], hi[t]);
             }
@@ -385,10 +418,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         }
         fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&full[st]);
-          mbar_arrive(&raw_empty[rs]);
-        }
+        if (lane == 0) mbar_arrive(&full[st]);
         if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
         if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
       }
@@ -415,20 +445,23 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         if (lane == 0) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
-          const uint32_t sb = smem_u32(stages + (size_t)st * stage_bytes);
-          const uint32_t lbo = (uint32_t)ncs * 16u;  // K chunk 1 follows all the core matrices of chunk 0
-          const uint64_t a_hi = tc_desc_k_major(sb, lbo, 128u);
-          const uint64_t a_lo = tc_desc_k_major(sb + p.half_bytes, lbo, 128u);
-          for (int n0 = 0; n0 < nb; n0 += 256) {
-            const int N = (nb - n0 < 256) ? (nb - n0) : 256;
-            const uint32_t idesc = tc_idesc_tf32(N);
-            const uint64_t b_hi = tc_desc_k_major(sb + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
-            const uint32_t d = tmem_base + (uint32_t)n0;
-            tc_mma_tf32(d, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-            if (p.terms == 3) {
-              const uint64_t b_lo = tc_desc_k_major(sb + p.half_bytes + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
-              tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-              tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+          const uint32_t sb0 = smem_u32(stages + (size_t)st * stage_bytes);
+          const uint32_t lbo = (uint32_t)ncs * 16u;  // K chunk c + 1 follows all the core matrices of chunk c
+          for (int kk = 0; kk < kLgStageK / kLgMmaK && !(p.debug & 1); ++kk) {  // debug & 1: timing experiment, no MMAs
+            const uint32_t sb = sb0 + (uint32_t)(2 * kk) * lbo;  // this K step: chunks 2 kk, 2 kk + 1
+            const uint64_t a_hi = tc_desc_k_major(sb, lbo, 128u);
+            const uint64_t a_lo = tc_desc_k_major(sb + p.half_bytes, lbo, 128u);
+            for (int n0 = 0; n0 < nb; n0 += 256) {
+              const int N = (nb - n0 < 256) ? (nb - n0) : 256;
+              const uint32_t idesc = tc_idesc_tf32(N);
+              const uint64_t b_hi = tc_desc_k_major(sb + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
+              const uint32_t d = tmem_base + (uint32_t)n0;
+              tc_mma_tf32(d, a_hi, b_hi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+              if (p.terms == 3) {
+                const uint64_t b_lo = tc_desc_k_major(sb + p.half_bytes + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
+                tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+              }
             }
           }
           tc_commit(&empty[st]);  // arrives when the MMAs above have read the stage

@@ -41,9 +41,11 @@ constexpr int kLgEpiWarps = 4;    // warps 0..3: TMEM lane quadrant == warp id
 constexpr int kLgMmaWarp = 4;     // warp 4: lane 0 issues every tcgen05.mma
 constexpr int kLgLoadWarp = 5;    // warp 5: lane 0 streams raw rows of A into the raw ring (TMA bulk copies)
 constexpr int kLgProdWarps = 16;  // warps 6..21: 4 K rows x 64 columns of a stage each
-constexpr int kLgRawStages = 4;   // raw ring depth (one K step = 8 rows each)
+constexpr int kLgPrefetchStages = 6;  // L2 prefetch distance beyond the raw ring, in stages
+constexpr int kLgRawStages = 2;   // raw ring depth (kLgStageK rows each)
 constexpr int kLgSyrkThreads = (kLgEpiWarps + 2 + kLgProdWarps) * 32;
-constexpr int kLgStageK = 8;      // K extent of one tf32 tcgen05.mma == rows per stage
+constexpr int kLgMmaK = 8;        // K extent of one tf32 tcgen05.mma
+constexpr int kLgStageK = 16;     // rows per stage == two MMA K steps (halves the barrier hand-offs per row)
 constexpr int kLgMaxStages = 8;
 
 struct LgSyrkParams {
@@ -56,10 +58,11 @@ struct LgSyrkParams {
   int stages;          // ring depth
   int terms;           // 3: hi*hi + hi*lo + lo*hi; 1: plain TF32
   int is_lm;
-  uint32_t half_bytes; // bytes of the hi (== lo) part of a stage: max(128, np) / 32 KB
+  int debug;           // timing experiments only (env TOB200_LG_DEBUG): 1 no MMAs, 2 no transform, 4 no copies
+  uint32_t half_bytes; // bytes of the hi (== lo) part of a stage == of a raw stage: kLgStageK x max(128, np) floats
 };
 
-__host__ __device__ inline uint32_t lg_syrk_half_bytes(int np) { return (uint32_t)((np < 128 ? 128 : np) / 32) * 1024u; }
+__host__ __device__ inline uint32_t lg_syrk_half_bytes(int np) { return (uint32_t)(np < 128 ? 128 : np) * (uint32_t)kLgStageK * 4u; }
 __host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages) {
   // [1 KB alignment slack | operand stages (hi + lo) | raw stages | barriers]
   return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np) + (size_t)kLgRawStages * lg_syrk_half_bytes(np) + 512;

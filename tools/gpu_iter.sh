@@ -12,13 +12,12 @@ timeout 300 python tools/run_once.py C5 592 2
 TOB200_LG_TF32_TERMS=1 timeout 300 python tools/run_once.py C5 592 2
 timeout 300 python tools/run_once.py C2 100000 5
 timeout 300 python tools/run_once.py C3 100000 5
+timeout 300 python bench.py --config C2 --steps 10 --warmup 3 --no-cpu-baseline
+TOB200_HOST_CHUNKS=1 timeout 300 python bench.py --config C2 --steps 10 --warmup 3 --no-cpu-baseline
+TOB200_HOST_CHUNKS=8 timeout 300 python bench.py --config C2 --steps 10 --warmup 3 --no-cpu-baseline
 } 2>&1 | tee $out/timings_$tag.txt
 if [ -n "$NCU" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wpp_lm_run -s 1 -c 1 \
-  -f -o $out/prof_wpp_C4_$tag python tools/run_once.py C4 16384 2 > $out/ncu_full_C4_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lg_syrk -s 0 -c 1 \
   -f -o $out/prof_lg_syrk_C5_$tag python tools/run_once.py C5 148 1 > $out/ncu_full_C5_syrk_$tag.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:lg_solve -s 0 -c 1 \
-  -f -o $out/prof_lg_solve_C5_$tag python tools/run_once.py C5 148 1 > $out/ncu_full_C5_solve_$tag.log 2>&1
 ls -la $out | tail
 fi
