@@ -528,12 +528,29 @@ __global__ void __launch_bounds__(kLgSolveThreads, 1) lg_solve_kernel(const __gr
           mirrored = true;
         }
         LG_T(2);
-        for (int a = tid >> 5; a < n; a += kLgSolveThreads / 32) {
-          const int ia = perm[a];
-          const float *hrow = Hp + (size_t)ia * np;
-          for (int b = tid & 31; b <= a; b += 32) {
-            const int jb = perm[b];
-            W[(size_t)a * np + b] = (ia == jb) ? dd[ia] : hrow[jb];
+        // row gather with eight independent loads in flight per lane (two rows x four 32-column chunks):
+        // the gathers hit L2 at random, so memory-level parallelism is what this loop runs on
+        for (int a0 = tid >> 5; a0 < n; a0 += 2 * (kLgSolveThreads / 32)) {
+          const int a1 = a0 + kLgSolveThreads / 32;
+          const bool two = a1 < n;
+          const int ia0 = perm[a0], ia1 = two ? perm[a1] : ia0;
+          const float *h0 = Hp + (size_t)ia0 * np, *h1 = Hp + (size_t)ia1 * np;
+          const int last = two ? a1 : a0;  // a1 > a0: the longer row bounds the chunk loop
+          for (int b0 = 0; b0 <= last; b0 += 128) {
+            float v0[4], v1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int b = b0 + 32 * q + (tid & 31);
+              const int jb = (b <= last) ? perm[b] : 0;
+              v0[q] = (b <= a0) ? ((ia0 == jb) ? dd[ia0] : h0[jb]) : 0.f;
+              v1[q] = (two && b <= a1) ? ((ia1 == jb) ? dd[ia1] : h1[jb]) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int b = b0 + 32 * q + (tid & 31);
+              if (b <= a0) W[(size_t)a0 * np + b] = v0[q];
+              if (two && b <= a1) W[(size_t)a1 * np + b] = v1[q];
+            }
           }
         }
         __syncthreads();
