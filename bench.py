@@ -116,7 +116,7 @@ def measured_tensor_peak():
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the bench size, from
 # the committed `ncu --set full` captures (profiles/r1_*_ncu_full_summary.txt); None where no capture at
 # the bench size exists (C4's capture ran 16384 of the 1M problems)
-NCU_TRAFFIC = {"C2": 244.811520e6 + 11.034112e6, "C3": 3.177813e9 + 13.342976e6, "C4": None}
+NCU_TRAFFIC = {"C2": 245.520640e6 + 11.821312e6, "C3": 3.178103e9 + 13.871360e6, "C4": None}
 
 
 def cpu_reference(cfg, sample_B, reps, nthreads=0):

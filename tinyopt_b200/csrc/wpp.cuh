@@ -21,10 +21,22 @@
 // solvers/gn.h:150-171, math.h:232-240, optimizers/optimizer.h:243-539.
 #pragma once
 
+#include <cstdio>
+
 #include "common.cuh"
 #include "lm_state.cuh"
 
 namespace tob200 {
+
+// optional per-phase cycle counters of warp 0 of block 0 (build with -DTOB200_WPP_TIMING; printed at kernel end)
+#ifdef TOB200_WPP_TIMING
+__device__ long long g_wpp_tm[16];
+#define WPP_T0() long long wpp_t0__ = clock64()
+#define WPP_T(k) do { const long long t__ = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) g_wpp_tm[k] += t__ - wpp_t0__; wpp_t0__ = t__; } while (0)
+#else
+#define WPP_T0()
+#define WPP_T(k)
+#endif
 
 constexpr int kWppRows = 32;      // rows per chunk == lanes
 constexpr int kWppThreads = 128;  // 4 independent warps per CTA
@@ -360,8 +372,10 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       if (++st == pipe.nstages) st = 0;
     }
   }
+  WPP_T0();
   for (int c = 0; c < nchunks; ++c) {
     pipe.wait();
+    WPP_T(0);
     const int row0 = c * kWppRows;
     const int nrows = (m - row0 < kWppRows) ? (m - row0) : kWppRows;
     const T *sa = pipe.stage_ptr(pipe.stage);
@@ -427,6 +441,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       }
     }
     __syncwarp();
+    WPP_T(1);
     // the stage is free again: refill it with chunk c + nstages
     if (c + (int)pipe.nstages < nchunks) {
       if (lane == 0) fence_proxy_async();
@@ -462,6 +477,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       }
     }
     __syncwarp();
+    WPP_T(2);
   }
   cost_only = __shfl_sync(0xffffffffu, cost_only, 0);
 #pragma unroll
@@ -543,6 +559,7 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
   int *perm = reinterpret_cast<int *>(ws + d.L.perm);
   int *inv = reinterpret_cast<int *>(ws + d.L.inv);
 
+  WPP_T0();
   T cost_t = cost_only;
   if (pass_rebuilt) {
     wpp_extract<T, NB, BLK>(acc, bi, bj, has_block, n, g, dg, temp);  // temp[0] <- r^T r
@@ -605,12 +622,16 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
         for (int j = lane; j < n; j += 32) hp[j * LDW + j] = dd[j];
       }
       __syncwarp();
-      if (wpp_ldlt_factor<T>(W, LDW, n, temp, lane)) {  // gn.h:150-156
+      WPP_T(3);
+      const bool fact_ok = wpp_ldlt_factor<T>(W, LDW, n, temp, lane);  // gn.h:150-156
+      WPP_T(4);
+      if (fact_ok) {
         for (int j = lane; j < n; j += 32) temp[j] = -g[j];
         __syncwarp();
         wpp_ldlt_solve<T>(W, LDW, n, perm, temp, dxs, lane);
         solver_failed = false;
       }
+      WPP_T(5);
     }
     if (!solver_failed) break;
     const int act = lm_on_solver_failure(s, o, cost, nres);
@@ -636,6 +657,7 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
     for (int j = lane; j < n; j += 32) xs[j] = O::add(xs[j], -last_dx[j]);
   }
   __syncwarp();
+  WPP_T(6);
 }
 
 __device__ __forceinline__ int64_t wpp_next(unsigned long long *counter, int lane) {
@@ -693,6 +715,16 @@ __global__ void __launch_bounds__(kWppThreads, 3) wpp_lm_run_kernel(const __grid
     if (lane == 0) lm_write_result(s, &p.results[pr]);
     __syncwarp();
   }
+#ifdef TOB200_WPP_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long tot = 0;
+    for (int k = 0; k < 7; ++k) tot += g_wpp_tm[k];
+    printf("wpp warp 0: kcycles: tma wait %lld phase1 %lld phase2 %lld extract+pivot+layout %lld factor %lld solve %lld "
+           "state+update %lld total %lld\n", g_wpp_tm[0] / 1000, g_wpp_tm[1] / 1000, g_wpp_tm[2] / 1000, g_wpp_tm[3] / 1000,
+           g_wpp_tm[4] / 1000, g_wpp_tm[5] / 1000, g_wpp_tm[6] / 1000, tot / 1000);
+    for (int k = 0; k < 16; ++k) g_wpp_tm[k] = 0;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
