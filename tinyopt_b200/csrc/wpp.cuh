@@ -41,6 +41,10 @@ __device__ long long g_wpp_tm[16];
 constexpr int kWppRows = 32;      // rows per chunk == lanes
 constexpr int kWppThreads = 128;  // 4 independent warps per CTA
 constexpr int kWppMaxStages = 4;
+#ifndef TOB200_WPP_LDLT_COLS
+#define TOB200_WPP_LDLT_COLS 2
+#endif
+constexpr int kWppLdltCols = TOB200_WPP_LDLT_COLS;  // columns per step of the warp LDL^T fast path (<= 4; 2 measured best)
 
 // geometry: the (n+1) columns of [J|r] are cut into NB blocks of BLK columns (BLK = 4 for n <= 27,
 // 8 above), NP = NB*BLK padded columns, NB*(NB+1)/2 <= 28 upper-triangular blocks = busy lanes
@@ -54,7 +58,7 @@ __host__ __device__ constexpr int wpp_ldw(int np) { return ((np / 4) & 1) ? np :
 __host__ __device__ constexpr int wpp_nps(int np) { return ((np / 4) & 1) ? np : np + 4; }
 
 struct WppSmem {  // byte offsets inside one warp's shared memory
-  uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, stages, stage_bytes, jbuf, total;
+  uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, tx, stages, stage_bytes, jbuf, total;
 };
 __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   WppSmem L;
@@ -64,12 +68,15 @@ __host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
   L.xs = o; o += np * 4;
   L.last_dx = o; o += np * 4;
   L.g = o; o += np * 4;
-  L.dxs = o; o += np * 4;
   L.temp = o; o += np * 4;
   L.dg = o; o += np * 4;
-  L.dd = o; o += np * 4;
   L.perm = o; o += np * 4;
+  // dxs, dd, inv and tx are dead while the factorisation runs: together they are its kWppLdltCols x np
+  // buffer of D_j L_{k+c,j} rows
+  L.dxs = o; o += np * 4;
+  L.dd = o; o += np * 4;
   L.inv = o; o += np * 4;
+  L.tx = o; o += np * 4;
   o = (o + 127u) & ~127u;
   L.stages = o;
   L.stage_bytes = ((uint32_t)kWppRows * (uint32_t)(n + 1) * 4u + 127u) & ~127u;  // A rows, then y
@@ -209,15 +216,98 @@ __device__ __forceinline__ void wpp_pivot_order(const float *dd, int n, int *per
   __syncwarp();
 }
 
-// unpivoted left-looking LDL^T of the already permuted W (lower triangle, pitch ldw)
+// unpivoted left-looking LDL^T of the already permuted W (lower triangle, pitch ldw).
+//
+// Fast path: kWppLdltCols columns per step while the pivots are valid.  The dot product of column
+// k + c is sum_{j<k} L_ij (D_j L_{k+c,j}) followed by the terms j = k .. k + c - 1, and its first k
+// terms do not depend on the columns k .. k + c - 1 — so the columns of a step share one sweep over the
+// rows of L (one load of L_ij feeds every column's fma chain: with two columns 4 loads per 16 fmas instead
+// of 6 and four independent chains per lane instead of two; 3 and 4 columns measured slower), the pivots travel by shuffle instead of through shared
+// memory, and the remaining terms are appended as the columns before become final.  Every chain
+// still receives its terms in the order j = 0, 1, .., so the factor is bit-identical to the one-column
+// loop below, which remains as the path for zero / NaN pivots and for the last n % kWppLdltCols columns.
 template <typename T>
-__device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, T *temp, int lane) {
+__device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, T *temp, T *tbuf, int tp, int lane) {
   using O = Ops<T>;
 #define WW(i, j) W[(i) * ldw + (j)]
   if (n == 1) return !(WW(0, 0) < (T)0);
   int sign = 0;
   bool found_zero_pivot = false, ret = true;
-  for (int k = 0; k < n; ++k) {
+  int k = 0;
+  constexpr int C = kWppLdltCols;
+  bool bail = false;
+  for (; k + C <= n && !bail; ) {
+    // T_c[j] = D_j L_{k+c,j}, j < k, c < C (tbuf rows of pitch tp)
+    for (int j = lane; j < k; j += 32) {
+      const T d = WW(j, j);
+#pragma unroll
+      for (int c = 0; c < C; ++c) tbuf[c * tp + j] = O::mul(d, WW(k + c, j));
+    }
+    __syncwarp();
+    const int r0 = k + lane, r1 = k + lane + 32;  // lane c owns row k + c
+    const bool h0 = r0 < n, h1 = r1 < n;
+    const T *w0 = &WW(h0 ? r0 : k, 0);
+    const T *w1 = &WW(h1 ? r1 : k, 0);
+    T s0[C], s1[C];  // chains of columns k .. k + C - 1 for rows r0, r1
+#pragma unroll
+    for (int c = 0; c < C; ++c) { s0[c] = (T)0; s1[c] = (T)0; }
+    int j = 0;
+#pragma unroll 2
+    for (; j + 4 <= k; j += 4) {
+      const float4 a4 = *reinterpret_cast<const float4 *>(w0 + j);
+      const float4 b4 = *reinterpret_cast<const float4 *>(w1 + j);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float4 t4 = *reinterpret_cast<const float4 *>(tbuf + c * tp + j);
+        s0[c] = O::fma(a4.x, t4.x, s0[c]); s1[c] = O::fma(b4.x, t4.x, s1[c]);
+        s0[c] = O::fma(a4.y, t4.y, s0[c]); s1[c] = O::fma(b4.y, t4.y, s1[c]);
+        s0[c] = O::fma(a4.z, t4.z, s0[c]); s1[c] = O::fma(b4.z, t4.z, s1[c]);
+        s0[c] = O::fma(a4.w, t4.w, s0[c]); s1[c] = O::fma(b4.w, t4.w, s1[c]);
+      }
+    }
+    for (; j < k; ++j) {
+      const T a = w0[j], b = w1[j];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const T t = tbuf[c * tp + j];
+        s0[c] = O::fma(a, t, s0[c]);
+        s1[c] = O::fma(b, t, s1[c]);
+      }
+    }
+    // finish the C columns one after the other; column c first takes the terms j = k .. k + c - 1
+    T l0[C], l1[C];  // the final L values of my rows in columns k .. k + C - 1 (lane c: D_{k+c} in l0[c])
+    T dk[C];
+    int done = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (!bail) {
+#pragma unroll
+        for (int cc = 0; cc < c; ++cc) {
+          const T tk = O::mul(dk[cc], __shfl_sync(0xffffffffu, l0[cc], c));  // D_{k+cc} L_{k+c,k+cc}
+          if (lane > cc) s0[c] = O::fma(l0[cc], tk, s0[c]);
+          s1[c] = O::fma(l1[cc], tk, s1[c]);
+        }
+        const T e0 = O::sub(h0 ? w0[k + c] : (T)0, s0[c]), e1 = O::sub(h1 ? w1[k + c] : (T)0, s1[c]);
+        const T piv = __shfl_sync(0xffffffffu, e0, c);
+        if (!(O::abs(piv) > (T)0)) {
+          bail = true;  // columns k .. k + c - 1 are final and stored; the rest goes through the loop below
+        } else {
+          if (sign == 1) { if (piv < (T)0) sign = 2; }
+          else if (sign == -1) { if (piv > (T)0) sign = 2; }
+          else if (sign == 0) { if (piv > (T)0) sign = 1; else sign = -1; }
+          dk[c] = piv;
+          l0[c] = lane == c ? piv : O::div(e0, piv);
+          l1[c] = O::div(e1, piv);
+          if (lane >= c && h0) WW(r0, k + c) = l0[c];
+          if (h1) WW(r1, k + c) = l1[c];
+          done = c + 1;
+        }
+      }
+    }
+    __syncwarp();
+    k += done;
+  }
+  for (; k < n; ++k) {
     if (k > 0) {
       for (int j = lane; j < k; j += 32) temp[j] = O::mul(WW(j, j), WW(k, j));
       __syncwarp();
@@ -623,7 +713,7 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
       }
       __syncwarp();
       WPP_T(3);
-      const bool fact_ok = wpp_ldlt_factor<T>(W, LDW, n, temp, lane);  // gn.h:150-156
+      const bool fact_ok = wpp_ldlt_factor<T>(W, LDW, n, temp, dxs, NB * BLK, lane);  // gn.h:150-156
       WPP_T(4);
       if (fact_ok) {
         for (int j = lane; j < n; j += 32) temp[j] = -g[j];
@@ -794,7 +884,7 @@ __global__ void __launch_bounds__(kWppThreads, 2) wpp_build_solve_kernel(const _
     wpp_pivot_order(dd, n, perm, inv, lane);
     wpp_store_permuted<T, NB, BLK>(W, acc, bi, bj, has_block, n, dd, inv, nullptr);
     __syncwarp();
-    const bool ok = wpp_ldlt_factor<T>(W, LDW, n, temp, lane);  // math.h:232-240
+    const bool ok = wpp_ldlt_factor<T>(W, LDW, n, temp, dxs, NP, lane);  // math.h:232-240
     if (ok) {
       for (int j = lane; j < n; j += 32) temp[j] = -g[j];  // solvers/gn.h:155
       __syncwarp();
