@@ -119,10 +119,19 @@ def measured_tensor_peak():
 NCU_TRAFFIC = {"C2": 245.520640e6 + 11.821312e6, "C3": 3.178103e9 + 13.871360e6, "C4": None}
 
 
+def host_threads():
+    """Every host core this process may run on — NOT OMP_NUM_THREADS, which torchrun pins to 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference(cfg, sample_B, reps, nthreads=0):
     """The reference's CPU implementation of the path = the oracle port (Eigen is not in the image,
-    so the reference itself cannot be compiled: DESIGN.md §3), OpenMP over problems."""
+    so the reference itself cannot be compiled: DESIGN.md §3), OpenMP over problems, all host cores."""
     from oracle import oracle as O
+    nthreads = nthreads or host_threads()
     dt = np.float64 if cfg["dtype"] == "f64" else np.float32
     A, y, xs, x0 = O.synth_generate(sample_B, cfg["m"], cfg["n"], dt, seed=SEED, alpha=ALPHA, sigma=SIGMA)
     opt = O.default_options(**cfg["opts"])

@@ -243,17 +243,33 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   float *raw = reinterpret_cast<float *>(stages + (size_t)p.stages * stage_bytes);  // kLgRawStages x half_bytes
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(raw) + (size_t)kLgRawStages * p.half_bytes);
   uint64_t *full = bars, *empty = bars + kLgMaxStages, *tmem_full = bars + 2 * kLgMaxStages, *tmem_empty = tmem_full + 1;
-  uint64_t *raw_full = tmem_empty + 1, *raw_empty = raw_full + kLgRawStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kLgRawStages);
+  uint64_t *raw_full = tmem_empty + 1, *raw_empty = raw_full + kLgMaxStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kLgMaxStages);
+  // Ring geometry per strip.  The operand region (p.stages stages of the widest strip) and the raw region
+  // (kLgRawStages of them) are re-cut for every strip into stages of ITS width ncs, so a strip of 128 / 256
+  // columns runs 8 / 4 stages deep in the bytes that give the 512-column strip two: the narrow strips
+  // need few tensor cycles per stage and are otherwise bound by the hand-off and TMA latency.  Stage s
+  // of a strip owns barrier s; every role walks the same (strip, stage) sequence, so the use count of
+  // each barrier — whose parity is what a wait needs — is tracked per barrier in a bit mask.  Stages
+  // of different strips overlap at different offsets: a new strip starts only after the MMAs of the one
+  // before have completed (tmem_full), which drains both rings.
+  const uint32_t op_region = (uint32_t)p.stages * stage_bytes, raw_region = (uint32_t)kLgRawStages * p.half_bytes;
+  auto ring_geom = [&](int ncs, uint32_t &hb, uint32_t &S, uint32_t &R) {
+    hb = (uint32_t)ncs * (uint32_t)kLgStageK * 4u;  // bytes of the hi (== lo) part of a stage == of a raw stage
+    S = op_region / (2u * hb);
+    R = raw_region / hb;
+    if (S > (uint32_t)kLgMaxStages) S = kLgMaxStages;
+    if (R > (uint32_t)kLgMaxStages) R = kLgMaxStages;
+  };
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < kLgMaxStages; ++s) {
       mbar_init(&full[s], kLgProdWarps);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, kLgEpiWarps);
-    for (int s = 0; s < kLgRawStages; ++s) {
+    for (int s = 0; s < kLgMaxStages; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], kLgProdWarps);
     }
@@ -290,45 +306,52 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     // producers select 0 for them.
     // lane 0 owns the barrier; lanes 0..15 each issue one row copy (one instruction for the whole stage),
     // lanes 16..31 prefetch the rows of the stage after the ring into L2
-    uint32_t rs = 0, rph = 0;
+    uint32_t rawe_bits = 0, item = 0;  // bit s: parity of the use count of raw stage s
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       int64_t pr; int h;
       unit_of(idx, pr, h);
       if (lg_skip(p, pr)) continue;
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < 2; ++half, ++item) {
         const int r = half == 0 ? h : p.nstrips - 1 - h;
         if (half == 1 && r == h) break;
         const int c0 = 128 * r;
         const int ncs = (np - c0 < 128) ? 128 : (np - c0);
+        uint32_t hb, S, R, rs = 0;
+        ring_geom(ncs, hb, S, R);
         const int ccnt = (n - c0 < ncs) ? (n - c0) : ncs;  // real columns (> 0: c0 <= np - 32 < n)
         const uint32_t row_bytes = (uint32_t)ccnt * 4u;
         const float *Ap = p.A + (size_t)pr * m * n + c0;
         // L2 prefetch runs kLgPrefetchStages stages ahead of the copies (no shared memory needed): with two
         // raw stages alone only ~40 KB per SM would be in flight, far below what HBM latency needs
-        for (int d = kLgRawStages; d < kLgRawStages + kLgPrefetchStages; ++d) {
+        for (int d = 0; d < (int)R + kLgPrefetchStages; ++d) {
           const int prow = d * kLgStageK + (lane & 15);
           if (lane >= 16 && prow < m) tma_prefetch_l2(Ap + (size_t)prow * n, row_bytes);
         }
+        // drain (the rings are re-cut for this strip) — after the prefetches above, so that the first
+        // stages of the new strip are on their way into L2 while the old strip finishes
+        if (item > 0 && lane == 0) mbar_wait(tmem_full, (item - 1u) & 1u);
+        __syncwarp();
         for (int ks = 0; ks < ksteps; ++ks) {
           const int row0 = ks * kLgStageK;
           const int rows = (m - row0 < kLgStageK) ? (m - row0) : kLgStageK;
           if (lane == 0) {
-            mbar_wait(&raw_empty[rs], rph ^ 1u);
+            mbar_wait(&raw_empty[rs], ((rawe_bits >> rs) & 1u) ^ 1u);
             fence_proxy_async();  // the producers' generic reads of this stage precede the async writes
             if (p.debug & 4) mbar_arrive(&raw_full[rs]);  // timing experiment: no copies
             else mbar_expect_tx(&raw_full[rs], (uint32_t)rows * row_bytes);
           }
           __syncwarp();
           if (!(p.debug & 4)) {
-            float *dst = raw + (size_t)rs * (p.half_bytes / 4);
+            float *dst = raw + (size_t)rs * (hb / 4);
             if (lane < rows) {
               tma_bulk_g2s(dst + (size_t)lane * ncs, Ap + (size_t)(row0 + lane) * n, row_bytes, &raw_full[rs]);
             } else if (lane >= 16) {
-              const int prow = row0 + (kLgRawStages + kLgPrefetchStages) * kLgStageK + (lane - 16);
+              const int prow = row0 + ((int)R + kLgPrefetchStages) * kLgStageK + (lane - 16);
               if (prow < m) tma_prefetch_l2(Ap + (size_t)prow * n, row_bytes);
             }
           }
-          if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
+          rawe_bits ^= 1u << rs;
+          if (++rs == R) rs = 0;
         }
       }
     }
@@ -341,18 +364,20 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     // TF32 hi + lo, conflict-free 16-byte stores (one per column and part).
     const int w = warp - (kLgLoadWarp + 1);
     const int kc = w >> 2, cg = w & 3;  // K chunk (rows 4 kc .. 4 kc + 3 of the stage), column group of 128
-    uint32_t st = 0, ph = 0;    // operand ring position and its phase parity
-    uint32_t rs = 0, rph = 0;   // raw ring
+    uint32_t empty_bits = 0, rawf_bits = 0, item = 0;  // per-barrier use-count parities (see ring_geom)
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       int64_t pr; int h;
       unit_of(idx, pr, h);
       if (lg_skip(p, pr)) continue;
-     for (int half = 0; half < 2; ++half) {
+     for (int half = 0; half < 2; ++half, ++item) {
       const int r = half == 0 ? h : p.nstrips - 1 - h;
       if (half == 1 && r == h) break;
       const int c0 = 128 * r;
       const int ncs = (np - c0 < 128) ? 128 : (np - c0);  // columns staged (the A operand needs 128)
       const uint32_t lbo = (uint32_t)ncs * 16u;
+      uint32_t hb, S, R, st = 0, rs = 0;
+      ring_geom(ncs, hb, S, R);
+      if (item > 0) mbar_wait(tmem_full, (item - 1u) & 1u);  // drain: the rings are re-cut for this strip
       const int rr0 = 128 * cg + lane;  // my operand rows: rr0 + 32 q, q = 0..3
       const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
       // row scales: lane l keeps s of row 32 g + l for the group g of two stages being consumed and
@@ -372,18 +397,20 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         float sc[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) sc[t] = __shfl_sync(0xffffffffu, sg_cur, kLgStageK * (ks & 1) + 4 * kc + t);
-        mbar_wait(&raw_full[rs], rph);
-        const uint32_t rsrc = raw_u32 + rs * p.half_bytes + (uint32_t)((4 * kc) * ncs + rr0) * 4u;
+        mbar_wait(&raw_full[rs], (rawf_bits >> rs) & 1u);
+        const uint32_t rsrc = raw_u32 + rs * hb + (uint32_t)((4 * kc) * ncs + rr0) * 4u;
         const int row0 = ks * kLgStageK + 4 * kc;
         if (p.debug & 2) {  // timing experiment: barrier protocol only
-          mbar_wait(&empty[st], ph ^ 1u);
+          mbar_wait(&empty[st], ((empty_bits >> st) & 1u) ^ 1u);
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&full[st]);
             mbar_arrive(&raw_empty[rs]);
           }
-          if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
-          if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
+          empty_bits ^= 1u << st;
+          rawf_bits ^= 1u << rs;
+          if (++st == S) st = 0;
+          if (++rs == R) rs = 0;
           continue;
         }
         float bv[4][4];  // [q][t]: column rr0 + 32 q, row 4 kc + t
@@ -398,8 +425,8 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         // the raw stage is consumed once the values are in registers: release it before the transform
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[rs]);
-        mbar_wait(&empty[st], ph ^ 1u);
-        const uint32_t sb = stages_u32 + st * stage_bytes;
+        mbar_wait(&empty[st], ((empty_bits >> st) & 1u) ^ 1u);
+        const uint32_t sb = stages_u32 + st * 2u * hb;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = rr0 + 32 * q;  // operand row (column of A relative to c0)
@@ -413,20 +440,22 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
             }
             const uint32_t off = (uint32_t)kc * lbo + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
             sts_v4(sb + off, hi[0], hi[1], hi[2], hi[3]);
-            if (p.terms == 3) sts_v4(sb + p.half_bytes + off, lo[0], lo[1], lo[2], lo[3]);
+            if (p.terms == 3) sts_v4(sb + hb + off, lo[0], lo[1], lo[2], lo[3]);
           }
         }
         fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[st]);
-        if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
-        if (++rs == (uint32_t)kLgRawStages) { rs = 0; rph ^= 1u; }
+        empty_bits ^= 1u << st;
+        rawf_bits ^= 1u << rs;
+        if (++st == S) st = 0;
+        if (++rs == R) rs = 0;
       }
      }
     }
   } else if (warp == kLgMmaWarp) {
     // ===================== MMA issuer: one thread =====================
-    uint32_t st = 0, ph = 0, item = 0;
+    uint32_t full_bits = 0, item = 0;
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       int64_t pr; int h;
       unit_of(idx, pr, h);
@@ -436,6 +465,8 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       if (half == 1 && r == h) break;
       const int nb = np - 128 * r;  // accumulator columns of this strip
       const int ncs = nb < 128 ? 128 : nb;
+      uint32_t hb, S, R, st = 0;
+      ring_geom(ncs, hb, S, R);
       if (lane == 0) {
         mbar_wait(tmem_empty, (item & 1u) ^ 1u);  // the epilogue has drained the previous strip
         tc_fence_after();
@@ -443,14 +474,14 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       __syncwarp();
       for (int ks = 0; ks < ksteps; ++ks) {
         if (lane == 0) {
-          mbar_wait(&full[st], ph);
+          mbar_wait(&full[st], (full_bits >> st) & 1u);
           tc_fence_after();
-          const uint32_t sb0 = smem_u32(stages + (size_t)st * stage_bytes);
+          const uint32_t sb0 = smem_u32(stages) + st * 2u * hb;
           const uint32_t lbo = (uint32_t)ncs * 16u;  // K chunk c + 1 follows all the core matrices of chunk c
           for (int kk = 0; kk < kLgStageK / kLgMmaK && !(p.debug & 1); ++kk) {  // debug & 1: timing experiment, no MMAs
             const uint32_t sb = sb0 + (uint32_t)(2 * kk) * lbo;  // this K step: chunks 2 kk, 2 kk + 1
             const uint64_t a_hi = tc_desc_k_major(sb, lbo, 128u);
-            const uint64_t a_lo = tc_desc_k_major(sb + p.half_bytes, lbo, 128u);
+            const uint64_t a_lo = tc_desc_k_major(sb + hb, lbo, 128u);
             for (int n0 = 0; n0 < nb; n0 += 256) {
               const int N = (nb - n0 < 256) ? (nb - n0) : 256;
               const uint32_t idesc = tc_idesc_tf32(N);
@@ -458,7 +489,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
               const uint32_t d = tmem_base + (uint32_t)n0;
               tc_mma_tf32(d, a_hi, b_hi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
               if (p.terms == 3) {
-                const uint64_t b_lo = tc_desc_k_major(sb + p.half_bytes + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
+                const uint64_t b_lo = tc_desc_k_major(sb + hb + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
                 tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
                 tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
               }
@@ -468,7 +499,8 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
           if (ks == ksteps - 1) tc_commit(tmem_full);
         }
         __syncwarp();
-        if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1u; }
+        full_bits ^= 1u << st;
+        if (++st == S) st = 0;
       }
       ++item;
      }
