@@ -343,9 +343,39 @@ int lg_prepare(tob200_ctx *ctx, int64_t B, int m, int n, bool need_state, bool n
   return TOB200_OK;
 }
 
+// A [B][m][n] as the 2-D tensor {n columns, B * m rows} with boxes of {128 columns, kLgStageK rows} for the
+// TMA loader of lg_syrk_kernel.  cuTensorMapEncodeTiled is a driver entry point: fetched through the
+// runtime so that the library does not link libcuda directly.
+bool lg_encode_tmap(CUtensorMap *tm, const float *A, int64_t B, int m, int n) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    looked_up = true;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (EncodeFn)fn;
+  }
+  const int64_t rows = B * (int64_t)m;
+  if (!encode || m <= 0 || rows >= (int64_t)1 << 31 || (n % 4) != 0 || ((uintptr_t)A & 15) != 0) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)n * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kLgBoxCols, (cuuint32_t)kLgStageK};
+  const cuuint32_t estride[2] = {1, 1};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(A), gdim, gstride, box, estride,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 LgSyrkParams lg_syrk_params(tob200_ctx *ctx, const LgBuffers &b, const float *A, const float *scale,
                             const LmScalars<float> *rec, int64_t B, int m, int n, int is_lm) {
   LgSyrkParams sp;
+  std::memset(&sp.tmap, 0, sizeof(sp.tmap));
+  sp.use_tmap = (env_int("TOB200_LG_NO_TMAP", 0) == 0 && lg_encode_tmap(&sp.tmap, A, B, m, n)) ? 1 : 0;
   sp.A = A;
   sp.scale = scale;
   sp.rec = rec;

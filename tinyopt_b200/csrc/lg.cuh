@@ -26,6 +26,8 @@
 // solvers/gn.h:150-171, math.h:232-240, optimizers/optimizer.h:243-539.
 #pragma once
 
+#include <cstdio>
+
 #include "common.cuh"
 #include "lg_params.h"
 #include "lm_state.cuh"
@@ -222,6 +224,19 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
 __device__ __forceinline__ void sts_v4(uint32_t saddr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 2-D tiled TMA: one box of the tensor map (column c, row r = innermost-first coordinates) -> shared memory
+__device__ __forceinline__ void tma_load_box(void *smem_dst, const CUtensorMap *tmap, int c, int r, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c), "r"(r), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_box(const CUtensorMap *tmap, int c, int r) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c), "r"(r)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2(const void *gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
@@ -234,6 +249,10 @@ __device__ __forceinline__ bool lg_skip(const LgSyrkParams &p, int64_t pr) {
   return p.is_lm && !(fl & kFlagRebuild);
 }
 
+// timing experiment (TOB200_LG_DEBUG & 16): cycles the MMA thread of block 0 spends per strip index
+__device__ long long g_syrk_strip_cycles[8];
+__device__ int g_syrk_strip_count[8];
+
 __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid_constant__ LgSyrkParams p) {
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -241,7 +260,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   unsigned char *stages = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = 2u * p.half_bytes;
   float *raw = reinterpret_cast<float *>(stages + (size_t)p.stages * stage_bytes);  // kLgRawStages x half_bytes
-  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(raw) + (size_t)kLgRawStages * p.half_bytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(raw) + (size_t)kLgRawStages * lg_syrk_raw_bytes(p.np));
   uint64_t *full = bars, *empty = bars + kLgMaxStages, *tmem_full = bars + 2 * kLgMaxStages, *tmem_empty = tmem_full + 1;
   uint64_t *raw_full = tmem_empty + 1, *raw_empty = raw_full + kLgMaxStages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kLgMaxStages);
@@ -253,11 +272,12 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   // each barrier — whose parity is what a wait needs — is tracked per barrier in a bit mask.  Stages
   // of different strips overlap at different offsets: a new strip starts only after the MMAs of the one
   // before have completed (tmem_full), which drains both rings.
-  const uint32_t op_region = (uint32_t)p.stages * stage_bytes, raw_region = (uint32_t)kLgRawStages * p.half_bytes;
+  const uint32_t op_region = (uint32_t)p.stages * stage_bytes, raw_region = (uint32_t)kLgRawStages * lg_syrk_raw_bytes(p.np);
+  constexpr uint32_t kBoxBytes = kLgBoxCols * kLgStageK * 4;  // one TMA box: 16 rows x 128 columns
   auto ring_geom = [&](int ncs, uint32_t &hb, uint32_t &S, uint32_t &R) {
-    hb = (uint32_t)ncs * (uint32_t)kLgStageK * 4u;  // bytes of the hi (== lo) part of a stage == of a raw stage
+    hb = (uint32_t)ncs * (uint32_t)kLgStageK * 4u;  // bytes of the hi (== lo) part of an operand stage
     S = op_region / (2u * hb);
-    R = raw_region / hb;
+    R = raw_region / ((uint32_t)((ncs + kLgBoxCols - 1) / kLgBoxCols) * kBoxBytes);  // raw stage = whole boxes
     if (S > (uint32_t)kLgMaxStages) S = kLgMaxStages;
     if (R > (uint32_t)kLgMaxStages) R = kLgMaxStages;
   };
@@ -300,12 +320,11 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   const int ksteps = (m + kLgStageK - 1) / kLgStageK;
 
   if (warp == kLgLoadWarp) {
-    // ===================== loader: one thread streams raw rows of A with TMA bulk copies =====================
-    // A raw stage holds the 8 rows of one K step, columns [c0, c0 + ncs) of the strip (pitch ncs
-    // floats; one contiguous copy per row).  Pad columns >= n and rows >= m are simply not copied: the
-    // producers select 0 for them.
-    // lane 0 owns the barrier; lanes 0..15 each issue one row copy (one instruction for the whole stage),
-    // lanes 16..31 prefetch the rows of the stage after the ring into L2
+    // ===================== loader: streams raw rows of A with 2-D tensor-map TMA =====================
+    // A raw stage holds the kLgStageK rows of one stage, columns [c0, c0 + ncs) of the strip, as boxes of
+    // 128 columns (box b = [16 rows][128 floats], 8 KB).  Columns >= n are zero-filled by the TMA unit,
+    // rows >= m belong to the next problem: the producers select 0 for both.
+    // lane 0 owns the barrier; lane b < nbox issues the copy of box b, lane 16 + b its L2 prefetch
     uint32_t rawe_bits = 0, item = 0;  // bit s: parity of the use count of raw stage s
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       int64_t pr; int h;
@@ -318,14 +337,19 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         const int ncs = (np - c0 < 128) ? 128 : (np - c0);
         uint32_t hb, S, R, rs = 0;
         ring_geom(ncs, hb, S, R);
+        const int nbox = (ncs + kLgBoxCols - 1) / kLgBoxCols;  // boxes per stage (<= 4)
+        const uint32_t raw_stage = (uint32_t)nbox * kBoxBytes;
         const int ccnt = (n - c0 < ncs) ? (n - c0) : ncs;  // real columns (> 0: c0 <= np - 32 < n)
-        const uint32_t row_bytes = (uint32_t)ccnt * 4u;
         const float *Ap = p.A + (size_t)pr * m * n + c0;
-        // L2 prefetch runs kLgPrefetchStages stages ahead of the copies (no shared memory needed): with two
-        // raw stages alone only ~40 KB per SM would be in flight, far below what HBM latency needs
-        for (int d = 0; d < (int)R + kLgPrefetchStages; ++d) {
-          const int prow = d * kLgStageK + (lane & 15);
-          if (lane >= 16 && prow < m) tma_prefetch_l2(Ap + (size_t)prow * n, row_bytes);
+        const int grow0 = (int)(pr * m);  // first row of the problem in the {n, B * m} tensor
+        const int pf = (int)R + kLgPrefetchStages;  // L2 prefetch distance in stages
+        // The TMA unit retires roughly one bulk operation per 70 cycles per SM whatever its size, so a stage
+        // is ONE tensor copy per 128-column box (16 rows x 512 B, <= 4 per stage; 16 per-row copies + 16
+        // per-row prefetches made the loader the bottleneck at ~2300 cycles per stage for every strip width).
+        // L2 prefetch (same boxes) runs `pf` stages ahead: no shared memory needed.
+        if (p.use_tmap) {
+          for (int d = 0; d < pf; ++d)
+            if (lane < nbox && d * kLgStageK < m) tma_prefetch_box(&p.tmap, c0 + kLgBoxCols * lane, grow0 + d * kLgStageK);
         }
         // drain (the rings are re-cut for this strip) — after the prefetches above, so that the first
         // stages of the new strip are on their way into L2 while the old strip finishes
@@ -338,16 +362,26 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
             mbar_wait(&raw_empty[rs], ((rawe_bits >> rs) & 1u) ^ 1u);
             fence_proxy_async();  // the producers' generic reads of this stage precede the async writes
             if (p.debug & 4) mbar_arrive(&raw_full[rs]);  // timing experiment: no copies
-            else mbar_expect_tx(&raw_full[rs], (uint32_t)rows * row_bytes);
+            else if (p.use_tmap) mbar_expect_tx(&raw_full[rs], raw_stage);  // OOB parts of a box count too
+            else mbar_expect_tx(&raw_full[rs], (uint32_t)rows * (uint32_t)ccnt * 4u);
           }
           __syncwarp();
           if (!(p.debug & 4)) {
-            float *dst = raw + (size_t)rs * (hb / 4);
-            if (lane < rows) {
-              tma_bulk_g2s(dst + (size_t)lane * ncs, Ap + (size_t)(row0 + lane) * n, row_bytes, &raw_full[rs]);
-            } else if (lane >= 16) {
-              const int prow = row0 + ((int)R + kLgPrefetchStages) * kLgStageK + (lane - 16);
-              if (prow < m) tma_prefetch_l2(Ap + (size_t)prow * n, row_bytes);
+            unsigned char *dst = reinterpret_cast<unsigned char *>(raw) + (size_t)rs * raw_stage;
+            if (p.use_tmap) {
+              if (lane < nbox) {
+                tma_load_box(dst + (size_t)lane * kBoxBytes, &p.tmap, c0 + kLgBoxCols * lane, grow0 + row0, &raw_full[rs]);
+              } else if (lane >= 16 && lane - 16 < nbox && row0 + pf * kLgStageK < m) {
+                tma_prefetch_box(&p.tmap, c0 + kLgBoxCols * (lane - 16), grow0 + row0 + pf * kLgStageK);
+              }
+            } else if (lane < rows) {  // fallback: one bulk copy per row and box, same layout
+              for (int bx = 0; bx < nbox; ++bx) {
+                const int cc = ccnt - kLgBoxCols * bx;
+                if (cc > 0)
+                  tma_bulk_g2s(dst + (size_t)bx * kBoxBytes + (size_t)lane * (kLgBoxCols * 4),
+                               Ap + (size_t)(row0 + lane) * n + kLgBoxCols * bx,
+                               (uint32_t)(cc < kLgBoxCols ? cc : kLgBoxCols) * 4u, &raw_full[rs]);
+              }
             }
           }
           rawe_bits ^= 1u << rs;
@@ -359,7 +393,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     // ===================== producers =====================
     // An operand stage is the K-major image of 16 rows x ncs columns of diag(s) A (two MMA K steps):
     // operand row = column j of A, K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 4) of
-    // columns [128 cg, + 128) (cg = w % 4): lane l owns columns l + 32 q, q = 0..3, of that range —
+    // the cg-th quarter of the columns (cg = w % 4): lane l owns columns l + 32 q of that quarter —
     // conflict-free 4-byte reads of the raw stage (lane = consecutive column), scaled by s_i, split into
     // TF32 hi + lo, conflict-free 16-byte stores (one per column and part).
     const int w = warp - (kLgLoadWarp + 1);
@@ -377,8 +411,12 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       const uint32_t lbo = (uint32_t)ncs * 16u;
       uint32_t hb, S, R, st = 0, rs = 0;
       ring_geom(ncs, hb, S, R);
+      const uint32_t raw_stage = (uint32_t)((ncs + kLgBoxCols - 1) / kLgBoxCols) * kBoxBytes;
       if (item > 0) mbar_wait(tmem_full, (item - 1u) & 1u);  // drain: the rings are re-cut for this strip
-      const int rr0 = 128 * cg + lane;  // my operand rows: rr0 + 32 q, q = 0..3
+      // the strip's columns are spread over all four column groups (qn = ceil(ncs / 128) columns per lane),
+      // so a narrow strip costs every producer warp proportionally less instead of idling twelve of them
+      const int qn = (ncs + 127) / 128;
+      const int rr0 = 32 * qn * cg + lane;  // my operand rows: rr0 + 32 q, q < qn
       const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
       // row scales: lane l keeps s of row 32 g + l for the group g of two stages being consumed and
       // for the next one (one coalesced load per 32 rows, a whole group ahead of its use); the four
@@ -398,7 +436,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
 #pragma unroll
         for (int t = 0; t < 4; ++t) sc[t] = __shfl_sync(0xffffffffu, sg_cur, kLgStageK * (ks & 1) + 4 * kc + t);
         mbar_wait(&raw_full[rs], (rawf_bits >> rs) & 1u);
-        const uint32_t rsrc = raw_u32 + rs * hb + (uint32_t)((4 * kc) * ncs + rr0) * 4u;
+        const uint32_t rsrc = raw_u32 + rs * raw_stage + (uint32_t)(4 * kc) * (kLgBoxCols * 4u);  // row 4 kc of box 0
         const int row0 = ks * kLgStageK + 4 * kc;
         if (p.debug & 2) {  // timing experiment: barrier protocol only
           mbar_wait(&empty[st], ((empty_bits >> st) & 1u) ^ 1u);
@@ -417,10 +455,12 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = rr0 + 32 * q;
-          const bool cok = rr < ncs && c0 + rr < n;  // rr < ncs is warp uniform (ncs is a multiple of 32)
+          const bool cok = q < qn && rr < ncs && c0 + rr < n;  // q < qn, rr < ncs: warp uniform
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            bv[q][t] = (cok && row0 + t < m) ? lds_f32(rsrc + (uint32_t)(t * ncs + 32 * q) * 4u) : 0.f;
+            bv[q][t] = (cok && row0 + t < m)
+                           ? lds_f32(rsrc + (uint32_t)(rr >> 7) * kBoxBytes + (uint32_t)(t * kLgBoxCols + (rr & 127)) * 4u)
+                           : 0.f;
         }
         // the raw stage is consumed once the values are in registers: release it before the transform
         __syncwarp();
@@ -430,7 +470,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = rr0 + 32 * q;  // operand row (column of A relative to c0)
-          if (rr < ncs) {
+          if (q < qn && rr < ncs) {
             float v[4], hi[4], lo[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -467,6 +507,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       const int ncs = nb < 128 ? 128 : nb;
       uint32_t hb, S, R, st = 0;
       ring_geom(ncs, hb, S, R);
+      const long long t_strip = (p.debug & 16) ? clock64() : 0;
       if (lane == 0) {
         mbar_wait(tmem_empty, (item & 1u) ^ 1u);  // the epilogue has drained the previous strip
         tc_fence_after();
@@ -501,6 +542,10 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         __syncwarp();
         full_bits ^= 1u << st;
         if (++st == S) st = 0;
+      }
+      if ((p.debug & 16) && lane == 0 && blockIdx.x == 0) {
+        g_syrk_strip_cycles[r & 7] += clock64() - t_strip;
+        g_syrk_strip_count[r & 7] += 1;
       }
       ++item;
      }
@@ -541,6 +586,16 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if ((p.debug & 16) && blockIdx.x == 0 && tid == 0) {
+    for (int r = 0; r < p.nstrips && r < 8; ++r) {
+      if (g_syrk_strip_count[r])
+        printf("syrk block 0: strip %d: %d x %lld kcycles (%lld cycles per 16-row stage)\n", r, g_syrk_strip_count[r],
+               g_syrk_strip_cycles[r] / g_syrk_strip_count[r] / 1000,
+               g_syrk_strip_cycles[r] / g_syrk_strip_count[r] / (ksteps > 0 ? ksteps : 1));
+      g_syrk_strip_cycles[r] = 0;
+      g_syrk_strip_count[r] = 0;
+    }
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 

@@ -80,7 +80,7 @@ cudaError_t launch_lg_eval(const LgEvalParams &p, int num_sms, cudaStream_t st) 
 
 int lg_syrk_stages(int np) {
   const size_t stage = 2 * (size_t)lg_syrk_half_bytes(np);
-  int s = (int)((200 * 1024 - (size_t)kLgRawStages * lg_syrk_half_bytes(np)) / stage);
+  int s = (int)((200 * 1024 - (size_t)kLgRawStages * lg_syrk_raw_bytes(np)) / stage);
   if (s > kLgMaxStages) s = kLgMaxStages;
   if (s < 2) s = 2;
   return s;

@@ -2,6 +2,8 @@
 // lg_solve.cuh; launchers: lg_kernels.cu; orchestration: api.cu).
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "lm_state.cuh"
 
 namespace tob200 {
@@ -48,7 +50,11 @@ constexpr int kLgMmaK = 8;        // K extent of one tf32 tcgen05.mma
 constexpr int kLgStageK = 16;     // rows per stage == two MMA K steps (halves the barrier hand-offs per row)
 constexpr int kLgMaxStages = 8;
 
+constexpr int kLgBoxCols = 128;   // raw stages are built from TMA boxes of kLgStageK rows x 128 columns (8 KB)
+
 struct LgSyrkParams {
+  alignas(64) CUtensorMap tmap;  // A as a 2-D tensor {n columns, B * m rows}, box {128, kLgStageK}; valid iff use_tmap
+  int use_tmap;        // 0: per-row bulk copies into the same box layout (tensor map could not be encoded)
   const float *A;      // [B][m][n]
   const float *scale;  // [B][m] row scale, or nullptr (materialised J)
   const LmScalars<float> *rec;  // nullptr: every problem
@@ -63,9 +69,14 @@ struct LgSyrkParams {
 };
 
 __host__ __device__ inline uint32_t lg_syrk_half_bytes(int np) { return (uint32_t)(np < 128 ? 128 : np) * (uint32_t)kLgStageK * 4u; }
+// bytes of one raw stage of the widest strip: whole boxes
+__host__ __device__ inline uint32_t lg_syrk_raw_bytes(int np) {
+  const int w = np < 128 ? 128 : np;
+  return (uint32_t)((w + kLgBoxCols - 1) / kLgBoxCols) * (uint32_t)(kLgBoxCols * kLgStageK * 4);
+}
 __host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages) {
   // [1 KB alignment slack | operand stages (hi + lo) | raw stages | barriers]
-  return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np) + (size_t)kLgRawStages * lg_syrk_half_bytes(np) + 512;
+  return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np) + (size_t)kLgRawStages * lg_syrk_raw_bytes(np) + 512;
 }
 
 constexpr int kLgSolveThreads = 512;
