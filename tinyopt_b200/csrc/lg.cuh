@@ -272,12 +272,25 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   // each barrier — whose parity is what a wait needs — is tracked per barrier in a bit mask.  Stages
   // of different strips overlap at different offsets: a new strip starts only after the MMAs of the one
   // before have completed (tmem_full), which drains both rings.
+  const int np_ = p.np;
   const uint32_t op_region = (uint32_t)p.stages * stage_bytes, raw_region = (uint32_t)kLgRawStages * lg_syrk_raw_bytes(p.np);
   constexpr uint32_t kBoxBytes = kLgBoxCols * kLgStageK * 4;  // one TMA box: 16 rows x 128 columns
-  auto ring_geom = [&](int ncs, uint32_t &hb, uint32_t &S, uint32_t &R) {
-    hb = (uint32_t)ncs * (uint32_t)kLgStageK * 4u;  // bytes of the hi (== lo) part of an operand stage
-    S = op_region / (2u * hb);
-    R = raw_region / ((uint32_t)((ncs + kLgBoxCols - 1) / kLgBoxCols) * kBoxBytes);  // raw stage = whole boxes
+  // A stage holds RS rows: 16 for the wide strips, 32 / 64 for strips of <= 256 / 128 columns when the widest
+  // strip has 512, so that every stage carries about the same bytes and the per-stage hand-off cost
+  // (~1400 cycles whatever the width) is paid per byte, not per 16 rows.
+  const int np_boxes = ((np_ < 128 ? 128 : np_) + kLgBoxCols - 1) / kLgBoxCols;
+  auto ring_geom = [&](int ncs, int &RS, uint32_t &hb, uint32_t &S, uint32_t &R) {
+    const int ncg = (ncs + kLgBoxCols - 1) / kLgBoxCols;  // column groups == boxes per 16 rows
+    int rmul = np_boxes / ncg;                             // whole 16-row boxes that fit the widest raw stage
+    if (rmul > 4) rmul = 4;
+    for (;; rmul >>= 1) {
+      if (rmul < 1) rmul = 1;
+      RS = kLgStageK * rmul;
+      hb = (uint32_t)ncs * (uint32_t)RS * 4u;  // bytes of the hi (== lo) part of an operand stage
+      S = op_region / (2u * hb);
+      R = raw_region / ((uint32_t)(rmul * ncg) * kBoxBytes);  // raw stage = whole boxes
+      if ((S >= 2 && R >= 2) || rmul == 1) break;
+    }
     if (S > (uint32_t)kLgMaxStages) S = kLgMaxStages;
     if (R > (uint32_t)kLgMaxStages) R = kLgMaxStages;
   };
@@ -317,7 +330,6 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     if (rotate) h = (int)((h + (idx - blockIdx.x) / gridDim.x) % upp);
   };
   const int m = p.m, n = p.n, np = p.np;
-  const int ksteps = (m + kLgStageK - 1) / kLgStageK;
 
   if (warp == kLgLoadWarp) {
     // ===================== loader: streams raw rows of A with 2-D tensor-map TMA =====================
@@ -336,8 +348,11 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         const int c0 = 128 * r;
         const int ncs = (np - c0 < 128) ? 128 : (np - c0);
         uint32_t hb, S, R, rs = 0;
-        ring_geom(ncs, hb, S, R);
-        const int nbox = (ncs + kLgBoxCols - 1) / kLgBoxCols;  // boxes per stage (<= 4)
+        int RS;
+        ring_geom(ncs, RS, hb, S, R);
+        const int ksteps = (m + RS - 1) / RS;
+        const int ncg = (ncs + kLgBoxCols - 1) / kLgBoxCols;
+        const int nbox = ncg * (RS / kLgStageK);  // boxes per stage (<= 4): box b = (row box b / ncg, column box b % ncg)
         const uint32_t raw_stage = (uint32_t)nbox * kBoxBytes;
         const int ccnt = (n - c0 < ncs) ? (n - c0) : ncs;  // real columns (> 0: c0 <= np - 32 < n)
         const float *Ap = p.A + (size_t)pr * m * n + c0;
@@ -349,15 +364,16 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         // L2 prefetch (same boxes) runs `pf` stages ahead: no shared memory needed.
         if (p.use_tmap) {
           for (int d = 0; d < pf; ++d)
-            if (lane < nbox && d * kLgStageK < m) tma_prefetch_box(&p.tmap, c0 + kLgBoxCols * lane, grow0 + d * kLgStageK);
+            if (lane < nbox && d * RS + kLgStageK * (lane / ncg) < m)
+              tma_prefetch_box(&p.tmap, c0 + kLgBoxCols * (lane % ncg), grow0 + d * RS + kLgStageK * (lane / ncg));
         }
         // drain (the rings are re-cut for this strip) — after the prefetches above, so that the first
         // stages of the new strip are on their way into L2 while the old strip finishes
         if (item > 0 && lane == 0) mbar_wait(tmem_full, (item - 1u) & 1u);
         __syncwarp();
         for (int ks = 0; ks < ksteps; ++ks) {
-          const int row0 = ks * kLgStageK;
-          const int rows = (m - row0 < kLgStageK) ? (m - row0) : kLgStageK;
+          const int row0 = ks * RS;
+          const int rows = (m - row0 < RS) ? (m - row0) : RS;
           if (lane == 0) {
             mbar_wait(&raw_empty[rs], ((rawe_bits >> rs) & 1u) ^ 1u);
             fence_proxy_async();  // the producers' generic reads of this stage precede the async writes
@@ -370,17 +386,21 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
             unsigned char *dst = reinterpret_cast<unsigned char *>(raw) + (size_t)rs * raw_stage;
             if (p.use_tmap) {
               if (lane < nbox) {
-                tma_load_box(dst + (size_t)lane * kBoxBytes, &p.tmap, c0 + kLgBoxCols * lane, grow0 + row0, &raw_full[rs]);
-              } else if (lane >= 16 && lane - 16 < nbox && row0 + pf * kLgStageK < m) {
-                tma_prefetch_box(&p.tmap, c0 + kLgBoxCols * (lane - 16), grow0 + row0 + pf * kLgStageK);
+                tma_load_box(dst + (size_t)lane * kBoxBytes, &p.tmap, c0 + kLgBoxCols * (lane % ncg),
+                             grow0 + row0 + kLgStageK * (lane / ncg), &raw_full[rs]);
+              } else if (lane >= 16 && lane - 16 < nbox) {
+                const int prow = row0 + pf * RS + kLgStageK * ((lane - 16) / ncg);
+                if (prow < m) tma_prefetch_box(&p.tmap, c0 + kLgBoxCols * ((lane - 16) % ncg), grow0 + prow);
               }
-            } else if (lane < rows) {  // fallback: one bulk copy per row and box, same layout
-              for (int bx = 0; bx < nbox; ++bx) {
-                const int cc = ccnt - kLgBoxCols * bx;
-                if (cc > 0)
-                  tma_bulk_g2s(dst + (size_t)bx * kBoxBytes + (size_t)lane * (kLgBoxCols * 4),
-                               Ap + (size_t)(row0 + lane) * n + kLgBoxCols * bx,
-                               (uint32_t)(cc < kLgBoxCols ? cc : kLgBoxCols) * 4u, &raw_full[rs]);
+            } else {  // fallback: one bulk copy per row and column box, same layout
+              for (int rw = lane; rw < rows; rw += 32) {
+                for (int bx = 0; bx < ncg; ++bx) {
+                  const int cc = ccnt - kLgBoxCols * bx;
+                  if (cc > 0)
+                    tma_bulk_g2s(dst + (size_t)((rw / kLgStageK) * ncg + bx) * kBoxBytes + (size_t)(rw % kLgStageK) * (kLgBoxCols * 4),
+                                 Ap + (size_t)(row0 + rw) * n + kLgBoxCols * bx,
+                                 (uint32_t)(cc < kLgBoxCols ? cc : kLgBoxCols) * 4u, &raw_full[rs]);
+                }
               }
             }
           }
@@ -391,13 +411,13 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     }
   } else if (warp > kLgLoadWarp) {
     // ===================== producers =====================
-    // An operand stage is the K-major image of 16 rows x ncs columns of diag(s) A (two MMA K steps):
-    // operand row = column j of A, K = row i.  Warp w transposes rows 4 kc .. 4 kc + 3 (kc = w / 4) of
-    // the cg-th quarter of the columns (cg = w % 4): lane l owns columns l + 32 q of that quarter —
-    // conflict-free 4-byte reads of the raw stage (lane = consecutive column), scaled by s_i, split into
-    // TF32 hi + lo, conflict-free 16-byte stores (one per column and part).
+    // An operand stage is the K-major image of RS rows x ncs columns of diag(s) A (RS / 8 MMA K steps):
+    // operand row = column j of A, K = row i.  The stage is cut into K chunks of 4 rows and column groups
+    // of 128; warp w owns chunk kc = w / ncg of group cg = w % ncg (RS / 4 * ncg <= 16 warps), lane l the
+    // columns l + 32 q of the group — conflict-free 4-byte reads of the raw boxes (lane = consecutive
+    // column), scaled by s_i, split into TF32 hi + lo, conflict-free 16-byte stores (one per column and
+    // part).  Sixteen elements per lane and stage whatever the strip width.
     const int w = warp - (kLgLoadWarp + 1);
-    const int kc = w >> 2, cg = w & 3;  // K chunk (rows 4 kc .. 4 kc + 3 of the stage), column group of 128
     uint32_t empty_bits = 0, rawf_bits = 0, item = 0;  // per-barrier use-count parities (see ring_geom)
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       int64_t pr; int h;
@@ -410,35 +430,36 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       const int ncs = (np - c0 < 128) ? 128 : (np - c0);  // columns staged (the A operand needs 128)
       const uint32_t lbo = (uint32_t)ncs * 16u;
       uint32_t hb, S, R, st = 0, rs = 0;
-      ring_geom(ncs, hb, S, R);
-      const uint32_t raw_stage = (uint32_t)((ncs + kLgBoxCols - 1) / kLgBoxCols) * kBoxBytes;
+      int RS;
+      ring_geom(ncs, RS, hb, S, R);
+      const int ksteps = (m + RS - 1) / RS;
+      const int ncg = (ncs + kLgBoxCols - 1) / kLgBoxCols;
+      const uint32_t raw_stage = (uint32_t)(ncg * (RS / kLgStageK)) * kBoxBytes;
+      const int kc = w / ncg, cg = w % ncg;
+      const bool mine = kc < RS / 4;  // warp uniform; idle warps only keep the barrier protocol
       if (item > 0) mbar_wait(tmem_full, (item - 1u) & 1u);  // drain: the rings are re-cut for this strip
-      // the strip's columns are spread over all four column groups (qn = ceil(ncs / 128) columns per lane),
-      // so a narrow strip costs every producer warp proportionally less instead of idling twelve of them
-      const int qn = (ncs + 127) / 128;
-      const int rr0 = 32 * qn * cg + lane;  // my operand rows: rr0 + 32 q, q < qn
+      const int rr0 = kLgBoxCols * cg + lane;  // my operand rows: rr0 + 32 q, q = 0..3
       const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
-      // row scales: lane l keeps s of row 32 g + l for the group g of two stages being consumed and
-      // for the next one (one coalesced load per 32 rows, a whole group ahead of its use); the four
-      // values a K step needs are shuffled out of it
-      auto load_scale_group = [&](int g) {
-        const int row = 32 * g + lane;
-        return (row < m) ? (sp ? sp[row] : 1.f) : 0.f;
+      // row scales of my four rows: lanes 0..3 load them two stages ahead of their use, shuffled out below
+      auto load_scale = [&](int ks) {
+        const int row = ks * RS + 4 * kc + (lane & 3);
+        return (mine && ks < ksteps && row < m) ? (sp ? sp[row] : 1.f) : 0.f;
       };
-      float sg_cur = load_scale_group(0), sg_next = load_scale_group(1);
+      float sc_a = load_scale(0), sc_b = load_scale(1);
       const uint32_t raw_u32 = smem_u32(raw), stages_u32 = smem_u32(stages);
       for (int ks = 0; ks < ksteps; ++ks) {
-        if ((ks & 1) == 0 && ks > 0) {
-          sg_cur = sg_next;
-          sg_next = load_scale_group((ks >> 1) + 1);
-        }
+        const float sc_cur = sc_a;
+        sc_a = sc_b;
+        sc_b = load_scale(ks + 2);
         float sc[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) sc[t] = __shfl_sync(0xffffffffu, sg_cur, kLgStageK * (ks & 1) + 4 * kc + t);
+        for (int t = 0; t < 4; ++t) sc[t] = __shfl_sync(0xffffffffu, sc_cur, t);
         mbar_wait(&raw_full[rs], (rawf_bits >> rs) & 1u);
-        const uint32_t rsrc = raw_u32 + rs * raw_stage + (uint32_t)(4 * kc) * (kLgBoxCols * 4u);  // row 4 kc of box 0
-        const int row0 = ks * kLgStageK + 4 * kc;
-        if (p.debug & 2) {  // timing experiment: barrier protocol only
+        // row 4 kc + t of the stage sits in row box kc / 4, row 4 (kc % 4) + t of the box
+        const uint32_t rsrc = raw_u32 + rs * raw_stage + (uint32_t)((kc >> 2) * ncg) * kBoxBytes +
+                              (uint32_t)(4 * (kc & 3)) * (kLgBoxCols * 4u);
+        const int row0 = ks * RS + 4 * kc;
+        if ((p.debug & 2) || !mine) {  // idle warp (or timing experiment): barrier protocol only
           mbar_wait(&empty[st], ((empty_bits >> st) & 1u) ^ 1u);
           __syncwarp();
           if (lane == 0) {
@@ -455,11 +476,11 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = rr0 + 32 * q;
-          const bool cok = q < qn && rr < ncs && c0 + rr < n;  // q < qn, rr < ncs: warp uniform
+          const bool cok = rr < ncs && c0 + rr < n;  // rr < ncs is warp uniform (ncs is a multiple of 32)
 #pragma unroll
           for (int t = 0; t < 4; ++t)
             bv[q][t] = (cok && row0 + t < m)
-                           ? lds_f32(rsrc + (uint32_t)(rr >> 7) * kBoxBytes + (uint32_t)(t * kLgBoxCols + (rr & 127)) * 4u)
+                           ? lds_f32(rsrc + (uint32_t)cg * kBoxBytes + (uint32_t)(t * kLgBoxCols + 32 * q + lane) * 4u)
                            : 0.f;
         }
         // the raw stage is consumed once the values are in registers: release it before the transform
@@ -470,7 +491,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = rr0 + 32 * q;  // operand row (column of A relative to c0)
-          if (q < qn && rr < ncs) {
+          if (rr < ncs) {
             float v[4], hi[4], lo[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -506,7 +527,9 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       const int nb = np - 128 * r;  // accumulator columns of this strip
       const int ncs = nb < 128 ? 128 : nb;
       uint32_t hb, S, R, st = 0;
-      ring_geom(ncs, hb, S, R);
+      int RS;
+      ring_geom(ncs, RS, hb, S, R);
+      const int ksteps = (m + RS - 1) / RS;
       const long long t_strip = (p.debug & 16) ? clock64() : 0;
       if (lane == 0) {
         mbar_wait(tmem_empty, (item & 1u) ^ 1u);  // the epilogue has drained the previous strip
@@ -519,7 +542,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
           tc_fence_after();
           const uint32_t sb0 = smem_u32(stages) + st * 2u * hb;
           const uint32_t lbo = (uint32_t)ncs * 16u;  // K chunk c + 1 follows all the core matrices of chunk c
-          for (int kk = 0; kk < kLgStageK / kLgMmaK && !(p.debug & 1); ++kk) {  // debug & 1: timing experiment, no MMAs
+          for (int kk = 0; kk < RS / kLgMmaK && !(p.debug & 1); ++kk) {  // debug & 1: timing experiment, no MMAs
             const uint32_t sb = sb0 + (uint32_t)(2 * kk) * lbo;  // this K step: chunks 2 kk, 2 kk + 1
             const uint64_t a_hi = tc_desc_k_major(sb, lbo, 128u);
             const uint64_t a_lo = tc_desc_k_major(sb + hb, lbo, 128u);
@@ -544,7 +567,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         if (++st == S) st = 0;
       }
       if ((p.debug & 16) && lane == 0 && blockIdx.x == 0) {
-        g_syrk_strip_cycles[r & 7] += clock64() - t_strip;
+        g_syrk_strip_cycles[r & 7] += (clock64() - t_strip) * kLgStageK / RS;  // per 16 rows
         g_syrk_strip_count[r & 7] += 1;
       }
       ++item;
@@ -591,7 +614,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       if (g_syrk_strip_count[r])
         printf("syrk block 0: strip %d: %d x %lld kcycles (%lld cycles per 16-row stage)\n", r, g_syrk_strip_count[r],
                g_syrk_strip_cycles[r] / g_syrk_strip_count[r] / 1000,
-               g_syrk_strip_cycles[r] / g_syrk_strip_count[r] / (ksteps > 0 ? ksteps : 1));
+               g_syrk_strip_cycles[r] / g_syrk_strip_count[r] / ((m + kLgStageK - 1) / kLgStageK));
       g_syrk_strip_cycles[r] = 0;
       g_syrk_strip_count[r] = 0;
     }
