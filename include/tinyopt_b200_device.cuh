@@ -148,6 +148,71 @@ __host__ __device__ inline double cos(double x) { return ::cos(x); }
 __host__ __device__ inline float atan(float x) { return ::atanf(x); }
 __host__ __device__ inline double atan(double x) { return ::atan(x); }
 
+// ---- M-estimators: losses/robust_norms.h restated for device functors ----
+// Each takes the squared norm n2 of a residual block and the squared threshold th2 and returns the
+// robust loss together with the scale s = d loss / d n2 the reference returns as `J_scale`
+// (robust_norms.h: "the scale can then be used to solve JtJ * dx = Jt * res * s").  Templated on the
+// scalar, so they also differentiate through Jets.  Pinned by tests/robust_norms.cpp's closed forms and
+// its scale == autodiff-derivative check (tests/cuda/test_device_functor.cu, host side).
+namespace losses {
+template <typename S>
+struct Robust {
+  S loss, scale;
+};
+template <typename T, int N> __host__ __device__ inline T value_of(const Jet<T, N> &s) { return s.a; }
+__host__ __device__ inline float value_of(float s) { return s; }
+__host__ __device__ inline double value_of(double s) { return s; }
+
+/// robust_norms.h:32-55: loss = min(n2, th2), scale in {1, 0}
+template <typename S, typename T>
+__host__ __device__ inline Robust<S> Truncated(const S &n2, T th2) {
+  if (value_of(n2) <= th2) return {n2, S((T)1)};
+  return {S(th2), S((T)0)};
+}
+/// robust_norms.h:67-103: loss = n2 (inlier) or 2 th n - th2, scale = th / n
+template <typename S, typename T>
+__host__ __device__ inline Robust<S> Huber(const S &n2, T th2) {
+  if (value_of(n2) <= th2) return {n2, S((T)1)};
+  const T th = sqrt(th2);
+  const S n = sqrt(n2);
+  return {(T)2 * th * n - th2, th / n};
+}
+/// robust_norms.h:118-152: loss = th2 (1 - (1 - n2 / th2)^3) (inlier) or th2, scale = 3 (th2 - n2)^2 / th2^2 or 0
+template <typename S, typename T>
+__host__ __device__ inline Robust<S> Tukey(const S &n2, T th2) {
+  if (value_of(n2) <= th2) {
+    const S s = (T)1 - n2 / th2;
+    const S d = th2 - n2;
+    return {th2 * ((T)1 - s * s * s), (T)3 * d * d / (th2 * th2)};
+  }
+  return {S(th2), S((T)0)};
+}
+/// robust_norms.h:165-191: loss = th atan2(n2, th), scale = 1 / (n2^2 / th2 + 1)
+template <typename S, typename T>
+__host__ __device__ inline Robust<S> Arctan(const S &n2, T th2) {
+  const T th = sqrt(th2);
+  return {th * atan(n2 / th), (T)1 / (n2 * n2 / th2 + (T)1)};  // th > 0: atan2(n2, th) == atan(n2 / th)
+}
+/// robust_norms.h:204-228: loss = th2 log(1 + n2 / th2), scale = 1 / (1 + n2 / th2)
+template <typename S, typename T>
+__host__ __device__ inline Robust<S> Cauchy(const S &n2, T th2) {
+  const S s = (T)1 + n2 / th2;
+  return {th2 * log(s), (T)1 / s};
+}
+/// robust_norms.h:241-265: loss = n2 / (n2 + th2), scale = th2 / (n2 + th2)^2
+template <typename S, typename T>
+__host__ __device__ inline Robust<S> GemanMcClure(const S &n2, T th2) {
+  const S e = n2 + th2;
+  return {n2 / e, th2 / (e * e)};
+}
+/// robust_norms.h:278-303: loss = -log(exp(-n2) + exp(-th2)), scale = 1 / (exp(-th2) exp(n2) + 1)
+template <typename S, typename T>
+__host__ __device__ inline Robust<S> BlakeZisserman(const S &n2, T th2) {
+  const T eps = exp(-th2);
+  return {-log(exp(-n2) + eps), (T)1 / (eps * exp(n2) + (T)1)};
+}
+}  // namespace losses
+
 // ---- the accumulation site (a1: grad = J^T r, H = J^T J, cost = |r|^2; diff/optimize_autodiff.h:151-164)
 // One Emit lives in the registers of one thread for one pass.  Every accumulator receives its terms
 // in emission order: cost = fma(r, r, cost); g_j = fma(J_j, r, g_j); H_jk = fma(J_j, J_k, H_jk), j <= k.

@@ -197,7 +197,45 @@ static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
   for (tob200_result *q : {ra, rb, rc}) cudaFree(q);
 }
 
+// ---- 0. robust norms (host side: they are __host__ __device__) -------------------------------------
+// tests/robust_norms.cpp:53-110: loss == the closed form (+-1e-5) and the returned scale == d loss / d n2
+// (the reference checks it against its autodiff; here against the Jet of this header), th = 1.3, an
+// inlier (n2 = 0.3), a mid value (0.5) and an outlier (n2 = 2.3^2).
+template <typename F, typename E>
+static void check_norm(const char *name, F f, E expected) {
+  const double th = 1.3, th2 = th * th;
+  for (double n2 : {0.3, 0.5, 2.3 * 2.3}) {
+    const auto r = f(n2, th2);
+    CHECK(std::fabs(r.loss - expected(n2, th, th2)) < 1e-5);
+    const auto rj = f(dev::Jet<double, 1>(n2, 0), th2);
+    CHECK(std::fabs(rj.loss.a - r.loss) < 1e-12);
+    CHECK(std::fabs(rj.loss.v[0] - r.scale) < 1e-5);
+    if (std::fabs(rj.loss.v[0] - r.scale) >= 1e-5)
+      std::printf("  %s n2=%g: scale %g vs derivative %g\n", name, n2, r.scale, rj.loss.v[0]);
+  }
+}
+static void test_robust_norms() {
+  namespace L = dev::losses;
+  check_norm("Truncated", [](auto n2, double th2) { return L::Truncated(n2, th2); },
+             [](double n2, double th, double th2) { return std::sqrt(n2) > th ? th2 : n2; });
+  check_norm("Huber", [](auto n2, double th2) { return L::Huber(n2, th2); },
+             [](double n2, double th, double th2) { const double n = std::sqrt(n2); return n > th ? 2.0 * th * n - th2 : n2; });
+  check_norm("Tukey", [](auto n2, double th2) { return L::Tukey(n2, th2); },
+             [](double n2, double th, double th2) { return std::sqrt(n2) > th ? th2 : th2 * (1.0 - std::pow(1.0 - n2 / th2, 3.0)); });
+  check_norm("Arctan", [](auto n2, double th2) { return L::Arctan(n2, th2); },
+             [](double n2, double th, double) { return th * std::atan2(n2, th); });
+  check_norm("Cauchy", [](auto n2, double th2) { return L::Cauchy(n2, th2); },
+             [](double n2, double, double th2) { return th2 * std::log(1.0 + n2 / th2); });
+  check_norm("GemanMcClure", [](auto n2, double th2) { return L::GemanMcClure(n2, th2); },
+             [](double n2, double, double th2) { return n2 / (n2 + th2); });
+  check_norm("BlakeZisserman", [](auto n2, double th2) { return L::BlakeZisserman(n2, th2); },
+             [](double n2, double, double th2) { return -std::log(std::exp(-n2) + std::exp(-th2)); });
+  std::printf("robust norms: 7 M-estimators x 3 points: closed forms and scale == Jet derivative: %s\n",
+              g_failures ? "FAILED" : "ok");
+}
+
 int main() {
+  test_robust_norms();  // host arithmetic: runs with or without a GPU
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     std::printf("no CUDA device: the device functor path has no CPU fallback\n");

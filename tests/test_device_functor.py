@@ -26,6 +26,8 @@ def test_device_functor_builds_and_fails_loudly_without_gpu():
     p = subprocess.run([EXE], capture_output=True, text=True)
     assert p.returncode == 3, p.stdout + p.stderr
     assert "no CPU fallback" in p.stdout
+    # the M-estimators of the header are host arithmetic too: pinned by tests/robust_norms.cpp's closed forms
+    assert "robust norms: 7 M-estimators x 3 points: closed forms and scale == Jet derivative: ok" in p.stdout
 
 
 @pytest.mark.gpu
@@ -34,4 +36,5 @@ def test_device_functor_on_gpu():
     p = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "all device functor checks passed" in p.stdout
+    assert "closed forms and scale == Jet derivative: ok" in p.stdout
     assert "sqrt2 (Jet functor): x[0]=1.414213562373095" in p.stdout and "iters=5 stop=1" in p.stdout
