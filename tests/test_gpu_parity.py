@@ -303,7 +303,64 @@ def test_wpp_kernel_family(ctx):
     assert ctx.kernel_family(torch.float32, 12) == 1 and ctx.kernel_family(torch.float32, 13) == 2
     assert ctx.kernel_family(torch.float32, 55) == 2 and ctx.kernel_family(torch.float32, 56) == 3
     assert ctx.kernel_family(torch.float32, 57) == 0 and ctx.kernel_family(torch.float32, 512) == 3
-    assert ctx.kernel_family(torch.float64, 9) == 0
+    assert ctx.kernel_family(torch.float64, 8) == 1 and ctx.kernel_family(torch.float64, 9) == 2
+    assert ctx.kernel_family(torch.float64, 55) == 2 and ctx.kernel_family(torch.float64, 56) == 0
+
+
+WPP_SHAPES_F64 = [(64, 60, 9), (50, 37, 12), (40, 64, 13), (33, 90, 27), (35, 100, 28), (24, 200, 50), (9, 131, 55)]
+
+
+@pytest.mark.parametrize("B,m,n", WPP_SHAPES_F64)
+def test_wpp_double_lm_run_parity(ctx, B, m, n):
+    """double for 9 <= n <= 55 (the warp-per-problem family's scalar paths): the same canonical op
+    sequence as the oracle -> bit-exact x, costs, lambda, iteration counts under tinyopt's defaults."""
+    import tinyopt_b200 as tb
+    for layout in (tb.PROBLEM_MAJOR, tb.TILE32):
+        xo, ro, out = run_both(ctx, np.float64, B, m, n, layout=layout)
+        assert_lm_parity(np.float64, xo, ro, out)
+    assert (ro["stop_reason"] > 0).all()
+
+
+@pytest.mark.parametrize("B,m,n", [(30, 40, 10), (21, 77, 30), (12, 120, 50)])
+def test_wpp_double_build_solve_parity(ctx, B, m, n):
+    import tinyopt_b200 as tb
+    dtype = np.float64
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=3)
+    r, J = O.synth_eval(A, y, x0)
+    lam = np.full(B, 1e-4, dtype)
+    lam[::3] = 0
+    dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+    out = ctx.build_solve(torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(lam).cuda(), B=B,
+                          layout=tb.PROBLEM_MAJOR, want_H=True, want_g=True)
+    ctx.sync()
+    assert np.array_equal(out["status"].cpu().numpy(), st)
+    assert np.array_equal(out["cost"].cpu().numpy(), cost)
+    assert np.array_equal(out["g"].cpu().numpy(), g)
+    assert np.array_equal(out["H"].cpu().numpy(), H)
+    assert np.array_equal(out["dx"].cpu().numpy(), dx)
+    assert rel_err(out["dx"].cpu().numpy(), dx) <= 1e-10
+
+
+def test_wpp_double_degenerate(ctx):
+    """ties on the diagonal (Eigen's first-maximum order, the serial replay), a zero matrix and an indefinite
+    one through the double warp kernels."""
+    import tinyopt_b200 as tb
+    n, m, B = 20, 25, 4
+    rng = np.random.default_rng(3)
+    J = rng.standard_normal((B, m, n))
+    J[0] = 0; J[0, :n, :] = np.eye(n) * 2.0          # H = 4 I: every diagonal entry ties
+    J[1] = 0                                         # zero matrix: ZeroSign, accepted, dx = 0
+    J[2, :, 5] = J[2, :, 7]                          # two identical columns: singular, tie at (5, 7)
+    r = rng.standard_normal((B, m))
+    lam = np.zeros(B)
+    dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+    out = ctx.build_solve(torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(lam).cuda(), B=B,
+                          layout=tb.PROBLEM_MAJOR, want_H=True, want_g=True)
+    ctx.sync()
+    assert np.array_equal(out["status"].cpu().numpy(), st)
+    ok = st == 0
+    assert np.array_equal(out["dx"].cpu().numpy()[ok], dx[ok], equal_nan=True)
+    assert np.array_equal(out["H"].cpu().numpy(), H)
 
 
 @pytest.mark.parametrize("B,m,n", WPP_SHAPES)

@@ -227,9 +227,13 @@ int to_native_layout(tob200_ctx *ctx, int family, int layout, int64_t B, int m, 
   return TOB200_OK;
 }
 
-// launch geometry of a warp-per-problem kernel (family 2, float only)
+// launch geometry of a warp-per-problem kernel (family 2)
 typedef cudaError_t (*WppEntry)(int, int, int, const void *, const TppLaunch &, int *);
-inline WppEntry wpp_entry_for(int n) { return wpp_blk_for(n) == 4 ? wpp_entry_f32_blk4 : wpp_entry_f32_blk8; }
+template <typename T>
+inline WppEntry wpp_entry_for(int n) {
+  if (sizeof(T) == 8) return wpp_blk_for(n) == 4 ? wpp_entry_f64_blk4 : wpp_entry_f64_blk8;
+  return wpp_blk_for(n) == 4 ? wpp_entry_f32_blk4 : wpp_entry_f32_blk8;
+}
 
 template <typename T>
 int wpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, const T *A, const T *y, WppData<T> *d,
@@ -245,18 +249,19 @@ int wpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, const T *A
   d->m = m;
   d->n = n;
   d->stages = stages;
-  d->L = wpp_smem_layout(n, np, stages);
+  d->L = wpp_smem_layout(n, np, stages, (uint32_t)sizeof(T));
   // TMA bulk copies need 16-byte aligned sources and sizes for every chunk of every problem
-  d->use_tma = (aligned16(A) && aligned16(y) && ((int64_t)m * n) % 4 == 0 && m % 4 == 0) ? 1 : 0;
+  const int64_t per16 = 16 / (int64_t)sizeof(T);
+  d->use_tma = (aligned16(A) && aligned16(y) && ((int64_t)m * n) % per16 == 0 && m % per16 == 0) ? 1 : 0;
   d->counter = ctx->tile_counter;
   cfg->block = kWppThreads;
   cfg->smem = (size_t)d->L.total * warps;
   cfg->stream = ctx->stream;
-  const auto key = std::make_tuple(100 + blk, nb, kind, cfg->block, cfg->smem);
+  const auto key = std::make_tuple(100 * (int)sizeof(T) / 4 + blk, nb, kind, cfg->block, cfg->smem);
   auto it = ctx->occupancy.find(key);
   int per_sm = 0;
   if (it == ctx->occupancy.end()) {
-    cudaError_t e = wpp_entry_for(n)(kTppQuery, nb, kind, nullptr, *cfg, &per_sm);
+    cudaError_t e = wpp_entry_for<T>(n)(kTppQuery, nb, kind, nullptr, *cfg, &per_sm);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "occupancy query");
     if (per_sm < 1) return fail(ctx, TOB200_ERR_CUDA, "kernel does not fit on an SM (shared memory / registers)");
     ctx->occupancy[key] = per_sm;
@@ -276,11 +281,9 @@ int wpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, const T *A
   return TOB200_OK;
 }
 
-// float-only family: the double instantiation exists only so that the templates below compile
 template <typename T>
 int wpp_launch(tob200_ctx *ctx, int n, int kind, const void *params, const TppLaunch &cfg) {
-  if (sizeof(T) != 4) return fail(ctx, TOB200_ERR_UNSUPPORTED, "warp-per-problem kernels are float only");
-  CK(wpp_entry_for(n)(kTppLaunch, wpp_nb_for(n), kind, params, cfg, nullptr));
+  CK(wpp_entry_for<T>(n)(kTppLaunch, wpp_nb_for(n), kind, params, cfg, nullptr));
   ctx->launches++;
   return TOB200_OK;
 }
@@ -837,7 +840,7 @@ int tob200_kernel_family(int dtype, int n) {
     if (n <= kWppMaxN_f32) return 2;
     return (n <= kLgMaxN && n % 4 == 0) ? 3 : 0;  // rows must stay 16-byte aligned for the bulk copies
   }
-  if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : 0;
+  if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : (n <= kWppMaxN_f64 ? 2 : 0);  // family 2: scalar paths
   return 0;
 }
 

@@ -60,30 +60,31 @@ __host__ __device__ constexpr int wpp_nps(int np) { return ((np / 4) & 1) ? np :
 struct WppSmem {  // byte offsets inside one warp's shared memory
   uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, tx, stages, stage_bytes, jbuf, total;
 };
-__host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages) {
+// es = sizeof(scalar): 4 (float) or 8 (double)
+__host__ __device__ inline WppSmem wpp_smem_layout(int n, int np_, int stages, uint32_t es = 4) {
   WppSmem L;
   const uint32_t np = (uint32_t)np_;
   uint32_t o = 0;
   L.bars = o; o += 64;
-  L.xs = o; o += np * 4;
-  L.last_dx = o; o += np * 4;
-  L.g = o; o += np * 4;
-  L.temp = o; o += np * 4;
-  L.dg = o; o += np * 4;
-  L.perm = o; o += np * 4;
+  L.xs = o; o += np * es;
+  L.last_dx = o; o += np * es;
+  L.g = o; o += np * es;
+  L.temp = o; o += np * es;
+  L.dg = o; o += np * es;
+  L.perm = o; o += np * es;
   // dxs, dd, inv and tx are dead while the factorisation runs: together they are its kWppLdltCols x np
   // buffer of D_j L_{k+c,j} rows
-  L.dxs = o; o += np * 4;
-  L.dd = o; o += np * 4;
-  L.inv = o; o += np * 4;
-  L.tx = o; o += np * 4;
+  L.dxs = o; o += np * es;
+  L.dd = o; o += np * es;
+  L.inv = o; o += np * es;
+  L.tx = o; o += np * es;
   o = (o + 127u) & ~127u;
   L.stages = o;
-  L.stage_bytes = ((uint32_t)kWppRows * (uint32_t)(n + 1) * 4u + 127u) & ~127u;  // A rows, then y
+  L.stage_bytes = ((uint32_t)kWppRows * (uint32_t)(n + 1) * es + 127u) & ~127u;  // A rows, then y
   o += (uint32_t)stages * L.stage_bytes;
-  L.jbuf = o; o += (uint32_t)kWppRows * (uint32_t)wpp_nps(np_) * 4u;
+  L.jbuf = o; o += (uint32_t)kWppRows * (uint32_t)wpp_nps(np_) * es;
   // the LDLT working matrix aliases [stages .. jbuf end): make sure it fits
-  const uint32_t wbytes = np * (uint32_t)wpp_ldw(np_) * 4u;
+  const uint32_t wbytes = np * (uint32_t)wpp_ldw(np_) * es;
   if (o - L.stages < wbytes) o = L.stages + wbytes;
   L.total = (o + 127u) & ~127u;
   return L;
@@ -137,7 +138,7 @@ struct WppPipe {
     T *sy = sa + (size_t)kWppRows * n;
     if (use_tma) {
       if (lane == 0) {
-        const uint32_t ba = (uint32_t)nrows * (uint32_t)n * 4u, by = (uint32_t)nrows * 4u;
+        const uint32_t ba = (uint32_t)nrows * (uint32_t)n * (uint32_t)sizeof(T), by = (uint32_t)nrows * (uint32_t)sizeof(T);
         mbar_expect_tx(&bars[st], ba + by);
         tma_bulk_g2s(sa, ap + (size_t)row0 * n, ba, &bars[st]);
         tma_bulk_g2s(sy, yp + row0, by, &bars[st]);
@@ -164,6 +165,50 @@ struct WppPipe {
 
 // pos2orig of the pivot order for the diagonal dd[0..n) (n <= 64); writes perm[pos] = orig and
 // inv[orig] = pos.  "First maximum wins" and NaN handling as in Eigen's maxCoeff visitor.
+// Eigen's pivot search replayed literally on the diagonal by lane 0 (any scalar type): at step k the FIRST
+// largest |d| among positions k..n-1 is swapped to k (maxCoeff visitor: strict >, so a NaN never wins
+// and a NaN sitting at k stays).  The slow path of the double instantiation and of cov_kernels.cu.
+template <typename T>
+__device__ void wpp_pivot_order_serial(const T *dd, int n, int *perm, int *inv, int lane) {
+  using O = Ops<T>;
+  if (lane == 0) {
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    for (int k = 0; k < n; ++k) {
+      int p = k;
+      T best = O::abs(dd[perm[k]]);
+      for (int i = k + 1; i < n; ++i) {
+        const T v = O::abs(dd[perm[i]]);
+        if (v > best) { best = v; p = i; }
+      }
+      const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+    }
+    for (int k = 0; k < n; ++k) inv[perm[k]] = k;
+  }
+  __syncwarp();
+}
+
+// double: the same fast path (position = number of larger |d|, valid when all |d| are distinct and
+// none is NaN — a NaN equals nothing, not even itself, so its own count gives it away), else the replay
+__device__ __forceinline__ void wpp_pivot_order(const double *dd, int n, int *perm, int *inv, int lane) {
+  const int i0 = lane, i1 = lane + 32;
+  const double a0 = i0 < n ? fabs(dd[i0]) : 0.0, a1 = i1 < n ? fabs(dd[i1]) : 0.0;
+  int gt0 = 0, gt1 = 0, eq0 = 0, eq1 = 0;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const double v = fabs(dd[j]);
+    gt0 += v > a0; eq0 += v == a0;
+    gt1 += v > a1; eq1 += v == a1;
+  }
+  const bool amb = (i0 < n && eq0 != 1) || (i1 < n && eq1 != 1);
+  if (!__any_sync(0xffffffffu, amb)) {
+    if (i0 < n) { perm[gt0] = i0; inv[i0] = gt0; }
+    if (i1 < n) { perm[gt1] = i1; inv[i1] = gt1; }
+    __syncwarp();
+    return;
+  }
+  wpp_pivot_order_serial<double>(dd, n, perm, inv, lane);
+}
+
 __device__ __forceinline__ void wpp_pivot_order(const float *dd, int n, int *perm, int *inv, int lane) {
   const int i0 = lane, i1 = lane + 32;
   uint32_t k0 = 0, k1 = 0;  // 0: NaN (never wins), otherwise 1 + bits(|d|) (monotone in |d|)
@@ -216,6 +261,55 @@ __device__ __forceinline__ void wpp_pivot_order(const float *dd, int n, int *per
   __syncwarp();
 }
 
+// unpivoted left-looking LDL^T of the already permuted W (lower triangle, pitch ldw), lane = row, one
+// column per step, scalar loads: any scalar type.  Same bookkeeping (sign, zero pivots) and the same
+// per-element operation order as the float fast path below / the oracle's ldlt_factor_.
+template <typename T>
+__device__ bool wpp_ldlt_factor_generic(T *W, int ldw, int n, T *temp, int lane) {
+  using O = Ops<T>;
+#define WW(i, j) W[(i) * ldw + (j)]
+  if (n == 1) return !(WW(0, 0) < (T)0);
+  int sign = 0;
+  bool found_zero_pivot = false, ret = true;
+  for (int k = 0; k < n; ++k) {
+    if (k > 0) {
+      for (int j = lane; j < k; j += 32) temp[j] = O::mul(WW(j, j), WW(k, j));
+      __syncwarp();
+      for (int i = k + lane; i < n; i += 32) {  // row k itself: A_kk -= A10 . temp
+        T s = (T)0;
+        for (int j = 0; j < k; ++j) s = O::fma(WW(i, j), temp[j], s);
+        WW(i, k) = O::sub(WW(i, k), s);
+      }
+      __syncwarp();
+    }
+    const T akk = WW(k, k);
+    const bool pivot_is_valid = O::abs(akk) > (T)0;
+    if (k == 0 && !pivot_is_valid) {  // the whole diagonal is zero
+      bool z = true;
+      for (int j = 0; j < n; ++j)
+        for (int i = j + 1 + lane; i < n; i += 32) z = z && (WW(i, j) == (T)0);
+      return __all_sync(0xffffffffu, z);
+    }
+    if (k < n - 1) {
+      if (pivot_is_valid) {
+        for (int i = k + 1 + lane; i < n; i += 32) WW(i, k) = O::div(WW(i, k), akk);
+      } else {
+        bool z = true;
+        for (int i = k + 1 + lane; i < n; i += 32) z = z && (WW(i, k) == (T)0);
+        ret = ret && __all_sync(0xffffffffu, z);
+      }
+      __syncwarp();
+    }
+    if (found_zero_pivot && pivot_is_valid) ret = false;
+    else if (!pivot_is_valid) found_zero_pivot = true;
+    if (sign == 1) { if (akk < (T)0) sign = 2; }
+    else if (sign == -1) { if (akk > (T)0) sign = 2; }
+    else if (sign == 0) { if (akk > (T)0) sign = 1; else if (akk < (T)0) sign = -1; }
+  }
+  return ret && (sign == 1 || sign == 0);
+#undef WW
+}
+
 // unpivoted left-looking LDL^T of the already permuted W (lower triangle, pitch ldw).
 //
 // Fast path: kWppLdltCols columns per step while the pivots are valid.  The dot product of column
@@ -229,6 +323,9 @@ __device__ __forceinline__ void wpp_pivot_order(const float *dd, int n, int *per
 template <typename T>
 __device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, T *temp, T *tbuf, int tp, int lane) {
   using O = Ops<T>;
+  if constexpr (sizeof(T) != 4) {  // the vector loads below are float specific
+    return wpp_ldlt_factor_generic<T>(W, ldw, n, temp, lane);
+  } else {
 #define WW(i, j) W[(i) * ldw + (j)]
   if (n == 1) return !(WW(0, 0) < (T)0);
   int sign = 0;
@@ -366,6 +463,7 @@ __device__ __forceinline__ bool wpp_ldlt_factor(T *W, int ldw, int n, T *temp, T
   }
   return ret && (sign == 1 || sign == 0);
 #undef WW
+  }
 }
 
 // x (shared, n values, original order) <- P^T L^-T D^+ L^-1 P b;  n <= 64
@@ -442,11 +540,18 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
   T *jbuf = reinterpret_cast<T *>(ws + d.L.jbuf);
   // accumulators as packed FP32 pairs (acc[u][2 h], acc[u][2 h + 1]): FFMA2 (fma.rn.f32x2) does two
   // IEEE fused multiply-adds per issue slot, same roundings as two scalar fmas
+  constexpr bool kF32 = sizeof(T) == 4;  // the vector / FFMA2 paths are float specific; double takes scalar ones
   unsigned long long acc2[BLK][BLK / 2];
 #pragma unroll
   for (int u = 0; u < BLK; ++u)
 #pragma unroll
     for (int h = 0; h < BLK / 2; ++h) acc2[u][h] = 0ull;
+  if constexpr (!kF32) {
+#pragma unroll
+    for (int u = 0; u < BLK; ++u)
+#pragma unroll
+      for (int v = 0; v < BLK; ++v) acc[u][v] = (T)0;
+  }
   cost_only = (T)0;
 
   const int nchunks = (m + kWppRows - 1) / kWppRows;
@@ -478,16 +583,21 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       T ri, sc = (T)1;
       if (kSynth) {
         T t = (T)0;
-        if ((n & 1) == 0) {  // even n: rows are 8-byte aligned, two columns per load
-          const float2 *a2 = reinterpret_cast<const float2 *>(arow);
-          const float2 *x2 = reinterpret_cast<const float2 *>(xs);
+        bool done = false;
+        if constexpr (kF32) {
+          if ((n & 1) == 0) {  // even n: rows are 8-byte aligned, two columns per load
+            const float2 *a2 = reinterpret_cast<const float2 *>(arow);
+            const float2 *x2 = reinterpret_cast<const float2 *>(xs);
 #pragma unroll 8
-          for (int j = 0; j < n / 2; ++j) {
-            const float2 av = a2[j], xv = x2[j];
-            t = O::fma(av.x, xv.x, t);
-            t = O::fma(av.y, xv.y, t);
+            for (int j = 0; j < n / 2; ++j) {
+              const float2 av = a2[j], xv = x2[j];
+              t = O::fma(av.x, xv.x, t);
+              t = O::fma(av.y, xv.y, t);
+            }
+            done = true;
           }
-        } else {
+        }
+        if (!done) {
 #pragma unroll 8
           for (int j = 0; j < n; ++j) t = O::fma(arow[j], xs[j], t);
         }
@@ -498,6 +608,16 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
         ri = sy[lane];
       }
       if (do_rebuild) {
+       if constexpr (!kF32) {
+        T *jrow = jbuf + lane * NPS;
+#pragma unroll 4
+        for (int j = 0; j < NP; ++j) {
+          T v = (T)0;
+          if (j < n) v = kSynth ? O::mul(sc, arow[j]) : arow[j];
+          else if (j == n) v = ri;
+          jrow[j] = v;
+        }
+       } else {
         float4 *jrow = reinterpret_cast<float4 *>(jbuf + lane * NPS);
         if ((n & 1) == 0) {
           const float2 *a2 = reinterpret_cast<const float2 *>(arow);
@@ -526,6 +646,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
             jrow[q4] = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
+       }
       } else {
         jbuf[lane * NPS + n] = ri;
       }
@@ -544,6 +665,17 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       if (has_block) {
         const T *pa = jbuf + bi * BLK;
         const T *pb = jbuf + bj * BLK;
+       if constexpr (!kF32) {
+        for (int i = 0; i < nrows; ++i) {
+          T a[BLK], b[BLK];
+#pragma unroll
+          for (int u = 0; u < BLK; ++u) { a[u] = pa[i * NPS + u]; b[u] = pb[i * NPS + u]; }
+#pragma unroll
+          for (int u = 0; u < BLK; ++u)
+#pragma unroll
+            for (int v = 0; v < BLK; ++v) acc[u][v] = O::fma(a[u], b[v], acc[u][v]);
+        }
+       } else {
 #pragma unroll 2
         for (int i = 0; i < nrows; ++i) {
           T a[BLK], b[BLK];
@@ -559,6 +691,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
 #pragma unroll
             for (int h = 0; h < BLK / 2; ++h) ffma2_bcast(acc2[u][h], a[u], b[2 * h], b[2 * h + 1]);
         }
+       }
       }
     } else if (lane == 0) {  // cost-only pass (solvers/gn.h:98-105): sum r_i^2 in row order
       for (int i = 0; i < nrows; ++i) {
@@ -570,13 +703,15 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     WPP_T(2);
   }
   cost_only = __shfl_sync(0xffffffffu, cost_only, 0);
+  if constexpr (kF32) {
 #pragma unroll
-  for (int u = 0; u < BLK; ++u)
+    for (int u = 0; u < BLK; ++u)
 #pragma unroll
-    for (int h = 0; h < BLK / 2; ++h) {
-      acc[u][2 * h] = __uint_as_float((uint32_t)acc2[u][h]);
-      acc[u][2 * h + 1] = __uint_as_float((uint32_t)(acc2[u][h] >> 32));
-    }
+      for (int h = 0; h < BLK / 2; ++h) {
+        acc[u][2 * h] = __uint_as_float((uint32_t)acc2[u][h]);
+        acc[u][2 * h + 1] = __uint_as_float((uint32_t)(acc2[u][h] >> 32));
+      }
+  }
 }
 
 // ---- moving the register blocks of [J|r]^T [J|r] out ---------------------------------------------------
@@ -769,7 +904,7 @@ struct WppRunParams {
 };
 
 template <typename T, int NB, int BLK>
-__global__ void __launch_bounds__(kWppThreads, 3) wpp_lm_run_kernel(const __grid_constant__ WppRunParams<T> p) {
+__global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 3 : 1) wpp_lm_run_kernel(const __grid_constant__ WppRunParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x / 32;
@@ -832,7 +967,7 @@ struct WppBuildSolveParams {
 };
 
 template <typename T, int NB, int BLK>
-__global__ void __launch_bounds__(kWppThreads, 2) wpp_build_solve_kernel(const __grid_constant__ WppBuildSolveParams<T> p) {
+__global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 2 : 1) wpp_build_solve_kernel(const __grid_constant__ WppBuildSolveParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x / 32;

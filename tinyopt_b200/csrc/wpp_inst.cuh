@@ -39,10 +39,27 @@ cudaError_t wpp_entry_one(int op, int kind, const void *params, const TppLaunch 
     }                                                                                      \
   }
 
+// the double instantiation also serves n = 9..12 (n + 1 <= 12: three blocks of 4)
+#define TOB200_WPP_ENTRY_DEFINE3(name, T, BLK)                                             \
+  TOB200_WPP_ENTRY_DECL(name) {                                                            \
+    switch (nb) {                                                                          \
+      case 3: return wpp_entry_one<T, 3, BLK>(op, kind, params, cfg, out);                 \
+      case 4: return wpp_entry_one<T, 4, BLK>(op, kind, params, cfg, out);                 \
+      case 5: return wpp_entry_one<T, 5, BLK>(op, kind, params, cfg, out);                 \
+      case 6: return wpp_entry_one<T, 6, BLK>(op, kind, params, cfg, out);                 \
+      case 7: return wpp_entry_one<T, 7, BLK>(op, kind, params, cfg, out);                 \
+      default: return cudaErrorInvalidValue;                                               \
+    }                                                                                      \
+  }
+
 constexpr int kWppMinN_f32 = kTppMaxN_f32 + 1;  // 13
 constexpr int kWppMaxN_f32 = 55;                // n + 1 <= 7 * 8
+constexpr int kWppMinN_f64 = kTppMaxN_f64 + 1;  // 9
+constexpr int kWppMaxN_f64 = 55;
 
 TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk4);  // n = 13..27
 TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk8);  // n = 28..55
+TOB200_WPP_ENTRY_DECL(wpp_entry_f64_blk4);  // n = 9..27, scalar paths (functional coverage of double)
+TOB200_WPP_ENTRY_DECL(wpp_entry_f64_blk8);  // n = 28..55
 
 }  // namespace tob200
