@@ -219,7 +219,9 @@ int tob200_lm_run_host_f64(tob200_ctx *ctx, const tob200_options *opt, const dou
  * A batched `Optimizer_<SolverLM>` whose per-problem state (x, lambda_, prev_lambda_, bad_factor_,
  * rebuild flag, H_, grad_, Output counters) lives on the device.  Each tob200_solver_step is one
  * Optimizer_::Step + the OptimizeAcc update (optimizer.h:266-309) for every still-running problem,
- * fed with the residual blocks the caller's lambda produced at the current x. */
+ * fed with the residual blocks the caller's lambda produced at the current x.
+ * n <= 55, float and double (kernel families 1 and 2); bit-identical to tob200_lm_run_* for the same
+ * residual blocks. */
 int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob200_options *opt,
                          tob200_solver **out);
 int tob200_solver_destroy(tob200_solver *s);

@@ -243,6 +243,8 @@ int main() {
     test_covariance(ctx);
     test_family_equivalence<double>(ctx, 6, 30);
     test_family_equivalence<float>(ctx, 12, 40);
+    test_family_equivalence<float>(ctx, 20, 64);    // warp-per-problem family behind the same SolverType seam
+    test_family_equivalence<double>(ctx, 30, 90);
     test_misuse(ctx);
   } catch (const Error &e) {
     std::printf("tinyopt::b200::Error (%d): %s\n", e.code, e.what());

@@ -166,28 +166,43 @@ def _prior_acc(x, g, H):
     return r * r
 
 
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_solver_matches_fused_run(ctx, dtype):
-    """The host-driven loop fed with the family's residual blocks must reproduce tob200_lm_run and
-    the oracle exactly (same op sequence once J is materialised: sc * a_j is rounded before use in
-    both)."""
+@pytest.mark.parametrize("dtype,B,m,n", [(np.float64, 300, 30, 6), (np.float32, 300, 30, 6),
+                                         (np.float32, 64, 90, 20), (np.float64, 64, 90, 20),
+                                         (np.float32, 40, 120, 50), (np.float64, 24, 100, 40),
+                                         (np.float64, 33, 40, 9), (np.float32, 17, 131, 55)])
+def test_solver_matches_fused_run(ctx, dtype, B, m, n):
+    """The host-driven loop (the SolverType seam, thread- and warp-per-problem families) fed with the
+    family's residual blocks must reproduce tob200_lm_run and the oracle exactly (same op sequence once J
+    is materialised: sc * a_j is rounded before use in both)."""
     import tinyopt_b200 as tb
     tdt = torch.float64 if dtype == np.float64 else torch.float32
-    B, m, n = 300, 30, 6
+    layout = tb.TILE32 if ctx.kernel_family(tdt, n) == 1 else tb.PROBLEM_MAJOR
     kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dtype == np.float32 else {}
     A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=3)
     xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
-    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, tdt, p0=3, layout=tb.TILE32)
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, tdt, p0=3, layout=layout)
     s = tb.BatchSolver(ctx, B, n, tdt, tb.options(**kw))
     s.reset(dx0)
-    while s.num_active() > 0:
-        r, J = ctx.synth_eval(dA, dy, s.x, layout=tb.TILE32)
-        s.step(J, r, layout=tb.TILE32)
+    steps = 0
+    while s.num_active() > 0 and steps < 200:
+        r, J = ctx.synth_eval(dA, dy, s.x, layout=layout)
+        s.step(J, r, layout=layout)
+        steps += 1
     res = s.results()
     assert np.array_equal(res["num_iters"], ro["num_iters"])
     assert np.array_equal(res["stop_reason"], ro["stop_reason"])
     assert np.array_equal(s.x.cpu().numpy(), xo)
     assert np.array_equal(res["final_cost"], ro["final_cost"])
+    # Output::final_hessian (un-damped J^T J of the last rebuild) and Output::Covariance() = its inverse
+    H = s.final_hessian().cpu().numpy()
+    cov, st = s.covariance()
+    ctx.sync()
+    assert (st.cpu().numpy() == 0).all()
+    assert np.array_equal(H, np.swapaxes(H, 1, 2))
+    eye_err = np.abs(np.einsum("bij,bjk->bik", cov.cpu().numpy(), H) - np.eye(n)).max()
+    assert eye_err < (1e-9 if dtype == np.float64 else 1e-4), eye_err
+    for b in range(min(B, 3)):
+        assert np.array_equal(cov[b].cpu().numpy(), O.inv_cov(H[b]))
     s.close()
 
 

@@ -693,6 +693,8 @@ struct tob200_solver {
   int32_t *needs = nullptr;
   unsigned long long *n_active = nullptr;  // device
   bool is_reset = false;
+  int family = 1;          // 1: thread per problem (H_, grad_ tile-interleaved), 2: warp per problem ([B][NP * LDW], [B][NP])
+  size_t h_bytes = 0, g_bytes = 0;
 };
 
 namespace {
@@ -710,8 +712,28 @@ int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m
     if (m < 0) return fail(ctx, TOB200_ERR_INVALID, "m < 0");
     if (!J || !r) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
     if (!aligned16(J) || !aligned16(r)) return fail(ctx, TOB200_ERR_INVALID, "J and r must be 16-byte aligned");
-    int rc = to_native_layout<T>(ctx, 1, layout, B, m, n, &J, &r);
+    int rc = to_native_layout<T>(ctx, s->family, layout, B, m, n, &J, &r);
     if (rc != TOB200_OK) return rc;
+  }
+  if (s->family == 2) {  // warp per problem (wpp_step.cuh)
+    WppStepParams<T> p;
+    TppLaunch cfg;
+    int rc = wpp_configure<T>(ctx, n, reset ? 1 : m, B, kWppStep, J, r, &p.d, &cfg);
+    if (rc != TOB200_OK) return rc;
+    p.opt = make_dev_options<T>(s->opt);
+    p.rec = (StateRec<T> *)s->rec;
+    p.x = (T *)s->x;
+    p.last_dx = (T *)s->last_dx;
+    p.H = (T *)s->H;
+    p.g = (T *)s->g;
+    p.needs = s->needs;
+    p.n_active = s->n_active;
+    p.reset = reset;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaMemsetAsync(s->n_active, 0, sizeof(unsigned long long), ctx->stream));
+    if ((rc = wpp_launch<T>(ctx, n, kWppStep, &p, cfg)) != TOB200_OK) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    return TOB200_OK;
   }
   TppStepParams<T> p;
   TppLaunch cfg;
@@ -1114,8 +1136,9 @@ int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob
   int rc = check_options(ctx, opt);
   if (rc != TOB200_OK) return rc;
   if (B < 1 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 1 and n >= 1");
-  if (tob200_kernel_family(dtype, n) != 1)
-    return fail(ctx, TOB200_ERR_UNSUPPORTED, "solver: n has no kernel yet for this dtype");
+  const int family = tob200_kernel_family(dtype, n);
+  if (family != 1 && family != 2)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "solver: n has no kernel yet for this dtype (n <= 55)");
   DeviceGuard guard(ctx->device);
   tob200_solver *s = new (std::nothrow) tob200_solver();
   if (!s) return fail(ctx, TOB200_ERR_NOMEM, "host allocation failed");
@@ -1134,8 +1157,17 @@ int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob
   alloc(&s->rec, rec_bytes * B);
   alloc(&s->x, elt * B * n);
   alloc(&s->last_dx, elt * B * n);
-  alloc(&s->H, elt * ntiles * tri_count(n) * kTile);
-  alloc(&s->g, elt * ntiles * n * kTile);
+  s->family = family;
+  if (family == 1) {
+    s->h_bytes = elt * ntiles * tri_count(n) * kTile;
+    s->g_bytes = elt * ntiles * n * kTile;
+  } else {
+    const int np = wpp_nb_for(n) * wpp_blk_for(n);
+    s->h_bytes = elt * (size_t)B * np * wpp_ldw(np);
+    s->g_bytes = elt * (size_t)B * np;
+  }
+  alloc(&s->H, s->h_bytes);
+  alloc(&s->g, s->g_bytes);
   alloc((void **)&s->needs, sizeof(int32_t) * B);
   alloc((void **)&s->n_active, sizeof(unsigned long long));
   if (e != cudaSuccess) {
@@ -1168,9 +1200,8 @@ int tob200_solver_reset(tob200_solver *s, const void *x0) {
   DeviceGuard guard(ctx->device);
   const size_t elt = s->dtype == TOB200_F32 ? 4 : 8;
   CK(cudaMemcpyAsync(s->x, x0, elt * s->B * s->n, cudaMemcpyDeviceToDevice, ctx->stream));
-  const size_t ntiles = (size_t)((s->B + kTile - 1) / kTile);
-  CK(cudaMemsetAsync(s->H, 0, elt * ntiles * tri_count(s->n) * kTile, ctx->stream));
-  CK(cudaMemsetAsync(s->g, 0, elt * ntiles * s->n * kTile, ctx->stream));
+  CK(cudaMemsetAsync(s->H, 0, s->h_bytes, ctx->stream));
+  CK(cudaMemsetAsync(s->g, 0, s->g_bytes, ctx->stream));
   int rc = s->dtype == TOB200_F32 ? solver_step_impl<float>(s, nullptr, nullptr, 0, 0, 1)
                                   : solver_step_impl<double>(s, nullptr, nullptr, 0, 0, 1);
   if (rc == TOB200_OK) s->is_reset = true;
@@ -1216,6 +1247,18 @@ int tob200_solver_final_hessian(tob200_solver *s, double *H) {
   if (!s || !H) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "NULL argument");
   tob200_ctx *ctx = s->ctx;
   DeviceGuard guard(ctx->device);
+  if (s->family == 2) {
+    const int np = wpp_nb_for(s->n) * wpp_blk_for(s->n), ldw = wpp_ldw(np);
+    if (s->dtype == TOB200_F32)
+      wpp_final_hessian_kernel<float><<<(unsigned)s->B, 128, 0, ctx->stream>>>(
+          (const float *)s->H, (const StateRec<float> *)s->rec, s->opt.solver_type, s->B, s->n, np, ldw, H);
+    else
+      wpp_final_hessian_kernel<double><<<(unsigned)s->B, 128, 0, ctx->stream>>>(
+          (const double *)s->H, (const StateRec<double> *)s->rec, s->opt.solver_type, s->B, s->n, np, ldw, H);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return TOB200_OK;
+  }
   const unsigned grid = (unsigned)((s->B + 127) / 128);
   if (s->dtype == TOB200_F32)
     final_hessian_kernel<float><<<grid, 128, 0, ctx->stream>>>((const float *)s->H, (const StateRec<float> *)s->rec,

@@ -769,7 +769,8 @@ __device__ __forceinline__ void wpp_store_permuted(T *W, const T (&acc)[BLK][BLK
 template <typename T, int NB, int BLK>
 __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions<T> &o, const WppData<T> &d,
                                                unsigned char *ws, T *hp, bool pass_rebuilt, int bi, int bj,
-                                               bool has_block, const T (&acc)[BLK][BLK], T cost_only, int lane) {
+                                               bool has_block, const T (&acc)[BLK][BLK], T cost_only, int lane,
+                                               bool always_persist = false) {
   using O = Ops<T>;
   constexpr int LDW = wpp_ldw(NB * BLK);
   const int n = d.n, nres = d.m;
@@ -815,8 +816,9 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
   }
   // Will a cost-only iteration possibly follow this one?  Only then does H_ have to outlive the
   // next pass (optimizer.h:295: eval_only = !last_was_success, after a step that did not succeed).
+  // (the step solver keeps H_ in HBM between calls and exports it as Output::final_hessian: always)
   const bool may_need_stale_h =
-      !pass_rebuilt || (!(cost - s.final_cost < 0.0) && !(s.flags & kFlagLastWasSuccess));
+      always_persist || !pass_rebuilt || (!(cost - s.final_cost < 0.0) && !(s.flags & kFlagLastWasSuccess));
 
   bool solver_failed = true, early_return = false;
   const uint8_t max_tries = lm_max_tries(o);

@@ -3,10 +3,11 @@
 
 #include "tpp_inst.cuh"  // TppLaunch, TppOp
 #include "wpp.cuh"
+#include "wpp_step.cuh"
 
 namespace tob200 {
 
-enum WppKind { kWppRun = 0, kWppBuildSolve = 1 };
+enum WppKind { kWppRun = 0, kWppBuildSolve = 1, kWppStep = 2 };
 
 template <typename T, int NB, int BLK>
 cudaError_t wpp_entry_one(int op, int kind, const void *params, const TppLaunch &cfg, int *out) {
@@ -14,6 +15,7 @@ cudaError_t wpp_entry_one(int op, int kind, const void *params, const TppLaunch 
   switch (kind) {
     case kWppRun: fn = (const void *)wpp_lm_run_kernel<T, NB, BLK>; break;
     case kWppBuildSolve: fn = (const void *)wpp_build_solve_kernel<T, NB, BLK>; break;
+    case kWppStep: fn = (const void *)wpp_step_kernel<T, NB, BLK>; break;
     default: return cudaErrorInvalidValue;
   }
   if (op == kTppQuery) {
