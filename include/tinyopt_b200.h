@@ -139,7 +139,7 @@ int tob200_copy_to_host(tob200_ctx *ctx, void *dst_host, const void *src_device,
 int64_t tob200_tiled_elems(int64_t B, int m, int n);
 /* Which kernel family serves (dtype, n): 1 thread-per-problem registers (n <= 12 float, n <= 8 double),
  * 2 warp-per-problem shared-memory tiles (n <= 55, float and double), 3 tensor-core J^T J + blocked
- * LDLT (56 <= n <= 512, n % 4 == 0, float), 0 none. */
+ * LDLT (56 <= n <= 512, float; n % 4 != 0 runs on a zero-padded copy), 0 none. */
 int tob200_kernel_family(int dtype, int n);
 
 /* ---- layout ----------------------------------------------------------------------------------- */

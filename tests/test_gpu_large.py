@@ -105,7 +105,8 @@ def test_jtj_matches_float64(ctx, B, m, n):
 
 
 # ---- a1 + a5 + a6: one Build + Solve -----------------------------------------------------------------
-@pytest.mark.parametrize("B,m,n", [(4, 256, 64), (3, 300, 100), (3, 1024, 256), (2, 2048, 512)])
+@pytest.mark.parametrize("B,m,n", [(4, 256, 64), (3, 300, 100), (3, 1024, 256), (2, 2048, 512),
+                                   (4, 256, 57), (3, 300, 101), (2, 900, 258), (2, 1100, 511)])  # n % 4 != 0: padded copy
 def test_lg_build_solve_parity(ctx, B, m, n):
     assert ctx.kernel_family(torch.float32, n) == 3
     A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=3)
@@ -151,7 +152,8 @@ def robust_decisions(B, m, n, p0=0, **optkw):
     return (r64["sign_margin"] > 2e-5) & (r64["thr_margin"] > 0.1)
 
 
-@pytest.mark.parametrize("B,m,n,min_robust", [(6, 256, 64, 0), (150, 300, 60, 0.5), (5, 700, 128, 0), (3, 1500, 320, 0), (3, 2048, 512, 0)])
+@pytest.mark.parametrize("B,m,n,min_robust", [(6, 256, 64, 0), (150, 300, 60, 0.5), (5, 700, 128, 0), (3, 1500, 320, 0), (3, 2048, 512, 0),
+                                              (150, 300, 57, 0.5), (6, 500, 99, 0), (3, 1200, 258, 0)])  # n % 4 != 0: padded copy
 def test_lg_lm_run_parity(ctx, B, m, n, min_robust):
     xo, ro, out = run_both(ctx, B, m, n)
     rg = out.results

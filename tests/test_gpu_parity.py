@@ -302,7 +302,8 @@ WPP_SHAPES = [(40, 500, 50), (33, 37, 13), (17, 64, 20), (9, 100, 27), (21, 96, 
 def test_wpp_kernel_family(ctx):
     assert ctx.kernel_family(torch.float32, 12) == 1 and ctx.kernel_family(torch.float32, 13) == 2
     assert ctx.kernel_family(torch.float32, 55) == 2 and ctx.kernel_family(torch.float32, 56) == 3
-    assert ctx.kernel_family(torch.float32, 57) == 0 and ctx.kernel_family(torch.float32, 512) == 3
+    assert ctx.kernel_family(torch.float32, 57) == 3 and ctx.kernel_family(torch.float32, 512) == 3
+    assert ctx.kernel_family(torch.float32, 513) == 0
     assert ctx.kernel_family(torch.float64, 8) == 1 and ctx.kernel_family(torch.float64, 9) == 2
     assert ctx.kernel_family(torch.float64, 55) == 2 and ctx.kernel_family(torch.float64, 56) == 0
 

@@ -535,9 +535,28 @@ int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_
     ctx->launches++;
   } else if (family == 3) {
     if (sizeof(T) != 4) return fail(ctx, TOB200_ERR_UNSUPPORTED, "large-n kernels are float only");
-    if ((rc = lg_build_solve(ctx, (const float *)J, (const float *)r, B, m, n, (const float *)lambda, (float *)dx, cost,
-                             (float *)H_out, (float *)g_out, status)) != TOB200_OK)
+    if (n % 4 != 0) {  // zero-padded copy, see lm_run_impl
+      const int n4 = (n + 3) & ~3;
+      if ((rc = ensure_scratch(ctx, 21, (size_t)B * m * n4 * 4)) != TOB200_OK) return rc;
+      if ((rc = ensure_scratch(ctx, 22, (size_t)B * n4 * 4)) != TOB200_OK) return rc;
+      if (H_out && (rc = ensure_scratch(ctx, 23, (size_t)B * n4 * n4 * 4)) != TOB200_OK) return rc;
+      if (g_out && (rc = ensure_scratch(ctx, 20, (size_t)B * n4 * 4)) != TOB200_OK) return rc;
+      float *J4 = (float *)ctx->scratch[21], *dx4 = (float *)ctx->scratch[22];
+      float *H4 = H_out ? (float *)ctx->scratch[23] : nullptr, *g4 = g_out ? (float *)ctx->scratch[20] : nullptr;
+      CK(launch_repitch((const float *)J, B, m, n, J4, m, n4, ctx->stream));
+      CK(cudaMemsetAsync(dx4, 0, (size_t)B * n4 * 4, ctx->stream));
+      if ((rc = lg_build_solve(ctx, J4, (const float *)r, B, m, n4, (const float *)lambda, dx4, cost, H4, g4, status)) !=
+          TOB200_OK)
+        return rc;
+      // rejected problems leave dx untouched (the caller's contract): copy only into the accepted ones
+      CK(launch_repitch_masked(dx4, status, B, n4, (float *)dx, n, ctx->stream));
+      if (H_out) CK(launch_repitch(H4, B, n4, n4, (float *)H_out, n, n, ctx->stream));
+      if (g_out) CK(launch_repitch(g4, 1, (int)B, n4, (float *)g_out, (int)B, n, ctx->stream));
+      ctx->launches += 3;
+    } else if ((rc = lg_build_solve(ctx, (const float *)J, (const float *)r, B, m, n, (const float *)lambda, (float *)dx,
+                                    cost, (float *)H_out, (float *)g_out, status)) != TOB200_OK) {
       return rc;
+    }
   } else {
     WppBuildSolveParams<T> p;
     if ((rc = wpp_configure<T>(ctx, n, m, B, kWppBuildSolve, J, r, &p.d, &cfg)) != TOB200_OK) return rc;
@@ -583,9 +602,27 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     ctx->launches++;
   } else if (family == 3) {
     if (sizeof(T) != 4) return fail(ctx, TOB200_ERR_UNSUPPORTED, "large-n kernels are float only");
-    if ((rc = lg_lm_run(ctx, opt, (const float *)A, (const float *)y, (float)alpha, B, m, n, (float *)x, results)) !=
-        TOB200_OK)
+    if (n % 4 != 0 && opt->check_min_H_diag > 0.f)
+      return fail(ctx, TOB200_ERR_UNSUPPORTED, "check_min_H_diag with n % 4 != 0 (n > 55): the zero pad columns would trip it");
+    if (n % 4 != 0) {
+      // The TMA / vector paths want 16-byte aligned rows: run the problem with n4 = n rounded up to 4 on a
+      // zero-padded copy of A and x.  The pad columns of J are zero, so H gets zero rows / columns there:
+      // they sort last in Eigen's pivot order, the leading n x n factorisation is untouched, the zero
+      // pivots are legal (zero column below them) and D^+ gives dx = 0 for the pads.
+      const int n4 = (n + 3) & ~3;
+      if ((rc = ensure_scratch(ctx, 21, (size_t)B * m * n4 * 4)) != TOB200_OK) return rc;
+      if ((rc = ensure_scratch(ctx, 22, (size_t)B * n4 * 4)) != TOB200_OK) return rc;
+      float *A4 = (float *)ctx->scratch[21], *x4 = (float *)ctx->scratch[22];
+      CK(launch_repitch((const float *)A, B, m, n, A4, m, n4, ctx->stream));
+      CK(launch_repitch((const float *)x, 1, (int)B, n, x4, (int)B, n4, ctx->stream));
+      ctx->launches += 2;
+      if ((rc = lg_lm_run(ctx, opt, A4, (const float *)y, (float)alpha, B, m, n4, x4, results)) != TOB200_OK) return rc;
+      CK(launch_repitch(x4, 1, (int)B, n4, (float *)x, (int)B, n, ctx->stream));
+      ctx->launches++;
+    } else if ((rc = lg_lm_run(ctx, opt, (const float *)A, (const float *)y, (float)alpha, B, m, n, (float *)x,
+                               results)) != TOB200_OK) {
       return rc;
+    }
   } else {
     WppRunParams<T> p;
     if ((rc = wpp_configure<T>(ctx, n, m, B, kWppRun, A, y, &p.d, &cfg)) != TOB200_OK) return rc;
@@ -860,7 +897,7 @@ int tob200_kernel_family(int dtype, int n) {
   if (dtype == TOB200_F32) {
     if (n <= kTppMaxN_f32) return 1;
     if (n <= kWppMaxN_f32) return 2;
-    return (n <= kLgMaxN && n % 4 == 0) ? 3 : 0;  // rows must stay 16-byte aligned for the bulk copies
+    return n <= kLgMaxN ? 3 : 0;  // n % 4 != 0 goes through a zero-padded copy (rows 16-byte aligned for TMA)
   }
   if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : (n <= kWppMaxN_f64 ? 2 : 0);  // family 2: scalar paths
   return 0;

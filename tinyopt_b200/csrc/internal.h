@@ -18,6 +18,11 @@ template <typename T>
 cudaError_t launch_synth_eval(const T *A, const T *y, T alpha, int layout, int64_t B, int m, int n, const T *x, T *r,
                               T *J, cudaStream_t st);
 
+cudaError_t launch_repitch(const float *src, int64_t B, int rs, int ps, float *dst, int rd, int pd, cudaStream_t st);
+
+cudaError_t launch_repitch_masked(const float *src, const int32_t *status, int64_t B, int ps, float *dst, int nd,
+                                  cudaStream_t st);
+
 // cov_kernels.cu: InvCov / MaxStdDev, one warp per problem (n <= 64)
 template <typename T>
 cudaError_t launch_cov_warp(const T *H, int64_t B, int n, T *cov, T *max_std, int32_t *status, int num_sms,

@@ -196,6 +196,46 @@ cudaError_t launch_synth_eval(const T *A, const T *y, T alpha, int layout, int64
   return cudaGetLastError();
 }
 
+// dst[b][i][c] (i < rd, c < pd) <- src[b][i][c] where that exists (i < rs, c < ps), else 0: pads / strips
+// rows and columns of a batch of row-major matrices (the large-n family wants n % 4 == 0)
+__global__ void repitch_kernel(const float *src, int64_t B, int rs, int ps, float *dst, int rd, int pd) {
+  const int64_t total = B * (int64_t)rd * pd;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % pd);
+    const int64_t q = e / pd;
+    const int i = (int)(q % rd);
+    const int64_t b = q / rd;
+    dst[e] = (i < rs && c < ps) ? src[(b * rs + i) * (int64_t)ps + c] : 0.f;
+  }
+}
+cudaError_t launch_repitch(const float *src, int64_t B, int rs, int ps, float *dst, int rd, int pd, cudaStream_t st) {
+  const int64_t total = B * (int64_t)rd * pd;
+  if (total <= 0) return cudaSuccess;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  repitch_kernel<<<(unsigned)grid, 256, 0, st>>>(src, B, rs, ps, dst, rd, pd);
+  return cudaGetLastError();
+}
+
+// dst[b][0..nd) <- src[b][0..nd) for the problems with status[b] == 0 (dx of a rejected solve stays untouched)
+__global__ void repitch_masked_kernel(const float *src, const int32_t *status, int64_t B, int ps, float *dst, int nd) {
+  const int64_t total = B * (int64_t)nd;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / nd;
+    const int c = (int)(e % nd);
+    if (status[b] == 0) dst[e] = src[b * ps + c];
+  }
+}
+cudaError_t launch_repitch_masked(const float *src, const int32_t *status, int64_t B, int ps, float *dst, int nd,
+                                  cudaStream_t st) {
+  const int64_t total = B * (int64_t)nd;
+  if (total <= 0) return cudaSuccess;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  repitch_masked_kernel<<<(unsigned)grid, 256, 0, st>>>(src, status, B, ps, dst, nd);
+  return cudaGetLastError();
+}
+
 #define INST(T)                                                                                                   \
   template cudaError_t launch_retile<T>(const T *, int64_t, int, int, T *, cudaStream_t);                          \
   template cudaError_t launch_untile<T>(const T *, int64_t, int, int, T *, cudaStream_t);                          \
