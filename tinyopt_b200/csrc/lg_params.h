@@ -82,6 +82,7 @@ __host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages) {
 constexpr int kLgSolveThreads = 512;
 constexpr int kLgPanel = 32;  // factorisation panel width (16 / 2 CTAs per SM was measured slower: more tiles, more barriers)
 constexpr int kLgBlk = 32;    // substitution block == warp
+constexpr int kLgTilePitch = 36;  // pitch of the phase-1 W tiles: 16-byte aligned rows (cp.async 16, LDS.128 of L)
 
 struct LgSolveParams {
   // ---- per problem inputs ----
@@ -126,7 +127,7 @@ __host__ __device__ inline LgSolveSmem lg_solve_smem(int np) {
   L.inv = o; o += vl;
   L.tt = o; o += kLgPanel * kLgPanel;
   {  // double-buffered W tile; also the 16 per-warp 32 x 33 transpose tiles of lg_mirror_upper
-    const int a = 2 * np * (kLgPanel + 1), b = (kLgSolveThreads / 32) * 32 * 33;
+    const int a = 2 * np * kLgTilePitch, b = (kLgSolveThreads / 32) * 32 * 33;
     L.tile = o; o += a > b ? a : b;
   }
   L.misc = o; o += 32;

@@ -147,9 +147,9 @@ __device__ void lg_pivot_order(const float *dd, int n, int np, int *perm, int *i
   LG_T(12);
 }
 
-// 4-byte asynchronous global -> shared copy (LDGSTS): the W tiles of phase 1 are double buffered
-__device__ __forceinline__ void lg_cp_async4(float *dst, const float *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+// 16-byte asynchronous global -> shared copy (LDGSTS): the W tiles of phase 1 are double buffered
+__device__ __forceinline__ void lg_cp_async16(float *dst, const float *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void lg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -185,8 +185,8 @@ __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolve
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float *dsm = sm + L.dsm;
   float *tt = sm + L.tt;      // [32 j][32 c]: T of phase 1, then T2 of phase 2
-  float *tile0 = sm + L.tile;  // 2 x [rows][33]
-  const int tile_elems = np * (kLgPanel + 1);
+  float *tile0 = sm + L.tile;  // 2 x [rows][kLgTilePitch]
+  const int tile_elems = np * kLgTilePitch;
   int *misc = reinterpret_cast<int *>(sm + L.misc);  // 0: sign, 1: found_zero_pivot, 2: ret, 3: nonzero-below flag
   if (n == 1) {
     const float a = W[0];
@@ -202,15 +202,22 @@ __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolve
     const int i = kb + tid;  // my row
     const bool active = tid < nrows;
     float areg[kLgPanel], S[kLgPanel];
-    unsigned long long S2[kLgPanel / 2];  // phase-1 accumulators, packed pairs (S[2 q], S[2 q + 1])
+    // phase-1 accumulators: a 4 x 8 register tile (rows 4 rg .. 4 rg + 3 below kb, panel columns 8 cg .. 8 cg + 7)
+    // as packed pairs, so that every L value feeds 8 and every T value 4 fmas (a 1 x 32 tile loaded 9 words
+    // per 32 fmas and was LSU bound); the sums change hands to thread = row through shared memory afterwards
+    const int rg = tid >> 2, cg = tid & 3;
+    unsigned long long S2[4][4];
 #pragma unroll
-    for (int c = 0; c < kLgPanel; ++c) areg[c] = 0.f;
+    for (int c = 0; c < kLgPanel; ++c) { areg[c] = 0.f; S[c] = 0.f; }
 #pragma unroll
-    for (int q = 0; q < kLgPanel / 2; ++q) S2[q] = 0ull;
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) S2[a][h] = 0ull;
     auto issue_tile = [&](int jc, float *tile) {
-      constexpr int rpw = 32 / kLgPanel;  // rows per warp instruction
-      for (int rr = warp * rpw + lane / kLgPanel; rr < nrows; rr += (kLgSolveThreads / 32) * rpw)
-        lg_cp_async4(tile + rr * (kLgPanel + 1) + lane % kLgPanel, W + (size_t)(kb + rr) * np + jc + lane % kLgPanel);
+      for (int idx = tid; idx < nrows * (kLgPanel / 4); idx += kLgSolveThreads) {
+        const int rr = idx / (kLgPanel / 4), q = idx % (kLgPanel / 4);
+        lg_cp_async16(tile + rr * kLgTilePitch + 4 * q, W + (size_t)(kb + rr) * np + jc + 4 * q);
+      }
       lg_cp_async_commit();
     };
     if (kb > 0) issue_tile(0, tile0);
@@ -231,27 +238,53 @@ __device__ bool lg_ldlt_factor(float *W, int n, int np, float *sm, const LgSolve
       if (jc + kLgPanel < kb) issue_tile(jc + kLgPanel, tile0 + (tb ^ 1) * tile_elems);  // overlaps the FMAs below
       for (int e = tid; e < kLgPanel * kLgPanel; e += kLgSolveThreads) {
         const int j = e / kLgPanel, c = e % kLgPanel;
-        tt[j * kLgPanel + c] = (c < pw) ? __fmul_rn(dsm[jc + j], tile[c * (kLgPanel + 1) + j]) : 0.f;
+        tt[j * kLgPanel + c] = (c < pw) ? __fmul_rn(dsm[jc + j], tile[c * kLgTilePitch + j]) : 0.f;
       }
       __syncthreads();
-      if (active) {
-        const float *trow = tile + tid * (kLgPanel + 1);
-#pragma unroll 4
-        for (int j = 0; j < kLgPanel; ++j) {
-          const float w = trow[j];
-          const float4 *t4 = reinterpret_cast<const float4 *>(tt + j * kLgPanel);
+      if (4 * rg < nrows) {
+        const float *lrow = tile + (4 * rg) * kLgTilePitch;
+#pragma unroll 2
+        for (int j4 = 0; j4 < kLgPanel; j4 += 4) {
+          float4 w[4];
 #pragma unroll
-          for (int q = 0; q < kLgPanel / 4; ++q) {
-            const float4 tv = t4[q];
-            lg_ffma2(S2[2 * q], w, tv.x, tv.y);
-            lg_ffma2(S2[2 * q + 1], w, tv.z, tv.w);
+          for (int a = 0; a < 4; ++a) w[a] = *reinterpret_cast<const float4 *>(lrow + a * kLgTilePitch + j4);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float4 *t4 = reinterpret_cast<const float4 *>(tt + (j4 + jj) * kLgPanel + 8 * cg);
+            const float4 t0 = t4[0], t1 = t4[1];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const float wv = jj == 0 ? w[a].x : (jj == 1 ? w[a].y : (jj == 2 ? w[a].z : w[a].w));
+              lg_ffma2(S2[a][0], wv, t0.x, t0.y);
+              lg_ffma2(S2[a][1], wv, t0.z, t0.w);
+              lg_ffma2(S2[a][2], wv, t1.x, t1.y);
+              lg_ffma2(S2[a][3], wv, t1.z, t1.w);
+            }
           }
         }
       }
     }
-    __syncthreads();  // tt is free
+    __syncthreads();  // tt and both tile buffers are free
+    if (kb > 0) {
+      // hand the sums over: [row][33] (thread = row reads its 32 values conflict free)
+      float *sbuf = tile0;
+      if (4 * rg < nrows) {
 #pragma unroll
-    for (int q = 0; q < kLgPanel / 2; ++q) { S[2 * q] = lg_lo(S2[q]); S[2 * q + 1] = lg_hi(S2[q]); }
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float *d = sbuf + (4 * rg + a) * (kLgPanel + 1) + 8 * cg + 2 * h;
+            d[0] = lg_lo(S2[a][h]);
+            d[1] = lg_hi(S2[a][h]);
+          }
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < kLgPanel; ++c) S[c] = sbuf[tid * (kLgPanel + 1) + c];
+      }
+      __syncthreads();  // sbuf (== tile buffer 0) is reused by the next panel's first tile
+    }
     LG_T(14);
     // ---- phase 2a: diagonal block (lanes < kLgPanel) and the rows of warp 0 below it, warp 0 ----
     if (warp == 0) {
