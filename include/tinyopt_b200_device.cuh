@@ -28,6 +28,7 @@
 
 #include "tinyopt_b200.h"
 #include "lm_state.cuh"  // -I<repo>/tinyopt_b200/csrc
+#include "wpp.cuh"       // the warp-per-problem building blocks (n <= 55)
 
 namespace tinyopt {
 namespace b200 {
@@ -343,6 +344,245 @@ template <int N, typename T, typename F>
 cudaError_t OptimizeBatchManual(const F &f, T *x, int64_t B, const tob200_options &options,
                                 tob200_result *results, cudaStream_t stream = nullptr) {
   return detail::launch<T, N, false, F>(f, x, B, options, results, stream);
+}
+
+// ================================================================================================
+// Warp per problem (n <= 55, float and double): the same functor source, run in LOCKSTEP by the 32
+// lanes of a warp for one problem.  Derivatives are warp-distributed: every lane carries the value and
+// the two partials d/dx_lane, d/dx_{lane+32} (a Jet<T, 2> seeded per lane), so a Jet operation costs three
+// scalar operations per lane whatever n is.  emit(r) writes the augmented row [J_i | r_i] into the packed
+// row buffer of wpp.cuh (lane l stores its two entries); every 32 rows the warp folds the buffer into
+// its register blocks of [J|r]^T [J|r] exactly as the library's own warp-per-problem kernel does, and the
+// pass ends in the same wpp_after_pass (pivoted LDL^T, LM state machine).  Accumulation order = emission
+// order, so the result is bit-identical to tob200_lm_run_* for a functor that emits the same values.
+// The functor must be templated on the type of x and of emit:
+//   template <typename X, typename E> __device__ void operator()(int64_t p, const X &x, E &emit) const
+// (x[j] yields Jet<T, 2> on rebuild passes and T on cost-only passes) and must be free of lane-dependent
+// control flow.
+// ================================================================================================
+template <typename T>
+struct WarpXJet {
+  const T *xs;
+  int lane;
+  __device__ __forceinline__ Jet<T, 2> operator[](int j) const {
+    Jet<T, 2> r;
+    r.a = xs[j];
+    r.v[0] = (lane == j) ? (T)1 : (T)0;
+    r.v[1] = (lane + 32 == j) ? (T)1 : (T)0;
+    return r;
+  }
+};
+template <typename T>
+struct WarpXScalar {
+  const T *xs;
+  __device__ __forceinline__ T operator[](int j) const { return xs[j]; }
+};
+
+template <typename T, int N>
+struct WarpEmit {
+  static constexpr int BLK = tob200::wpp_blk_for(N), NB = tob200::wpp_nb_for(N), NP = NB * BLK,
+                       NPS = tob200::wpp_nps(NP);
+  static constexpr bool kF32 = sizeof(T) == 4;
+  T *jbuf;
+  int lane, bi, bj;
+  bool has_block, want_j;
+  unsigned long long acc2[BLK][BLK / 2];  // float: packed pairs for FFMA2
+  T acc[BLK][BLK];
+  T cost;
+  int nres, fill;
+
+  __device__ WarpEmit(T *jbuf_, int lane_, int bi_, int bj_, bool has_block_, bool rebuild)
+      : jbuf(jbuf_), lane(lane_), bi(bi_), bj(bj_), has_block(has_block_), want_j(rebuild), cost((T)0), nres(0), fill(0) {
+#pragma unroll
+    for (int u = 0; u < BLK; ++u) {
+#pragma unroll
+      for (int h = 0; h < BLK / 2; ++h) acc2[u][h] = 0ull;
+#pragma unroll
+      for (int v = 0; v < BLK; ++v) acc[u][v] = (T)0;
+    }
+    // the factor matrix aliases the row buffer: clear the pad columns of all 32 rows before the pass
+    constexpr int w = NP - (N + 1);
+    if (w > 0)
+      for (int e = lane; e < 32 * w; e += 32) jbuf[(e / w) * NPS + N + 1 + (e % w)] = (T)0;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void row_done() {
+    ++nres;
+    if (++fill == 32) flush();
+  }
+  /// residual as a warp-distributed Jet (rebuild passes of OptimizeBatchAutoDiffWarp)
+  __device__ __forceinline__ void operator()(const Jet<T, 2> &r) {
+    T *row = jbuf + fill * NPS;
+    if (lane < N) row[lane] = r.v[0];
+    if (lane + 32 < N) row[lane + 32] = r.v[1];
+    if (lane == 0) row[N] = r.a;
+    row_done();
+  }
+  /// residual with its full Jacobian row (every lane holds the same row; rebuild passes of ...ManualWarp)
+  __device__ __forceinline__ void operator()(T r, const T (&J)[N]) {
+    T *row = jbuf + fill * NPS;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if ((j & 31) == lane) row[j] = J[j];
+    if (lane == 0) row[N] = r;
+    row_done();
+  }
+  /// cost-only residual
+  __device__ __forceinline__ void operator()(T r) {
+    cost = Ops<T>::fma(r, r, cost);
+    ++nres;
+  }
+  // fold the buffered rows into the register blocks (wpp.cuh phase 2, same operation order)
+  __device__ __forceinline__ void flush() {
+    __syncwarp();
+    if (has_block) {
+      const T *pa = jbuf + bi * BLK, *pb = jbuf + bj * BLK;
+      if constexpr (kF32) {
+#pragma unroll 2
+        for (int i = 0; i < fill; ++i) {
+          T a[BLK], b[BLK];
+#pragma unroll
+          for (int q = 0; q < BLK / 4; ++q) {
+            const float4 av = *reinterpret_cast<const float4 *>(pa + i * NPS + 4 * q);
+            const float4 bv = *reinterpret_cast<const float4 *>(pb + i * NPS + 4 * q);
+            a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
+            b[4 * q] = bv.x; b[4 * q + 1] = bv.y; b[4 * q + 2] = bv.z; b[4 * q + 3] = bv.w;
+          }
+#pragma unroll
+          for (int u = 0; u < BLK; ++u)
+#pragma unroll
+            for (int h = 0; h < BLK / 2; ++h) tob200::ffma2_bcast(acc2[u][h], a[u], b[2 * h], b[2 * h + 1]);
+        }
+      } else {
+        for (int i = 0; i < fill; ++i) {
+          T a[BLK], b[BLK];
+#pragma unroll
+          for (int u = 0; u < BLK; ++u) { a[u] = pa[i * NPS + u]; b[u] = pb[i * NPS + u]; }
+#pragma unroll
+          for (int u = 0; u < BLK; ++u)
+#pragma unroll
+            for (int v = 0; v < BLK; ++v) acc[u][v] = Ops<T>::fma(a[u], b[v], acc[u][v]);
+        }
+      }
+    }
+    __syncwarp();
+    fill = 0;
+  }
+  __device__ __forceinline__ void finish() {
+    if (fill) flush();
+    if constexpr (kF32) {
+#pragma unroll
+      for (int u = 0; u < BLK; ++u)
+#pragma unroll
+        for (int h = 0; h < BLK / 2; ++h) {
+          acc[u][2 * h] = __uint_as_float((uint32_t)acc2[u][h]);
+          acc[u][2 * h + 1] = __uint_as_float((uint32_t)(acc2[u][h] >> 32));
+        }
+    }
+  }
+};
+
+namespace detail {
+
+template <typename T, int N, bool kAutoDiff, typename F>
+__global__ void __launch_bounds__(tob200::kWppThreads, sizeof(T) == 4 ? 2 : 1)
+    functor_warp_lm_run_kernel(F f, tob200::DevOptions<T> opt, tob200::WppSmem L, T *x, tob200_result *results, int64_t B,
+                               unsigned long long *counter, T *hpersist) {
+  using namespace tob200;
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int BLK = wpp_blk_for(N), NB = wpp_nb_for(N), NP = NB * BLK, LDW = wpp_ldw(NP);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x / 32;
+  unsigned char *ws = smem + (size_t)wid * L.total;
+  T *xs = reinterpret_cast<T *>(ws + L.xs);
+  T *last_dx = reinterpret_cast<T *>(ws + L.last_dx);
+  T *jbuf = reinterpret_cast<T *>(ws + L.jbuf);
+  T *hp = hpersist + ((size_t)blockIdx.x * (kWppThreads / 32) + wid) * (NP * LDW);
+  int bi, bj;
+  bool has_block;
+  wpp_block_of_lane<NB>(lane, bi, bj, has_block);
+  const bool is_lm = opt.solver_type == 0;
+  WppData<T> d;  // what wpp_after_pass reads: n, the residual count of the pass, the layout
+  d.A = nullptr; d.y = nullptr; d.B = B; d.m = 0; d.n = N; d.stages = 0; d.use_tma = 0; d.L = L; d.counter = counter;
+  d.hpersist = hpersist;
+
+  for (int64_t pr = wpp_next(counter, lane); pr < B; pr = wpp_next(counter, lane)) {
+    for (int j = lane; j < NP; j += 32) {
+      xs[j] = j < N ? x[pr * N + j] : (T)0;
+      last_dx[j] = (T)0;
+    }
+    LmScalars<T> s;
+    s.reset_scalars(opt);
+    __syncwarp();
+    while (!s.done()) {
+      const bool do_rebuild = !is_lm || s.rebuild();
+      WarpEmit<T, N> emit(jbuf, lane, bi, bj, has_block, do_rebuild);
+      if constexpr (kAutoDiff) {
+        if (do_rebuild) f(pr, WarpXJet<T>{xs, lane}, emit);
+        else f(pr, WarpXScalar<T>{xs}, emit);
+      } else {
+        f(pr, WarpXScalar<T>{xs}, emit, do_rebuild);
+      }
+      emit.finish();
+      d.m = emit.nres;
+      wpp_after_pass<T, NB, BLK>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane);
+    }
+    for (int j = lane; j < N; j += 32) x[pr * N + j] = xs[j];
+    if (lane == 0) lm_write_result(s, &results[pr]);
+    __syncwarp();
+  }
+}
+
+template <typename T, int N, bool kAutoDiff, typename F>
+cudaError_t launch_warp(const F &f, T *x, int64_t B, const tob200_options &options, tob200_result *results,
+                        cudaStream_t stream) {
+  using namespace tob200;
+  static_assert(N >= 1 && N <= 55, "warp-per-problem family: n <= 55");
+  if (B <= 0) return cudaSuccess;
+  if (options.use_ldlt != 1) return cudaErrorInvalidValue;
+  constexpr int BLK = wpp_blk_for(N), NB = wpp_nb_for(N), NP = NB * BLK, LDW = wpp_ldw(NP);
+  static_assert(NB <= 7, "n + 1 columns must fit 28 register blocks");
+  const WppSmem L = wpp_smem_layout(N, NP, 0, (uint32_t)sizeof(T));
+  const int warps = kWppThreads / 32;
+  const size_t smem = (size_t)L.total * warps;
+  auto kern = functor_warp_lm_run_kernel<T, N, kAutoDiff, F>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0, dev = 0, sms = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWppThreads, smem)) != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t grid = (int64_t)per_sm * sms;
+  const int64_t need = (B + warps - 1) / warps;
+  if (grid > need) grid = need;
+  unsigned long long *counter = nullptr;
+  T *hp = nullptr;
+  if ((e = cudaMallocAsync(&counter, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync(&hp, (size_t)grid * warps * NP * LDW * sizeof(T), stream)) != cudaSuccess) return e;
+  cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+  kern<<<(unsigned)grid, kWppThreads, smem, stream>>>(f, make_dev_options<T>(options), L, x, results, B, counter, hp);
+  e = cudaGetLastError();
+  cudaFreeAsync(hp, stream);
+  cudaFreeAsync(counter, stream);
+  return e;
+}
+
+}  // namespace detail
+
+/// tinyopt::Optimize(x, residuals, options) with automatic differentiation for n <= 55, one problem per warp.
+/// f : `template <typename X, typename E> __device__ void operator()(int64_t p, const X &x, E &emit) const`
+template <int N, typename T, typename F>
+cudaError_t OptimizeBatchAutoDiffWarp(const F &f, T *x, int64_t B, const tob200_options &options,
+                                      tob200_result *results, cudaStream_t stream = nullptr) {
+  return detail::launch_warp<T, N, true, F>(f, x, B, options, results, stream);
+}
+/// The accumulation contract for n <= 55, one problem per warp.
+/// f : `template <typename X, typename E> __device__ void operator()(int64_t p, const X &x, E &emit, bool want_jacobian) const`
+///     — emit(r, Jrow) per residual (every lane passes the same full row), or emit(r) when !want_jacobian
+template <int N, typename T, typename F>
+cudaError_t OptimizeBatchManualWarp(const F &f, T *x, int64_t B, const tob200_options &options,
+                                    tob200_result *results, cudaStream_t stream = nullptr) {
+  return detail::launch_warp<T, N, false, F>(f, x, B, options, results, stream);
 }
 
 }  // namespace device

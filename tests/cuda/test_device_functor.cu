@@ -117,6 +117,52 @@ struct PolyAuto {  // templated on the scalar: Jets on rebuild passes, plain T o
   }
 };
 
+// the same family for the warp-per-problem functor kernels (n <= 55): templated on the type of x and emit
+template <typename T, int N>
+struct PolyWarpManual {
+  const T *A, *y;
+  int m;
+  T alpha, alpha3;
+  template <typename X, typename E>
+  __device__ void operator()(int64_t p, const X &x, E &emit, bool want_j) const {
+    using O = tob200::Ops<T>;
+    const T *Ap = A + (size_t)p * m * N, *yp = y + (size_t)p * m;
+    for (int i = 0; i < m; ++i) {
+      T a[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[j] = Ap[(size_t)i * N + j];
+      T t = (T)0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) t = O::fma(a[j], x[j], t);
+      const T t2 = O::mul(t, t);
+      const T r = O::fma(t, O::fma(alpha, t2, (T)1), -yp[i]);
+      if (want_j) {
+        const T sc = O::fma(alpha3, t2, (T)1);
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[j] = O::mul(sc, a[j]);
+        emit(r, a);
+      } else {
+        emit(r);
+      }
+    }
+  }
+};
+template <typename T, int N>
+struct PolyWarpAuto {
+  const T *A, *y;
+  int m;
+  T alpha;
+  template <typename X, typename E>
+  __device__ void operator()(int64_t p, const X &x, E &emit) const {
+    const T *Ap = A + (size_t)p * m * N, *yp = y + (size_t)p * m;
+    for (int i = 0; i < m; ++i) {
+      auto t = x[0] * Ap[(size_t)i * N];
+      for (int j = 1; j < N; ++j) t = t + x[j] * Ap[(size_t)i * N + j];
+      emit(t + alpha * (t * t * t) - yp[i]);
+    }
+  }
+};
+
 static int synth(tob200_ctx *c, int64_t B, int m, int n, double *A, double *y, double *xs, double *x0) {
   return tob200_synth_generate_f64(c, 20261017ull, 0, B, m, n, 0.1, 1e-2, TOB200_LAYOUT_PROBLEM_MAJOR, A, y, xs, x0);
 }
@@ -132,7 +178,7 @@ static int lm_run(tob200_ctx *c, const tob200_options *o, const float *A, const 
   return tob200_lm_run_f32(c, o, A, y, 0.1f, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, x, r);
 }
 
-template <typename T, int N>
+template <typename T, int N, bool kWarp = false>
 static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
   T *A, *y, *xs, *x0, *xa, *xb, *xc;
   tob200_result *ra, *rb, *rc;
@@ -149,10 +195,17 @@ static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
   CU(cudaDeviceSynchronize());
   CHECK(lm_run(ctx, &opt, A, y, B, m, N, xa, ra) == TOB200_OK);  // the library's own kernels (oracle-pinned)
   CHECK(tob200_sync(ctx) == TOB200_OK);
-  PolyManual<T, N> fm{A, y, m, (T)0.1, (T)3 * (T)0.1};
-  CU((dev::OptimizeBatchManual<N>(fm, xb, B, opt, rb)));
-  PolyAuto<T, N> fa{A, y, m, (T)0.1};
-  CU((dev::OptimizeBatchAutoDiff<N>(fa, xc, B, opt, rc)));
+  if constexpr (kWarp) {
+    PolyWarpManual<T, N> fm{A, y, m, (T)0.1, (T)3 * (T)0.1};
+    CU((dev::OptimizeBatchManualWarp<N>(fm, xb, B, opt, rb)));
+    PolyWarpAuto<T, N> fa{A, y, m, (T)0.1};
+    CU((dev::OptimizeBatchAutoDiffWarp<N>(fa, xc, B, opt, rc)));
+  } else {
+    PolyManual<T, N> fm{A, y, m, (T)0.1, (T)3 * (T)0.1};
+    CU((dev::OptimizeBatchManual<N>(fm, xb, B, opt, rb)));
+    PolyAuto<T, N> fa{A, y, m, (T)0.1};
+    CU((dev::OptimizeBatchAutoDiff<N>(fa, xc, B, opt, rc)));
+  }
   CU(cudaDeviceSynchronize());
   std::vector<T> ha((size_t)B * N), hb(ha.size()), hc(ha.size());
   std::vector<tob200_result> qa((size_t)B), qb(qa.size()), qc(qa.size());
@@ -187,11 +240,14 @@ static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
   }
   // Jets: same decisions on (nearly) every problem — a threshold may flip where a test lands within
   // rounding of it — and the same solution to the north star's tolerance
-  CHECK(same_iters_ad >= B - B / 200);
+  // (float: the stop tests of a few % of the problems land within FP32 rounding of their threshold — the float
+  //  oracle disagrees with the double one on those too, tests/test_gpu_large.py::robust_decisions)
+  CHECK(same_iters_ad >= B - B / (sizeof(T) == 8 ? 200 : 20));
   CHECK(worst / xmax <= tol);
-  std::printf("family<%s> n=%d m=%d B=%lld: iters=%lld manual functor == lm_run bit for bit; Jets: %lld/%lld same "
+  std::printf("family<%s> n=%d m=%d B=%lld%s: iters=%lld manual functor == lm_run bit for bit; Jets: %lld/%lld same "
               "iteration count + stop reason, max rel dx %.2e\n",
-              sizeof(T) == 8 ? "double" : "float", N, m, (long long)B, (long long)iters, (long long)same_iters_ad,
+              sizeof(T) == 8 ? "double" : "float", N, m, (long long)B, kWarp ? " (warp per problem)" : "", (long long)iters,
+              (long long)same_iters_ad,
               (long long)B, worst / xmax);
   for (T *q : {A, y, xs, x0, xa, xb, xc}) cudaFree(q);
   for (tob200_result *q : {ra, rb, rc}) cudaFree(q);
@@ -249,6 +305,10 @@ int main() {
   test_sqrt2();
   test_family<double, 6>(ctx, 4096, 30, 1e-10);
   test_family<float, 12>(ctx, 4096, 200, 1e-4);
+  test_family<float, 20, true>(ctx, 2048, 64, 1e-4);   // warp-per-problem functor kernels
+  test_family<float, 50, true>(ctx, 1024, 200, 1e-4);
+  test_family<double, 20, true>(ctx, 1024, 64, 1e-10);
+  test_family<double, 6, true>(ctx, 1024, 30, 1e-10);   // a small n through the warp kernels too
   tob200_destroy(ctx);
   if (g_failures) {
     std::printf("%d check(s) failed\n", g_failures);
