@@ -416,3 +416,38 @@ def test_wpp_layouts_agree(ctx):
     _, _, out_p = run_both(ctx, np.float32, 70, 60, 33, layout=tb.PROBLEM_MAJOR)
     _, _, out_t = run_both(ctx, np.float32, 70, 60, 33, layout=tb.TILE32)
     assert torch.equal(out_t.x, out_p.x) and np.array_equal(out_t.results, out_p.results)
+
+
+# ---- seeded sweep over ragged shapes: every family below n = 56, both precisions ---------------------
+def _random_cases(seed, count):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(count):
+        dtype = np.float64 if rng.random() < 0.5 else np.float32
+        n = int(rng.integers(1, 56))
+        m = int(rng.integers(max(1, n // 2), 3 * n + 8))   # under- and over-determined, odd sizes, m % 4 != 0
+        B = int(rng.integers(1, 70))
+        layout = int(rng.integers(0, 2))
+        cases.append((dtype, B, m, n, layout))
+    return cases
+
+
+@pytest.mark.parametrize("dtype,B,m,n,layout", _random_cases(20261017, 48))
+def test_random_shapes_bitexact(ctx, dtype, B, m, n, layout):
+    """Ragged shapes through tob200_lm_run_* (thread- and warp-per-problem families, TMA and non-TMA
+    loaders, both layouts, rank-deficient m < n systems that only the LM damping makes solvable): bit-exact
+    x, costs, lambdas and iteration counts against the oracle."""
+    import tinyopt_b200 as tb
+    xo, ro, out = run_both(ctx, dtype, B, m, n, layout=tb.TILE32 if layout == 0 else tb.PROBLEM_MAJOR, p0=n * 1000 + m)
+    assert_lm_parity(dtype, xo, ro, out)
+
+
+def test_shape_sequence_keeps_shared_memory_limit(ctx):
+    """Regression: one kernel instantiation serves shapes with different shared-memory footprints; a small
+    shape must not lower the limit under a larger one whose launch geometry is cached."""
+    import tinyopt_b200 as tb
+    for dtype, seq in ((np.float32, [(20, 82, 39), (20, 64, 36), (20, 82, 39), (9, 300, 12), (9, 5, 12), (9, 300, 12)]),
+                       (np.float64, [(12, 66, 26), (12, 30, 25), (12, 66, 26)])):
+        for (B, m, n) in seq:
+            xo, ro, out = run_both(ctx, dtype, B, m, n, layout=tb.PROBLEM_MAJOR)
+            assert_lm_parity(dtype, xo, ro, out)

@@ -70,6 +70,7 @@ int fail(tob200_ctx *ctx, int code, const std::string &msg) {
   return code;
 }
 int fail_cuda(tob200_ctx *ctx, cudaError_t e, const char *what) {
+  cudaGetLastError();  // a failed launch leaves its (non-sticky) error behind: do not let the next call trip on it
   return fail(ctx, e == cudaErrorMemoryAllocation ? TOB200_ERR_NOMEM : TOB200_ERR_CUDA,
               std::string(what) + ": " + cudaGetErrorString(e));
 }
