@@ -194,3 +194,18 @@ def test_lg_phase_timers_and_launch_count(ctx):
     assert ctx.launch_count - l0 >= 4
     ms = [ctx.last_phase_ms(k) for k in range(3)]
     assert all(t > 0 and c >= 1 for t, c in ms)
+
+
+@pytest.mark.parametrize("n", [56, 59, 61, 66, 127, 129, 190, 255, 333, 385, 450, 509])
+def test_lg_every_n_lm_run(ctx, n):
+    """Odd sizes of the large-n family (strip boundaries +-1, n % 4 != 0 through the padded copy, partial
+    TMA boxes): x within 1e-4 of the oracle, iteration counts identical where the decisions are robust."""
+    B, m = 5, 2 * n + 37
+    xo, ro, out = run_both(ctx, B, m, n, p0=n)
+    robust = robust_decisions(B, m, n, p0=n)
+    rg = out.results
+    assert np.array_equal(rg["num_iters"][robust], ro["num_iters"][robust])
+    assert (np.abs(rg["num_iters"].astype(int) - ro["num_iters"].astype(int)) <= 1).all()
+    same = rg["num_iters"] == ro["num_iters"]
+    if same.any():
+        assert rel_err(out.x.cpu().numpy()[same], xo[same]) <= 1e-4

@@ -451,3 +451,28 @@ def test_shape_sequence_keeps_shared_memory_limit(ctx):
         for (B, m, n) in seq:
             xo, ro, out = run_both(ctx, dtype, B, m, n, layout=tb.PROBLEM_MAJOR)
             assert_lm_parity(dtype, xo, ro, out)
+
+
+@pytest.mark.parametrize("dtype,B,m,n,layout", _random_cases(777, 24))
+def test_random_build_solve_bitexact(ctx, dtype, B, m, n, layout):
+    """Ragged shapes through tob200_build_solve_* (Build + damping + LDLT alone): status, cost, g, damped H
+    and dx bit-exact against the oracle, LM and Gauss-Newton rows mixed."""
+    import tinyopt_b200 as tb
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=7 * n + m)
+    r, J = O.synth_eval(A, y, x0)
+    lam = np.full(B, 1e-4, dtype)
+    lam[::3] = 0
+    lam[1::5] = dtype(0.25)
+    dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+    Jd, rd = torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda()
+    lay = tb.PROBLEM_MAJOR if layout else tb.TILE32
+    if lay == tb.TILE32:
+        Jd, rd = tb.to_tile32(Jd), tb.to_tile32(rd)
+    out = ctx.build_solve(Jd, rd, torch.from_numpy(lam).cuda(), B=B, layout=lay, want_H=True, want_g=True)
+    ctx.sync()
+    assert np.array_equal(out["status"].cpu().numpy(), st)
+    ok = st == 0
+    assert np.array_equal(out["cost"].cpu().numpy(), cost)
+    assert np.array_equal(out["g"].cpu().numpy(), g)
+    assert np.array_equal(out["H"].cpu().numpy(), H)
+    assert np.array_equal(out["dx"].cpu().numpy()[ok], dx[ok])

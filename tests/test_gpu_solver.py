@@ -223,3 +223,37 @@ def test_final_hessian_covariance(ctx):
     assert (res["stop_reason"] >= 1).all() and (res["stop_reason"] < 5).all()
     assert np.abs(np.linalg.inv(H[0]) - Cy).max() < 1e-5
     assert np.abs(x[0] - y).max() < 1e-6
+
+
+def _random_solver_cases(seed, count):
+    rng = np.random.default_rng(seed)
+    return [(np.float64 if rng.random() < 0.5 else np.float32, int(rng.integers(1, 50)), 0, int(rng.integers(1, 56)))
+            for _ in range(count)]
+
+
+@pytest.mark.parametrize("dtype,B,_m,n", _random_solver_cases(4242, 16))
+def test_random_solver_matches_oracle(ctx, dtype, B, _m, n):
+    """The SolverType seam over ragged shapes (both families, both precisions, m around n): host-driven
+    loop == oracle bit for bit."""
+    import tinyopt_b200 as tb
+    rng = np.random.default_rng(n * 131 + B)
+    m = int(rng.integers(max(1, n // 2), 3 * n + 8))
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    layout = tb.TILE32 if ctx.kernel_family(tdt, n) == 1 else tb.PROBLEM_MAJOR
+    kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dtype == np.float32 else {}
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=17)
+    xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, tdt, p0=17, layout=layout)
+    s = tb.BatchSolver(ctx, B, n, tdt, tb.options(**kw))
+    s.reset(dx0)
+    steps = 0
+    while s.num_active() > 0 and steps < 200:
+        r, J = ctx.synth_eval(dA, dy, s.x, layout=layout)
+        s.step(J, r, layout=layout)
+        steps += 1
+    res = s.results()
+    assert np.array_equal(res["num_iters"], ro["num_iters"])
+    assert np.array_equal(res["stop_reason"], ro["stop_reason"])
+    assert np.array_equal(s.x.cpu().numpy(), xo)
+    assert np.array_equal(res["final_cost"], ro["final_cost"])
+    s.close()
