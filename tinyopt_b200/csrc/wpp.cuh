@@ -136,17 +136,19 @@ struct WppPipe {
   __device__ __forceinline__ void issue(const T *ap, const T *yp, int n, int row0, int nrows, uint32_t st, int lane) {
     T *sa = stage_ptr(st);
     T *sy = sa + (size_t)kWppRows * n;
+    // (y is NOT staged: the 32 values of a chunk are one coalesced load straight into the lanes' registers,
+    //  a chunk ahead of their use — the TMA unit retires about one bulk operation per 70 cycles per SM
+    //  whatever its size, and a 128-byte copy cost as much of it as the 6 KB one)
+    (void)sy; (void)yp;
     if (use_tma) {
       if (lane == 0) {
-        const uint32_t ba = (uint32_t)nrows * (uint32_t)n * (uint32_t)sizeof(T), by = (uint32_t)nrows * (uint32_t)sizeof(T);
-        mbar_expect_tx(&bars[st], ba + by);
+        const uint32_t ba = (uint32_t)nrows * (uint32_t)n * (uint32_t)sizeof(T);
+        mbar_expect_tx(&bars[st], ba);
         tma_bulk_g2s(sa, ap + (size_t)row0 * n, ba, &bars[st]);
-        tma_bulk_g2s(sy, yp + row0, by, &bars[st]);
       }
     } else {  // unaligned shapes: plain coalesced loads, completed before anyone reads
       const T *ga = ap + (size_t)row0 * n;
       for (int e = lane; e < nrows * n; e += 32) sa[e] = ga[e];
-      for (int e = lane; e < nrows; e += 32) sy[e] = yp[row0 + e];
     }
   }
   __device__ __forceinline__ void wait() {
@@ -568,13 +570,14 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     }
   }
   WPP_T0();
+  T ycur = lane < m ? yp[lane] : (T)0;  // y (or r) of my row of chunk 0
   for (int c = 0; c < nchunks; ++c) {
-    pipe.wait();
-    WPP_T(0);
     const int row0 = c * kWppRows;
     const int nrows = (m - row0 < kWppRows) ? (m - row0) : kWppRows;
+    const T ynext = (row0 + kWppRows + lane < m) ? yp[row0 + kWppRows + lane] : (T)0;  // in flight during this chunk
+    pipe.wait();
+    WPP_T(0);
     const T *sa = pipe.stage_ptr(pipe.stage);
-    const T *sy = sa + (size_t)kWppRows * n;
     // ---- phase 1 (lane = row): canonical t-chain, residual r_i, Jacobian scale sc_i, then the
     // ---- augmented packed row [sc_i a_i | r_i | 0 ..] written with 16-byte stores (pitch / 4 odd:
     // ---- conflict free); the pad columns are rewritten for every row, so they never go stale ----
@@ -602,10 +605,10 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
           for (int j = 0; j < n; ++j) t = O::fma(arow[j], xs[j], t);
         }
         const T t2 = O::mul(t, t);
-        ri = O::fma(t, O::fma(alpha, t2, (T)1), -sy[lane]);
+        ri = O::fma(t, O::fma(alpha, t2, (T)1), -ycur);
         sc = O::fma(alpha3, t2, (T)1);
       } else {
-        ri = sy[lane];
+        ri = ycur;
       }
       if (do_rebuild) {
        if constexpr (!kF32) {
@@ -701,6 +704,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     }
     __syncwarp();
     WPP_T(2);
+    ycur = ynext;
   }
   cost_only = __shfl_sync(0xffffffffu, cost_only, 0);
   if constexpr (kF32) {
