@@ -164,7 +164,7 @@ int tob200_build_solve_f64(tob200_ctx *ctx, const double *J, const double *r, in
 
 /* ---- a1 alone: the product site H = J^T diag(s^2) J on the tensor cores (tcgen05, 3xTF32) --------
  * Replaces `H = J.transpose() * J` (diff/optimize_autodiff.h:156, diff/num_diff.h:297) for
- * 4 <= n <= 512, n % 4 == 0 (float).  J: [B][m][n] problem-major; row_scale: [B][m] or NULL
+ * 1 <= n <= 512 (float; n % 4 != 0 through a zero-padded copy).  J: [B][m][n] problem-major; row_scale: [B][m] or NULL
  * (J_i = s_i a_i: the polynomial family's Jacobian from A);  H: [B][n][n] full symmetric. */
 int tob200_jtj_f32(tob200_ctx *ctx, const float *J, const float *row_scale, int64_t B, int m, int n,
                    float *H);

@@ -82,7 +82,8 @@ def test_solve_ldlt_ties_and_rejections(ctx):
 
 
 # ---- a1 alone: JᵀJ on the tensor cores ---------------------------------------------------------------
-@pytest.mark.parametrize("B,m,n", [(3, 8, 64), (2, 100, 128), (3, 37, 200), (2, 1000, 256), (2, 333, 320), (2, 2048, 512), (5, 64, 4), (2, 50, 60)])
+@pytest.mark.parametrize("B,m,n", [(3, 8, 64), (2, 100, 128), (3, 37, 200), (2, 1000, 256), (2, 333, 320), (2, 2048, 512), (5, 64, 4), (2, 50, 60),
+                                   (3, 40, 7), (2, 90, 61), (2, 700, 257), (4, 33, 1)])  # n % 4 != 0: padded copy
 def test_jtj_matches_float64(ctx, B, m, n):
     rng = np.random.default_rng(m * n)
     J = rng.uniform(-1, 1, (B, m, n)).astype(np.float32)

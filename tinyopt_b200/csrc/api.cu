@@ -1061,11 +1061,24 @@ int tob200_build_solve_f64(tob200_ctx *ctx, const double *J, const double *r, in
 
 int tob200_jtj_f32(tob200_ctx *ctx, const float *J, const float *row_scale, int64_t B, int m, int n, float *H) {
   if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
-  if (B < 0 || m < 0 || n < 4 || n > kLgMaxN || n % 4) return fail(ctx, TOB200_ERR_INVALID, "need 4 <= n <= 512, n % 4 == 0");
+  if (B < 0 || m < 0 || n < 1 || n > kLgMaxN) return fail(ctx, TOB200_ERR_INVALID, "need 1 <= n <= 512");
   if (B == 0) return TOB200_OK;
   if (!J || !H) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
   if (!aligned16(J)) return fail(ctx, TOB200_ERR_INVALID, "J must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
+  if (n % 4 != 0) {  // zero-padded copy (16-byte aligned rows for the TMA path), result stripped again
+    const int n4 = (n + 3) & ~3;
+    int rc;
+    if ((rc = ensure_scratch(ctx, 21, (size_t)B * m * n4 * 4)) != TOB200_OK) return rc;
+    if ((rc = ensure_scratch(ctx, 23, (size_t)B * n4 * n4 * 4)) != TOB200_OK) return rc;
+    float *J4 = (float *)ctx->scratch[21], *H4 = (float *)ctx->scratch[23];
+    CK(launch_repitch(J, B, m, n, J4, m, n4, ctx->stream));
+    if ((rc = tob200_jtj_f32(ctx, J4, row_scale, B, m, n4, H4)) != TOB200_OK) return rc;
+    CK(launch_repitch(H4, B, n4, n4, H, n, n, ctx->stream));
+    ctx->launches += 2;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    return TOB200_OK;
+  }
   LgBuffers b;
   int rc = lg_prepare(ctx, B, m, n, false, false, &b);
   if (rc != TOB200_OK) return rc;
