@@ -476,3 +476,25 @@ def test_random_build_solve_bitexact(ctx, dtype, B, m, n, layout):
     assert np.array_equal(out["g"].cpu().numpy(), g)
     assert np.array_equal(out["H"].cpu().numpy(), H)
     assert np.array_equal(out["dx"].cpu().numpy()[ok], dx[ok])
+
+
+@pytest.mark.parametrize("dtype,B,m,n,tiled", [(np.float64, 30007, 30, 6, True), (np.float64, 30007, 30, 6, False),
+                                               (np.float32, 9001, 120, 20, False), (np.float32, 70, 40, 12, True)])
+def test_host_entry_chunked_pipeline(ctx, dtype, B, m, n, tiled):
+    """tob200_lm_run_host_* (host buffers; inputs above 32 MB go through the 4-chunk upload / solve / download
+    pipeline, B is not a multiple of the chunk or tile size): identical to the device-resident run, and to
+    the oracle on a slice."""
+    import tinyopt_b200 as tb
+    oo, go = both_options(dtype)
+    layout = tb.TILE32 if tiled else tb.PROBLEM_MAJOR
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, TDT[dtype], layout=layout)
+    out = ctx.optimize_batch(dA, dy, dx0, go, layout=layout)
+    Ah, yh, xh = dA.cpu().numpy(), dy.cpu().numpy(), dx0.cpu().numpy().copy()
+    res = ctx.optimize_batch_host(Ah, yh, xh, go, layout=layout, B=B)
+    assert np.array_equal(xh, out.x.cpu().numpy())
+    for k in ("num_iters", "stop_reason", "final_cost", "last_lambda", "num_builds"):
+        assert np.array_equal(res[k], out.results[k]), k
+    sl = slice(B - 40, B)   # the tail: the last, partial chunk / tile
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype)
+    xo, ro, _ = O.synth_lm_run(A[sl], y[sl], x0[sl], oo)
+    assert np.array_equal(xh[sl], xo) and np.array_equal(res["num_iters"][sl], ro["num_iters"])
