@@ -143,7 +143,7 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 template <typename T>
 int tpp_min_blocks_rt(int n) {  // tpp_min_blocks<T, N>() for a run-time n
-  if (sizeof(T) == 8) return n <= 2 ? 4 : (n <= 6 ? 3 : 2);
+  if (sizeof(T) == 8) return n <= 2 ? 4 : (n <= 6 ? TOB200_TPP_MINB_F64_MID : 2);
   return n <= 6 ? 4 : (n <= 8 ? 3 : 2);
 }
 

@@ -32,9 +32,12 @@ __host__ __device__ inline size_t tpp_warp_smem_bytes(int n, int rows, int stage
 
 // Resident CTAs per SM each kernel is compiled for (__launch_bounds__): fixes the register budget
 // (65536 / (128 * k)).  Chosen from ptxas -v so that nothing spills.
+#ifndef TOB200_TPP_MINB_F64_MID
+#define TOB200_TPP_MINB_F64_MID 3  // resident CTAs per SM for double, 3 <= n <= 6 (C2)
+#endif
 template <typename T, int N>
 __host__ __device__ constexpr int tpp_min_blocks() {
-  if (sizeof(T) == 8) return N <= 2 ? 4 : (N <= 6 ? 3 : 2);
+  if (sizeof(T) == 8) return N <= 2 ? 4 : (N <= 6 ? TOB200_TPP_MINB_F64_MID : 2);
   return N <= 6 ? 4 : (N <= 8 ? 3 : 2);
 }
 
@@ -190,6 +193,31 @@ __device__ __forceinline__ void tpp_pass(TppPipe<T, N> &pipe, const TppData<T> &
       const T *sr = sj + pipe.r_off;
       if (do_rebuild) {
         int rr = 0;
+#ifdef TOB200_TPP_ROWS4
+        for (; rr + 4 <= nrows; rr += 4) {  // four rows in flight: four independent t-chains
+          T a0[N], a1[N], a2[N], a3[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            a0[j] = sj[(rr * N + j) * kTile];
+            a1[j] = sj[((rr + 1) * N + j) * kTile];
+            a2[j] = sj[((rr + 2) * N + j) * kTile];
+            a3[j] = sj[((rr + 3) * N + j) * kTile];
+          }
+          T r0, r1, r2, r3;
+          tpp_row_residual<T, N, kSynth>(a0, sr[rr * kTile], x, alpha, alpha3, true, r0);
+          tpp_row_residual<T, N, kSynth>(a1, sr[(rr + 1) * kTile], x, alpha, alpha3, true, r1);
+          tpp_row_residual<T, N, kSynth>(a2, sr[(rr + 2) * kTile], x, alpha, alpha3, true, r2);
+          tpp_row_residual<T, N, kSynth>(a3, sr[(rr + 3) * kTile], x, alpha, alpha3, true, r3);
+          cost = O::fma(r0, r0, cost);
+          cost = O::fma(r1, r1, cost);
+          cost = O::fma(r2, r2, cost);
+          cost = O::fma(r3, r3, cost);
+          tpp_row_accumulate<T, N>(a0, r0, hu, g);
+          tpp_row_accumulate<T, N>(a1, r1, hu, g);
+          tpp_row_accumulate<T, N>(a2, r2, hu, g);
+          tpp_row_accumulate<T, N>(a3, r3, hu, g);
+        }
+#endif
         for (; rr + 2 <= nrows; rr += 2) {
           T a0[N], a1[N];
 #pragma unroll
