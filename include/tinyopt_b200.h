@@ -71,7 +71,7 @@ typedef struct tob200_options {
   int32_t check_final_cost;        /* options.h:43 */
   int32_t use_step_quality_approx; /* options.h:46 */
   float grad_clipping;             /* options.h:49 */
-  int32_t use_ldlt;                /* options.h:59 (only use_ldlt = 1 is implemented) */
+  int32_t use_ldlt;                /* options.h:59; 0 = H.inverse() path (gn.h:157-163), n <= 55 only */
   int32_t H_is_full;               /* options.h:61 */
   float check_min_H_diag;          /* options.h:63 */
   int32_t save_last;               /* options.h:66 */

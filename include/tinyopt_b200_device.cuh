@@ -310,7 +310,6 @@ cudaError_t launch(const F &f, T *x, int64_t B, const tob200_options &options, t
   static_assert(N >= 1 && N <= (sizeof(T) == 8 ? 8 : 12),
                 "thread-per-problem family: n <= 12 (float) / n <= 8 (double)");
   if (B <= 0) return cudaSuccess;
-  if (options.use_ldlt != 1) return cudaErrorInvalidValue;  // only the LDLT path (options.h:59) exists
   constexpr int NT = tri_count(N);
   const int64_t Bpad = (B + 31) / 32 * 32;
   T *hg = nullptr;
@@ -524,7 +523,8 @@ __global__ void __launch_bounds__(tob200::kWppThreads, sizeof(T) == 4 ? 2 : 1)
       }
       emit.finish();
       d.m = emit.nres;
-      wpp_after_pass<T, NB, BLK>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane);
+      if (opt.use_ldlt) wpp_after_pass<T, NB, BLK, false>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane);
+      else wpp_after_pass<T, NB, BLK, true>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane);
     }
     for (int j = lane; j < N; j += 32) x[pr * N + j] = xs[j];
     if (lane == 0) lm_write_result(s, &results[pr]);
@@ -538,7 +538,6 @@ cudaError_t launch_warp(const F &f, T *x, int64_t B, const tob200_options &optio
   using namespace tob200;
   static_assert(N >= 1 && N <= 55, "warp-per-problem family: n <= 55");
   if (B <= 0) return cudaSuccess;
-  if (options.use_ldlt != 1) return cudaErrorInvalidValue;
   constexpr int BLK = wpp_blk_for(N), NB = wpp_nb_for(N), NP = NB * BLK, LDW = wpp_ldw(NP);
   static_assert(NB <= 7, "n + 1 columns must fit 28 register blocks");
   const WppSmem L = wpp_smem_layout(N, NP, 0, (uint32_t)sizeof(T));

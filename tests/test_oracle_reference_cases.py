@@ -404,3 +404,76 @@ def test_fit_circle():
     out = O.optimize([0.0, 0.0, 1.0], nlls_acc(rj), O.default_options(damping_init=1e1))
     assert out.Succeeded()
     assert out.x == pytest.approx([2, 7, 2], abs=1e-5)
+
+
+# ---- hessian.use_ldlt = false: dx = -H.inverse() * grad (solvers/gn.h:157-163) ---------------------
+def test_rectangle_inverse_path():
+    """tests/userdef_params_jet.cpp:85-125 (float, `use_ldlt = false`, damping_init = 0.1).  The
+    manifold of params_trait<Rectangle>::PlusEq (:68-76) is additive in u = (p1.x, p1.y, width,
+    height), so the test is a plain 4-parameter problem in u; `area()` there is the diagonal's norm."""
+    f = np.float32
+
+    def rj(u, want_j):
+        w, h = u[2], u[3]
+        d = np.sqrt(w * w + h * h)
+        hm = max(h, f(1e-8))
+        r = np.array([d - f(200), f(100) * (w / hm - f(2)), u[0] + f(0.5) * w - f(1), u[1] + f(0.5) * h - f(2)], f)
+        J = None
+        if want_j:
+            J = np.array([[0, 0, w / d, h / d],
+                          [0, 0, f(100) / hm, -f(100) * w / (hm * hm)],
+                          [1, 0, 0.5, 0],
+                          [0, 1, 0, 0.5]], f)
+        return r, J
+
+    out = O.optimize(np.array([0, 0, 1, 1], f), nlls_acc(rj), O.default_options(use_ldlt=0, damping_init=1e-1),
+                     dtype=np.float32)
+    assert out.Succeeded()
+    u = out.x.astype(np.float64)
+    assert math.hypot(u[2], u[3]) == pytest.approx(200, abs=1e-3)      # the reference asserts 1e-5 on its
+    assert u[0] + 0.5 * u[2] == pytest.approx(1, abs=1e-4)              # own float trajectory; the restated
+    assert u[1] + 0.5 * u[3] == pytest.approx(2, abs=1e-4)              # Jacobian is analytic, not Jets
+    assert u[2] == pytest.approx(2 * u[3], abs=1e-3)
+    # and the inverse path lands where the LDLT path does
+    ref = O.optimize(np.array([0, 0, 1, 1], f), nlls_acc(rj), O.default_options(damping_init=1e-1), dtype=np.float32)
+    assert ref.Succeeded() and out.x == pytest.approx(ref.x, rel=1e-4)
+
+
+@pytest.mark.parametrize("dtype,x0", [(np.float32, 1.0), (np.float64, 0.7), (np.float64, -0.9)])
+def test_sqrt2_inverse_path(dtype, x0):
+    """benchmarks/dense.cpp:27-52: the sqrt(2) benchmarks run with `use_ldlt = false`, i.e. the
+    Dims == 1 branch `H(0,0) > FloatEpsilon ? -H.inverse() * grad : 0` (gn.h:158-160)."""
+    f = dtype
+
+    def loss(x, want_j):
+        return f(x[0] * x[0] - f(2)), (f(2) * x[0] if want_j else None)
+
+    out = O.optimize(x0, nlls_acc(loss), O.default_options(use_ldlt=0), dtype=dtype)
+    assert out.Succeeded() and out.Converged()
+    assert abs(out.x[0]) == pytest.approx(math.sqrt(2.0), abs=1e-5)
+    ref = O.optimize(x0, nlls_acc(loss), O.default_options(), dtype=dtype)
+    assert out.num_iters == ref.num_iters and out.x[0] == pytest.approx(ref.x[0], rel=1e-6)
+
+
+def test_inverse_path_guard_and_singular_system():
+    """gn.h:158-160: a scalar H at or below FloatEpsilon gives dx = 0 instead of a division;
+    gn.h:162: above one dimension there is no check at all, so a singular H ends the run through
+    Step's NaN/Inf guard (optimizer.h:405-425) where the LDLT path solves the damped system."""
+    def flat(x, g, H):  # J = 0: H = 0 <= FloatEpsilon
+        if g is not None:
+            g[0] = 0.0
+            H[0, 0] = 0.0
+        return 1.0
+    out = O.optimize(1.0, flat, O.default_options(use_ldlt=0))
+    assert out.x[0] == 1.0 and out.deltas2[0] == 0.0
+
+    def rank1(x, g, H):  # J = [1 0]: second row and column of H are zero
+        r = x[0] - 2.0
+        if g is not None:
+            g[:] = (r, 0.0)
+            H[:, :] = ((1.0, 0.0), (0.0, 0.0))
+        return r * r
+    bad = O.optimize(np.array([1.0, 1.0]), rank1, O.default_options(use_ldlt=0))
+    assert bad.stop_reason == K["kSystemHasNaNOrInf"]
+    good = O.optimize(np.array([1.0, 1.0]), rank1, O.default_options())
+    assert good.Converged() and good.x[0] == pytest.approx(2.0, abs=1e-6) and good.x[1] == 1.0

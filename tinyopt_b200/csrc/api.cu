@@ -231,7 +231,11 @@ int to_native_layout(tob200_ctx *ctx, int family, int layout, int64_t B, int m, 
 // launch geometry of a warp-per-problem kernel (family 2)
 typedef cudaError_t (*WppEntry)(int, int, int, const void *, const TppLaunch &, int *);
 template <typename T>
-inline WppEntry wpp_entry_for(int n) {
+inline WppEntry wpp_entry_for(int n, int kind) {
+  if (kind == kWppRunInv || kind == kWppStepInv) {
+    if (sizeof(T) == 8) return wpp_blk_for(n) == 4 ? wpp_entry_f64_blk4_inv : wpp_entry_f64_blk8_inv;
+    return wpp_blk_for(n) == 4 ? wpp_entry_f32_blk4_inv : wpp_entry_f32_blk8_inv;
+  }
   if (sizeof(T) == 8) return wpp_blk_for(n) == 4 ? wpp_entry_f64_blk4 : wpp_entry_f64_blk8;
   return wpp_blk_for(n) == 4 ? wpp_entry_f32_blk4 : wpp_entry_f32_blk8;
 }
@@ -262,7 +266,7 @@ int wpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, const T *A
   auto it = ctx->occupancy.find(key);
   int per_sm = 0;
   if (it == ctx->occupancy.end()) {
-    cudaError_t e = wpp_entry_for<T>(n)(kTppQuery, nb, kind, nullptr, *cfg, &per_sm);
+    cudaError_t e = wpp_entry_for<T>(n, kind)(kTppQuery, nb, kind, nullptr, *cfg, &per_sm);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "occupancy query");
     if (per_sm < 1) return fail(ctx, TOB200_ERR_CUDA, "kernel does not fit on an SM (shared memory / registers)");
     ctx->occupancy[key] = per_sm;
@@ -284,7 +288,7 @@ int wpp_configure(tob200_ctx *ctx, int n, int m, int64_t B, int kind, const T *A
 
 template <typename T>
 int wpp_launch(tob200_ctx *ctx, int n, int kind, const void *params, const TppLaunch &cfg) {
-  CK(wpp_entry_for<T>(n)(kTppLaunch, wpp_nb_for(n), kind, params, cfg, nullptr));
+  CK(wpp_entry_for<T>(n, kind)(kTppLaunch, wpp_nb_for(n), kind, params, cfg, nullptr));
   ctx->launches++;
   return TOB200_OK;
 }
@@ -498,7 +502,6 @@ int check_options(tob200_ctx *ctx, const tob200_options *o) {
   if (!o) return fail(ctx, TOB200_ERR_INVALID, "options is NULL");
   if (o->solver_type != 0 && o->solver_type != 1)
     return fail(ctx, TOB200_ERR_UNSUPPORTED, "solver_type must be LevenbergMarquardt (0) or GaussNewton (1)");
-  if (!o->use_ldlt) return fail(ctx, TOB200_ERR_UNSUPPORTED, "hessian.use_ldlt = false is not implemented");
   if (o->max_iters < 0 || o->max_iters > 65535) return fail(ctx, TOB200_ERR_INVALID, "max_iters out of range");
   if (o->max_consec_failures < 0 || o->max_consec_failures > 255 || o->max_total_failures < 0 ||
       o->max_total_failures > 255)
@@ -586,6 +589,8 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
   DeviceGuard guard(ctx->device);
   const int family = tob200_kernel_family(dtype_of<T>(), n);
   if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n has no kernel yet for this dtype");
+  if (!opt->use_ldlt && family == 3)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "hessian.use_ldlt = false (H.inverse()) is implemented for n <= 55 only");
   if (record_events) CK(cudaEventRecord(ctx->ev0, ctx->stream));
   if ((rc = to_native_layout<T>(ctx, family, layout, B, m, n, &A, &y)) != TOB200_OK) return rc;
   TppLaunch cfg;
@@ -626,13 +631,14 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     }
   } else {
     WppRunParams<T> p;
-    if ((rc = wpp_configure<T>(ctx, n, m, B, kWppRun, A, y, &p.d, &cfg)) != TOB200_OK) return rc;
+    const int kind = opt->use_ldlt ? kWppRun : kWppRunInv;  // options.h:59
+    if ((rc = wpp_configure<T>(ctx, n, m, B, kind, A, y, &p.d, &cfg)) != TOB200_OK) return rc;
     p.opt = make_dev_options<T>(*opt);
     p.alpha = alpha;
     p.alpha3 = (T)3 * alpha;
     p.x = x;
     p.results = results;
-    if ((rc = wpp_launch<T>(ctx, n, kWppRun, &p, cfg)) != TOB200_OK) return rc;
+    if ((rc = wpp_launch<T>(ctx, n, kind, &p, cfg)) != TOB200_OK) return rc;
   }
   if (record_events) CK(cudaEventRecord(ctx->ev1, ctx->stream));
   return TOB200_OK;
@@ -756,7 +762,8 @@ int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m
   if (s->family == 2) {  // warp per problem (wpp_step.cuh)
     WppStepParams<T> p;
     TppLaunch cfg;
-    int rc = wpp_configure<T>(ctx, n, reset ? 1 : m, B, kWppStep, J, r, &p.d, &cfg);
+    const int kind = s->opt.use_ldlt ? kWppStep : kWppStepInv;  // options.h:59
+    int rc = wpp_configure<T>(ctx, n, reset ? 1 : m, B, kind, J, r, &p.d, &cfg);
     if (rc != TOB200_OK) return rc;
     p.opt = make_dev_options<T>(s->opt);
     p.rec = (StateRec<T> *)s->rec;
@@ -769,7 +776,7 @@ int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m
     p.reset = reset;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaMemsetAsync(s->n_active, 0, sizeof(unsigned long long), ctx->stream));
-    if ((rc = wpp_launch<T>(ctx, n, kWppStep, &p, cfg)) != TOB200_OK) return rc;
+    if ((rc = wpp_launch<T>(ctx, n, kind, &p, cfg)) != TOB200_OK) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     return TOB200_OK;
   }

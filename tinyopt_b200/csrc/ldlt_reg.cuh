@@ -150,4 +150,73 @@ struct LdltReg {
   }
 };
 
+// `hessian.use_ldlt = false` (include/tinyopt/solvers/gn.h:157-163): dx = -H^-1 g with no check on
+// invertibility, restated as a partial-pivot LU solve in the canonical order of the oracle
+// (right-looking elimination, first largest |entry| of the column is the pivot, upper solve with the
+// updates of x_i applied for j = n-1 .. i+1).  The option is off the hot path, so the full matrix
+// lives in thread-local memory behind a real call and the default LDLT path keeps its registers.
+template <typename T, int N>
+__device__ __noinline__ void lu_solve_local(T *M, T *b) {
+  using O = Ops<T>;
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    T best = O::abs(M[k * N + k]);
+#pragma unroll 1
+    for (int i = k + 1; i < N; ++i) {
+      const T v = O::abs(M[i * N + k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    if (p != k) {
+#pragma unroll 1
+      for (int j = 0; j < N; ++j) {
+        const T t = M[k * N + j];
+        M[k * N + j] = M[p * N + j];
+        M[p * N + j] = t;
+      }
+      const T t = b[k];
+      b[k] = b[p];
+      b[p] = t;
+    }
+    const T piv = M[k * N + k];
+#pragma unroll 1
+    for (int i = k + 1; i < N; ++i) {
+      const T f = O::div(M[i * N + k], piv);
+#pragma unroll 1
+      for (int j = k + 1; j < N; ++j) M[i * N + j] = O::fma(-f, M[k * N + j], M[i * N + j]);
+      b[i] = O::fma(-f, b[k], b[i]);
+    }
+  }
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; --i) {
+    T s = b[i];
+#pragma unroll 1
+    for (int j = N - 1; j > i; --j) s = O::fma(-M[i * N + j], b[j], s);
+    b[i] = O::div(s, M[i * N + i]);
+  }
+}
+
+// hu: packed upper triangle of the (damped) symmetric H_, g: gradient -> dx
+template <typename T, int N>
+__device__ __forceinline__ void solve_inverse_reg(const T (&hu)[tri_count(N)], const T (&g)[N], T (&dx)[N]) {
+  using O = Ops<T>;
+  if (N == 1) {  // gn.h:158-160: guarded scalar inverse, zero step otherwise
+    dx[0] = hu[0] > O::float_eps() ? O::mul(-O::div((T)1, hu[0]), g[0]) : (T)0;
+    return;
+  }
+  T M[N * N], b[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) M[i * N + j] = hu[tri_index(N, i < j ? i : j, i < j ? j : i)];
+    b[i] = -g[i];
+  }
+  lu_solve_local<T, N>(M, b);
+#pragma unroll
+  for (int i = 0; i < N; ++i) dx[i] = b[i];
+}
+
 }  // namespace tob200

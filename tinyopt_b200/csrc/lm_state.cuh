@@ -23,7 +23,7 @@ namespace tob200 {
 // device copy of tob200_options, thresholds pre-widened exactly as the reference widens them
 template <typename T>
 struct DevOptions {
-  int solver_type, check_final_cost, use_step_quality_approx;
+  int solver_type, check_final_cost, use_step_quality_approx, use_ldlt;
   int use_squared_norm, downscale_by_2, normalize;
   int max_iters, max_total_failures, max_consec_failures;
   T grad_clipping, check_min_H_diag;
@@ -38,6 +38,7 @@ inline DevOptions<T> make_dev_options(const tob200_options &o) {
   d.solver_type = o.solver_type;
   d.check_final_cost = o.check_final_cost;
   d.use_step_quality_approx = o.use_step_quality_approx;
+  d.use_ldlt = o.use_ldlt;
   d.use_squared_norm = o.use_squared_norm;
   d.downscale_by_2 = o.downscale_by_2;
   d.normalize = o.normalize;
@@ -376,10 +377,15 @@ __device__ __forceinline__ void lm_after_pass(LmState<T, N> &s, const DevOptions
         for (int j = 0; j < N; ++j) hg.st_h(tri_index(N, j, j), hu[tri_index(N, j, j)]);
       }
       // Solve (gn.h:150-156)
-      if (L::factor(hu, tr)) {
+      if (o.use_ldlt) {
+        if (L::factor(hu, tr)) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) dx[j] = -g[j];
-        L::solve(hu, tr, dx);
+          for (int j = 0; j < N; ++j) dx[j] = -g[j];
+          L::solve(hu, tr, dx);
+          solver_failed = false;
+        }
+      } else {  // gn.h:157-163: -H^-1 g, never fails
+        solve_inverse_reg<T, N>(hu, g, dx);
         solver_failed = false;
       }
     }

@@ -495,6 +495,91 @@ __device__ __forceinline__ void wpp_ldlt_solve(const T *W, int ldw, int n, const
 #undef WW
 }
 
+// `hessian.use_ldlt = false` (include/tinyopt/solvers/gn.h:157-163): x <- -H^-1 g by partial-pivot LU
+// in the oracle's canonical order (see lu_solve_local in ldlt_reg.cuh), warp-cooperative.  W holds
+// the lower triangle of the unpermuted damped H_ on entry and is destroyed; b is n scratch values.
+// Lanes own columns in the elimination (the rhs is column n) and rows in the upper solve; n <= 64.
+// Off the hot path, so a real call: the LDLT path keeps its registers.
+template <typename T>
+__device__ __noinline__ void wpp_lu_solve(T *W, int ldw, int n, const T *g, T *b, T *x, int lane) {
+  using O = Ops<T>;
+  constexpr unsigned kFull = 0xffffffffu;
+#define WW(i, j) W[(i) * ldw + (j)]
+  if (n == 1) {  // gn.h:158-160
+    if (lane == 0) x[0] = WW(0, 0) > O::float_eps() ? O::mul(-O::div((T)1, WW(0, 0)), g[0]) : (T)0;
+    __syncwarp();
+    return;
+  }
+  for (int e = lane; e < n * n; e += 32) {
+    const int i = e / n, j = e - i * n;
+    if (j > i) WW(i, j) = WW(j, i);
+  }
+  for (int j = lane; j < n; j += 32) b[j] = -g[j];
+  __syncwarp();
+  for (int k = 0; k < n; ++k) {
+    // first largest |entry| of column k at or below the diagonal (a NaN diagonal keeps p = k)
+    T best = O::abs(WW(k, k));
+    int p = k;
+    for (int i = k + 1 + lane; i < n; i += 32) {
+      const T v = O::abs(WW(i, k));
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      const T ob = __shfl_xor_sync(kFull, best, off);
+      const int op = __shfl_xor_sync(kFull, p, off);
+      if (ob > best || (ob == best && op < p)) {
+        best = ob;
+        p = op;
+      }
+    }
+    if (p != k) {
+      for (int j = lane; j < n; j += 32) {
+        const T t = WW(k, j);
+        WW(k, j) = WW(p, j);
+        WW(p, j) = t;
+      }
+      if (lane == 0) {
+        const T t = b[k];
+        b[k] = b[p];
+        b[p] = t;
+      }
+      __syncwarp();
+    }
+    const T piv = WW(k, k);
+    for (int j = k + 1 + lane; j <= n; j += 32) {
+      const bool rhs = j == n;
+      const T akj = rhs ? b[k] : WW(k, j);
+      for (int i = k + 1; i < n; ++i) {
+        const T f = O::div(WW(i, k), piv);
+        if (rhs) b[i] = O::fma(-f, akj, b[i]);
+        else WW(i, j) = O::fma(-f, akj, WW(i, j));
+      }
+    }
+    __syncwarp();
+  }
+  // U x = b from the last row, x_i taking its updates in the order j = n-1 .. i+1
+  T s0 = lane < n ? b[lane] : (T)0, s1 = lane + 32 < n ? b[lane + 32] : (T)0;
+  for (int j = n - 1; j >= 0; --j) {
+    T xj = j < 32 ? s0 : s1;
+    if (lane == (j & 31)) xj = O::div(xj, WW(j, j));
+    xj = __shfl_sync(kFull, xj, j & 31);
+    if (lane == (j & 31)) {
+      if (j < 32) s0 = xj;
+      else s1 = xj;
+    }
+    if (lane < j) s0 = O::fma(-WW(lane, j), xj, s0);
+    if (lane + 32 < j) s1 = O::fma(-WW(lane + 32, j), xj, s1);
+  }
+  if (lane < n) x[lane] = s0;
+  if (lane + 32 < n) x[lane + 32] = s1;
+  __syncwarp();
+#undef WW
+}
+
 // sequential (canonical) sum of squares of a shared vector, computed by lane 0, broadcast
 template <typename T>
 __device__ __forceinline__ T wpp_sqnorm(const T *v, int n, int lane) {
@@ -770,7 +855,9 @@ __device__ __forceinline__ void wpp_store_permuted(T *W, const T (&acc)[BLK][BLK
 }
 
 // Everything after the data pass for one problem, warp-cooperative; mirrors lm_after_pass.
-template <typename T, int NB, int BLK>
+// INV selects the `hessian.use_ldlt = false` solve at compile time: the real call to wpp_lu_solve
+// inside the retry loop would otherwise cost the LDLT kernels registers (measured -3% on C4).
+template <typename T, int NB, int BLK, bool INV = false>
 __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions<T> &o, const WppData<T> &d,
                                                unsigned char *ws, T *hp, bool pass_rebuilt, int bi, int bj,
                                                bool has_block, const T (&acc)[BLK][BLK], T cost_only, int lane,
@@ -837,7 +924,15 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
         dd[j] = damp ? (T)((double)base * sc) : base;
       }
       __syncwarp();
-      wpp_pivot_order(dd, n, perm, inv, lane);
+      if constexpr (!INV) {
+        wpp_pivot_order(dd, n, perm, inv, lane);
+      } else {  // the LU of the inverse path pivots by itself: lay H_ out unpermuted
+        for (int j = lane; j < n; j += 32) {
+          perm[j] = j;
+          inv[j] = j;
+        }
+        __syncwarp();
+      }
       if (pass_rebuilt) {
         wpp_store_permuted<T, NB, BLK>(W, acc, bi, bj, has_block, n, dd, inv, may_need_stale_h ? hp : nullptr);
       } else {  // cost-only pass, or a retry of one: lay the persistent H_ out, publish its new diagonal
@@ -854,12 +949,17 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
       }
       __syncwarp();
       WPP_T(3);
-      const bool fact_ok = wpp_ldlt_factor<T>(W, LDW, n, temp, dxs, NB * BLK, lane);  // gn.h:150-156
-      WPP_T(4);
-      if (fact_ok) {
-        for (int j = lane; j < n; j += 32) temp[j] = -g[j];
-        __syncwarp();
-        wpp_ldlt_solve<T>(W, LDW, n, perm, temp, dxs, lane);
+      if constexpr (!INV) {
+        const bool fact_ok = wpp_ldlt_factor<T>(W, LDW, n, temp, dxs, NB * BLK, lane);  // gn.h:150-156
+        WPP_T(4);
+        if (fact_ok) {
+          for (int j = lane; j < n; j += 32) temp[j] = -g[j];
+          __syncwarp();
+          wpp_ldlt_solve<T>(W, LDW, n, perm, temp, dxs, lane);
+          solver_failed = false;
+        }
+      } else {  // gn.h:157-163: -H^-1 g, never fails
+        wpp_lu_solve<T>(W, LDW, n, g, temp, dxs, lane);
         solver_failed = false;
       }
       WPP_T(5);
@@ -909,7 +1009,7 @@ struct WppRunParams {
   tob200_result *results;  // [B]
 };
 
-template <typename T, int NB, int BLK>
+template <typename T, int NB, int BLK, bool INV = false>
 __global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 3 : 1) wpp_lm_run_kernel(const __grid_constant__ WppRunParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -940,7 +1040,7 @@ __global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 3 : 1) wpp_lm_ru
       const bool do_rebuild = !is_lm || s.rebuild();
       T acc[BLK][BLK], cost_only;
       wpp_pass<T, NB, BLK, true>(pipe, p.d, ws, pr, lane, do_rebuild, p.alpha, p.alpha3, bi, bj, has_block, acc, cost_only);
-      wpp_after_pass<T, NB, BLK>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane);
+      wpp_after_pass<T, NB, BLK, INV>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane);
     }
     for (int j = lane; j < n; j += 32) p.x[pr * n + j] = xs[j];
     if (lane == 0) lm_write_result(s, &p.results[pr]);

@@ -7,25 +7,32 @@
 
 namespace tob200 {
 
-enum WppKind { kWppRun = 0, kWppBuildSolve = 1, kWppStep = 2 };
+// the *Inv kinds are the `hessian.use_ldlt = false` variants (wpp_lu_solve); they are instantiated in
+// their own translation units (wpp_inst_*_inv.cu) behind the *_inv entries
+enum WppKind { kWppRun = 0, kWppBuildSolve = 1, kWppStep = 2, kWppRunInv = 3, kWppStepInv = 4 };
 
 template <typename T, int NB, int BLK>
 cudaError_t wpp_entry_one(int op, int kind, const void *params, const TppLaunch &cfg, int *out) {
   const void *fn = nullptr;
   switch (kind) {
+#ifdef TOB200_WPP_INV_TU
+    case kWppRunInv: fn = (const void *)wpp_lm_run_kernel<T, NB, BLK, true>; break;
+    case kWppStepInv: fn = (const void *)wpp_step_kernel<T, NB, BLK, true>; break;
+#else
     case kWppRun: fn = (const void *)wpp_lm_run_kernel<T, NB, BLK>; break;
     case kWppBuildSolve: fn = (const void *)wpp_build_solve_kernel<T, NB, BLK>; break;
     case kWppStep: fn = (const void *)wpp_step_kernel<T, NB, BLK>; break;
+#endif
     default: return cudaErrorInvalidValue;
   }
   // The dynamic shared-memory limit of a kernel is raised monotonically: the same instantiation serves
   // shapes with different footprints, and lowering the attribute for a small one would make a later
   // launch of a larger (occupancy-cached) one fail with "invalid argument".
-  static size_t smem_limit[4] = {0, 0, 0, 0};
-  if (cfg.smem > smem_limit[kind & 3]) {
+  static size_t smem_limit[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cfg.smem > smem_limit[kind & 7]) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
-    smem_limit[kind & 3] = cfg.smem;
+    smem_limit[kind & 7] = cfg.smem;
   }
   if (op == kTppQuery) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, fn, cfg.block, cfg.smem);
   void *args[] = {const_cast<void *>(params)};
@@ -68,5 +75,9 @@ TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk4);  // n = 13..27
 TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk8);  // n = 28..55
 TOB200_WPP_ENTRY_DECL(wpp_entry_f64_blk4);  // n = 9..27, scalar paths (functional coverage of double)
 TOB200_WPP_ENTRY_DECL(wpp_entry_f64_blk8);  // n = 28..55
+TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk4_inv);  // kWppRunInv / kWppStepInv of the same ranges
+TOB200_WPP_ENTRY_DECL(wpp_entry_f32_blk8_inv);
+TOB200_WPP_ENTRY_DECL(wpp_entry_f64_blk4_inv);
+TOB200_WPP_ENTRY_DECL(wpp_entry_f64_blk8_inv);
 
 }  // namespace tob200

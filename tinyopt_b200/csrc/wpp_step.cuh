@@ -42,7 +42,7 @@ __device__ __forceinline__ void wpp_state_store(const LmScalars<T> &s, StateRec<
   r.num_failures = s.num_failures; r.num_consec_failures = s.num_consec_failures;
 }
 
-template <typename T, int NB, int BLK>
+template <typename T, int NB, int BLK, bool INV = false>
 __global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 2 : 1) wpp_step_kernel(const __grid_constant__ WppStepParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 2 : 1) wpp_step_
     T acc[BLK][BLK], cost_only;
     wpp_pass<T, NB, BLK, false>(pipe, p.d, ws, pr, lane, do_rebuild, (T)0, (T)0, bi, bj, has_block, acc, cost_only);
     T *hp = p.H + (size_t)pr * (NP * LDW);
-    wpp_after_pass<T, NB, BLK>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane, true);
+    wpp_after_pass<T, NB, BLK, INV>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane, true);
     for (int j = lane; j < n; j += 32) {
       p.x[pr * n + j] = xs[j];
       p.last_dx[pr * n + j] = last_dx[j];
