@@ -48,6 +48,18 @@ static void test_sqrt2(const Context &ctx) {
     CHECK(o2[0].num_iters == 5 && o2[0].stop_reason == StopReason::kMinError);
     CHECK(o2[1].stop_reason == StopReason::kMaxConsecNoDecr);
   }
+  {  // benchmarks/dense.cpp:39-52: the reference's own sqrt(2) benchmark runs with hessian.use_ldlt = false
+    Options inv = options;
+    inv.hessian.use_ldlt = false;
+    std::vector<double> x2(B);
+    for (int64_t p = 0; p < B; ++p) x2[p] = (p % 3 == 0) ? 1.0 : (p % 3 == 1 ? -0.3 : 3.2);
+    auto o3 = OptimizeBatch<double>(ctx, x2.data(), B, 1, 1, residuals, inv);
+    for (int64_t p = 0; p < B; ++p) {
+      CHECK(o3[p].Converged());
+      CHECK(o3[p].num_iters == outs[p].num_iters);
+      CHECK(std::fabs(x2[p] - xs[p]) < 1e-12);
+    }
+  }
   std::printf("sqrt2: x[0]=%.16g iters=%d stop=%d\n", xs[0], (int)outs[0].num_iters, (int)outs[0].stop_reason);
 }
 

@@ -179,7 +179,7 @@ static int lm_run(tob200_ctx *c, const tob200_options *o, const float *A, const 
 }
 
 template <typename T, int N, bool kWarp = false>
-static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
+static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol, bool use_ldlt = true) {
   T *A, *y, *xs, *x0, *xa, *xb, *xc;
   tob200_result *ra, *rb, *rc;
   CU(cudaMalloc(&A, (size_t)B * m * N * sizeof(T)));
@@ -191,6 +191,7 @@ static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
   tob200_options opt;
   tob200_options_default(&opt);
   if (sizeof(T) == 4) { opt.min_rerr_dec = 1e-5f; opt.min_step_norm2 = 1e-9f; }  // SURVEY §8d float options
+  opt.use_ldlt = use_ldlt ? 1 : 0;  // 0: dx = -H.inverse() * grad (solvers/gn.h:157-163)
   for (T *q : {xa, xb, xc}) CU(cudaMemcpyAsync(q, x0, (size_t)B * N * sizeof(T), cudaMemcpyDeviceToDevice, nullptr));
   CU(cudaDeviceSynchronize());
   CHECK(lm_run(ctx, &opt, A, y, B, m, N, xa, ra) == TOB200_OK);  // the library's own kernels (oracle-pinned)
@@ -244,9 +245,9 @@ static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol) {
   //  oracle disagrees with the double one on those too, tests/test_gpu_large.py::robust_decisions)
   CHECK(same_iters_ad >= B - B / (sizeof(T) == 8 ? 200 : 20));
   CHECK(worst / xmax <= tol);
-  std::printf("family<%s> n=%d m=%d B=%lld%s: iters=%lld manual functor == lm_run bit for bit; Jets: %lld/%lld same "
+  std::printf("family<%s> n=%d m=%d B=%lld%s%s: iters=%lld manual functor == lm_run bit for bit; Jets: %lld/%lld same "
               "iteration count + stop reason, max rel dx %.2e\n",
-              sizeof(T) == 8 ? "double" : "float", N, m, (long long)B, kWarp ? " (warp per problem)" : "", (long long)iters,
+              sizeof(T) == 8 ? "double" : "float", N, m, (long long)B, kWarp ? " (warp per problem)" : "", use_ldlt ? "" : " (use_ldlt = false)", (long long)iters,
               (long long)same_iters_ad,
               (long long)B, worst / xmax);
   for (T *q : {A, y, xs, x0, xa, xb, xc}) cudaFree(q);
@@ -309,6 +310,11 @@ int main() {
   test_family<float, 50, true>(ctx, 1024, 200, 1e-4);
   test_family<double, 20, true>(ctx, 1024, 64, 1e-10);
   test_family<double, 6, true>(ctx, 1024, 30, 1e-10);   // a small n through the warp kernels too
+  // hessian.use_ldlt = false: the thread-local LU, the warp LU, and one against the other (n = 6 runs
+  // thread per problem inside tob200_lm_run and warp per problem in the functor kernel)
+  test_family<double, 6>(ctx, 1024, 30, 1e-10, false);
+  test_family<float, 20, true>(ctx, 1024, 64, 1e-4, false);
+  test_family<double, 6, true>(ctx, 1024, 30, 1e-10, false);
   tob200_destroy(ctx);
   if (g_failures) {
     std::printf("%d check(s) failed\n", g_failures);
