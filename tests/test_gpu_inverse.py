@@ -152,3 +152,34 @@ def test_inverse_path_guard_and_singular_system(ctx):
         o = O.optimize(np.ones(n), rank1_acc, O.default_options())
         assert o.Converged() and (res["stop_reason"] == o.stop_reason).all()
         assert np.array_equal(x, np.tile(o.x, (3, 1)))
+
+
+@pytest.mark.parametrize("dtype,B,m,n", [(np.float64, 200, 30, 6), (np.float32, 100, 50, 10),
+                                         (np.float32, 40, 90, 20), (np.float64, 24, 100, 40),
+                                         (np.float32, 17, 131, 55)])
+def test_inverse_path_solver_seam(ctx, dtype, B, m, n):
+    """The host-driven loop (tob200_solver_*: tpp_step_kernel / the kWppStepInv kernels) with
+    `use_ldlt = false`, fed with the synthetic family's residual blocks, equals the oracle exactly;
+    the final Hessian it exports is still the un-damped J^T J (solvers/lm.h:157-171)."""
+    import tinyopt_b200 as tb
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    layout = tb.TILE32 if ctx.kernel_family(tdt, n) == 1 else tb.PROBLEM_MAJOR
+    kw = dict(use_ldlt=0, **(dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dtype == np.float32 else {}))
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=5)
+    xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, tdt, p0=5, layout=layout)
+    s = tb.BatchSolver(ctx, B, n, tdt, tb.options(**kw))
+    s.reset(dx0)
+    steps = 0
+    while s.num_active() > 0 and steps < 200:
+        r, J = ctx.synth_eval(dA, dy, s.x, layout=layout)
+        s.step(J, r, layout=layout)
+        steps += 1
+    res = s.results()
+    assert np.array_equal(res["num_iters"], ro["num_iters"])
+    assert np.array_equal(res["stop_reason"], ro["stop_reason"])
+    assert np.array_equal(s.x.cpu().numpy(), xo)
+    assert np.array_equal(res["final_cost"], ro["final_cost"])
+    H = s.final_hessian().cpu().numpy()
+    assert np.array_equal(H, np.swapaxes(H, 1, 2)) and (np.einsum("bii->bi", H) > 0).all()
+    s.close()
