@@ -164,6 +164,17 @@ template <typename T, int N> __host__ __device__ inline T value_of(const Jet<T, 
 __host__ __device__ inline float value_of(float s) { return s; }
 __host__ __device__ inline double value_of(double s) { return s; }
 
+/// std::numeric_limits<T>::min(): the reference clamps the outlier scales of Huber / Arctan / Cauchy with
+/// max<T>(numeric_limits<T>::min(), scale) so that an extreme outlier never zeroes a Jacobian row
+/// (robust_norms.h:95,184,221; for Jets the comparison is on the value part, as ceres::Jet's operator<)
+__host__ __device__ inline float min_normal_of(float) { return 1.175494351e-38f; }
+__host__ __device__ inline double min_normal_of(double) { return 2.2250738585072014e-308; }
+template <typename S>
+__host__ __device__ inline S clamp_scale(const S &scale) {
+  const auto lo = min_normal_of(value_of(scale));
+  return value_of(scale) < lo ? S(lo) : scale;  // max(lo, scale): lo wins only if strictly larger
+}
+
 /// robust_norms.h:32-55: loss = min(n2, th2), scale in {1, 0}
 template <typename S, typename T>
 __host__ __device__ inline Robust<S> Truncated(const S &n2, T th2) {
@@ -176,7 +187,7 @@ __host__ __device__ inline Robust<S> Huber(const S &n2, T th2) {
   if (value_of(n2) <= th2) return {n2, S((T)1)};
   const T th = sqrt(th2);
   const S n = sqrt(n2);
-  return {(T)2 * th * n - th2, th / n};
+  return {(T)2 * th * n - th2, clamp_scale(S(th / n))};
 }
 /// robust_norms.h:118-152: loss = th2 (1 - (1 - n2 / th2)^3) (inlier) or th2, scale = 3 (th2 - n2)^2 / th2^2 or 0
 template <typename S, typename T>
@@ -192,13 +203,13 @@ __host__ __device__ inline Robust<S> Tukey(const S &n2, T th2) {
 template <typename S, typename T>
 __host__ __device__ inline Robust<S> Arctan(const S &n2, T th2) {
   const T th = sqrt(th2);
-  return {th * atan(n2 / th), (T)1 / (n2 * n2 / th2 + (T)1)};  // th > 0: atan2(n2, th) == atan(n2 / th)
+  return {th * atan(n2 / th), clamp_scale(S((T)1 / (n2 * n2 / th2 + (T)1)))};  // th > 0: atan2(n2, th) == atan(n2 / th)
 }
 /// robust_norms.h:204-228: loss = th2 log(1 + n2 / th2), scale = 1 / (1 + n2 / th2)
 template <typename S, typename T>
 __host__ __device__ inline Robust<S> Cauchy(const S &n2, T th2) {
   const S s = (T)1 + n2 / th2;
-  return {th2 * log(s), (T)1 / s};
+  return {th2 * log(s), clamp_scale(S((T)1 / s))};
 }
 /// robust_norms.h:241-265: loss = n2 / (n2 + th2), scale = th2 / (n2 + th2)^2
 template <typename S, typename T>

@@ -69,7 +69,8 @@ class Trace(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc)."""
     srcs = [os.path.join(_HERE, f) for f in ("tinyopt_oracle.c", "oracle_impl.inc", "tinyopt_oracle.h", "Makefile")]
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    sos = [_SO] + [os.path.join(_HERE, f"libtinyopt_oracle_fast_{v}.so") for v in ("v3", "v4")]
+    stale = any((not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs) for so in sos)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
                        stdout=subprocess.DEVNULL)
@@ -77,6 +78,19 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_lib_fast = None
+
+
+def _declare(l: C.CDLL) -> C.CDLL:
+    l.too_max_threads.restype = C.c_int
+    l.too_options_default.argtypes = [C.POINTER(Options)]
+    for suf in ("f32", "f64"):
+        for name in ("too_solve_ldlt", "too_inv_cov", "too_build_solve", "too_optimize",
+                     "too_synth_lm_run"):
+            getattr(l, f"{name}_{suf}").restype = C.c_int
+        for name in ("too_synth_generate", "too_synth_eval"):
+            getattr(l, f"{name}_{suf}").restype = None
+    return l
 
 
 def lib() -> C.CDLL:
@@ -87,16 +101,28 @@ def lib() -> C.CDLL:
         except Exception:  # no compiler on the box: use the prebuilt .so that travelled
             if not os.path.exists(_SO):
                 raise
-        _lib = C.CDLL(_SO)
-        _lib.too_max_threads.restype = C.c_int
-        _lib.too_options_default.argtypes = [C.POINTER(Options)]
-        for suf in ("f32", "f64"):
-            for name in ("too_solve_ldlt", "too_inv_cov", "too_build_solve", "too_optimize",
-                         "too_synth_lm_run"):
-                getattr(_lib, f"{name}_{suf}").restype = C.c_int
-            for name in ("too_synth_generate", "too_synth_eval"):
-                getattr(_lib, f"{name}_{suf}").restype = None
+        _lib = _declare(C.CDLL(_SO))
     return _lib
+
+
+def fast_variant() -> str:
+    """'v4' (AVX-512) if this host's cores have it, else 'v3' (AVX2 + FMA)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = f.read()
+        return "v4" if (" avx512f" in flags and " avx512vl" in flags and " avx512bw" in flags and " avx512dq" in flags) else "v3"
+    except OSError:
+        return "v3"
+
+
+def lib_fast() -> C.CDLL:
+    """The -DTOO_FAST build: the same arithmetic scheduled for a wide core (oracle/Makefile); its
+    results are bit-identical to lib()'s, it only serves as the faster CPU baseline."""
+    global _lib_fast
+    if _lib_fast is None:
+        lib()  # builds everything
+        _lib_fast = _declare(C.CDLL(os.path.join(_HERE, f"libtinyopt_oracle_fast_{fast_variant()}.so")))
+    return _lib_fast
 
 
 def default_options(**kw) -> Options:
@@ -292,14 +318,21 @@ def synth_eval(A: np.ndarray, y: np.ndarray, x: np.ndarray, alpha: float = ALPHA
 
 
 def synth_lm_run(A: np.ndarray, y: np.ndarray, x0: np.ndarray, options: Options | None = None,
-                 alpha: float = ALPHA, nthreads: int = 0):
-    """Batched LM over the family.  Returns (x[B,n], results structured array, threads used)."""
+                 alpha: float = ALPHA, nthreads: int = 0, fast: bool = False, reverse_rows: bool = False):
+    """Batched LM over the family.  Returns (x[B,n], results structured array, threads used).
+    fast=True runs the -DTOO_FAST build (same results, scheduled for throughput).  reverse_rows=True
+    (census only) sums the residual rows m-1 .. 0: another valid order, NOT the canonical one."""
     A = np.ascontiguousarray(A); y = np.ascontiguousarray(y, dtype=A.dtype)
     B, m, n = A.shape
     x = np.array(x0, dtype=A.dtype, order="C", copy=True)
     res = np.zeros(B, RESULT_DTYPE)
     opt = options if options is not None else default_options()
-    used = getattr(lib(), f"too_synth_lm_run_{_suf(A.dtype)}")(
-        C.c_int64(B), C.c_int(m), C.c_int(n), _ptr(A), _ptr(y), _ct(A.dtype)(alpha), _ptr(x),
-        C.byref(opt), _ptr(res), C.c_int(nthreads))
+    l = lib_fast() if fast else lib()
+    l.too_census_set_row_order(C.c_int(1 if reverse_rows else 0))
+    try:
+        used = getattr(l, f"too_synth_lm_run_{_suf(A.dtype)}")(
+            C.c_int64(B), C.c_int(m), C.c_int(n), _ptr(A), _ptr(y), _ct(A.dtype)(alpha), _ptr(x),
+            C.byref(opt), _ptr(res), C.c_int(nthreads))
+    finally:
+        l.too_census_set_row_order(C.c_int(0))
     return x, res, used

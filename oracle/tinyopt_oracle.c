@@ -6,6 +6,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -46,6 +47,10 @@ int too_max_threads(void) {
   return 1;
 #endif
 }
+
+/* census only (tools/margin_census.py): 1 = accumulate the rows in reverse order */
+static int too_census_row_order_ = 0;
+void too_census_set_row_order(int rev) { too_census_row_order_ = rev; }
 
 /* stateless counter RNG of the synthetic family:
  * u(seed,p,k) = splitmix64-finaliser(seed ^ (p * golden + k)) */

@@ -169,6 +169,11 @@ int too_synth_lm_run_f32(int64_t B, int m, int n, const float *A, const float *y
 
 int too_max_threads(void);
 
+/* Decision-margin census only: rev != 0 makes too_synth_lm_run_* accumulate the residual rows in
+ * reverse order (a different, equally valid summation order - what Eigen's GEMM is to this
+ * restatement).  Never set by tests of the canonical sequence. */
+void too_census_set_row_order(int rev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@
 //      1e-10 (double) / 1e-4 (float) relative (the Jet derivative rounds differently from the closed form).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -244,6 +245,20 @@ static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol, bool use_
   // (float: the stop tests of a few % of the problems land within FP32 rounding of their threshold — the float
   //  oracle disagrees with the double one on those too, tests/test_gpu_large.py::robust_decisions)
   CHECK(same_iters_ad >= B - B / (sizeof(T) == 8 ? 200 : 20));
+  // tests/test_device_functor.py re-checks the float cases problem by problem with the oracle's decision
+  // margins (every problem whose decisions clear FP32 noise must agree): dump {lm_run, Jets} x {iters, stop}
+  if (const char *dir = std::getenv("TOB200_FUNCTOR_DUMP")) {
+    char path[1024];
+    std::snprintf(path, sizeof(path), "%s/jets_%s_n%d_m%d_B%lld_%s_%s.bin", dir, sizeof(T) == 8 ? "f64" : "f32", N, m,
+                  (long long)B, kWarp ? "warp" : "thread", use_ldlt ? "ldlt" : "inv");
+    if (FILE *f = std::fopen(path, "wb")) {
+      for (int64_t p = 0; p < B; ++p) {
+        const int32_t rec[4] = {qa[p].num_iters, qa[p].stop_reason, qc[p].num_iters, qc[p].stop_reason};
+        std::fwrite(rec, sizeof(rec), 1, f);
+      }
+      std::fclose(f);
+    }
+  }
   CHECK(worst / xmax <= tol);
   std::printf("family<%s> n=%d m=%d B=%lld%s%s: iters=%lld manual functor == lm_run bit for bit; Jets: %lld/%lld same "
               "iteration count + stop reason, max rel dx %.2e\n",

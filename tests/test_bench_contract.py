@@ -9,6 +9,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_json_contract():
@@ -24,7 +26,21 @@ def test_reference_arm_json_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))   # not OMP_NUM_THREADS
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("C2") and d["gpu_launches"] == 0
+    # headline = C4 (the config BASELINE.json quotes at 1/2/4/8 GPUs), C2 / C3 / C5 as sub-records, and the
+    # `config` object is the one our arm prints for the same workload (the driver compares them)
+    import bench
+    assert d["config"] == bench.config_of("C4") and d["gpu_launches"] == 0
+    assert [c["name"] for c in d["configs"]] == ["C2", "C3", "C5"]
+    for c in d["configs"]:
+        assert c["config"] == bench.config_of(c["name"]) and c["value"] > 0 and c["cpu_baseline"]["kind"] == "port"
+
+
+def test_reference_arm_single_config():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C2", "--steps", "2",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr
+    d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][0])
+    assert d["config"]["workload"].startswith("C2") and "configs" not in d and d["dtype"] == "f64"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -26,8 +26,16 @@ def ctx():
 
 
 def rel_err(a, b):
+    """Worst PER-PROBLEM relative error: leading axis = problems, each problem's max |a - b| over its own
+    entries divided by its own max |b| (a batch-global ratio would let a problem with a small solution be
+    off by far more than the bar)."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+    if a.ndim == 0:
+        return float(np.abs(a - b) / max(np.abs(b), 1e-300))
+    a = a.reshape(a.shape[0], -1); b = b.reshape(b.shape[0], -1)
+    if a.shape[0] == 0:
+        return 0.0
+    return float((np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-300)).max())
 
 
 def spd(rng, n, cond=50.0):
@@ -120,10 +128,10 @@ def test_lg_build_solve_parity(ctx, B, m, n):
     for p in range(B):
         o = O.build_solve(J[p], r[p], float(lam[p]))
         assert out["status"][p].item() == o["status"] == 0
-        assert rel_err(out["dx"][p].cpu().numpy(), o["dx"]) <= 1e-4, (p, rel_err(out["dx"][p].cpu().numpy(), o["dx"]))
+        assert rel_err(out["dx"][p].cpu().numpy()[None], o["dx"][None]) <= 1e-4, (p, rel_err(out["dx"][p].cpu().numpy()[None], o["dx"][None]))
         assert rel_err(out["cost"][p].item(), o["cost"]) <= 1e-5
-        assert rel_err(out["g"][p].cpu().numpy(), o["g"]) <= 1e-5
-        assert rel_err(out["H"][p].cpu().numpy(), o["H"]) <= 1e-5
+        assert rel_err(out["g"][p].cpu().numpy()[None], o["g"][None]) <= 1e-5
+        assert rel_err(out["H"][p].cpu().numpy()[None], o["H"][None]) <= 1e-5
 
 
 # ---- a7-a10: the whole LM loop -----------------------------------------------------------------------
@@ -131,7 +139,7 @@ def run_both(ctx, B, m, n, p0=0, **optkw):
     import tinyopt_b200 as tb
     kw = {**FLOAT_OPTS, **optkw}
     A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=p0)
-    xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+    xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw), fast=m * n >= 1 << 18)  # same bits, sooner
     dA, dy, _, dx0 = ctx.synth_generate(B, m, n, torch.float32, p0=p0, layout=tb.PROBLEM_MAJOR)
     out = ctx.optimize_batch(dA, dy, dx0, tb.options(**kw), layout=tb.PROBLEM_MAJOR)
     return xo, ro, out
@@ -149,7 +157,8 @@ def robust_decisions(B, m, n, p0=0, **optkw):
     on many of them)."""
     kw = {**FLOAT_OPTS, **optkw}
     A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=p0)
-    _, r64, _ = O.synth_lm_run(A.astype(np.float64), y.astype(np.float64), x0.astype(np.float64), O.default_options(**kw))
+    _, r64, _ = O.synth_lm_run(A.astype(np.float64), y.astype(np.float64), x0.astype(np.float64), O.default_options(**kw),
+                               fast=m * n >= 1 << 18)
     return (r64["sign_margin"] > 2e-5) & (r64["thr_margin"] > 0.1)
 
 
@@ -166,6 +175,30 @@ def test_lg_lm_run_parity(ctx, B, m, n, min_robust):
     assert rel_err(out.x.cpu().numpy(), xo) <= 1e-4
     assert rel_err(rg["final_cost"], ro["final_cost"]) <= 1e-4
     assert (ro["stop_reason"] > 0).all() and (rg["stop_reason"] > 0).all()
+
+
+def test_lg_lm_run_parity_real_c5_shape(ctx):
+    """The REAL C5 shape (n = 512, m = 4096).  The decision-margin census of the whole C5 batch
+    (profiles/r2_margin_census.json, tools/margin_census.py) shows what this workload is: every problem
+    converges in 3 Steps and takes a 4th whose cost change is ~1e-8 relative — below FP32 resolution of a
+    sum of 4096 squares — so the SIGN of that last derr (optimizer.h:429) is rounding noise for 99.8 % of
+    the problems, in ANY float implementation (the float oracle agrees with its own double re-run on the
+    stop reason of only 50 %).  The margin-robust set is therefore empty by construction and cannot be the
+    filter here.  What IS well defined, and asserted unconditionally on every problem: the iteration count
+    (both outcomes of the noise decision stop at Step 4: accepted -> kMinRelError, rejected -> roll-back +
+    kMinDeltaNorm), the solution to 1e-4 per problem (the two outcomes differ by the last, < 3e-5, step),
+    the final cost, and that every stop is one of those two."""
+    B, m, n = 16, 4096, 512
+    xo, ro, out = run_both(ctx, B, m, n)
+    rg = out.results
+    assert np.array_equal(rg["num_iters"], ro["num_iters"])                     # ALL problems, no filter
+    assert set(np.unique(rg["stop_reason"])) <= {2, 3} and set(np.unique(ro["stop_reason"])) <= {2, 3}
+    assert rel_err(out.x.cpu().numpy(), xo) <= 1e-4
+    assert rel_err(rg["final_cost"], ro["final_cost"]) <= 1e-4
+    assert np.array_equal(rg["num_builds"], rg["num_iters"])                     # every pass rebuilt H (no eval-only pass)
+    # where the decisions ARE robust (if any problem is), the stop reasons agree too
+    robust = robust_decisions(B, m, n)
+    assert np.array_equal(rg["stop_reason"][robust], ro["stop_reason"][robust])
 
 
 @pytest.mark.parametrize("optkw", [dict(solver_type=1), dict(max_iters=2), dict(damping_init=10.0, max_consec_failures=2),

@@ -36,8 +36,16 @@ def both_options(dtype, **kw):
 
 
 def rel_err(a, b):
+    """Worst PER-PROBLEM relative error: leading axis = problems, each problem's max |a - b| over its own
+    entries divided by its own max |b| (a batch-global ratio would let a problem with a small solution be
+    off by far more than the bar)."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+    if a.ndim == 0:
+        return float(np.abs(a - b) / max(np.abs(b), 1e-300))
+    a = a.reshape(a.shape[0], -1); b = b.reshape(b.shape[0], -1)
+    if a.shape[0] == 0:
+        return 0.0
+    return float((np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-300)).max())
 
 
 # ---- synthetic generator: device == oracle, bit for bit ------------------------------------------

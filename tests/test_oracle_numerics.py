@@ -107,3 +107,22 @@ def test_batch_runner_equals_single_calls():
         o = O.optimize(x0[b], acc)
         assert o.num_iters == r1["num_iters"][b] and o.stop_reason == r1["stop_reason"][b]
         assert o.x == pytest.approx(x1[b], rel=1e-9)
+
+
+@pytest.mark.parametrize("B,m,n,dtype,kw", [
+    (300, 30, 6, np.float64, {}), (200, 200, 12, np.float32, dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)),
+    (40, 500, 50, np.float32, dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)), (40, 61, 33, np.float32, {}),
+    (12, 300, 57, np.float64, {}), (3, 517, 130, np.float32, dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)),
+    (50, 45, 9, np.float64, dict(solver_type=1)), (30, 20, 17, np.float32, dict(damping_init=10.0))])
+def test_fast_build_is_bit_identical(B, m, n, dtype, kw):
+    """The -DTOO_FAST build (rows in blocks of 8, interleaved chains, vectorised k loops: the CPU arm
+    bench.py reports beside the canonical one) gives the SAME bits as the canonical restatement —
+    every accumulator still receives its terms in row order."""
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=5)
+    opt = O.default_options(**kw)
+    x1, r1, _ = O.synth_lm_run(A, y, x0, opt)
+    for nt in (1, 3):
+        x2, r2, _ = O.synth_lm_run(A, y, x0, opt, nthreads=nt, fast=True)
+        assert np.array_equal(x1, x2)
+        for k in r1.dtype.names:
+            assert np.array_equal(r1[k], r2[k]), k

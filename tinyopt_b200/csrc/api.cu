@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <tuple>
@@ -359,15 +360,14 @@ bool lg_encode_tmap(CUtensorMap *tm, const float *A, int64_t B, int m, int n) {
                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn encode = nullptr;
-  static bool looked_up = false;
-  if (!looked_up) {
-    looked_up = true;
+  static std::once_flag looked_up;
+  std::call_once(looked_up, [] {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
       encode = (EncodeFn)fn;
-  }
+  });
   const int64_t rows = B * (int64_t)m;
   if (!encode || m <= 0 || rows >= (int64_t)1 << 31 || (n % 4) != 0 || ((uintptr_t)A & 15) != 0) return false;
   const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)rows};
@@ -648,9 +648,17 @@ template <typename T>
 int lm_run_host_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T *y, T alpha, int layout,
                      int64_t B, int m, int n, T *x, tob200_result *results) {
   if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  {  // before any allocation or copy is queued
+    const int rc0 = check_options(ctx, opt);
+    if (rc0 != TOB200_OK) return rc0;
+  }
   if (B < 0 || m < 0 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 0, m >= 0, n >= 1");
   if (B == 0) return TOB200_OK;
   if (!A || !y || !x || !results) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+  if (layout != TOB200_LAYOUT_TILE32 && layout != TOB200_LAYOUT_PROBLEM_MAJOR)
+    return fail(ctx, TOB200_ERR_INVALID, "unknown layout");
+  if (tob200_kernel_family(dtype_of<T>(), n) == 0)
+    return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n has no kernel yet for this dtype");
   DeviceGuard guard(ctx->device);
   const bool tiled = layout == TOB200_LAYOUT_TILE32;
   const size_t ea = tiled ? (size_t)tob200_tiled_elems(B, m, n) : (size_t)B * m * n;
@@ -730,6 +738,9 @@ int lm_run_host_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, con
 // ================================================================================================
 struct tob200_solver {
   tob200_ctx *ctx = nullptr;
+  // copies of what destroy needs: the solver may outlive its context (a garbage-collected Python
+  // BatchSolver after Context.close()); destroy must not dereference ctx
+  int device = 0;
   int dtype = 0, n = 0;
   int64_t B = 0;
   tob200_options opt;
@@ -1201,6 +1212,7 @@ int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob
   tob200_solver *s = new (std::nothrow) tob200_solver();
   if (!s) return fail(ctx, TOB200_ERR_NOMEM, "host allocation failed");
   s->ctx = ctx;
+  s->device = ctx->device;
   s->dtype = dtype;
   s->n = n;
   s->B = B;
@@ -1238,8 +1250,8 @@ int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob
 
 int tob200_solver_destroy(tob200_solver *s) {
   if (!s) return TOB200_OK;
-  DeviceGuard guard(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
+  DeviceGuard guard(s->device);
+  cudaDeviceSynchronize();  // not ctx->stream: the context may already be gone (cudaFree synchronises anyway)
   cudaFree(s->rec);
   cudaFree(s->x);
   cudaFree(s->last_dx);

@@ -4,7 +4,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace tob200 {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: the raised limit is
+// remembered per (device, kernel) — a second context on another GPU of the same process must set it again
+// — and raised monotonically (the same instantiation serves shapes with different footprints; lowering it
+// for a small one would make a later launch of a larger, occupancy-cached one fail with "invalid
+// argument").  Thread safe: contexts on different devices may be driven by different threads.
+// Defined once in misc_kernels.cu.
+cudaError_t raise_smem_limit(const void *fn, size_t smem);
 
 // misc_kernels.cu
 template <typename T>

@@ -66,11 +66,9 @@ cudaError_t launch_lg_import_h(const float *in, int64_t B, int n, int np, float 
 
 cudaError_t launch_lg_eval(const LgEvalParams &p, int num_sms, cudaStream_t st) {
   const size_t smem = lg_eval_smem_bytes(p.n);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = raise_smem_limit((const void *)lg_eval_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   int64_t grid = 2 * (int64_t)num_sms;
   if (grid > p.B) grid = p.B;
@@ -88,11 +86,9 @@ int lg_syrk_stages(int np) {
 
 cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st) {
   const size_t smem = lg_syrk_smem_bytes(p.np, p.stages);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(lg_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = raise_smem_limit((const void *)lg_syrk_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   int64_t grid = num_sms;  // one CTA per SM: each owns the SM's whole TMEM
   const int64_t total = (int64_t)((p.nstrips + 1) / 2) * p.B;  // work units: strip pairs
@@ -103,11 +99,9 @@ cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st) 
 
 cudaError_t launch_lg_solve(const LgSolveParams &p, int grid, cudaStream_t st) {
   const size_t smem = (size_t)lg_solve_smem(p.np).total * 4;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(lg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = raise_smem_limit((const void *)lg_solve_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   lg_solve_kernel<<<(unsigned)grid, kLgSolveThreads, smem, st>>>(p);
   return cudaGetLastError();

@@ -8,20 +8,40 @@
 
 namespace tob200 {
 
+cudaError_t raise_smem_limit(const void *fn, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> limit;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &cur = limit[std::make_pair(dev, fn)];
+  if (smem > cur) {
+    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    cur = smem;
+  }
+  return cudaSuccess;
+}
+
+
 // ---- PROBLEM_MAJOR [B][mn] -> TILE32 [ntiles][mn][32]: 32x32 transposes through shared memory ----
 template <typename T>
 __global__ void retile_kernel(const T *__restrict__ src, int64_t B, int64_t mn, T *__restrict__ dst) {
   __shared__ T tile[32][33];
-  const int64_t t = blockIdx.x;
-  const int64_t e0 = (int64_t)blockIdx.y * 32;
-  for (int pl = threadIdx.y; pl < 32; pl += blockDim.y) {
-    const int64_t p = t * 32 + pl, e = e0 + threadIdx.x;
-    tile[pl][threadIdx.x] = (p < B && e < mn) ? src[p * mn + e] : (T)0;
-  }
-  __syncthreads();
-  for (int el = threadIdx.y; el < 32; el += blockDim.y) {
-    const int64_t e = e0 + el;
-    if (e < mn) dst[(t * mn + e) * 32 + threadIdx.x] = tile[threadIdx.x][el];
+  // element chunks on grid.x (2^31 - 1 blocks), tiles on a grid-stride loop over grid.y (<= 65535)
+  const int64_t e0 = (int64_t)blockIdx.x * 32;
+  const int64_t ntiles = (B + 31) / 32;
+  for (int64_t t = blockIdx.y; t < ntiles; t += gridDim.y) {
+    for (int pl = threadIdx.y; pl < 32; pl += blockDim.y) {
+      const int64_t p = t * 32 + pl, e = e0 + threadIdx.x;
+      tile[pl][threadIdx.x] = (p < B && e < mn) ? src[p * mn + e] : (T)0;
+    }
+    __syncthreads();
+    for (int el = threadIdx.y; el < 32; el += blockDim.y) {
+      const int64_t e = e0 + el;
+      if (e < mn) dst[(t * mn + e) * 32 + threadIdx.x] = tile[threadIdx.x][el];
+    }
+    __syncthreads();
   }
 }
 
@@ -30,7 +50,7 @@ cudaError_t launch_retile(const T *src, int64_t B, int m, int n, T *dst, cudaStr
   const int64_t mn = (int64_t)m * n;
   if (B <= 0 || mn <= 0) return cudaSuccess;
   const int64_t ntiles = (B + 31) / 32;
-  dim3 grid((unsigned)ntiles, (unsigned)((mn + 31) / 32)), block(32, 8);
+  dim3 grid((unsigned)((mn + 31) / 32), (unsigned)(ntiles < 65535 ? ntiles : 65535)), block(32, 8);
   retile_kernel<T><<<grid, block, 0, st>>>(src, B, mn, dst);
   return cudaGetLastError();
 }
@@ -39,16 +59,19 @@ cudaError_t launch_retile(const T *src, int64_t B, int m, int n, T *dst, cudaStr
 template <typename T>
 __global__ void untile_kernel(const T *__restrict__ src, int64_t B, int64_t mn, T *__restrict__ dst) {
   __shared__ T tile[32][33];
-  const int64_t t = blockIdx.x;
-  const int64_t e0 = (int64_t)blockIdx.y * 32;
-  for (int el = threadIdx.y; el < 32; el += blockDim.y) {
-    const int64_t e = e0 + el;
-    tile[el][threadIdx.x] = e < mn ? src[(t * mn + e) * 32 + threadIdx.x] : (T)0;
-  }
-  __syncthreads();
-  for (int pl = threadIdx.y; pl < 32; pl += blockDim.y) {
-    const int64_t p = t * 32 + pl, e = e0 + threadIdx.x;
-    if (p < B && e < mn) dst[p * mn + e] = tile[threadIdx.x][pl];
+  const int64_t e0 = (int64_t)blockIdx.x * 32;
+  const int64_t ntiles = (B + 31) / 32;
+  for (int64_t t = blockIdx.y; t < ntiles; t += gridDim.y) {
+    for (int el = threadIdx.y; el < 32; el += blockDim.y) {
+      const int64_t e = e0 + el;
+      tile[el][threadIdx.x] = e < mn ? src[(t * mn + e) * 32 + threadIdx.x] : (T)0;
+    }
+    __syncthreads();
+    for (int pl = threadIdx.y; pl < 32; pl += blockDim.y) {
+      const int64_t p = t * 32 + pl, e = e0 + threadIdx.x;
+      if (p < B && e < mn) dst[p * mn + e] = tile[threadIdx.x][pl];
+    }
+    __syncthreads();
   }
 }
 
@@ -57,7 +80,7 @@ cudaError_t launch_untile(const T *src, int64_t B, int m, int n, T *dst, cudaStr
   const int64_t mn = (int64_t)m * n;
   if (B <= 0 || mn <= 0) return cudaSuccess;
   const int64_t ntiles = (B + 31) / 32;
-  dim3 grid((unsigned)ntiles, (unsigned)((mn + 31) / 32)), block(32, 8);
+  dim3 grid((unsigned)((mn + 31) / 32), (unsigned)(ntiles < 65535 ? ntiles : 65535)), block(32, 8);
   untile_kernel<T><<<grid, block, 0, st>>>(src, B, mn, dst);
   return cudaGetLastError();
 }

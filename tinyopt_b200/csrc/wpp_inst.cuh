@@ -25,14 +25,9 @@ cudaError_t wpp_entry_one(int op, int kind, const void *params, const TppLaunch 
 #endif
     default: return cudaErrorInvalidValue;
   }
-  // The dynamic shared-memory limit of a kernel is raised monotonically: the same instantiation serves
-  // shapes with different footprints, and lowering the attribute for a small one would make a later
-  // launch of a larger (occupancy-cached) one fail with "invalid argument".
-  static size_t smem_limit[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (cfg.smem > smem_limit[kind & 7]) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+  {  // per (device, kernel), monotonic, thread safe: internal.h
+    cudaError_t e = raise_smem_limit(fn, cfg.smem);
     if (e != cudaSuccess) return e;
-    smem_limit[kind & 7] = cfg.smem;
   }
   if (op == kTppQuery) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, fn, cfg.block, cfg.smem);
   void *args[] = {const_cast<void *>(params)};
