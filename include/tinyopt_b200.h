@@ -206,6 +206,16 @@ int tob200_lm_run_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A
 int tob200_lm_run_f64(tob200_ctx *ctx, const tob200_options *opt, const double *A, const double *y,
                       double alpha, int layout, int64_t B, int m, int n, double *x,
                       tob200_result *results);
+/* The same run that also returns Output::final_hessian (optimizer.h:313-316): the last H_ of every problem,
+ * un-damped as SolverLM::Hessian() does (solvers/lm.h:157-171: diagonal / (1 + prev_lambda_)), widened to
+ * double, [B][n][n] row-major, full symmetric.  Honoured only when options.save_last != 0 (options.h:66, the
+ * reference's default); final_hessian may be NULL.  Every kernel family (n <= 512 float, n <= 55 double). */
+int tob200_lm_run_ex_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y,
+                         float alpha, int layout, int64_t B, int m, int n, float *x,
+                         tob200_result *results, double *final_hessian);
+int tob200_lm_run_ex_f64(tob200_ctx *ctx, const tob200_options *opt, const double *A, const double *y,
+                         double alpha, int layout, int64_t B, int m, int n, double *x,
+                         tob200_result *results, double *final_hessian);
 /* Same call with HOST buffers (pageable or pinned): H2D of A, y, x0, the run, D2H of x and
  * results, all inside; returns when the results are in host memory. */
 int tob200_lm_run_host_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A_host,
@@ -234,6 +244,19 @@ void *tob200_solver_x(tob200_solver *s);
 const int32_t *tob200_solver_needs(tob200_solver *s);
 int tob200_solver_step_f32(tob200_solver *s, const float *J, const float *r, int layout, int m);
 int tob200_solver_step_f64(tob200_solver *s, const double *J, const double *r, int layout, int m);
+/* The manual accumulation contract `acc(x, grad, H) -> Cost` (docs/API.md:37-57,137-170; examples
+ * tests/optimize_easy.cpp:35-80 (Rosenbrock with its true Hessian), tests/types.cpp:97-108,
+ * benchmarks/dense.cpp:57-66 ("Prior n": a diagonal H)): the caller's lambda has filled, for every problem,
+ * what the reference hands it as the solver-owned grad_ and H_ (solvers/gn.h:109-113) and returned the cost.
+ *   grad [B][n], H [B][n][n] row-major - only the UPPER triangle (row <= col) is read, as
+ *   `H.selfadjointView<Upper>()` does (docs/API.md:170); cost [B] = Cost::cost (a double, cost.h:93),
+ *   num_residuals [B] = Cost::num_resisuals (1 for a scalar cost, cost.h:22).
+ * Problems whose `needs` entry is 0 (cost-only Step: the nullptr_t call of the reference) read only cost and
+ * num_residuals; finished ones (-1) read nothing.  Same Step / OptimizeAcc bookkeeping as tob200_solver_step. */
+int tob200_solver_step_hg_f32(tob200_solver *s, const float *grad, const float *H, const double *cost,
+                              const int32_t *num_residuals);
+int tob200_solver_step_hg_f64(tob200_solver *s, const double *grad, const double *H, const double *cost,
+                              const int32_t *num_residuals);
 /* Number of problems still running (synchronises the stream). */
 int tob200_solver_num_active(tob200_solver *s, int64_t *n_active);
 /* Copy the per-problem results to `results` ([B], device). */

@@ -261,6 +261,29 @@ struct Emit {
     cost = Ops<T>::fma(r, r, cost);
     ++nres;
   }
+  /// ROBUST residual: the M-estimator re-weights the accumulation inside the same pass —
+  /// `rb = losses::Huber(r * r, th2)` etc. gives the loss and the scale of losses/robust_norms.h, and, as its
+  /// header says (robust_norms.h:16-29: "the scale can then be used to solve JtJ * dx = Jt * res * s"):
+  ///   cost += loss ;  g_j = fma(J_j, r * scale, g_j) ;  H_jk = fma(J_j, J_k, H_jk)
+  __device__ __forceinline__ void robust(T r, const T (&J)[N], T loss, T scale) {
+    using O = Ops<T>;
+    cost = O::add(cost, loss);
+    ++nres;
+    if (!want_j) return;
+    const T rs = O::mul(r, scale);
+#pragma unroll
+    for (int j = 0; j < N; ++j) g[j] = O::fma(J[j], rs, g[j]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int k = j; k < N; ++k) hu[tri_index(N, j, k)] = O::fma(J[j], J[k], hu[tri_index(N, j, k)]);
+    }
+  }
+  /// robust residual of a cost-only pass
+  __device__ __forceinline__ void robust(T loss) {
+    cost = Ops<T>::add(cost, loss);
+    ++nres;
+  }
 };
 
 namespace detail {
@@ -400,6 +423,7 @@ struct WarpEmit {
   T acc[BLK][BLK];
   T cost;
   int nres, fill;
+  bool robust_cost = false;  // the pass emitted robust residuals: `cost` (sum of losses) is the pass's cost
 
   __device__ WarpEmit(T *jbuf_, int lane_, int bi_, int bj_, bool has_block_, bool rebuild)
       : jbuf(jbuf_), lane(lane_), bi(bi_), bj(bj_), has_block(has_block_), want_j(rebuild), cost((T)0), nres(0), fill(0) {
@@ -413,7 +437,7 @@ struct WarpEmit {
     // the factor matrix aliases the row buffer: clear the pad columns of all 32 rows before the pass
     constexpr int w = NP - (N + 1);
     if (w > 0)
-      for (int e = lane; e < 32 * w; e += 32) jbuf[(e / w) * NPS + N + 1 + (e % w)] = (T)0;
+      for (int e = lane; e < 32 * w; e += 32) jbuf[(e / w) * NPS + tob200::wpp_col<BLK>(N + 1 + (e % w))] = (T)0;
     __syncwarp();
   }
   __device__ __forceinline__ void row_done() {
@@ -423,9 +447,9 @@ struct WarpEmit {
   /// residual as a warp-distributed Jet (rebuild passes of OptimizeBatchAutoDiffWarp)
   __device__ __forceinline__ void operator()(const Jet<T, 2> &r) {
     T *row = jbuf + fill * NPS;
-    if (lane < N) row[lane] = r.v[0];
-    if (lane + 32 < N) row[lane + 32] = r.v[1];
-    if (lane == 0) row[N] = r.a;
+    if (lane < N) row[tob200::wpp_col<BLK>(lane)] = r.v[0];
+    if (lane + 32 < N) row[tob200::wpp_col<BLK>(lane + 32)] = r.v[1];
+    if (lane == 0) row[tob200::wpp_col<BLK>(N)] = r.a;
     row_done();
   }
   /// residual with its full Jacobian row (every lane holds the same row; rebuild passes of ...ManualWarp)
@@ -433,8 +457,8 @@ struct WarpEmit {
     T *row = jbuf + fill * NPS;
 #pragma unroll
     for (int j = 0; j < N; ++j)
-      if ((j & 31) == lane) row[j] = J[j];
-    if (lane == 0) row[N] = r;
+      if ((j & 31) == lane) row[tob200::wpp_col<BLK>(j)] = J[j];
+    if (lane == 0) row[tob200::wpp_col<BLK>(N)] = r;
     row_done();
   }
   /// cost-only residual
@@ -442,11 +466,31 @@ struct WarpEmit {
     cost = Ops<T>::fma(r, r, cost);
     ++nres;
   }
+  /// ROBUST residual (see Emit::robust): the row goes into the block accumulation as [J | r * scale], so that
+  /// its augmented column gives g = sum J^T (r * scale); the cost is the sum of the losses, kept by every lane
+  /// (the corner of the augmented matrix would hold sum (r * scale)^2 instead: `robust_cost` tells the kernel)
+  __device__ __forceinline__ void robust(T r, const T (&J)[N], T loss, T scale) {
+    cost = Ops<T>::add(cost, loss);
+    robust_cost = true;
+    if (!want_j) { ++nres; return; }
+    T *row = jbuf + fill * NPS;
+    const T rs = Ops<T>::mul(r, scale);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if ((j & 31) == lane) row[tob200::wpp_col<BLK>(j)] = J[j];
+    if (lane == 0) row[tob200::wpp_col<BLK>(N)] = rs;
+    row_done();
+  }
+  __device__ __forceinline__ void robust(T loss) {
+    cost = Ops<T>::add(cost, loss);
+    robust_cost = true;
+    ++nres;
+  }
   // fold the buffered rows into the register blocks (wpp.cuh phase 2, same operation order)
   __device__ __forceinline__ void flush() {
     __syncwarp();
     if (has_block) {
-      const T *pa = jbuf + bi * BLK, *pb = jbuf + bj * BLK;
+      const T *pa = jbuf + tob200::wpp_col<BLK>(bi * BLK), *pb = jbuf + tob200::wpp_col<BLK>(bj * BLK);
       if constexpr (kF32) {
 #pragma unroll 2
         for (int i = 0; i < fill; ++i) {
@@ -534,8 +578,10 @@ __global__ void __launch_bounds__(tob200::kWppThreads, sizeof(T) == 4 ? 2 : 1)
       }
       emit.finish();
       d.m = emit.nres;
-      if (opt.use_ldlt) wpp_after_pass<T, NB, BLK, false>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane);
-      else wpp_after_pass<T, NB, BLK, true>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane);
+      const double cost_d = (double)emit.cost;  // robust passes: the sum of the losses replaces the corner r^T r
+      const double *cd = emit.robust_cost ? &cost_d : nullptr;
+      if (opt.use_ldlt) wpp_after_pass<T, NB, BLK, false>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane, false, cd, emit.nres);
+      else wpp_after_pass<T, NB, BLK, true>(s, opt, d, ws, hp, do_rebuild, bi, bj, has_block, emit.acc, emit.cost, lane, false, cd, emit.nres);
     }
     for (int j = lane; j < N; j += 32) x[pr * N + j] = xs[j];
     if (lane == 0) lm_write_result(s, &results[pr]);

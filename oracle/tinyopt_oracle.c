@@ -52,6 +52,12 @@ int too_max_threads(void) {
 static int too_census_row_order_ = 0;
 void too_census_set_row_order(int rev) { too_census_row_order_ = rev; }
 
+/* robust variant of the synthetic family: kind 0 = none, 1..7 = the M-estimators of
+ * losses/robust_norms.h applied per residual inside the accumulation; th2 = squared threshold */
+static int too_synth_robust_kind_ = 0;
+static double too_synth_robust_th2_ = 1.0;
+void too_synth_set_robust(int kind, double th2) { too_synth_robust_kind_ = kind; too_synth_robust_th2_ = th2; }
+
 /* stateless counter RNG of the synthetic family:
  * u(seed,p,k) = splitmix64-finaliser(seed ^ (p * golden + k)) */
 static inline uint64_t too_hash64_(uint64_t seed, uint64_t p, uint64_t k) {

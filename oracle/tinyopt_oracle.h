@@ -167,6 +167,19 @@ int too_synth_lm_run_f64(int64_t B, int m, int n, const double *A, const double 
 int too_synth_lm_run_f32(int64_t B, int m, int n, const float *A, const float *y, float alpha,
                          float *x, const too_options *opt, too_result *results, int nthreads);
 
+/* the same, also returning Output::final_hessian per problem ([B][n][n] doubles, optimizer.h:313-316) */
+int too_synth_lm_run_fh_f64(int64_t B, int m, int n, const double *A, const double *y, double alpha,
+                            double *x, const too_options *opt, too_result *results, int nthreads,
+                            double *final_hessian);
+int too_synth_lm_run_fh_f32(int64_t B, int m, int n, const float *A, const float *y, float alpha,
+                            float *x, const too_options *opt, too_result *results, int nthreads,
+                            double *final_hessian);
+
+/* Robust variant of the family (losses/robust_norms.h:16-29): while kind != 0 every residual of
+ * too_synth_lm_run_* goes through M-estimator `kind` (1 Truncated, 2 Huber, 3 Tukey, 4 Arctan, 5 Cauchy,
+ * 6 GemanMcClure, 7 BlakeZisserman) with squared threshold th2:  cost += loss, grad += J^T r * scale, H += J^T J. */
+void too_synth_set_robust(int kind, double th2);
+
 int too_max_threads(void);
 
 /* Decision-margin census only: rev != 0 makes too_synth_lm_run_* accumulate the residual rows in

@@ -164,6 +164,51 @@ struct PolyWarpAuto {
   }
 };
 
+// ---- the family with every residual passed through an M-estimator inside the accumulation ----
+// kind: 1 Truncated, 2 Huber, 3 Tukey, 4 Arctan, 5 Cauchy, 6 GemanMcClure, 7 BlakeZisserman (robust_norms.h)
+template <typename T, int N>
+struct PolyRobust {
+  const T *A, *y;
+  int m, kind;
+  T alpha, alpha3, th2;
+  __device__ dev::losses::Robust<T> rho(T n2) const {
+    namespace L = dev::losses;
+    switch (kind) {
+      case 1: return L::Truncated(n2, th2);
+      case 2: return L::Huber(n2, th2);
+      case 3: return L::Tukey(n2, th2);
+      case 4: return L::Arctan(n2, th2);
+      case 5: return L::Cauchy(n2, th2);
+      case 6: return L::GemanMcClure(n2, th2);
+      default: return L::BlakeZisserman(n2, th2);
+    }
+  }
+  template <typename X, typename E>
+  __device__ void operator()(int64_t p, const X &x, E &emit, bool want_j) const {
+    using O = tob200::Ops<T>;
+    const T *Ap = A + (size_t)p * m * N, *yp = y + (size_t)p * m;
+    for (int i = 0; i < m; ++i) {
+      T a[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[j] = Ap[(size_t)i * N + j];
+      T t = (T)0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) t = O::fma(a[j], x[j], t);
+      const T t2 = O::mul(t, t);
+      const T r = O::fma(t, O::fma(alpha, t2, (T)1), -yp[i]);
+      const dev::losses::Robust<T> rb = rho(O::mul(r, r));
+      if (want_j) {
+        const T sc = O::fma(alpha3, t2, (T)1);
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[j] = O::mul(sc, a[j]);
+        emit.robust(r, a, rb.loss, rb.scale);
+      } else {
+        emit.robust(rb.loss);
+      }
+    }
+  }
+};
+
 static int synth(tob200_ctx *c, int64_t B, int m, int n, double *A, double *y, double *xs, double *x0) {
   return tob200_synth_generate_f64(c, 20261017ull, 0, B, m, n, 0.1, 1e-2, TOB200_LAYOUT_PROBLEM_MAJOR, A, y, xs, x0);
 }
@@ -269,6 +314,53 @@ static void test_family(tob200_ctx *ctx, int64_t B, int m, double tol, bool use_
   for (tob200_result *q : {ra, rb, rc}) cudaFree(q);
 }
 
+// ---- 4. robust re-weighting inside the accumulation, on the device; the result goes to the Python side
+// (tests/test_device_functor.py), which holds it against the oracle's robust variant of the family ----
+template <typename T, int N, bool kWarp>
+static void test_robust(tob200_ctx *ctx, int64_t B, int m, int kind, double th2) {
+  const char *dir = std::getenv("TOB200_FUNCTOR_DUMP");
+  T *A, *y, *xs, *x0, *x;
+  tob200_result *res;
+  CU(cudaMalloc(&A, (size_t)B * m * N * sizeof(T)));
+  CU(cudaMalloc(&y, (size_t)B * m * sizeof(T)));
+  for (T **q : {&xs, &x0, &x}) CU(cudaMalloc(q, (size_t)B * N * sizeof(T)));
+  CU(cudaMalloc(&res, (size_t)B * sizeof(tob200_result)));
+  CHECK(synth(ctx, B, m, N, A, y, xs, x0) == TOB200_OK);
+  CHECK(tob200_sync(ctx) == TOB200_OK);
+  tob200_options opt;
+  tob200_options_default(&opt);
+  if (sizeof(T) == 4) { opt.min_rerr_dec = 1e-5f; opt.min_step_norm2 = 1e-9f; }
+  CU(cudaMemcpy(x, x0, (size_t)B * N * sizeof(T), cudaMemcpyDeviceToDevice));
+  PolyRobust<T, N> f{A, y, m, kind, (T)0.1, (T)3 * (T)0.1, (T)th2};
+  if constexpr (kWarp) CU((dev::OptimizeBatchManualWarp<N>(f, x, B, opt, res)));
+  else CU((dev::OptimizeBatchManual<N>(f, x, B, opt, res)));
+  CU(cudaDeviceSynchronize());
+  std::vector<T> hx((size_t)B * N);
+  std::vector<tob200_result> hr((size_t)B);
+  CU(cudaMemcpy(hx.data(), x, hx.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hr.data(), res, hr.size() * sizeof(tob200_result), cudaMemcpyDeviceToHost));
+  int64_t iters = 0;
+  for (int64_t p = 0; p < B; ++p) iters += hr[p].num_iters;
+  CHECK(iters >= B);
+  if (dir) {
+    char path[1024];
+    std::snprintf(path, sizeof(path), "%s/robust_k%d_%s_n%d_m%d_B%lld_%s.bin", dir, kind, sizeof(T) == 8 ? "f64" : "f32", N, m,
+                  (long long)B, kWarp ? "warp" : "thread");
+    if (FILE *fp = std::fopen(path, "wb")) {
+      for (int64_t p = 0; p < B; ++p) {
+        const double rec[4] = {(double)hr[p].num_iters, (double)hr[p].stop_reason, hr[p].final_cost, (double)hr[p].num_failures};
+        std::fwrite(rec, sizeof(rec), 1, fp);
+        for (int j = 0; j < N; ++j) { const double v = (double)hx[p * N + j]; std::fwrite(&v, sizeof(v), 1, fp); }
+      }
+      std::fclose(fp);
+    }
+  }
+  std::printf("robust kind %d <%s> n=%d m=%d B=%lld%s: iters=%lld\n", kind, sizeof(T) == 8 ? "double" : "float", N, m, (long long)B,
+              kWarp ? " (warp per problem)" : "", (long long)iters);
+  for (T *q : {A, y, xs, x0, x}) cudaFree(q);
+  cudaFree(res);
+}
+
 // ---- 0. robust norms (host side: they are __host__ __device__) -------------------------------------
 // tests/robust_norms.cpp:53-110: loss == the closed form (+-1e-5) and the returned scale == d loss / d n2
 // (the reference checks it against its autodiff; here against the Jet of this header), th = 1.3, an
@@ -330,6 +422,12 @@ int main() {
   test_family<double, 6>(ctx, 1024, 30, 1e-10, false);
   test_family<float, 20, true>(ctx, 1024, 64, 1e-4, false);
   test_family<double, 6, true>(ctx, 1024, 30, 1e-10, false);
+  // robust re-weighting fused into the accumulation (every M-estimator; both functor kernel families)
+  for (int kind = 1; kind <= 7; ++kind) test_robust<double, 6, false>(ctx, 512, 30, kind, 0.01);
+  test_robust<float, 12, false>(ctx, 512, 60, 2, 0.01);
+  test_robust<float, 20, true>(ctx, 256, 64, 2, 0.01);
+  test_robust<double, 20, true>(ctx, 256, 64, 6, 0.01);
+  test_robust<double, 6, true>(ctx, 256, 30, 3, 0.0625);
   tob200_destroy(ctx);
   if (g_failures) {
     std::printf("%d check(s) failed\n", g_failures);

@@ -64,3 +64,30 @@ def test_device_functor_on_gpu(tmp_path):
         assert robust.mean() >= 0.85, (f.name, robust.mean())
         same = (rec[:, 0] == rec[:, 2]) & (rec[:, 1] == rec[:, 3])
         assert same[robust].all(), (f.name, int((~same & robust).sum()))
+
+    # robust re-weighting inside the accumulation, ON THE DEVICE, against the oracle's robust
+    # variant of the family.  M-estimators built from IEEE +, -, *, /, sqrt only (Truncated, Huber, Tukey,
+    # Geman-McClure) must agree bit for bit - solution, iteration count, stop reason, failures, final cost; the
+    # ones through atan / log / exp (Arctan, Cauchy, Blake-Zisserman: libm and CUDA round differently) to 1e-9
+    # relative on the problems that take the same number of Steps.
+    rdumps = sorted(tmp_path.glob("robust_*.bin"))
+    assert len(rdumps) == 11, rdumps
+    for f in rdumps:
+        kind, dt, n, m, B, fam = re.match(r"robust_k(\d)_(f\d+)_n(\d+)_m(\d+)_B(\d+)_(\w+)\.bin", f.name).groups()
+        kind, n, m, B = int(kind), int(n), int(m), int(B)
+        rec = np.fromfile(f, np.float64).reshape(B, 4 + n)
+        npdt = np.float32 if dt == "f32" else np.float64
+        kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dt == "f32" else {}
+        th2 = 0.0625 if (fam == "warp" and n == 6) else 0.01
+        A, y, xs, x0 = O.synth_generate(B, m, n, npdt)
+        xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw), robust=(kind, th2))
+        iters, stop, cost, fails, xg = rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4:]
+        if kind in (1, 2, 3, 6):
+            assert np.array_equal(iters, ro["num_iters"]) and np.array_equal(stop, ro["stop_reason"]), f.name
+            assert np.array_equal(fails, ro["num_failures"]) and np.array_equal(cost, ro["final_cost"]), f.name
+            assert np.array_equal(xg, xo.astype(np.float64)), f.name
+        else:
+            same = iters == ro["num_iters"]
+            assert same.mean() > 0.9, (f.name, same.mean())
+            err = np.abs(xg - xo)[same].max(axis=1) / np.maximum(np.abs(xo)[same].max(axis=1), 1e-300)
+            assert err.max() < 1e-9, (f.name, err.max())

@@ -506,3 +506,36 @@ def test_host_entry_chunked_pipeline(ctx, dtype, B, m, n, tiled):
     A, y, xs, x0 = O.synth_generate(B, m, n, dtype)
     xo, ro, _ = O.synth_lm_run(A[sl], y[sl], x0[sl], oo)
     assert np.array_equal(xh[sl], xo) and np.array_equal(res["num_iters"][sl], ro["num_iters"])
+
+
+# ---- Output::final_hessian from the device-resident loop (tob200_lm_run_ex_*) -------------------
+@pytest.mark.parametrize("dtype,B,m,n,exact", [(np.float64, 70, 30, 6, True), (np.float32, 70, 60, 12, True),
+                                               (np.float32, 40, 200, 50, True), (np.float64, 20, 64, 20, True),
+                                               (np.float32, 40, 64, 20, True), (np.float32, 5, 256, 64, False),
+                                               (np.float32, 4, 300, 57, False)])
+def test_final_hessian_of_lm_run(ctx, dtype, B, m, n, exact):
+    """optimizer.h:313-316 / solvers/lm.h:157-171: the last H_ with its damping removed (diagonal / (1 +
+    prev_lambda_) in Scalar), as doubles.  Families 1 and 2 equal the oracle bit for bit; the tensor-core family
+    (n >= 56, incl. the zero-padded n % 4 != 0 path) to FP32 accuracy.  hessian.save_last = false (the option the
+    reference's benchmarks run with) leaves the buffer untouched."""
+    import tinyopt_b200 as tb
+    oo, go = both_options(dtype)
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=11)
+    xo, ro, _, fho = O.synth_lm_run(A, y, x0, oo, want_hessian=True)
+    layout = tb.TILE32 if ctx.kernel_family(TDT[dtype], n) == 1 else tb.PROBLEM_MAJOR
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, TDT[dtype], p0=11, layout=layout)
+    out = ctx.optimize_batch(dA, dy, dx0, go, layout=layout, want_hessian=True)
+    fh = out.final_hessian.cpu().numpy()
+    assert np.array_equal(fh, np.swapaxes(fh, 1, 2))
+    if exact:
+        assert np.array_equal(out.x.cpu().numpy(), xo)
+        assert np.array_equal(fh, fho)
+    else:
+        same = out.results["num_iters"] == ro["num_iters"]     # same number of Builds -> the same last H_
+        assert same.any()
+        scale = np.abs(fho).max(axis=(1, 2))
+        assert (np.abs(fh - fho).max(axis=(1, 2)) / scale)[same].max() < 2e-5
+    oo2, go2 = both_options(dtype, save_last=0)
+    out2 = ctx.optimize_batch(dA, dy, dx0, go2, layout=layout, want_hessian=True)
+    assert not out2.final_hessian.any().item()
+    assert np.array_equal(out2.x.cpu().numpy(), out.x.cpu().numpy())

@@ -257,3 +257,146 @@ def test_random_solver_matches_oracle(ctx, dtype, B, _m, n):
     assert np.array_equal(s.x.cpu().numpy(), xo)
     assert np.array_equal(res["final_cost"], ro["final_cost"])
     s.close()
+
+
+# ---- the manual accumulation contract `acc(x, grad, H) -> Cost` with USER-FILLED accumulators ----
+def drive_hg(ctx, x0, acc_fn, opt, dtype, max_steps=400, poison_lower=True):
+    """Host-driven loop over tob200_solver_step_hg: `acc_fn(x_p, want_grad) -> (grad, H, cost, nres)` is the
+    caller's lambda (numpy, one problem at a time: it is the SAME function the oracle calls back, so both see
+    identical accumulators).  The strict lower triangle handed to the device is poisoned with NaN: only the
+    upper one may be read (docs/API.md:170)."""
+    import tinyopt_b200 as tb
+    B, n = x0.shape
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    s = tb.BatchSolver(ctx, B, n, dtype, opt)
+    s.reset(torch.from_numpy(x0).cuda())
+    steps = 0
+    while s.num_active() > 0 and steps < max_steps:
+        x = s.x.cpu().numpy()
+        needs = s.needs.cpu().numpy()
+        g = np.zeros((B, n), npdt); H = np.zeros((B, n, n), npdt); c = np.zeros(B); nr = np.ones(B, np.int32)
+        for p in range(B):
+            if needs[p] < 0:
+                continue
+            gp, Hp, cp, nrp = acc_fn(p, x[p], needs[p] == 1)
+            c[p], nr[p] = cp, nrp
+            if needs[p] == 1:
+                g[p], H[p] = gp, Hp
+                if poison_lower and opt.use_ldlt:
+                    H[p][np.tril_indices(n, -1)] = np.nan
+        s.step_hg(torch.from_numpy(g), torch.from_numpy(H), torch.from_numpy(c), torch.from_numpy(nr))
+        steps += 1
+    res = s.results()
+    x = s.x.cpu().numpy()
+    Hf = s.final_hessian().cpu().numpy()
+    s.close()
+    return x, res, Hf
+
+
+def oracle_hg(x0, acc_fn, kw, npdt):
+    outs = []
+    for p in range(x0.shape[0]):
+        def acc(xv, g, H, p=p):
+            gp, Hp, cp, nrp = acc_fn(p, xv.astype(npdt), g is not None)
+            if g is not None:
+                g[:] = gp
+                H[:, :] = Hp
+            return cp, nrp
+        outs.append(O.optimize(x0[p], acc, O.default_options(**kw), dtype=npdt))
+    return outs
+
+
+def assert_hg_parity(x, res, outs):
+    for p, o in enumerate(outs):
+        assert res["num_iters"][p] == o.num_iters and res["stop_reason"][p] == o.stop_reason, (p, res["num_iters"][p], o.num_iters)
+        assert res["num_failures"][p] == o.num_failures
+        assert np.array_equal(x[p], o.x), (p, x[p], o.x)
+        assert res["final_cost"][p] == o.final_cost and res["last_lambda"][p] == o.last_lambda
+
+
+def test_hg_rosenbrock_true_hessian(ctx):
+    """tests/optimize_easy.cpp:35-80: Rosenbrock through a lambda that fills the TRUE Hessian (not J^T J) and
+    the gradient, options max_iters = 200, min_rerr_dec = 0, max_consec_failures = 20; the reference asserts
+    Succeeded, Converged and x = (1, 1) +- 1e-5.  A batch of perturbed starting points; device == oracle bit for
+    bit (same accumulators in, same canonical Build / Solve / Step sequence)."""
+    import tinyopt_b200 as tb
+
+    def acc(p, v, want):
+        xv, yv = float(v[0]), float(v[1])
+        t1 = 1.0 - xv
+        t2 = yv - xv * xv
+        g = H = None
+        if want:
+            g = np.array([-2.0 * t1 - 400.0 * xv * t2, 200.0 * t2])
+            H = np.array([[2.0 - 400.0 * yv + 1200.0 * xv * xv, -400.0 * xv], [-400.0 * xv, 200.0]])
+        return g, H, t1 * t1 + 100.0 * t2 * t2, 1
+
+    rng = np.random.default_rng(3)
+    x0 = np.array([-1.2, 1.0]) + 0.05 * rng.standard_normal((40, 2))
+    x0[0] = [-1.2, 1.0]
+    kw = dict(max_iters=200, min_rerr_dec=0.0, max_consec_failures=20)
+    x, res, _ = drive_hg(ctx, x0, acc, tb.options(**kw), torch.float64)
+    outs = oracle_hg(x0, acc, kw, np.float64)
+    assert_hg_parity(x, res, outs)
+    assert outs[0].Succeeded() and outs[0].Converged()
+    assert abs(x[0, 0] - 1.0) < 1e-5 and abs(x[0, 1] - 1.0) < 1e-5           # the reference's own assertion
+    assert (res["stop_reason"] >= 0).all() and np.abs(x - 1.0).max() < 1e-4
+    assert (res["num_failures"] > 0).any()    # the indefinite true Hessian makes LM reject / re-damp on the way
+
+
+@pytest.mark.parametrize("dtype,n", [(torch.float64, 3), (torch.float64, 6), (torch.float64, 12), (torch.float32, 12),
+                                     (torch.float32, 30), (torch.float64, 40)])
+def test_hg_prior_diagonal_hessian(ctx, dtype, n):
+    """benchmarks/dense.cpp:57-66 "Prior n" (the reference's published benchmark rows): whitened prior
+    res = (x - y) / stdevs, grad = J res with J = diag(1 / stdevs), ONLY H.diagonal() is filled (the rest of
+    the pre-zeroed H_ stays zero), cost = res.squaredNorm() as a scalar Cost (one "residual")."""
+    import tinyopt_b200 as tb
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    rng = np.random.default_rng(n)
+    B = 37
+    y = rng.uniform(-1, 1, (B, n)).astype(npdt)
+    sd = rng.uniform(-1, 1, (B, n)).astype(npdt)
+    sd[np.abs(sd) < 0.05] = npdt(0.3)
+
+    def acc(p, v, want):
+        res = ((v - y[p]) / sd[p]).astype(npdt)
+        cost = npdt(0)
+        for r in res:
+            cost = npdt(cost + npdt(r * r))
+        g = H = None
+        if want:
+            g = (res / sd[p]).astype(npdt)
+            H = np.diag((npdt(1) / sd[p]) ** 2).astype(npdt)
+        return g, H, float(cost), 1
+
+    x0 = rng.uniform(-1, 1, (B, n)).astype(npdt)
+    kw = {} if npdt == np.float64 else dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)
+    x, res, Hf = drive_hg(ctx, x0, acc, tb.options(**kw), dtype)
+    outs = oracle_hg(x0, acc, kw, npdt)
+    assert_hg_parity(x, res, outs)
+    assert np.abs(x - y).max() < (1e-6 if npdt == np.float64 else 1e-3) and (res["stop_reason"] > 0).all()
+    for p in (0, B - 1):   # Output::final_hessian (lm.h:157-171): the un-damped user H
+        assert np.allclose(np.diag(Hf[p]), (1.0 / sd[p].astype(np.float64)) ** 2, rtol=1e-6 if npdt == np.float32 else 1e-14)
+
+
+def test_hg_singular_normal_matrix_float(ctx):
+    """tests/types.cpp:97-108: three Vec2f stacked into 6 parameters, res = x0 + x1 + x2 - 10: H = J^T J is 6 x 6
+    of rank 2, solved only thanks to the LM damping; the lambda returns the residual VECTOR (Cost = its squared
+    norm in float, 2 residuals).  Reference assertion: |x0 + x1 + x2 - 10| < 1e-5."""
+    import tinyopt_b200 as tb
+    J = np.array([[1, 0, 1, 0, 1, 0], [0, 1, 0, 1, 0, 1]], np.float32)
+    JtJ = (J.T @ J).astype(np.float32)
+
+    def acc4(p, v, want):
+        r = (v[0:2] + v[2:4] + v[4:6] - np.float32(10)).astype(np.float32)
+        cost = np.float32(np.float32(r[0] * r[0]) + np.float32(r[1] * r[1]))
+        if want:
+            return (J.T @ r).astype(np.float32), JtJ, float(cost), 2
+        return None, None, float(cost), 2
+
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(-1, 1, (16, 6)).astype(np.float32)
+    x, res, _ = drive_hg(ctx, x0, acc4, tb.options(), torch.float32)
+    outs = oracle_hg(x0, acc4, {}, np.float32)
+    assert_hg_parity(x, res, outs)
+    assert np.abs(x[:, 0:2] + x[:, 2:4] + x[:, 4:6] - 10).max() < 1e-5

@@ -10,7 +10,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtinyopt_b200.so")
+# TOB200_LIB_OVERRIDE: development A/B switch (tools/build_variant.sh builds libtinyopt_b200_<name>.so with
+# experiment flags); unset in every test / bench run that is reported
+LIB_PATH = os.environ.get("TOB200_LIB_OVERRIDE") or os.path.join(_HERE, "libtinyopt_b200.so")
 
 
 class Options(C.Structure):
@@ -70,6 +72,8 @@ SYMBOLS = {
     "tob200_last_phase_ms": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_i)]),
     "tob200_lm_run_f32": (_i, [_vp, _PO, _vp, _vp, _f, _i, _i64, _i, _i, _vp, _vp]),
     "tob200_lm_run_f64": (_i, [_vp, _PO, _vp, _vp, _d, _i, _i64, _i, _i, _vp, _vp]),
+    "tob200_lm_run_ex_f32": (_i, [_vp, _PO, _vp, _vp, _f, _i, _i64, _i, _i, _vp, _vp, _vp]),
+    "tob200_lm_run_ex_f64": (_i, [_vp, _PO, _vp, _vp, _d, _i, _i64, _i, _i, _vp, _vp, _vp]),
     "tob200_lm_run_host_f32": (_i, [_vp, _PO, _vp, _vp, _f, _i, _i64, _i, _i, _vp, _vp]),
     "tob200_lm_run_host_f64": (_i, [_vp, _PO, _vp, _vp, _d, _i, _i64, _i, _i, _vp, _vp]),
     "tob200_solver_create": (_i, [_vp, _i, _i64, _i, _PO, C.POINTER(_vp)]),
@@ -79,6 +83,8 @@ SYMBOLS = {
     "tob200_solver_needs": (_vp, [_vp]),
     "tob200_solver_step_f32": (_i, [_vp, _vp, _vp, _i, _i]),
     "tob200_solver_step_f64": (_i, [_vp, _vp, _vp, _i, _i]),
+    "tob200_solver_step_hg_f32": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "tob200_solver_step_hg_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "tob200_solver_num_active": (_i, [_vp, C.POINTER(_i64)]),
     "tob200_solver_results": (_i, [_vp, _vp]),
     "tob200_solver_final_hessian": (_i, [_vp, _vp]),

@@ -63,6 +63,7 @@ class Output:
     """Batched tinyopt::Output (output.h:26-145): one entry per problem."""
     x: torch.Tensor            # [B, n] solutions (device)
     results: np.ndarray        # structured array, RESULT_DTYPE, host
+    final_hessian: torch.Tensor | None = None   # [B, n, n] float64 (device): Output::final_hessian, un-damped
 
     @property
     def num_iters(self):
@@ -269,9 +270,10 @@ class Context:
     # ---- a7-a10 ---------------------------------------------------------------------------------
     def optimize_batch(self, A: torch.Tensor, y: torch.Tensor, x0: torch.Tensor, opt: Options | None = None, *,
                        alpha: float = 0.1, layout: int | None = None, results: torch.Tensor | None = None,
-                       sync: bool = True) -> Output:
+                       sync: bool = True, want_hessian: bool = False) -> Output:
         """One tinyopt::Optimize() per problem of the polynomial family, device resident
-        (tob200_lm_run_*).  x0 [B,n] is copied; the returned Output holds the solutions."""
+        (tob200_lm_run_*).  x0 [B,n] is copied; the returned Output holds the solutions.
+        want_hessian: also Output.final_hessian (tob200_lm_run_ex_*; needs options.save_last, the default)."""
         opt = opt if opt is not None else options()
         layout = _layout_of(A, layout)
         B, n = x0.shape
@@ -280,14 +282,21 @@ class Context:
         x = x0.to(dtype=dt, device=dev).clone().contiguous()
         if results is None:
             results = torch.empty((B, C.sizeof(_lib.Result)), dtype=torch.uint8, device=dev)
-        fn = getattr(self._lib, f"tob200_lm_run_{_suf(dt)}")
         ct = C.c_float if dt == torch.float32 else C.c_double
-        self._ck(fn(self._h, C.byref(opt), _p(A.contiguous()), _p(y.contiguous()), ct(alpha), layout, B, m, n,
-                    _p(x), _p(results)), "tob200_lm_run")
+        fh = None
+        if want_hessian:
+            fh = torch.zeros((B, n, n), dtype=torch.float64, device=dev)
+            fn = getattr(self._lib, f"tob200_lm_run_ex_{_suf(dt)}")
+            self._ck(fn(self._h, C.byref(opt), _p(A.contiguous()), _p(y.contiguous()), ct(alpha), layout, B, m, n,
+                        _p(x), _p(results), _p(fh)), "tob200_lm_run_ex")
+        else:
+            fn = getattr(self._lib, f"tob200_lm_run_{_suf(dt)}")
+            self._ck(fn(self._h, C.byref(opt), _p(A.contiguous()), _p(y.contiguous()), ct(alpha), layout, B, m, n,
+                        _p(x), _p(results)), "tob200_lm_run")
         if not sync:
-            return Output(x=x, results=results)  # raw device buffer; caller decodes after sync
+            return Output(x=x, results=results, final_hessian=fh)  # raw device buffer; caller decodes after sync
         self.sync()
-        return Output(x=x, results=decode_results(results))
+        return Output(x=x, results=decode_results(results), final_hessian=fh)
 
     def optimize_batch_host(self, A: np.ndarray, y: np.ndarray, x: np.ndarray, opt: Options | None = None, *,
                             alpha: float = 0.1, layout: int | None = None, B: int | None = None,
@@ -401,6 +410,22 @@ class BatchSolver:
         m = r.shape[1]
         fn = getattr(self.ctx._lib, f"tob200_solver_step_{_suf(self.dtype)}")
         self.ctx._ck(fn(self._h, _p(J.contiguous()), _p(r.contiguous()), layout, m), "tob200_solver_step")
+
+    def step_hg(self, grad: torch.Tensor, H: torch.Tensor, cost: torch.Tensor, num_residuals: torch.Tensor | None = None):
+        """One Step from USER-FILLED accumulators (tob200_solver_step_hg_*): what the reference's
+        `acc(x, grad, H) -> Cost` lambda leaves in grad_ / H_ and returns (docs/API.md:37-57,137-170).
+        grad [B,n], H [B,n,n] (only the upper triangle is read), cost [B] (float64), num_residuals [B] int32
+        (default 1: a scalar cost, cost.h:22)."""
+        dev = self.ctx.device
+        grad = grad.to(dtype=self.dtype, device=dev).contiguous()
+        H = H.to(dtype=self.dtype, device=dev).contiguous()
+        cost = cost.to(dtype=torch.float64, device=dev).contiguous()
+        if num_residuals is None:
+            num_residuals = torch.ones((self.B,), dtype=torch.int32, device=dev)
+        nres = num_residuals.to(dtype=torch.int32, device=dev).contiguous()
+        fn = getattr(self.ctx._lib, f"tob200_solver_step_hg_{_suf(self.dtype)}")
+        self.ctx._ck(fn(self._h, _p(grad), _p(H), _p(cost), _p(nres)), "tob200_solver_step_hg")
+        self._keep = (grad, H, cost, nres)  # the launch is asynchronous: keep the converted copies alive
 
     def num_active(self) -> int:
         v = C.c_int64(0)

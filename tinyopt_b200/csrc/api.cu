@@ -403,7 +403,7 @@ LgSyrkParams lg_syrk_params(tob200_ctx *ctx, const LgBuffers &b, const float *A,
 
 // the whole LM loop for 56 <= n <= 512 (float): three kernels per iteration over the active problems
 int lg_lm_run(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y, float alpha, int64_t B, int m,
-              int n, float *x, tob200_result *results) {
+              int n, float *x, tob200_result *results, double *final_hessian = nullptr, int n_out = 0) {
   LgBuffers b;
   int rc = lg_prepare(ctx, B, m, n, true, true, &b);
   if (rc != TOB200_OK) return rc;
@@ -449,6 +449,10 @@ int lg_lm_run(tob200_ctx *ctx, const tob200_options *opt, const float *A, const 
     CK(cudaMemcpyAsync(&active, b.n_active, sizeof(active), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (active == 0) break;
+  }
+  if (final_hessian) {  // Output::final_hessian (optimizer.h:313-316)
+    CK(launch_lg_final_hessian(b.H, b.hd, b.rec, opt->solver_type, B, n_out > 0 ? n_out : n, b.np, final_hessian, ctx->stream));
+    ctx->launches++;
   }
   return TOB200_OK;
 }
@@ -578,7 +582,7 @@ int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_
 
 template <typename T>
 int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T *y, T alpha, int layout, int64_t B,
-                int m, int n, T *x, tob200_result *results, bool record_events = true) {
+                int m, int n, T *x, tob200_result *results, bool record_events = true, double *final_hessian = nullptr) {
   if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
   int rc = check_options(ctx, opt);
   if (rc != TOB200_OK) return rc;
@@ -593,6 +597,7 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     return fail(ctx, TOB200_ERR_UNSUPPORTED, "hessian.use_ldlt = false (H.inverse()) is implemented for n <= 55 only");
   if (record_events) CK(cudaEventRecord(ctx->ev0, ctx->stream));
   if ((rc = to_native_layout<T>(ctx, family, layout, B, m, n, &A, &y)) != TOB200_OK) return rc;
+  if (!opt->save_last) final_hessian = nullptr;  // options.h:66 (hessian.save_last)
   TppLaunch cfg;
   if (family == 1) {
     TppRunParams<T> p;
@@ -604,6 +609,7 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     p.alpha3 = (T)3 * alpha;
     p.x = x;
     p.results = results;
+    p.final_hessian = final_hessian;
     CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppRun, &p, cfg, nullptr));
     ctx->launches++;
   } else if (family == 3) {
@@ -622,11 +628,11 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
       CK(launch_repitch((const float *)A, B, m, n, A4, m, n4, ctx->stream));
       CK(launch_repitch((const float *)x, 1, (int)B, n, x4, (int)B, n4, ctx->stream));
       ctx->launches += 2;
-      if ((rc = lg_lm_run(ctx, opt, A4, (const float *)y, (float)alpha, B, m, n4, x4, results)) != TOB200_OK) return rc;
+      if ((rc = lg_lm_run(ctx, opt, A4, (const float *)y, (float)alpha, B, m, n4, x4, results, final_hessian, n)) != TOB200_OK) return rc;
       CK(launch_repitch(x4, 1, (int)B, n4, (float *)x, (int)B, n, ctx->stream));
       ctx->launches++;
     } else if ((rc = lg_lm_run(ctx, opt, (const float *)A, (const float *)y, (float)alpha, B, m, n, (float *)x,
-                               results)) != TOB200_OK) {
+                               results, final_hessian, n)) != TOB200_OK) {
       return rc;
     }
   } else {
@@ -638,6 +644,7 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     p.alpha3 = (T)3 * alpha;
     p.x = x;
     p.results = results;
+    p.final_hessian = final_hessian;
     if ((rc = wpp_launch<T>(ctx, n, kind, &p, cfg)) != TOB200_OK) return rc;
   }
   if (record_events) CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -755,14 +762,27 @@ struct tob200_solver {
 namespace {
 
 template <typename T>
-int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m, int reset) {
+struct StepHG {  // tob200_solver_step_hg_*: caller-filled accumulators instead of J, r
+  const T *grad = nullptr, *H = nullptr;
+  const double *cost = nullptr;
+  const int32_t *nres = nullptr;
+};
+
+template <typename T>
+int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m, int reset, const StepHG<T> *hg = nullptr) {
   if (!s) return fail(nullptr, TOB200_ERR_INVALID, "solver is NULL");
   tob200_ctx *ctx = s->ctx;
   if (s->dtype != dtype_of<T>()) return fail(ctx, TOB200_ERR_INVALID, "solver dtype mismatch");
   DeviceGuard guard(ctx->device);
   const int n = s->n;
   const int64_t B = s->B;
-  if (!reset) {
+  if (hg) {
+    if (!s->is_reset) return fail(ctx, TOB200_ERR_INVALID, "tob200_solver_reset must be called first");
+    if (!hg->grad || !hg->H || !hg->cost || !hg->nres) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
+    J = nullptr;
+    r = nullptr;
+    m = 1;
+  } else if (!reset) {
     if (!s->is_reset) return fail(ctx, TOB200_ERR_INVALID, "tob200_solver_reset must be called first");
     if (m < 0) return fail(ctx, TOB200_ERR_INVALID, "m < 0");
     if (!J || !r) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
@@ -785,6 +805,10 @@ int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m
     p.needs = s->needs;
     p.n_active = s->n_active;
     p.reset = reset;
+    p.hg_grad = hg ? hg->grad : nullptr;
+    p.hg_H = hg ? hg->H : nullptr;
+    p.hg_cost = hg ? hg->cost : nullptr;
+    p.hg_nres = hg ? hg->nres : nullptr;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaMemsetAsync(s->n_active, 0, sizeof(unsigned long long), ctx->stream));
     if ((rc = wpp_launch<T>(ctx, n, kind, &p, cfg)) != TOB200_OK) return rc;
@@ -806,6 +830,10 @@ int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m
   p.needs = s->needs;
   p.n_active = s->n_active;
   p.reset = reset;
+  p.hg_grad = hg ? hg->grad : nullptr;
+  p.hg_H = hg ? hg->H : nullptr;
+  p.hg_cost = hg ? hg->cost : nullptr;
+  p.hg_nres = hg ? hg->nres : nullptr;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(cudaMemsetAsync(s->n_active, 0, sizeof(unsigned long long), ctx->stream));
   CK(tpp_entry_for<T>(n)(kTppLaunch, n, kTppStep, &p, cfg, nullptr));
@@ -1187,6 +1215,14 @@ int tob200_lm_run_f64(tob200_ctx *ctx, const tob200_options *opt, const double *
                       int layout, int64_t B, int m, int n, double *x, tob200_result *results) {
   return lm_run_impl<double>(ctx, opt, A, y, alpha, layout, B, m, n, x, results);
 }
+int tob200_lm_run_ex_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y, float alpha,
+                         int layout, int64_t B, int m, int n, float *x, tob200_result *results, double *final_hessian) {
+  return lm_run_impl<float>(ctx, opt, A, y, alpha, layout, B, m, n, x, results, true, final_hessian);
+}
+int tob200_lm_run_ex_f64(tob200_ctx *ctx, const tob200_options *opt, const double *A, const double *y, double alpha,
+                         int layout, int64_t B, int m, int n, double *x, tob200_result *results, double *final_hessian) {
+  return lm_run_impl<double>(ctx, opt, A, y, alpha, layout, B, m, n, x, results, true, final_hessian);
+}
 int tob200_lm_run_host_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y, float alpha,
                            int layout, int64_t B, int m, int n, float *x, tob200_result *results) {
   return lm_run_host_impl<float>(ctx, opt, A, y, alpha, layout, B, m, n, x, results);
@@ -1286,6 +1322,19 @@ int tob200_solver_step_f32(tob200_solver *s, const float *J, const float *r, int
 }
 int tob200_solver_step_f64(tob200_solver *s, const double *J, const double *r, int layout, int m) {
   return solver_step_impl<double>(s, J, r, layout, m, 0);
+}
+
+int tob200_solver_step_hg_f32(tob200_solver *s, const float *grad, const float *H, const double *cost,
+                              const int32_t *num_residuals) {
+  StepHG<float> hg;
+  hg.grad = grad; hg.H = H; hg.cost = cost; hg.nres = num_residuals;
+  return solver_step_impl<float>(s, nullptr, nullptr, 0, 0, 0, &hg);
+}
+int tob200_solver_step_hg_f64(tob200_solver *s, const double *grad, const double *H, const double *cost,
+                              const int32_t *num_residuals) {
+  StepHG<double> hg;
+  hg.grad = grad; hg.H = H; hg.cost = cost; hg.nres = num_residuals;
+  return solver_step_impl<double>(s, nullptr, nullptr, 0, 0, 0, &hg);
 }
 
 int tob200_solver_num_active(tob200_solver *s, int64_t *n_active) {

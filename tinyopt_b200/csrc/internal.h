@@ -53,6 +53,8 @@ cudaError_t launch_lg_init(LmScalars<float> *rec, const DevOptions<float> &opt, 
                            cudaStream_t st);
 cudaError_t launch_lg_export_h(const float *H, const float *dg, const float *lambda, int64_t B, int n, int np, float *out,
                                cudaStream_t st);
+cudaError_t launch_lg_final_hessian(const float *H, const float *hd, const LmScalars<float> *rec, int solver_type, int64_t B,
+                                    int n_out, int np, double *out, cudaStream_t st);
 cudaError_t launch_lg_import_h(const float *in, int64_t B, int n, int np, float *H, cudaStream_t st);
 cudaError_t launch_lg_eval(const LgEvalParams &p, int num_sms, cudaStream_t st);
 cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st);

@@ -44,6 +44,36 @@ __global__ void lg_import_h_kernel(const float *in, int64_t B, int n, int np, fl
   if (i <= j) H[(size_t)pr * np * np + (size_t)i * np + j] = in[e];
 }
 
+// Output::final_hessian for the large-n family (optimizer.h:313-316, lm.h:157-171): off-diagonals from the upper
+// triangle of H_, the persistent damped diagonal hd divided by 1 + prev_lambda_ (in float), widened to double;
+// n_out <= n leading rows / columns (n % 4 != 0 runs on a zero-padded copy)
+__global__ void lg_final_hessian_kernel(const float *H, const float *hd, const LmScalars<float> *rec, int solver_type,
+                                        int64_t B, int n_out, int np, double *out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * n_out * n_out) return;
+  const int64_t pr = e / ((int64_t)n_out * n_out);
+  const int ij = (int)(e % ((int64_t)n_out * n_out));
+  const int i = ij / n_out, j = ij % n_out;
+  const float *Hp = H + (size_t)pr * np * np;
+  float v;
+  if (i == j) {
+    v = hd[(size_t)pr * np + i];
+    const float pl = rec[pr].prev_lambda;
+    if (solver_type == 0 && pl > 0.f) v = __fdiv_rn(v, __fadd_rn(1.f, pl));
+  } else {
+    v = i < j ? Hp[(size_t)i * np + j] : Hp[(size_t)j * np + i];
+  }
+  out[e] = (double)v;
+}
+
+cudaError_t launch_lg_final_hessian(const float *H, const float *hd, const LmScalars<float> *rec, int solver_type, int64_t B,
+                                    int n_out, int np, double *out, cudaStream_t st) {
+  const int64_t total = B * n_out * n_out;
+  if (total <= 0) return cudaSuccess;
+  lg_final_hessian_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(H, hd, rec, solver_type, B, n_out, np, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_lg_init(LmScalars<float> *rec, const DevOptions<float> &opt, float *last_dx, int64_t B, int n,
                            cudaStream_t st) {
   const int64_t total = B * n;

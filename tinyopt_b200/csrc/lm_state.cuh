@@ -165,6 +165,17 @@ __device__ __forceinline__ bool lm_normalize_cost(const DevOptions<T> &o, T cost
   return nres > 0 && cost != 1.7976931348623157e+308;
 }
 
+// the same for a cost that arrives as the reference's `Cost::cost` itself (a double: user-filled accumulators,
+// tob200_solver_step_hg_*)
+template <typename T>
+__device__ __forceinline__ bool lm_normalize_cost_d(const DevOptions<T> &o, double cost_in, int nres, double &cost) {
+  cost = cost_in;
+  if (!o.use_squared_norm) cost = sqrt(cost);
+  if (o.downscale_by_2) cost *= 0.5f;
+  if (o.normalize && nres > 0) cost /= nres;
+  return nres > 0 && cost != 1.7976931348623157e+308;
+}
+
 // optimizer.h:356-357
 template <typename T>
 __device__ __forceinline__ uint8_t lm_max_tries(const DevOptions<T> &o) {
@@ -303,14 +314,15 @@ __device__ __forceinline__ int lm_update_action(LmScalars<T> &s, const DevOption
 template <typename T, int N, class HG>
 __device__ __forceinline__ void lm_after_pass(LmState<T, N> &s, const DevOptions<T> &o,
                                               bool pass_rebuilt, T (&hu)[tri_count(N)], T (&g)[N],
-                                              T cost_t, int nres, HG &hg) {
+                                              T cost_t, int nres, HG &hg, const double *cost_d = nullptr) {
   using O = Ops<T>;
   using L = LdltReg<T, N>;
   constexpr int NT = tri_count(N);
 
   // ---- Build, first attempt: cost_ = acc(...); NormalizeCost ----
   double cost;
-  bool built_ok = lm_normalize_cost(o, cost_t, nres, cost);
+  // (cost_d: the caller's accumulation lambda returned the cost itself, as a double: docs/API.md:37-57)
+  bool built_ok = cost_d ? lm_normalize_cost_d(o, *cost_d, nres, cost) : lm_normalize_cost(o, cost_t, nres, cost);
   T diag0[N];  // undamped diagonal, for the re-damping of a retry after a rebuild
   if (pass_rebuilt) {
     s.num_builds++;

@@ -285,6 +285,7 @@ struct TppRunParams {
   T alpha, alpha3;
   T *x;                    // [B][n] in/out
   tob200_result *results;  // [B]
+  double *final_hessian;   // [B][n][n] or nullptr: Output::final_hessian (optimizer.h:313-316, lm.h:157-171)
 };
 
 template <typename T, int N>
@@ -325,6 +326,23 @@ __global__ void __launch_bounds__(kTppThreads, tpp_min_blocks<T, N>())
 #pragma unroll
       for (int j = 0; j < N; ++j) p.x[pidx * N + j] = s.x[j];
       lm_write_result(s, &p.results[pidx]);
+      if (p.final_hessian) {
+        // SolverLM::Hessian() (lm.h:157-171): the persistent damped H_ with its diagonal divided by
+        // 1 + prev_lambda_ (in Scalar), widened to double (optimizer.h:315)
+        const bool undamp = is_lm && s.prev_lambda > (T)0;
+        const T sc = Ops<T>::add((T)1, s.prev_lambda);
+        double *o = p.final_hessian + (size_t)pidx * N * N;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+          for (int k = j; k < N; ++k) {
+            T v = hg.ld_h(tri_index(N, j, k));
+            if (j == k && undamp) v = Ops<T>::div(v, sc);
+            o[j * N + k] = (double)v;
+            o[k * N + j] = (double)v;
+          }
+        }
+      }
     }
   }
 }
@@ -428,6 +446,11 @@ struct TppStepParams {
   int32_t *needs;    // [B]
   unsigned long long *n_active;  // device counter, zeroed by the host before the launch
   int reset;         // 1: initialise the state instead of stepping (x already holds x0)
+  // tob200_solver_step_hg_*: the accumulators arrive filled by the caller (docs/API.md:37-57,137-170) instead of
+  // being formed from J, r: grad [B][n], H [B][n][n] (upper triangle read), cost [B], num_residuals [B]
+  const T *hg_grad, *hg_H;
+  const double *hg_cost;
+  const int32_t *hg_nres;
 };
 
 template <typename T, int N>
@@ -493,10 +516,29 @@ __global__ void __launch_bounds__(kTppThreads, tpp_min_blocks<T, N>())
     const bool active = !s.done();
     const bool do_rebuild = !is_lm || s.rebuild();
     T hu[NT], g[N], cost;
-    tpp_pass<T, N, false>(pipe, p.d, tile, lane, active, do_rebuild, s.x, (T)0, (T)0, hu, g, cost);
+    double cost_d = 0.0;
+    int nres = p.d.m;
+    if (p.hg_cost) {  // user-filled accumulators: what `acc(x, grad, H)` left in grad_, H_ and returned
+      cost = (T)0;
+      if (active) {
+        cost_d = p.hg_cost[pidx];
+        nres = p.hg_nres[pidx];
+        if (do_rebuild) {
+          const T *Hu = p.hg_H + (size_t)pidx * N * N;
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            g[j] = p.hg_grad[pidx * N + j];
+#pragma unroll
+            for (int k = j; k < N; ++k) hu[tri_index(N, j, k)] = Hu[j * N + k];
+          }
+        }
+      }
+    } else {
+      tpp_pass<T, N, false>(pipe, p.d, tile, lane, active, do_rebuild, s.x, (T)0, (T)0, hu, g, cost);
+    }
     if (active) {
       GlobalHG<T, N> hg{p.H + (size_t)tile * NT * kTile + lane, p.g + (size_t)tile * N * kTile + lane};
-      lm_after_pass<T, N>(s, p.opt, do_rebuild, hu, g, cost, p.d.m, hg);
+      lm_after_pass<T, N>(s, p.opt, do_rebuild, hu, g, cost, nres, hg, p.hg_cost ? &cost_d : nullptr);
       state_store(s, p.rec[pidx]);
 #pragma unroll
       for (int j = 0; j < N; ++j) {

@@ -41,6 +41,12 @@ __device__ long long g_wpp_tm[16];
 constexpr int kWppRows = 32;      // rows per chunk == lanes
 constexpr int kWppThreads = 128;  // 4 independent warps per CTA
 constexpr int kWppMaxStages = 4;
+#ifndef TOB200_WPP_AREG
+#define TOB200_WPP_AREG 0  // measured: C4 13.07 M it/s with the row of A held in registers vs 13.58 M without
+#endif
+#ifndef TOB200_WPP_FOLD_PIPE
+#define TOB200_WPP_FOLD_PIPE 0
+#endif
 #ifndef TOB200_WPP_LDLT_COLS
 #define TOB200_WPP_LDLT_COLS 2
 #endif
@@ -56,6 +62,15 @@ __host__ __device__ constexpr int wpp_ldw(int np) { return ((np / 4) & 1) ? np :
 // pitch of the packed [J|r] rows: multiple of 4 floats (16-byte loads) with pitch/4 odd
 // (conflict-free lane-per-row stores)
 __host__ __device__ constexpr int wpp_nps(int np) { return ((np / 4) & 1) ? np : np + 4; }
+
+// position of column c of [J|r] inside a packed row.  With 8-column blocks a lane reads its block row and its
+// block column with 16-byte loads at float offsets 8 bi / 8 bj: blocks b and b + 4 would sit 32 banks apart
+// (a 2-way conflict on every operand load of the quarter-warps that hold both: 16.7 % of all shared-memory
+// wavefronts of the C4 kernel, which is bound by exactly those wavefronts).  A 4-float gap after column 31
+// moves blocks 4..6 by 4 banks: every operand load is conflict-free.  (It is the pad that used to sit at the
+// end of the row, so the pitch does not change.)
+template <int BLK>
+__host__ __device__ constexpr int wpp_col(int c) { return BLK == 8 ? c + 4 * (c >> 5) : c; }
 
 struct WppSmem {  // byte offsets inside one warp's shared memory
   uint32_t bars, xs, last_dx, g, dxs, temp, dg, dd, perm, inv, tx, stages, stage_bytes, jbuf, total;
@@ -666,6 +681,62 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     // ---- phase 1 (lane = row): canonical t-chain, residual r_i, Jacobian scale sc_i, then the
     // ---- augmented packed row [sc_i a_i | r_i | 0 ..] written with 16-byte stores (pitch / 4 odd:
     // ---- conflict free); the pad columns are rewritten for every row, so they never go stale ----
+#if TOB200_WPP_AREG
+    // float, even n: the row of A is read from shared memory ONCE, into registers, and serves both the
+    // t-chain and the scaled copy (the kernel is bound by shared-memory wavefronts: this saves n / 2 8-byte
+    // loads per row).  Columns below NP - BLK are always Jacobian columns (n + 1 > NP - BLK), so only the last
+    // block needs run-time masks.
+    bool row_done = false;
+    if constexpr (kF32) {
+      if ((n & 1) == 0) {
+        row_done = true;
+        if (lane < nrows) {
+          constexpr int HQ = NP / 2, HS = (NP - BLK) / 2;
+          const int h = n / 2;
+          const float2 *a2 = reinterpret_cast<const float2 *>(sa + lane * n);
+          const float2 *x2 = reinterpret_cast<const float2 *>(xs);
+          float2 ar[HQ];
+#pragma unroll
+          for (int q = 0; q < HQ; ++q) ar[q] = (q < HS || q < h) ? a2[q] : make_float2(0.f, 0.f);
+          T ri, sc = (T)1;
+          if (kSynth) {
+            T t = (T)0;
+#pragma unroll
+            for (int q = 0; q < HQ; ++q) {
+              if (q < HS || q < h) {
+                const float2 xv = x2[q];
+                t = O::fma(ar[q].x, xv.x, t);
+                t = O::fma(ar[q].y, xv.y, t);
+              }
+            }
+            const T t2 = O::mul(t, t);
+            ri = O::fma(t, O::fma(alpha, t2, (T)1), -ycur);
+            sc = O::fma(alpha3, t2, (T)1);
+          } else {
+            ri = ycur;
+          }
+          if (do_rebuild) {
+            float4 *jrow = reinterpret_cast<float4 *>(jbuf + lane * NPS);
+#pragma unroll
+            for (int q4 = 0; q4 < NP / 4; ++q4) {
+              float2 lo = ar[2 * q4], hi = ar[2 * q4 + 1];
+              const int q0 = 2 * q4, q1 = 2 * q4 + 1;
+              if (kSynth) {  // (pairs at or beyond h hold zeros: scaling them is harmless and branch free)
+                lo.x = O::mul(sc, lo.x); lo.y = O::mul(sc, lo.y);
+                hi.x = O::mul(sc, hi.x); hi.y = O::mul(sc, hi.y);
+              }
+              if (q0 >= HS && q0 == h) lo = make_float2(ri, 0.f);
+              if (q1 >= HS && q1 == h) hi = make_float2(ri, 0.f);
+              jrow[wpp_col<BLK>(4 * q4) / 4] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+          } else {
+            jbuf[lane * NPS + wpp_col<BLK>(n)] = ri;
+          }
+        }
+      }
+    }
+    if (!row_done)
+#endif
     if (lane < nrows) {
       const T *arow = sa + lane * n;
       T ri, sc = (T)1;
@@ -703,7 +774,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
           T v = (T)0;
           if (j < n) v = kSynth ? O::mul(sc, arow[j]) : arow[j];
           else if (j == n) v = ri;
-          jrow[j] = v;
+          jrow[wpp_col<BLK>(j)] = v;
         }
        } else {
         float4 *jrow = reinterpret_cast<float4 *>(jbuf + lane * NPS);
@@ -718,7 +789,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
             else if (q0 == h) lo.x = ri;
             if (q1 < h) { hi = a2[q1]; if (kSynth) { hi.x = O::mul(sc, hi.x); hi.y = O::mul(sc, hi.y); } }
             else if (q1 == h) hi.x = ri;
-            jrow[q4] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            jrow[wpp_col<BLK>(4 * q4) / 4] = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
         } else {
 #pragma unroll 7
@@ -731,12 +802,12 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
               if (j < n) v[e] = kSynth ? O::mul(sc, arow[j]) : arow[j];
               else if (j == n) v[e] = ri;
             }
-            jrow[q4] = make_float4(v[0], v[1], v[2], v[3]);
+            jrow[wpp_col<BLK>(4 * q4) / 4] = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
        }
       } else {
-        jbuf[lane * NPS + n] = ri;
+        jbuf[lane * NPS + wpp_col<BLK>(n)] = ri;
       }
     }
     __syncwarp();
@@ -751,8 +822,8 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
     // ---- phase 2: lane = 8x8 block of the upper triangle ----
     if (do_rebuild) {
       if (has_block) {
-        const T *pa = jbuf + bi * BLK;
-        const T *pb = jbuf + bj * BLK;
+        const T *pa = jbuf + wpp_col<BLK>(bi * BLK);
+        const T *pb = jbuf + wpp_col<BLK>(bj * BLK);
        if constexpr (!kF32) {
         for (int i = 0; i < nrows; ++i) {
           T a[BLK], b[BLK];
@@ -762,6 +833,32 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
           for (int u = 0; u < BLK; ++u)
 #pragma unroll
             for (int v = 0; v < BLK; ++v) acc[u][v] = O::fma(a[u], b[v], acc[u][v]);
+        }
+       } else if (TOB200_WPP_FOLD_PIPE) {
+        // software pipeline: the operands of row i + 1 are requested before the 32 FFMA2 of row i issue
+        float4 av[BLK / 4], bv[BLK / 4];
+#pragma unroll
+        for (int q = 0; q < BLK / 4; ++q) {
+          av[q] = *reinterpret_cast<const float4 *>(pa + 4 * q);
+          bv[q] = *reinterpret_cast<const float4 *>(pb + 4 * q);
+        }
+        for (int i = 0; i < nrows; ++i) {
+          T a[BLK], b[BLK];
+#pragma unroll
+          for (int q = 0; q < BLK / 4; ++q) {
+            a[4 * q] = av[q].x; a[4 * q + 1] = av[q].y; a[4 * q + 2] = av[q].z; a[4 * q + 3] = av[q].w;
+            b[4 * q] = bv[q].x; b[4 * q + 1] = bv[q].y; b[4 * q + 2] = bv[q].z; b[4 * q + 3] = bv[q].w;
+          }
+          const int in = i + 1 < nrows ? i + 1 : i;  // (the last row re-reads itself: unused)
+#pragma unroll
+          for (int q = 0; q < BLK / 4; ++q) {
+            av[q] = *reinterpret_cast<const float4 *>(pa + in * NPS + 4 * q);
+            bv[q] = *reinterpret_cast<const float4 *>(pb + in * NPS + 4 * q);
+          }
+#pragma unroll
+          for (int u = 0; u < BLK; ++u)
+#pragma unroll
+            for (int h = 0; h < BLK / 2; ++h) ffma2_bcast(acc2[u][h], a[u], b[2 * h], b[2 * h + 1]);
         }
        } else {
 #pragma unroll 2
@@ -783,7 +880,7 @@ __device__ __forceinline__ void wpp_pass(WppPipe<T> &pipe, const WppData<T> &d, 
       }
     } else if (lane == 0) {  // cost-only pass (solvers/gn.h:98-105): sum r_i^2 in row order
       for (int i = 0; i < nrows; ++i) {
-        const T ri = jbuf[i * NPS + n];
+        const T ri = jbuf[i * NPS + wpp_col<BLK>(n)];
         cost_only = O::fma(ri, ri, cost_only);
       }
     }
@@ -861,10 +958,11 @@ template <typename T, int NB, int BLK, bool INV = false>
 __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions<T> &o, const WppData<T> &d,
                                                unsigned char *ws, T *hp, bool pass_rebuilt, int bi, int bj,
                                                bool has_block, const T (&acc)[BLK][BLK], T cost_only, int lane,
-                                               bool always_persist = false) {
+                                               bool always_persist = false, const double *cost_d = nullptr,
+                                               int nres_d = 0) {
   using O = Ops<T>;
   constexpr int LDW = wpp_ldw(NB * BLK);
-  const int n = d.n, nres = d.m;
+  const int n = d.n, nres = cost_d ? nres_d : d.m;
   T *W = reinterpret_cast<T *>(ws + d.L.stages);
   T *xs = reinterpret_cast<T *>(ws + d.L.xs);
   T *last_dx = reinterpret_cast<T *>(ws + d.L.last_dx);
@@ -885,7 +983,7 @@ __device__ __forceinline__ void wpp_after_pass(LmScalars<T> &s, const DevOptions
     __syncwarp();
   }
   double cost;
-  bool built_ok = lm_normalize_cost(o, cost_t, nres, cost);
+  bool built_ok = cost_d ? lm_normalize_cost_d(o, *cost_d, nres, cost) : lm_normalize_cost(o, cost_t, nres, cost);
   if (pass_rebuilt) {
     s.num_builds++;
     if (built_ok) {
@@ -1007,6 +1105,7 @@ struct WppRunParams {
   T alpha, alpha3;
   T *x;                    // [B][n] in/out
   tob200_result *results;  // [B]
+  double *final_hessian;   // [B][n][n] or nullptr: Output::final_hessian (optimizer.h:313-316, lm.h:157-171)
 };
 
 template <typename T, int NB, int BLK, bool INV = false>
@@ -1040,10 +1139,25 @@ __global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 3 : 1) wpp_lm_ru
       const bool do_rebuild = !is_lm || s.rebuild();
       T acc[BLK][BLK], cost_only;
       wpp_pass<T, NB, BLK, true>(pipe, p.d, ws, pr, lane, do_rebuild, p.alpha, p.alpha3, bi, bj, has_block, acc, cost_only);
-      wpp_after_pass<T, NB, BLK, INV>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane);
+      wpp_after_pass<T, NB, BLK, INV>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane,
+                                      p.final_hessian != nullptr);  // the final Hessian needs H_ of every Build kept
     }
     for (int j = lane; j < n; j += 32) p.x[pr * n + j] = xs[j];
     if (lane == 0) lm_write_result(s, &p.results[pr]);
+    if (p.final_hessian) {  // SolverLM::Hessian() (lm.h:157-171) from the persistent damped H_, widened to double
+      __syncwarp();
+      const bool undamp = is_lm && s.prev_lambda > (T)0;
+      const T sc = Ops<T>::add((T)1, s.prev_lambda);
+      double *o = p.final_hessian + (size_t)pr * n * n;
+      for (int e = lane; e < n * n; e += 32) {
+        const int j = e / n, k = e - j * n;
+        if (j > k) continue;
+        T v = hp[k * LDW + j];
+        if (j == k && undamp) v = Ops<T>::div(v, sc);
+        o[j * n + k] = (double)v;
+        o[k * n + j] = (double)v;
+      }
+    }
     __syncwarp();
   }
 #ifdef TOB200_WPP_TIMING

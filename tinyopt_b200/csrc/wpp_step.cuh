@@ -23,6 +23,10 @@ struct WppStepParams {
   int32_t *needs;    // [B]
   unsigned long long *n_active;  // device counter, zeroed by the host before the launch
   int reset;         // 1: initialise the state instead of stepping (x already holds x0)
+  // tob200_solver_step_hg_*: caller-filled accumulators (see TppStepParams)
+  const T *hg_grad, *hg_H;
+  const double *hg_cost;
+  const int32_t *hg_nres;
 };
 
 template <typename T>
@@ -83,9 +87,31 @@ __global__ void __launch_bounds__(kWppThreads, sizeof(T) == 4 ? 2 : 1) wpp_step_
     __syncwarp();
     const bool do_rebuild = !is_lm || s.rebuild();  // GN's Build always re-accumulates (gn.h:118-131)
     T acc[BLK][BLK], cost_only;
-    wpp_pass<T, NB, BLK, false>(pipe, p.d, ws, pr, lane, do_rebuild, (T)0, (T)0, bi, bj, has_block, acc, cost_only);
     T *hp = p.H + (size_t)pr * (NP * LDW);
-    wpp_after_pass<T, NB, BLK, INV>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane, true);
+    if (p.hg_cost) {
+      // user-filled accumulators (docs/API.md:37-57,137-170): the lane's block of the augmented matrix
+      // [H g; . cost] straight from the caller's H (upper triangle only is read) and grad
+      cost_only = (T)0;
+      const double cost_d = p.hg_cost[pr];
+      const T *Hu = p.hg_H + (size_t)pr * n * n, *gu = p.hg_grad + (size_t)pr * n;
+#pragma unroll
+      for (int u = 0; u < BLK; ++u)
+#pragma unroll
+        for (int v = 0; v < BLK; ++v) {
+          const int row = bi * BLK + u, col = bj * BLK + v;
+          T val = (T)0;
+          if (do_rebuild && has_block) {
+            if (row <= col && col < n) val = Hu[row * n + col];
+            else if (row < n && col == n) val = gu[row];
+          }
+          acc[u][v] = val;
+        }
+      wpp_after_pass<T, NB, BLK, INV>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane, true, &cost_d,
+                                      p.hg_nres[pr]);
+    } else {
+      wpp_pass<T, NB, BLK, false>(pipe, p.d, ws, pr, lane, do_rebuild, (T)0, (T)0, bi, bj, has_block, acc, cost_only);
+      wpp_after_pass<T, NB, BLK, INV>(s, p.opt, p.d, ws, hp, do_rebuild, bi, bj, has_block, acc, cost_only, lane, true);
+    }
     for (int j = lane; j < n; j += 32) {
       p.x[pr * n + j] = xs[j];
       p.last_dx[pr * n + j] = last_dx[j];
