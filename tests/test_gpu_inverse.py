@@ -65,15 +65,20 @@ def test_inverse_path_layouts_agree(ctx):
         assert np.array_equal(out_t.results, out_p.results)
 
 
-def test_inverse_path_large_n_is_an_error(ctx):
-    """n > 55 has no H.inverse() kernel: an error code, never a silent LDLT."""
+def test_inverse_path_large_n_runs_in_the_general_family(ctx):
+    """n > 55: H.inverse() is served by the general kernel family's partial-pivot LU (gn.cuh; bit-exact parity in
+    tests/test_gpu_general.py::test_inverse_path_above_55) - never a silent LDLT: the two solves give different
+    bits."""
     import tinyopt_b200 as tb
     B, m, n = 4, 128, 64
+    fl = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)
     dA, dy, _, dx0 = ctx.synth_generate(B, m, n, torch.float32, layout=tb.PROBLEM_MAJOR)
-    with pytest.raises(tb.TinyoptB200Error):
-        ctx.optimize_batch(dA, dy, dx0, tb.options(use_ldlt=0), layout=tb.PROBLEM_MAJOR)
-    out = ctx.optimize_batch(dA, dy, dx0, tb.options(min_rerr_dec=1e-5, min_step_norm2=1e-9), layout=tb.PROBLEM_MAJOR)
-    assert (out.results["stop_reason"] > 0).all()
+    A, y, xs, x0 = O.synth_generate(B, m, n, np.float32)
+    xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(use_ldlt=0, **fl))
+    out = ctx.optimize_batch(dA, dy, dx0, tb.options(use_ldlt=0, **fl), layout=tb.PROBLEM_MAJOR)
+    assert np.array_equal(out.x.cpu().numpy(), xo) and np.array_equal(out.results["num_iters"], ro["num_iters"])
+    out2 = ctx.optimize_batch(dA, dy, dx0, tb.options(**fl), layout=tb.PROBLEM_MAJOR)
+    assert (out2.results["stop_reason"] > 0).all() and not torch.equal(out.x, out2.x)
 
 
 def test_sqrt2_benchmark_options(ctx):

@@ -256,8 +256,8 @@ def test_lm_run_no_residuals_and_errors(ctx):
     assert (r["stop_reason"] == tb.StopReason.kSkipped).all() and (r["num_iters"] == 1).all()
     assert torch.equal(x0, torch.ones_like(x0))
     with pytest.raises(tb.TinyoptB200Error):
-        ctx.optimize_batch(torch.zeros((1, 4, 600, 32), device="cuda"), torch.zeros((1, 4, 32), device="cuda"),
-                           torch.zeros((3, 600), device="cuda"))   # n > 512: no kernel family
+        ctx.optimize_batch(torch.zeros((1, 4, 2100, 32), device="cuda"), torch.zeros((1, 4, 32), device="cuda"),
+                           torch.zeros((3, 2100), device="cuda"))   # n > 2048: no kernel family
 
 
 # ---- BASELINE.json config sizes: exact on a slice, properties on the whole batch -------------------
@@ -311,9 +311,10 @@ def test_wpp_kernel_family(ctx):
     assert ctx.kernel_family(torch.float32, 12) == 1 and ctx.kernel_family(torch.float32, 13) == 2
     assert ctx.kernel_family(torch.float32, 55) == 2 and ctx.kernel_family(torch.float32, 56) == 3
     assert ctx.kernel_family(torch.float32, 57) == 3 and ctx.kernel_family(torch.float32, 512) == 3
-    assert ctx.kernel_family(torch.float32, 513) == 0
+    assert ctx.kernel_family(torch.float32, 513) == 4 and ctx.kernel_family(torch.float32, 2048) == 4
+    assert ctx.kernel_family(torch.float32, 2049) == 0
     assert ctx.kernel_family(torch.float64, 8) == 1 and ctx.kernel_family(torch.float64, 9) == 2
-    assert ctx.kernel_family(torch.float64, 55) == 2 and ctx.kernel_family(torch.float64, 56) == 0
+    assert ctx.kernel_family(torch.float64, 55) == 2 and ctx.kernel_family(torch.float64, 56) == 4
 
 
 WPP_SHAPES_F64 = [(64, 60, 9), (50, 37, 12), (40, 64, 13), (33, 90, 27), (35, 100, 28), (24, 200, 50), (9, 131, 55)]

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "gn.cuh"
 #include "lg_params.h"
 #include "tpp_inst.cuh"
 #include "wpp_inst.cuh"
@@ -502,6 +503,111 @@ int lg_build_solve(tob200_ctx *ctx, const float *J, const float *r, int64_t B, i
   return TOB200_OK;
 }
 
+// ---- general family (gn.cuh): double above n = 55, any precision above n = 512, use_ldlt = false above 55 ----
+enum GnSlot { kGnH = 8, kGnHd, kGnG, kGnCost, kGnRs, kGnRec, kGnLastDx, kGnW, kGnActive };  // shares the large-n slots
+
+template <typename T>
+struct GnBuffers {
+  T *H, *hd, *g, *cost, *rs, *W, *last_dx;
+  LmScalars<T> *rec;
+  unsigned long long *n_active;
+  int solve_grid;
+};
+
+template <typename T>
+int gn_prepare(tob200_ctx *ctx, int64_t B, int m, int n, GnBuffers<T> *b) {
+  b->solve_grid = (int)(B < 2 * ctx->num_sms ? B : 2 * ctx->num_sms);
+  int rc;
+  if ((rc = ensure_scratch(ctx, kGnH, (size_t)B * n * n * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnHd, (size_t)B * n * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnG, (size_t)B * n * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnCost, (size_t)B * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnRs, (size_t)B * 2 * (m > 0 ? m : 1) * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnRec, (size_t)B * sizeof(LmScalars<T>))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnLastDx, (size_t)B * n * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnW, (size_t)b->solve_grid * n * n * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kGnActive, 64)) != TOB200_OK) return rc;
+  b->H = (T *)ctx->scratch[kGnH];
+  b->hd = (T *)ctx->scratch[kGnHd];
+  b->g = (T *)ctx->scratch[kGnG];
+  b->cost = (T *)ctx->scratch[kGnCost];
+  b->rs = (T *)ctx->scratch[kGnRs];
+  b->rec = (LmScalars<T> *)ctx->scratch[kGnRec];
+  b->last_dx = (T *)ctx->scratch[kGnLastDx];
+  b->W = (T *)ctx->scratch[kGnW];
+  b->n_active = (unsigned long long *)ctx->scratch[kGnActive];
+  return TOB200_OK;
+}
+
+// the whole LM loop: two kernels per iteration over the still-running problems (host orchestrated, like lg_lm_run)
+template <typename T>
+int gn_lm_run(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T *y, T alpha, int64_t B, int m, int n, T *x,
+              tob200_result *results, double *final_hessian) {
+  GnBuffers<T> b;
+  int rc = gn_prepare<T>(ctx, B, m, n, &b);
+  if (rc != TOB200_OK) return rc;
+  const DevOptions<T> dopt = make_dev_options<T>(*opt);
+  const int is_lm = opt->solver_type == 0;
+  ctx->phase_used = 0;
+  CK(launch_gn_init<T>(b.rec, dopt, b.last_dx, B, n, ctx->stream));
+  ctx->launches++;
+  GnAccumParams<T> ap;
+  ap.A = A; ap.y = y; ap.x = x; ap.rec = b.rec; ap.rs = b.rs; ap.g = b.g; ap.H = b.H; ap.cost = b.cost;
+  ap.B = B; ap.m = m; ap.n = n; ap.synth = 1; ap.is_lm = is_lm; ap.alpha = alpha; ap.alpha3 = (T)3 * alpha;
+  GnSolveParams<T> vp;
+  vp.H = b.H; vp.hd = b.hd; vp.g = b.g; vp.cost = b.cost; vp.W = b.W; vp.B = B; vp.n = n; vp.nres = m; vp.mode = 0; vp.opt = dopt;
+  vp.rec = b.rec; vp.x = x; vp.last_dx = b.last_dx; vp.results = results; vp.n_active = b.n_active; vp.lambda = nullptr;
+  vp.dx = nullptr; vp.cost_out = nullptr; vp.status = nullptr; vp.use_ldlt = opt->use_ldlt;
+  const int max_passes = opt->max_iters + 1 + (opt->check_final_cost ? 1 : 0);  // optimizer.h:248-250
+  for (int pass = 0; pass < max_passes; ++pass) {
+    int ev = lg_phase_begin(ctx, 0);
+    CK(launch_gn_accum<T>(ap, ctx->num_sms, ctx->stream));
+    ctx->launches++;
+    lg_phase_end(ctx, ev);
+    ev = lg_phase_begin(ctx, 2);
+    CK(cudaMemsetAsync(b.n_active, 0, sizeof(unsigned long long), ctx->stream));
+    CK(launch_gn_solve<T>(vp, b.solve_grid, ctx->stream));
+    ctx->launches++;
+    lg_phase_end(ctx, ev);
+    unsigned long long active = 0;
+    CK(cudaMemcpyAsync(&active, b.n_active, sizeof(active), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (active == 0) break;
+  }
+  if (final_hessian) {
+    CK((launch_gn_export_h<T, double>(b.H, b.hd, b.rec, nullptr, opt->solver_type, B, n, final_hessian, ctx->stream)));
+    ctx->launches++;
+  }
+  return TOB200_OK;
+}
+
+// one Build + Solve from materialised J, r
+template <typename T>
+int gn_build_solve(tob200_ctx *ctx, const T *J, const T *r, int64_t B, int m, int n, const T *lambda, T *dx, double *cost,
+                   T *H_out, T *g_out, int32_t *status) {
+  GnBuffers<T> b;
+  int rc = gn_prepare<T>(ctx, B, m, n, &b);
+  if (rc != TOB200_OK) return rc;
+  ctx->phase_used = 0;
+  GnAccumParams<T> ap;
+  ap.A = J; ap.y = r; ap.x = nullptr; ap.rec = nullptr; ap.rs = b.rs; ap.g = b.g; ap.H = b.H; ap.cost = b.cost;
+  ap.B = B; ap.m = m; ap.n = n; ap.synth = 0; ap.is_lm = 1; ap.alpha = (T)0; ap.alpha3 = (T)0;
+  CK(launch_gn_accum<T>(ap, ctx->num_sms, ctx->stream));
+  ctx->launches++;
+  if (g_out) CK(cudaMemcpyAsync(g_out, b.g, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (H_out) {
+    CK((launch_gn_export_h<T, T>(b.H, nullptr, nullptr, lambda, 0, B, n, H_out, ctx->stream)));
+    ctx->launches++;
+  }
+  GnSolveParams<T> vp;
+  vp.H = b.H; vp.hd = nullptr; vp.g = b.g; vp.cost = b.cost; vp.W = b.W; vp.B = B; vp.n = n; vp.nres = m; vp.mode = 1;
+  vp.opt = DevOptions<T>(); vp.rec = nullptr; vp.x = nullptr; vp.last_dx = nullptr; vp.results = nullptr; vp.n_active = nullptr;
+  vp.lambda = lambda; vp.dx = dx; vp.cost_out = cost; vp.status = status; vp.use_ldlt = 1;
+  CK(launch_gn_solve<T>(vp, b.solve_grid, ctx->stream));
+  ctx->launches++;
+  return TOB200_OK;
+}
+
 int check_options(tob200_ctx *ctx, const tob200_options *o) {
   if (!o) return fail(ctx, TOB200_ERR_INVALID, "options is NULL");
   if (o->solver_type != 0 && o->solver_type != 1)
@@ -523,12 +629,14 @@ int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_
   if (!aligned16(J) || !aligned16(r)) return fail(ctx, TOB200_ERR_INVALID, "J and r must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
   const int family = tob200_kernel_family(dtype_of<T>(), n);
-  if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "build_solve: n has no kernel yet for this dtype");
+  if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "build_solve: n is above the largest supported size (2048)");
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   int rc = to_native_layout<T>(ctx, family, layout, B, m, n, &J, &r);
   if (rc != TOB200_OK) return rc;
   TppLaunch cfg;
-  if (family == 1) {
+  if (family == 4) {
+    if ((rc = gn_build_solve<T>(ctx, J, r, B, m, n, lambda, dx, cost, H_out, g_out, status)) != TOB200_OK) return rc;
+  } else if (family == 1) {
     TppBuildSolveParams<T> p;
     if ((rc = tpp_configure<T>(ctx, n, m, B, kTppBuildSolve, &p.d, &cfg)) != TOB200_OK) return rc;
     p.d.J = J;
@@ -591,15 +699,16 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
   if (!A || !y || !x || !results) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
   if (!aligned16(A) || !aligned16(y)) return fail(ctx, TOB200_ERR_INVALID, "A and y must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
-  const int family = tob200_kernel_family(dtype_of<T>(), n);
-  if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n has no kernel yet for this dtype");
-  if (!opt->use_ldlt && family == 3)
-    return fail(ctx, TOB200_ERR_UNSUPPORTED, "hessian.use_ldlt = false (H.inverse()) is implemented for n <= 55 only");
+  int family = tob200_kernel_family(dtype_of<T>(), n);
+  if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n is above the largest supported size (2048)");
+  if (!opt->use_ldlt && family == 3) family = 4;  // hessian.use_ldlt = false (H.inverse()): the general family's LU
   if (record_events) CK(cudaEventRecord(ctx->ev0, ctx->stream));
   if ((rc = to_native_layout<T>(ctx, family, layout, B, m, n, &A, &y)) != TOB200_OK) return rc;
   if (!opt->save_last) final_hessian = nullptr;  // options.h:66 (hessian.save_last)
   TppLaunch cfg;
-  if (family == 1) {
+  if (family == 4) {
+    if ((rc = gn_lm_run<T>(ctx, opt, A, y, alpha, B, m, n, x, results, final_hessian)) != TOB200_OK) return rc;
+  } else if (family == 1) {
     TppRunParams<T> p;
     if ((rc = tpp_configure<T>(ctx, n, m, B, kTppRun, &p.d, &cfg)) != TOB200_OK) return rc;
     p.d.J = A;
@@ -944,9 +1053,10 @@ int tob200_kernel_family(int dtype, int n) {
   if (dtype == TOB200_F32) {
     if (n <= kTppMaxN_f32) return 1;
     if (n <= kWppMaxN_f32) return 2;
-    return n <= kLgMaxN ? 3 : 0;  // n % 4 != 0 goes through a zero-padded copy (rows 16-byte aligned for TMA)
+    if (n <= kLgMaxN) return 3;  // n % 4 != 0 goes through a zero-padded copy (rows 16-byte aligned for TMA)
+    return n <= kGnMaxN ? 4 : 0;
   }
-  if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : (n <= kWppMaxN_f64 ? 2 : 0);  // family 2: scalar paths
+  if (dtype == TOB200_F64) return n <= kTppMaxN_f64 ? 1 : (n <= kWppMaxN_f64 ? 2 : (n <= kGnMaxN ? 4 : 0));
   return 0;
 }
 

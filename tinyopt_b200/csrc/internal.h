@@ -61,3 +61,18 @@ cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st);
 cudaError_t launch_lg_solve(const LgSolveParams &p, int grid, cudaStream_t st);
 int lg_syrk_stages(int np);
 }  // namespace tob200
+
+// gn_kernels.cu (general family; parameter structs in gn.cuh)
+namespace tob200 {
+template <typename T> struct GnAccumParams;
+template <typename T> struct GnSolveParams;
+template <typename T>
+cudaError_t launch_gn_init(LmScalars<T> *rec, const DevOptions<T> &opt, T *last_dx, int64_t B, int n, cudaStream_t st);
+template <typename T>
+cudaError_t launch_gn_accum(const GnAccumParams<T> &p, int num_sms, cudaStream_t st);
+template <typename T>
+cudaError_t launch_gn_solve(const GnSolveParams<T> &p, int grid, cudaStream_t st);
+template <typename T, typename OutT>
+cudaError_t launch_gn_export_h(const T *H, const T *hd, const LmScalars<T> *rec, const T *lambda, int solver_type, int64_t B,
+                               int n, OutT *out, cudaStream_t st);
+}  // namespace tob200
