@@ -23,6 +23,8 @@
 #include <stdexcept>
 #include <string>
 #include <algorithm>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "tinyopt_b200.h"
@@ -223,6 +225,12 @@ inline int solver_step(tob200_solver *s, const float *J, const float *r, int m) 
 inline int solver_step(tob200_solver *s, const double *J, const double *r, int m) {
   return tob200_solver_step_f64(s, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, m);
 }
+inline int solver_step_hg(tob200_solver *s, const float *g, const float *H, const double *c, const int32_t *nr) {
+  return tob200_solver_step_hg_f32(s, g, H, c, nr);
+}
+inline int solver_step_hg(tob200_solver *s, const double *g, const double *H, const double *c, const int32_t *nr) {
+  return tob200_solver_step_hg_f64(s, g, H, c, nr);
+}
 inline int lm_run_host(tob200_ctx *c, const tob200_options *o, const float *A, const float *y, float alpha, int64_t B,
                        int m, int n, float *x, tob200_result *res) {
   return tob200_lm_run_host_f32(c, o, A, y, alpha, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, x, res);
@@ -325,6 +333,84 @@ std::vector<Output> OptimizeBatch(const Context &ctx, Scalar *xs, int64_t B, int
   return outs;
 }
 
+/// The MANUAL ACCUMULATION contract of the reference (docs/API.md:37-57,137-170) for a batch:
+/// `Cost acc(p, x, grad, H)` is the user's lambda, unchanged in meaning — it fills the solver-owned, pre-zeroed
+/// `grad` (n) and `H` (n x n row-major; filling only the upper triangle is enough, docs/API.md:170) and returns
+/// the cost (`Cost{cost, num_resisuals}`; a plain scalar cost counts as one residual, cost.h:22).  grad == H ==
+/// nullptr is the reference's `nullptr_t` cost-only call (solvers/gn.h:98-105).  The user may fill a true
+/// Hessian (tests/optimize_easy.cpp:35-80), a diagonal prior (benchmarks/dense.cpp:57-66), per-block
+/// `J^T J` sums (tests/types.cpp:97-108) ... — the device runs Build's tail, damping, Solve, Step and the
+/// OptimizeAcc update for every still-running problem (tob200_solver_step_hg_*).  n <= 55.
+template <typename Scalar, typename Acc>
+std::vector<Output> OptimizeBatchAcc(const Context &ctx, Scalar *xs, int64_t B, int n, Acc &&acc,
+                                     const Options &options = Options()) {
+  if (B < 0 || n < 1) throw std::invalid_argument("OptimizeBatchAcc: need B >= 0, n >= 1");
+  std::vector<Output> outs((size_t)B);
+  if (B == 0) return outs;
+  const tob200_options pod = options.pod();
+  tob200_solver *solver = nullptr;
+  ctx.check(tob200_solver_create(ctx.get(), scalar_traits<Scalar>::dtype, B, n, &pod, &solver), "tob200_solver_create");
+  struct Guard {
+    tob200_solver *s;
+    ~Guard() { tob200_solver_destroy(s); }
+  } guard{solver};
+  {
+    DeviceBuffer<Scalar> x0(ctx, (size_t)B * n);
+    x0.upload(xs, (size_t)B * n);
+    ctx.check(tob200_solver_reset(solver, x0.data()), "tob200_solver_reset");
+    ctx.sync();
+  }
+  const size_t nn = (size_t)n * n;
+  std::vector<Scalar> g((size_t)B * n), H((size_t)B * nn), x((size_t)B * n);
+  std::vector<double> cost((size_t)B, 0.0);
+  std::vector<int32_t> nres((size_t)B, 1), needs((size_t)B);
+  DeviceBuffer<Scalar> dg(ctx, g.size()), dH(ctx, H.size());
+  DeviceBuffer<double> dc(ctx, cost.size());
+  DeviceBuffer<int32_t> dn(ctx, nres.size());
+  int64_t active = B;
+  while (active > 0) {
+    ctx.check(tob200_copy_to_host(ctx.get(), x.data(), tob200_solver_x(solver), x.size() * sizeof(Scalar)), "copy x");
+    ctx.check(tob200_copy_to_host(ctx.get(), needs.data(), tob200_solver_needs(solver), needs.size() * sizeof(int32_t)),
+              "copy needs");
+    for (int64_t p = 0; p < B; ++p) {
+      if (needs[(size_t)p] < 0) continue;
+      Scalar *gp = nullptr, *Hp = nullptr;
+      if (needs[(size_t)p] == 1) {  // Build re-accumulates: the solver's clear() (solvers/gn.h:77-81)
+        gp = &g[(size_t)p * n];
+        Hp = &H[(size_t)p * nn];
+        std::fill(gp, gp + n, (Scalar)0);
+        std::fill(Hp, Hp + nn, (Scalar)0);
+      }
+      const Cost c = acc((size_t)p, (const Scalar *)&x[(size_t)p * n], gp, Hp);
+      cost[(size_t)p] = c.cost;
+      nres[(size_t)p] = c.num_resisuals;
+    }
+    dg.upload(g.data(), g.size());
+    dH.upload(H.data(), H.size());
+    dc.upload(cost.data(), cost.size());
+    dn.upload(nres.data(), nres.size());
+    ctx.check(detail::solver_step_hg(solver, dg.data(), dH.data(), dc.data(), dn.data()), "tob200_solver_step_hg");
+    ctx.check(tob200_solver_num_active(solver, &active), "tob200_solver_num_active");
+  }
+  DeviceBuffer<tob200_result> dres(ctx, (size_t)B);
+  ctx.check(tob200_solver_results(solver, dres.data()), "tob200_solver_results");
+  std::vector<tob200_result> res((size_t)B);
+  dres.download(res.data(), (size_t)B);
+  ctx.check(tob200_copy_to_host(ctx.get(), xs, tob200_solver_x(solver), (size_t)B * n * sizeof(Scalar)), "copy x");
+  std::vector<double> Hf;
+  if (options.hessian.save_last) {
+    DeviceBuffer<double> dHf(ctx, (size_t)B * nn);
+    ctx.check(tob200_solver_final_hessian(solver, dHf.data()), "tob200_solver_final_hessian");
+    Hf.resize((size_t)B * nn);
+    dHf.download(Hf.data(), Hf.size());
+  }
+  for (int64_t p = 0; p < B; ++p) {
+    outs[(size_t)p] = to_output(res[(size_t)p]);
+    if (!Hf.empty()) outs[(size_t)p].final_hessian.assign(Hf.begin() + (size_t)p * nn, Hf.begin() + (size_t)(p + 1) * nn);
+  }
+  return outs;
+}
+
 /// Output::Covariance(rescaled) (output.h:81-103) for a batch: InvCov (math.h:44-57) of every
 /// final_hessian through tob200_inv_cov_f64.  Entry p is the n*n row-major covariance, or empty where
 /// the reference returns nullopt (no final Hessian, or the LDLT rejects it).  `rescaled` multiplies by
@@ -372,6 +458,87 @@ std::vector<Output> OptimizePolynomialBatch(const Context &ctx, const Scalar *A,
   std::vector<Output> outs;
   outs.reserve(res.size());
   for (const auto &r : res) outs.push_back(to_output(r));
+  return outs;
+}
+
+/// One context per visible GPU (or per listed device): the batch of a call is split into CONTIGUOUS shards of
+/// independent problems, one per device, solved concurrently (one host thread per device; no data-path
+/// communication: the reference has no cross-problem term anywhere).
+class MultiContext {
+ public:
+  explicit MultiContext(const std::vector<int> &devices) {
+    for (int d : devices) ctxs_.emplace_back(new Context(d));
+    if (ctxs_.empty()) throw std::invalid_argument("MultiContext: no device");
+  }
+  /// every CUDA device the process can see
+  static std::vector<int> all_devices() {
+    std::vector<int> d;
+    for (int i = 0; i < 64; ++i) {
+      tob200_ctx *c = nullptr;
+      if (tob200_create(&c, i, nullptr) != TOB200_OK) break;
+      tob200_destroy(c);
+      d.push_back(i);
+    }
+    return d;
+  }
+  int size() const { return (int)ctxs_.size(); }
+  const Context &operator[](int i) const { return *ctxs_[(size_t)i]; }
+  /// contiguous block [lo, hi) of ceil(B / size()) problems of shard g (last shards may be short or empty)
+  void shard(int64_t B, int g, int64_t *lo, int64_t *hi) const {
+    const int64_t per = (B + size() - 1) / size();
+    *lo = std::min<int64_t>(B, (int64_t)g * per);
+    *hi = std::min<int64_t>(B, *lo + per);
+  }
+  /// run fn(g, ctx, lo, hi) for every shard concurrently; the first exception is rethrown
+  template <typename Fn>
+  void for_each_shard(int64_t B, Fn &&fn) const {
+    std::vector<std::thread> th;
+    std::vector<std::exception_ptr> err((size_t)size());
+    for (int g = 0; g < size(); ++g) {
+      int64_t lo, hi;
+      shard(B, g, &lo, &hi);
+      if (hi <= lo) continue;
+      th.emplace_back([&, g, lo, hi] {
+        try {
+          fn(g, *ctxs_[(size_t)g], lo, hi);
+        } catch (...) {
+          err[(size_t)g] = std::current_exception();
+        }
+      });
+    }
+    for (auto &t : th) t.join();
+    for (auto &e : err)
+      if (e) std::rethrow_exception(e);
+  }
+
+ private:
+  std::vector<std::unique_ptr<Context>> ctxs_;
+};
+
+/// OptimizePolynomialBatch over several GPUs: shard g solves problems [lo_g, hi_g) on its own device.
+template <typename Scalar>
+std::vector<Output> OptimizePolynomialBatch(const MultiContext &mc, const Scalar *A, const Scalar *y, Scalar alpha,
+                                            Scalar *xs, int64_t B, int m, int n, const Options &options = Options()) {
+  std::vector<Output> outs((size_t)(B > 0 ? B : 0));
+  mc.for_each_shard(B, [&](int, const Context &ctx, int64_t lo, int64_t hi) {
+    auto part = OptimizePolynomialBatch<Scalar>(ctx, A + (size_t)lo * m * n, y + (size_t)lo * m, alpha, xs + (size_t)lo * n,
+                                                hi - lo, m, n, options);
+    std::move(part.begin(), part.end(), outs.begin() + lo);
+  });
+  return outs;
+}
+
+/// OptimizeBatch (host residual lambda) over several GPUs; `residuals` is called with GLOBAL problem indices and must
+/// be safe to call concurrently for different problems.
+template <typename Scalar, typename Residuals>
+std::vector<Output> OptimizeBatch(const MultiContext &mc, Scalar *xs, int64_t B, int n, int m, Residuals &&residuals,
+                                  const Options &options = Options()) {
+  std::vector<Output> outs((size_t)(B > 0 ? B : 0));
+  mc.for_each_shard(B, [&](int, const Context &ctx, int64_t lo, int64_t hi) {
+    auto shifted = [&, lo](size_t p, const Scalar *x, Scalar *r, Scalar *J) { residuals(p + (size_t)lo, x, r, J); };
+    auto part = OptimizeBatch<Scalar>(ctx, xs + (size_t)lo * n, hi - lo, n, m, shifted, options);
+    std::move(part.begin(), part.end(), outs.begin() + lo);
+  });
   return outs;
 }
 

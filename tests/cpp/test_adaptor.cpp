@@ -244,6 +244,95 @@ static void test_misuse(const Context &ctx) {
   CHECK(threw);
 }
 
+// tests/optimize_easy.cpp:35-80: Rosenbrock through the manual accumulation contract with the TRUE Hessian
+// (docs/API.md:37-57); the reference asserts Succeeded, Converged, x = (1, 1) +- 1e-5.  And benchmarks/dense.cpp:57-66
+// "Prior n": only H.diagonal() is filled.
+static void test_accumulation_contract(const Context &ctx) {
+  const int64_t B = 33;
+  std::vector<double> xs(B * 2);
+  for (int64_t p = 0; p < B; ++p) { xs[2 * p] = -1.2 + 0.01 * (double)(p % 7); xs[2 * p + 1] = 1.0 - 0.01 * (double)(p % 5); }
+  Options options;
+  options.max_iters = 200;
+  options.min_rerr_dec = 0;
+  options.max_consec_failures = 20;
+  auto loss = [](size_t, const double *v, double *grad, double *H) {
+    const double x = v[0], y = v[1], t1 = 1.0 - x, t2 = y - x * x;
+    if (grad) {
+      grad[0] = -2.0 * t1 - 400.0 * x * t2;
+      grad[1] = 200.0 * t2;
+      H[0] = 2.0 - 400.0 * y + 1200.0 * x * x;
+      H[1] = -400.0 * x;  // (the lower triangle is left at zero: only the upper one is read, docs/API.md:170)
+      H[3] = 200.0;
+    }
+    Cost c;
+    c.cost = t1 * t1 + 100.0 * t2 * t2;
+    c.num_resisuals = 1;
+    return c;
+  };
+  auto outs = OptimizeBatchAcc<double>(ctx, xs.data(), B, 2, loss, options);
+  CHECK(outs[0].Succeeded() && outs[0].Converged());
+  CHECK(std::fabs(xs[0] - 1.0) < 1e-5 && std::fabs(xs[1] - 1.0) < 1e-5);
+  CHECK(outs[0].num_iters == 59 && outs[0].num_failures == 24);   // the oracle's trajectory for x0 = (-1.2, 1)
+  CHECK(outs[0].has_final_hessian() && std::fabs(outs[0].final_hessian[3] - 200.0) < 1e-9);
+  int conv = 0;
+  for (int64_t p = 0; p < B; ++p) conv += outs[p].Converged();
+  CHECK(conv >= B * 3 / 4);
+  // "Prior n"
+  const int n = 12;
+  std::vector<float> y(B * n), sd(B * n), x(B * n);
+  uint64_t s = 5;
+  auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (float)((double)(s >> 11) / 9007199254740992.0 * 2 - 1); };
+  for (auto &v : y) v = rnd();
+  for (auto &v : sd) { v = rnd(); if (std::fabs(v) < 0.05f) v = 0.3f; }
+  for (auto &v : x) v = rnd();
+  Options fo;
+  fo.min_rerr_dec = 1e-5f;
+  fo.min_step_norm2 = 1e-9f;
+  auto prior = [&](size_t p, const float *xv, float *grad, float *H) {
+    Cost c;
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float res = (xv[j] - y[p * n + j]) / sd[p * n + j];
+      acc += res * res;
+      if (grad) {
+        grad[j] = res / sd[p * n + j];
+        H[j * n + j] = (1.f / sd[p * n + j]) * (1.f / sd[p * n + j]);
+      }
+    }
+    c.cost = acc;
+    c.num_resisuals = 1;
+    return c;
+  };
+  auto po = OptimizeBatchAcc<float>(ctx, x.data(), B, n, prior, fo);
+  float worst = 0.f;
+  for (size_t i = 0; i < x.size(); ++i) worst = std::fmax(worst, std::fabs(x[i] - y[i]));
+  CHECK(worst < 1e-3f);
+  for (int64_t p = 0; p < B; ++p) CHECK(po[p].Converged());
+  std::printf("accumulation contract: Rosenbrock (true Hessian) iters[0]=%d failures[0]=%d, converged %d/%d; Prior 12: max |x - y| = %.2e\n",
+              (int)outs[0].num_iters, (int)outs[0].num_failures, conv, (int)B, (double)worst);
+}
+
+// every visible GPU behind one call: contiguous shards, one context and one host thread per device
+static void test_multi_device() {
+  const std::vector<int> devs = MultiContext::all_devices();
+  MultiContext mc(devs);
+  const int64_t B = 1000;
+  const int n = 6, m = 30;
+  std::vector<double> A(B * m * n), y(B * m), x1(B * n), x2;
+  uint64_t s = 17;
+  auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (double)(s >> 11) / 9007199254740992.0 * 2 - 1; };
+  for (auto &v : A) v = rnd() / std::sqrt((double)n);
+  for (auto &v : y) v = 0.3 * rnd();
+  for (auto &v : x1) v = 0.5 * rnd();
+  x2 = x1;
+  Context c0(0);
+  auto o1 = OptimizePolynomialBatch<double>(c0, A.data(), y.data(), 0.1, x1.data(), B, m, n);
+  auto o2 = OptimizePolynomialBatch<double>(mc, A.data(), y.data(), 0.1, x2.data(), B, m, n);
+  CHECK(std::memcmp(x1.data(), x2.data(), x1.size() * sizeof(double)) == 0);
+  for (int64_t p = 0; p < B; ++p) CHECK(o1[p].num_iters == o2[p].num_iters && o1[p].stop_reason == o2[p].stop_reason);
+  std::printf("multi-device: %d device(s), %lld problems in contiguous shards == single context\n", mc.size(), (long long)B);
+}
+
 int main() {
   try {
     Context ctx(0);
@@ -257,6 +346,8 @@ int main() {
     test_family_equivalence<float>(ctx, 12, 40);
     test_family_equivalence<float>(ctx, 20, 64);    // warp-per-problem family behind the same SolverType seam
     test_family_equivalence<double>(ctx, 30, 90);
+    test_accumulation_contract(ctx);
+    test_multi_device();
     test_misuse(ctx);
   } catch (const Error &e) {
     std::printf("tinyopt::b200::Error (%d): %s\n", e.code, e.what());
