@@ -57,11 +57,17 @@ struct tob200_ctx {
   cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_run[kMaxChunks] = {}, ev_side = nullptr;
   // large-n family: 3 = 3xTF32 (hi*hi + hi*lo + lo*hi, FP32-level accuracy), 1 = plain TF32
   int lg_tf32_terms = 3;  // env TOB200_LG_TF32_TERMS
+  int lg_fp16 = 1;        // env TOB200_LG_FP16: 1 = FP16 hi / lo split (kind::f16), 0 = TF32 split (kind::tf32)
   // device time of the last large-n call by phase (0 eval, 1 syrk, 2 solve): CUDA event pairs
   static constexpr int kMaxPhaseEvents = 3 * 80;
   std::vector<cudaEvent_t> phase_ev;  // 2 events per (iteration, phase)
   int phase_used = 0;
   int phase_kind[kMaxPhaseEvents] = {};
+  // host-orchestrated LM loops (large-n and general families): the number of still-running problems of pass k is
+  // read back asynchronously into pinned memory and only looked at after pass k + 1 has been queued, so the device
+  // never idles on a host round trip between passes (a surplus pass finds every problem done and exits at once)
+  unsigned long long *active_host = nullptr;  // [2] pinned
+  cudaEvent_t ev_active[2] = {};
 };
 
 namespace {
@@ -298,6 +304,7 @@ int wpp_launch(tob200_ctx *ctx, int n, int kind, const void *params, const TppLa
 
 // ---- large-n family (lg.cuh): host-orchestrated eval -> syrk -> solve per LM iteration ------------
 enum LgSlot { kLgH = 8, kLgHd, kLgG, kLgCost, kLgScale, kLgRec, kLgLastDx, kLgW, kLgActive, kLgDg };
+constexpr int kLgAmaxSlot = 6;  // [B] max |J_ij| per problem for the FP16-split J^T J (a free scratch slot)
 
 int lg_phase_begin(tob200_ctx *ctx, int kind) {
   if (ctx->phase_used + 2 > tob200_ctx::kMaxPhaseEvents * 2) return -1;
@@ -316,8 +323,26 @@ void lg_phase_end(tob200_ctx *ctx, int slot) {
   ctx->phase_used = slot + 2;
 }
 
+// pass-loop helper: queue the read-back of the active counter of pass `pass`; return the count of pass `pass - 1`
+// (already complete or nearly so: it was queued one whole pass earlier), or -1 for the first pass
+int lm_loop_poll(tob200_ctx *ctx, const unsigned long long *n_active_dev, int pass, long long *prev_active) {
+  if (!ctx->active_host) {
+    CK(cudaMallocHost((void **)&ctx->active_host, 2 * sizeof(unsigned long long)));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_active[i], cudaEventDisableTiming));
+  }
+  const int slot = pass & 1;
+  CK(cudaMemcpyAsync(&ctx->active_host[slot], n_active_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_active[slot], ctx->stream));
+  *prev_active = -1;
+  if (pass > 0) {
+    CK(cudaEventSynchronize(ctx->ev_active[slot ^ 1]));
+    *prev_active = (long long)ctx->active_host[slot ^ 1];
+  }
+  return TOB200_OK;
+}
+
 struct LgBuffers {
-  float *H, *hd, *g, *dg, *cost, *scale, *W, *last_dx;
+  float *H, *hd, *g, *dg, *cost, *scale, *W, *last_dx, *amax;
   LmScalars<float> *rec;
   unsigned long long *n_active;
   int np, solve_grid;
@@ -335,6 +360,7 @@ int lg_prepare(tob200_ctx *ctx, int64_t B, int m, int n, bool need_state, bool n
   if ((rc = ensure_scratch(ctx, kLgCost, (size_t)B * 4)) != TOB200_OK) return rc;
   if ((rc = ensure_scratch(ctx, kLgW, (size_t)b->solve_grid * np * np * 4)) != TOB200_OK) return rc;
   if ((rc = ensure_scratch(ctx, kLgActive, 64)) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, kLgAmaxSlot, (size_t)B * 4)) != TOB200_OK) return rc;
   if (need_scale && (rc = ensure_scratch(ctx, kLgScale, (size_t)B * (m > 0 ? m : 1) * 4)) != TOB200_OK) return rc;
   if (need_state) {
     if ((rc = ensure_scratch(ctx, kLgRec, (size_t)B * sizeof(LmScalars<float>))) != TOB200_OK) return rc;
@@ -350,6 +376,7 @@ int lg_prepare(tob200_ctx *ctx, int64_t B, int m, int n, bool need_state, bool n
   b->rec = (LmScalars<float> *)ctx->scratch[kLgRec];
   b->last_dx = (float *)ctx->scratch[kLgLastDx];
   b->n_active = (unsigned long long *)ctx->scratch[kLgActive];
+  b->amax = (float *)ctx->scratch[kLgAmaxSlot];
   return TOB200_OK;
 }
 
@@ -396,6 +423,8 @@ LgSyrkParams lg_syrk_params(tob200_ctx *ctx, const LgBuffers &b, const float *A,
   sp.nstrips = (b.np + 127) / 128;
   sp.stages = lg_syrk_stages(b.np);
   sp.terms = ctx->lg_tf32_terms;
+  sp.fp16 = ctx->lg_fp16;
+  sp.amax = b.amax;
   sp.is_lm = is_lm;
   sp.debug = env_int("TOB200_LG_DEBUG", 0);
   sp.half_bytes = lg_syrk_half_bytes(b.np);
@@ -414,7 +443,7 @@ int lg_lm_run(tob200_ctx *ctx, const tob200_options *opt, const float *A, const 
   CK(launch_lg_init(b.rec, dopt, b.last_dx, B, n, ctx->stream));
   ctx->launches++;
   LgEvalParams ep;
-  ep.A = A; ep.y = y; ep.x = x; ep.rec = b.rec; ep.scale_in = nullptr; ep.scale = b.scale; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost;
+  ep.A = A; ep.y = y; ep.x = x; ep.rec = b.rec; ep.scale_in = nullptr; ep.scale = b.scale; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost; ep.amax = b.amax;
   ep.B = B; ep.m = m; ep.n = n; ep.synth = 1; ep.is_lm = is_lm; ep.alpha = alpha; ep.alpha3 = 3.f * alpha;
   const LgSyrkParams sp = lg_syrk_params(ctx, b, A, b.scale, b.rec, B, m, n, is_lm);
   LgSolveParams vp;
@@ -446,10 +475,9 @@ int lg_lm_run(tob200_ctx *ctx, const tob200_options *opt, const float *A, const 
     CK(launch_lg_solve(vp, b.solve_grid, ctx->stream));
     ctx->launches++;
     lg_phase_end(ctx, ev);
-    unsigned long long active = 0;
-    CK(cudaMemcpyAsync(&active, b.n_active, sizeof(active), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (active == 0) break;
+    long long prev_active;
+    if ((rc = lm_loop_poll(ctx, b.n_active, pass, &prev_active)) != TOB200_OK) return rc;
+    if (prev_active == 0) break;  // pass - 1 already finished every problem: this pass was a no-op
   }
   if (final_hessian) {  // Output::final_hessian (optimizer.h:313-316)
     CK(launch_lg_final_hessian(b.H, b.hd, b.rec, opt->solver_type, B, n_out > 0 ? n_out : n, b.np, final_hessian, ctx->stream));
@@ -466,7 +494,7 @@ int lg_build_solve(tob200_ctx *ctx, const float *J, const float *r, int64_t B, i
   if (rc != TOB200_OK) return rc;
   ctx->phase_used = 0;
   LgEvalParams ep;
-  ep.A = J; ep.y = r; ep.x = nullptr; ep.rec = nullptr; ep.scale_in = nullptr; ep.scale = nullptr; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost;
+  ep.A = J; ep.y = r; ep.x = nullptr; ep.rec = nullptr; ep.scale_in = nullptr; ep.scale = nullptr; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost; ep.amax = b.amax;
   ep.B = B; ep.m = m; ep.n = n; ep.synth = 0; ep.is_lm = 1; ep.alpha = 0.f; ep.alpha3 = 0.f;
   int ev = lg_phase_begin(ctx, 0);
   if (m > 0) {
@@ -569,10 +597,9 @@ int gn_lm_run(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T *y
     CK(launch_gn_solve<T>(vp, b.solve_grid, ctx->stream));
     ctx->launches++;
     lg_phase_end(ctx, ev);
-    unsigned long long active = 0;
-    CK(cudaMemcpyAsync(&active, b.n_active, sizeof(active), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (active == 0) break;
+    long long prev_active;
+    if ((rc = lm_loop_poll(ctx, b.n_active, pass, &prev_active)) != TOB200_OK) return rc;
+    if (prev_active == 0) break;  // pass - 1 already finished every problem: this pass was a no-op
   }
   if (final_hessian) {
     CK((launch_gn_export_h<T, double>(b.H, b.hd, b.rec, nullptr, opt->solver_type, B, n, final_hessian, ctx->stream)));
@@ -1100,6 +1127,7 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
   ctx->wpp_stages = env_int("TOB200_WPP_STAGES", ctx->wpp_stages);
   ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
+  ctx->lg_fp16 = (env_int("TOB200_LG_FP16", 1) != 0 && ctx->lg_tf32_terms == 3) ? 1 : 0;
   ctx->host_chunks = env_int("TOB200_HOST_CHUNKS", ctx->host_chunks);
   if ((e = cudaMalloc((void **)&ctx->counters, sizeof(unsigned long long) * tob200_ctx::kNumCounters)) != cudaSuccess) {
     tob200_destroy(ctx);
@@ -1118,6 +1146,9 @@ int tob200_destroy(tob200_ctx *ctx) {
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   for (cudaEvent_t e : ctx->phase_ev) cudaEventDestroy(e);
   if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->active_host) cudaFreeHost(ctx->active_host);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->ev_active[i]) cudaEventDestroy(ctx->ev_active[i]);
   if (ctx->h2d_stream) {
     cudaStreamDestroy(ctx->h2d_stream);
     cudaStreamDestroy(ctx->d2h_stream);
@@ -1240,19 +1271,13 @@ int tob200_jtj_f32(tob200_ctx *ctx, const float *J, const float *row_scale, int6
   if (rc != TOB200_OK) return rc;
   ctx->phase_used = 0;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  int ev = lg_phase_begin(ctx, 1);
-  if (m > 0) {
-    const LgSyrkParams sp = lg_syrk_params(ctx, b, J, row_scale, nullptr, B, m, n, 1);
-    CK(launch_lg_syrk(sp, ctx->num_sms, ctx->stream));
-  } else {
-    CK(cudaMemsetAsync(b.H, 0, (size_t)B * b.np * b.np * 4, ctx->stream));
-  }
-  lg_phase_end(ctx, ev);
-  // the diagonal in FP32 (lg.cuh: the tensor core truncates its long same-sign sums)
+  // the diagonal in FP32 (lg.cuh: the tensor core truncates its long same-sign sums) and max |J_ij| per problem
+  // (the power-of-two scale of the FP16 split) first, then the tensor-core product
   const float *dg = nullptr;
+  int ev;
   if (m > 0) {
     LgEvalParams ep;
-    ep.A = J; ep.y = nullptr; ep.x = nullptr; ep.rec = nullptr; ep.scale_in = row_scale; ep.scale = nullptr; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost;
+    ep.A = J; ep.y = nullptr; ep.x = nullptr; ep.rec = nullptr; ep.scale_in = row_scale; ep.scale = nullptr; ep.g = b.g; ep.dg = b.dg; ep.cost = b.cost; ep.amax = b.amax;
     ep.B = B; ep.m = m; ep.n = n; ep.synth = 0; ep.is_lm = 1; ep.alpha = 0.f; ep.alpha3 = 0.f;
     ev = lg_phase_begin(ctx, 0);
     CK(launch_lg_eval(ep, ctx->num_sms, ctx->stream));
@@ -1260,6 +1285,14 @@ int tob200_jtj_f32(tob200_ctx *ctx, const float *J, const float *row_scale, int6
     ctx->launches++;
     dg = b.dg;
   }
+  ev = lg_phase_begin(ctx, 1);
+  if (m > 0) {
+    const LgSyrkParams sp = lg_syrk_params(ctx, b, J, row_scale, nullptr, B, m, n, 1);
+    CK(launch_lg_syrk(sp, ctx->num_sms, ctx->stream));
+  } else {
+    CK(cudaMemsetAsync(b.H, 0, (size_t)B * b.np * b.np * 4, ctx->stream));
+  }
+  lg_phase_end(ctx, ev);
   CK(launch_lg_export_h(b.H, dg, nullptr, B, n, b.np, H, ctx->stream));
   ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));

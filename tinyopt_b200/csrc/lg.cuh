@@ -28,6 +28,8 @@
 
 #include <cstdio>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "lg_params.h"
 #include "lm_state.cuh"
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
     }
     float gacc = 0.f;   // thread j < n: g_j, rows in order
     float dacc = 0.f;   // thread j < n: (J^T J)_jj, rows in order
+    float amx = 0.f;    // thread j < n: max_i |J_ij|
     float cacc = 0.f;   // lane 0 of warp w: sum of r_i^2 over its rows
     for (int c = 0; c < nchunks; ++c, ++it) {
       const uint32_t st = it % kLgEvalStages, ph = (it / kLgEvalStages) & 1u;
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
           gacc = __fmaf_rn(a, wbuf[i], gacc);
           const float jv = __fmul_rn(sbuf[i], a);
           dacc = __fmaf_rn(jv, jv, dacc);
+          amx = fmaxf(amx, fabsf(jv));
         }
       }
       __syncthreads();  // the stage and wbuf are free again
@@ -145,12 +149,23 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
       if (p.dg) p.dg[(size_t)pr * n + tid] = dacc;
     }
     if (lane == 0) cbuf[warp] = cacc;
+    if (p.amax && rebuild) {  // block maximum of |J_ij| (wbuf is free after the last chunk's barrier)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, off));
+      if (lane == 0) wbuf[warp] = amx;
+    }
     __syncthreads();
     if (tid == 0) {
       float cs = 0.f;
 #pragma unroll
       for (int w = 0; w < kLgEvalRows; ++w) cs = __fadd_rn(cs, cbuf[w]);
       p.cost[pr] = cs;
+      if (p.amax && rebuild) {
+        float mx = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLgEvalRows; ++w) mx = fmaxf(mx, wbuf[w]);
+        p.amax[pr] = mx;
+      }
     }
   }
 }
@@ -179,6 +194,16 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same for kind::f16 (A, B = FP16, D = FP32): K = 16 per instruction, the same 32 bytes of K per operand row
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // shared-memory matrix descriptor, K-major, no swizzle.  Canonical layout (16-byte units):
 // ((8, n), 2) : ((1, SBO), LBO) — a core matrix is 8 MN rows x 16 bytes (4 tf32 of K), rows 16 bytes
 // apart; SBO = byte distance between 8-row groups along MN, LBO = between the two 4-element K chunks
@@ -201,6 +226,31 @@ __device__ __forceinline__ float tc_round_tf32(float v) {
 // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
 __device__ __forceinline__ uint32_t tc_idesc_tf32(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+// instruction descriptor: D = F32, A = B = FP16 (format 0), both K-major, M = 128
+__device__ __forceinline__ uint32_t tc_idesc_f16(int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+// power-of-two scale of the FP16 split: |J_ij| * 2^e < 2^12 for every entry of the problem, so hi = fp16(v 2^e) never
+// overflows (fp16 max 65504), lo = fp16(v 2^e - hi) is a normal fp16 for every entry that matters, the products
+// hi hi' + hi lo' + lo hi' carry 22 significant bits - the accuracy class of the 3xTF32 split - and the FP32
+// accumulator stays far from its range (2^24 per product, m of them).  H = acc * 2^(-2e).
+__device__ __forceinline__ int lg_fp16_exp(float amax) {
+  if (!(amax > 0.f) || !(amax < 3.0e38f)) return 0;  // zero, NaN or Inf: nothing sensible to scale
+  int e;
+  frexpf(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
+  e = 12 - e;
+  return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+__device__ __forceinline__ uint32_t lg_pack_h2(float a, float b) {  // two FP16 (round to nearest) in one register
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float lg_h_lo(uint32_t h2) { return __half2float(__ushort_as_half((unsigned short)(h2 & 0xffffu))); }
+__device__ __forceinline__ float lg_h_hi(uint32_t h2) { return __half2float(__ushort_as_half((unsigned short)(h2 >> 16))); }
+__device__ __forceinline__ void sts_v4u(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -286,7 +336,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     for (;; rmul >>= 1) {
       if (rmul < 1) rmul = 1;
       RS = kLgStageK * rmul;
-      hb = (uint32_t)ncs * (uint32_t)RS * 4u;  // bytes of the hi (== lo) part of an operand stage
+      hb = (uint32_t)ncs * (uint32_t)RS * (p.fp16 ? 2u : 4u);  // bytes of the hi (== lo) part of an operand stage
       S = op_region / (2u * hb);
       R = raw_region / ((uint32_t)(rmul * ncg) * kBoxBytes);  // raw stage = whole boxes
       if ((S >= 2 && R >= 2) || rmul == 1) break;
@@ -408,6 +458,112 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
           if (++rs == R) rs = 0;
         }
       }
+    }
+  } else if (warp > kLgLoadWarp && p.fp16) {
+    // ===================== producers, FP16 split =====================
+    // Same protocol as the TF32 producers below; a 16-byte K chunk of the operand now holds EIGHT rows, so the
+    // stage is cut into chunks of 8 rows and, per 128-column group, two halves of 64 columns: warp w owns (chunk kc,
+    // group cg, half hq), lane l the columns 64 hq + l + 32 q, q = 0, 1 - sixteen elements per lane and stage as
+    // before, one 16-byte store per column and part.  Every value is scaled by the problem's power of two (exact),
+    // hi = fp16(v), lo = fp16(v - hi).
+    const int w = warp - (kLgLoadWarp + 1);
+    uint32_t empty_bits = 0, rawf_bits = 0, item = 0;
+    for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
+      int64_t pr; int h;
+      unit_of(idx, pr, h);
+      if (lg_skip(p, pr)) continue;
+      const float fs = ldexpf(1.f, lg_fp16_exp(p.amax ? p.amax[pr] : 1.f));
+     for (int half = 0; half < 2; ++half, ++item) {
+      const int r = half == 0 ? h : p.nstrips - 1 - h;
+      if (half == 1 && r == h) break;
+      const int c0 = 128 * r;
+      const int ncs = (np - c0 < 128) ? 128 : (np - c0);
+      const uint32_t lbo = (uint32_t)ncs * 16u;
+      uint32_t hb, S, R, st = 0, rs = 0;
+      int RS;
+      ring_geom(ncs, RS, hb, S, R);
+      const int ksteps = (m + RS - 1) / RS;
+      const int ncg = (ncs + kLgBoxCols - 1) / kLgBoxCols;
+      const uint32_t raw_stage = (uint32_t)(ncg * (RS / kLgStageK)) * kBoxBytes;
+      const int per = 2 * ncg;
+      const int kc = w / per, cg = (w % per) >> 1, hq = w & 1;
+      const bool mine = kc < RS / 8;
+      if (item > 0) mbar_wait(tmem_full, (item - 1u) & 1u);  // drain: the rings are re-cut for this strip
+      const int rr0 = kLgBoxCols * cg + 64 * hq + lane;  // my operand rows: rr0 + 32 q, q = 0, 1
+      const float *sp = p.scale ? p.scale + (size_t)pr * m : nullptr;
+      auto load_scale = [&](int ks) {
+        const int row = ks * RS + 8 * kc + (lane & 7);
+        return (mine && ks < ksteps && row < m) ? (sp ? sp[row] : 1.f) : 0.f;
+      };
+      float sc_a = load_scale(0), sc_b = load_scale(1);
+      const uint32_t raw_u32 = smem_u32(raw), stages_u32 = smem_u32(stages);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const float sc_cur = sc_a;
+        sc_a = sc_b;
+        sc_b = load_scale(ks + 2);
+        float sc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sc[t] = __shfl_sync(0xffffffffu, sc_cur, t);
+        mbar_wait(&raw_full[rs], (rawf_bits >> rs) & 1u);
+        // row 8 kc + t of the stage sits in row box kc / 2, row 8 (kc % 2) + t of the box
+        const uint32_t rsrc = raw_u32 + rs * raw_stage + (uint32_t)((kc >> 1) * ncg) * kBoxBytes +
+                              (uint32_t)(8 * (kc & 1)) * (kLgBoxCols * 4u);
+        const int row0 = ks * RS + 8 * kc;
+        if ((p.debug & 2) || !mine) {  // idle warp (or timing experiment): barrier protocol only
+          mbar_wait(&empty[st], ((empty_bits >> st) & 1u) ^ 1u);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&full[st]);
+            mbar_arrive(&raw_empty[rs]);
+          }
+          empty_bits ^= 1u << st;
+          rawf_bits ^= 1u << rs;
+          if (++st == S) st = 0;
+          if (++rs == R) rs = 0;
+          continue;
+        }
+        float bv[2][8];  // [q][t]: column rr0 + 32 q, row 8 kc + t
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int rr = rr0 + 32 * q;
+          const bool cok = rr < ncs && c0 + rr < n;
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            bv[q][t] = (cok && row0 + t < m)
+                           ? lds_f32(rsrc + (uint32_t)cg * kBoxBytes + (uint32_t)(t * kLgBoxCols + 64 * hq + 32 * q + lane) * 4u)
+                           : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        mbar_wait(&empty[st], ((empty_bits >> st) & 1u) ^ 1u);
+        const uint32_t sb = stages_u32 + st * 2u * hb;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int rr = rr0 + 32 * q;  // operand row (column of A relative to c0)
+          if (rr < ncs) {
+            float v[8];
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = __fmul_rn(__fmul_rn(bv[q][t], sc[t]), fs);  // J_ij, then * 2^e (exact)
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              hi[t2] = lg_pack_h2(v[2 * t2], v[2 * t2 + 1]);
+              lo[t2] = lg_pack_h2(__fsub_rn(v[2 * t2], lg_h_lo(hi[t2])), __fsub_rn(v[2 * t2 + 1], lg_h_hi(hi[t2])));
+            }
+            const uint32_t off = (uint32_t)kc * lbo + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
+            sts_v4u(sb + off, hi[0], hi[1], hi[2], hi[3]);
+            sts_v4u(sb + hb + off, lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[st]);
+        empty_bits ^= 1u << st;
+        rawf_bits ^= 1u << rs;
+        if (++st == S) st = 0;
+        if (++rs == R) rs = 0;
+      }
+     }
     }
   } else if (warp > kLgLoadWarp) {
     // ===================== producers =====================
@@ -542,20 +698,28 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
           tc_fence_after();
           const uint32_t sb0 = smem_u32(stages) + st * 2u * hb;
           const uint32_t lbo = (uint32_t)ncs * 16u;  // K chunk c + 1 follows all the core matrices of chunk c
-          for (int kk = 0; kk < RS / kLgMmaK && !(p.debug & 1); ++kk) {  // debug & 1: timing experiment, no MMAs
+          const int mma_k = p.fp16 ? 2 * kLgMmaK : kLgMmaK;  // rows per instruction: 32 bytes of K in either format
+          for (int kk = 0; kk < RS / mma_k && !(p.debug & 1); ++kk) {  // debug & 1: timing experiment, no MMAs
             const uint32_t sb = sb0 + (uint32_t)(2 * kk) * lbo;  // this K step: chunks 2 kk, 2 kk + 1
             const uint64_t a_hi = tc_desc_k_major(sb, lbo, 128u);
             const uint64_t a_lo = tc_desc_k_major(sb + hb, lbo, 128u);
             for (int n0 = 0; n0 < nb; n0 += 256) {
               const int N = (nb - n0 < 256) ? (nb - n0) : 256;
-              const uint32_t idesc = tc_idesc_tf32(N);
               const uint64_t b_hi = tc_desc_k_major(sb + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
+              const uint64_t b_lo = tc_desc_k_major(sb + hb + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
               const uint32_t d = tmem_base + (uint32_t)n0;
-              tc_mma_tf32(d, a_hi, b_hi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
-              if (p.terms == 3) {
-                const uint64_t b_lo = tc_desc_k_major(sb + hb + (uint32_t)(n0 / 8) * 128u, lbo, 128u);
-                tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-                tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+              if (p.fp16) {
+                const uint32_t idesc = tc_idesc_f16(N);
+                tc_mma_f16(d, a_hi, b_hi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
+              } else {
+                const uint32_t idesc = tc_idesc_tf32(N);
+                tc_mma_tf32(d, a_hi, b_hi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                if (p.terms == 3) {
+                  tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                  tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+                }
               }
             }
           }
@@ -584,6 +748,8 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       const int r = half == 0 ? h : p.nstrips - 1 - h;
       if (half == 1 && r == h) break;
       const int c0 = 128 * r, nb = np - c0;
+      // FP16 split: the accumulator holds H * 2^(2e): two exact multiplications by 2^-e bring it back
+      const float inv = p.fp16 ? ldexpf(1.f, -lg_fp16_exp(p.amax ? p.amax[pr] : 1.f)) : 1.f;
       mbar_wait(tmem_full, item & 1u);
       tc_fence_after();
       const int row = c0 + 32 * warp + lane;
@@ -596,8 +762,8 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4 *>(hrow + cb + 4 * q) =
-                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                            __uint_as_float(v[4 * q + 3]));
+                make_float4(__uint_as_float(v[4 * q]) * inv * inv, __uint_as_float(v[4 * q + 1]) * inv * inv,
+                            __uint_as_float(v[4 * q + 2]) * inv * inv, __uint_as_float(v[4 * q + 3]) * inv * inv);
         }
       }
       tc_fence_before();

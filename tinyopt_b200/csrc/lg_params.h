@@ -27,6 +27,8 @@ struct LgEvalParams {
   float *dg;        // [B][n] out (rebuild passes): diag(J^T J) in FP32, rows in order (the tensor core
                     // accumulates with truncation, which biases the long same-sign sums of the diagonal)
   float *cost;      // [B] out: sum r_i^2
+  float *amax;      // [B] out (rebuild passes) or nullptr: max |J_ij| of the problem — the FP16-split J^T J kernel
+                    // scales by a power of two derived from it
   int64_t B;
   int m, n;
   int synth;        // 1: polynomial family evaluated from A, y, x; 0: materialised J, r
@@ -62,6 +64,9 @@ struct LgSyrkParams {
   int64_t B;
   int m, n, np, nstrips;
   int stages;          // ring depth
+  const float *amax;   // [B] max |J_ij| per problem (fp16 != 0), from lg_eval_kernel
+  int fp16;            // 1: FP16 hi / lo split, tcgen05.mma.kind::f16 (K = 16 per instruction: twice the TF32 rate,
+                       // half the operand bytes); 0: TF32 split, kind::tf32
   int terms;           // 3: hi*hi + hi*lo + lo*hi; 1: plain TF32
   int is_lm;
   int debug;           // timing experiments only (env TOB200_LG_DEBUG): 1 no MMAs, 2 no transform, 4 no copies

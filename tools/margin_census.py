@@ -90,7 +90,7 @@ def census(name, cfg, sample, chunk_bytes=1 << 30):
         "robust_fraction": acc["robust"] / N,
         "same_num_iters_under_reversed_row_order": acc["same_it_rev"] / N,
         "same_decisions_under_reversed_row_order": acc["same_rev"] / N,
-        "robust_and_same_under_reversed_order": acc["same_rev_robust"] / max(1, acc["robust"]),
+        "robust_and_same_under_reversed_order": (acc["same_rev_robust"] / acc["robust"]) if acc["robust"] else 1.0,
         "max_rel_dx_under_reversed_order": acc["max_dx_rev"],
         "sign_margin_quantiles": {q: float(np.quantile(sq, float(q))) for q in ("0.001", "0.01", "0.1", "0.5")},
         "thr_margin_quantiles": {q: float(np.quantile(tq, float(q))) for q in ("0.001", "0.01", "0.1", "0.5")},

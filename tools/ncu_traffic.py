@@ -25,7 +25,6 @@ for spec in sys.argv[1:]:
         return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
     out[name] = {"kernel": r[hdr.index("Kernel Name")].split("<")[0].split("(")[0].replace("void ", "").split("::")[-1],
                  "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
-                 "duration_ns": val("gpu__time_duration.sum") * (1.0 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1.0),
                  "problems": int(problems), "bench_problems": int(bench_problems),
                  "source": f"ncu --set full --clock-control none, {os.path.basename(rep)} (profiles/r2_*_ncu_full_summary.txt)"}
 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
