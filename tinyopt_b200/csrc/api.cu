@@ -57,6 +57,7 @@ struct tob200_ctx {
   cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_run[kMaxChunks] = {}, ev_side = nullptr;
   // large-n family: 3 = 3xTF32 (hi*hi + hi*lo + lo*hi, FP32-level accuracy), 1 = plain TF32
   int lg_tf32_terms = 3;  // env TOB200_LG_TF32_TERMS
+  int lg_raw_stages = kLgRawStages;  // env TOB200_LG_RAW_STAGES (2..6)
   int lg_fp16 = 1;        // env TOB200_LG_FP16: 1 = FP16 hi / lo split (kind::f16), 0 = TF32 split (kind::tf32)
   // device time of the last large-n call by phase (0 eval, 1 syrk, 2 solve): CUDA event pairs
   static constexpr int kMaxPhaseEvents = 3 * 80;
@@ -421,13 +422,17 @@ LgSyrkParams lg_syrk_params(tob200_ctx *ctx, const LgBuffers &b, const float *A,
   sp.n = n;
   sp.np = b.np;
   sp.nstrips = (b.np + 127) / 128;
-  sp.stages = lg_syrk_stages(b.np);
-  sp.terms = ctx->lg_tf32_terms;
   sp.fp16 = ctx->lg_fp16;
+  sp.raw_stages = ctx->lg_raw_stages;
+  // the raw ring may not crowd out the operand ring: at least two operand stages of the widest strip must remain
+  while (sp.raw_stages > 2 && (size_t)sp.raw_stages * lg_syrk_raw_bytes(b.np) + 4 * (size_t)lg_syrk_half_bytes(b.np, sp.fp16) > 200 * 1024)
+    --sp.raw_stages;
+  sp.stages = lg_syrk_stages(b.np, sp.raw_stages, sp.fp16);
+  sp.terms = ctx->lg_tf32_terms;
   sp.amax = b.amax;
   sp.is_lm = is_lm;
   sp.debug = env_int("TOB200_LG_DEBUG", 0);
-  sp.half_bytes = lg_syrk_half_bytes(b.np);
+  sp.half_bytes = lg_syrk_half_bytes(b.np, sp.fp16);
   return sp;
 }
 
@@ -1128,6 +1133,9 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->wpp_stages = env_int("TOB200_WPP_STAGES", ctx->wpp_stages);
   ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
   ctx->lg_fp16 = (env_int("TOB200_LG_FP16", 1) != 0 && ctx->lg_tf32_terms == 3) ? 1 : 0;
+  ctx->lg_raw_stages = env_int("TOB200_LG_RAW_STAGES", kLgRawStages);  // 2..5 measured equal on C5 (12.43 .. 12.57 ms): not the limiter
+  if (ctx->lg_raw_stages < 2) ctx->lg_raw_stages = 2;
+  if (ctx->lg_raw_stages > 6) ctx->lg_raw_stages = 6;
   ctx->host_chunks = env_int("TOB200_HOST_CHUNKS", ctx->host_chunks);
   if ((e = cudaMalloc((void **)&ctx->counters, sizeof(unsigned long long) * tob200_ctx::kNumCounters)) != cudaSuccess) {
     tob200_destroy(ctx);

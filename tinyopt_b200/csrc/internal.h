@@ -59,7 +59,7 @@ cudaError_t launch_lg_import_h(const float *in, int64_t B, int n, int np, float 
 cudaError_t launch_lg_eval(const LgEvalParams &p, int num_sms, cudaStream_t st);
 cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st);
 cudaError_t launch_lg_solve(const LgSolveParams &p, int grid, cudaStream_t st);
-int lg_syrk_stages(int np);
+int lg_syrk_stages(int np, int raw_stages, int fp16);
 }  // namespace tob200
 
 // gn_kernels.cu (general family; parameter structs in gn.cuh)

@@ -106,16 +106,17 @@ cudaError_t launch_lg_eval(const LgEvalParams &p, int num_sms, cudaStream_t st) 
   return cudaGetLastError();
 }
 
-int lg_syrk_stages(int np) {
-  const size_t stage = 2 * (size_t)lg_syrk_half_bytes(np);
-  int s = (int)((200 * 1024 - (size_t)kLgRawStages * lg_syrk_raw_bytes(np)) / stage);
+int lg_syrk_stages(int np, int raw_stages, int fp16) {
+  const size_t stage = 2 * (size_t)lg_syrk_half_bytes(np, fp16);
+  const size_t budget = 200 * 1024, raw = (size_t)raw_stages * lg_syrk_raw_bytes(np);
+  int s = raw + 2 * stage <= budget ? (int)((budget - raw) / stage) : 2;
   if (s > kLgMaxStages) s = kLgMaxStages;
   if (s < 2) s = 2;
   return s;
 }
 
 cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st) {
-  const size_t smem = lg_syrk_smem_bytes(p.np, p.stages);
+  const size_t smem = lg_syrk_smem_bytes(p.np, p.stages, p.raw_stages, p.fp16);
   {
     cudaError_t e = raise_smem_limit((const void *)lg_syrk_kernel, smem);
     if (e != cudaSuccess) return e;

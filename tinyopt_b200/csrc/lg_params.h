@@ -46,7 +46,7 @@ constexpr int kLgMmaWarp = 4;     // warp 4: lane 0 issues every tcgen05.mma
 constexpr int kLgLoadWarp = 5;    // warp 5: lane 0 streams raw rows of A into the raw ring (TMA bulk copies)
 constexpr int kLgProdWarps = 16;  // warps 6..21: 4 K rows x 64 columns of a stage each
 constexpr int kLgPrefetchStages = 6;  // L2 prefetch distance beyond the raw ring, in stages
-constexpr int kLgRawStages = 2;   // raw ring depth (kLgStageK rows each)
+constexpr int kLgRawStages = 2;   // default raw ring depth of the widest strip (LgSyrkParams::raw_stages; env TOB200_LG_RAW_STAGES)
 constexpr int kLgSyrkThreads = (kLgEpiWarps + 2 + kLgProdWarps) * 32;
 constexpr int kLgMmaK = 8;        // K extent of one tf32 tcgen05.mma
 constexpr int kLgStageK = 16;     // rows per stage == two MMA K steps (halves the barrier hand-offs per row)
@@ -63,7 +63,8 @@ struct LgSyrkParams {
   float *H;            // [B][np][np]: strip r writes rows [128 r, 128 r + 128), columns >= 128 r
   int64_t B;
   int m, n, np, nstrips;
-  int stages;          // ring depth
+  int stages;          // operand ring depth (stages of the widest strip)
+  int raw_stages;      // raw ring depth (stages of the widest strip)
   const float *amax;   // [B] max |J_ij| per problem (fp16 != 0), from lg_eval_kernel
   int fp16;            // 1: FP16 hi / lo split, tcgen05.mma.kind::f16 (K = 16 per instruction: twice the TF32 rate,
                        // half the operand bytes); 0: TF32 split, kind::tf32
@@ -73,15 +74,17 @@ struct LgSyrkParams {
   uint32_t half_bytes; // bytes of the hi (== lo) part of a stage == of a raw stage: kLgStageK x max(128, np) floats
 };
 
-__host__ __device__ inline uint32_t lg_syrk_half_bytes(int np) { return (uint32_t)(np < 128 ? 128 : np) * (uint32_t)kLgStageK * 4u; }
+__host__ __device__ inline uint32_t lg_syrk_half_bytes(int np, int fp16 = 0) {
+  return (uint32_t)(np < 128 ? 128 : np) * (uint32_t)kLgStageK * (fp16 ? 2u : 4u);
+}
 // bytes of one raw stage of the widest strip: whole boxes
 __host__ __device__ inline uint32_t lg_syrk_raw_bytes(int np) {
   const int w = np < 128 ? 128 : np;
   return (uint32_t)((w + kLgBoxCols - 1) / kLgBoxCols) * (uint32_t)(kLgBoxCols * kLgStageK * 4);
 }
-__host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages) {
+__host__ __device__ inline size_t lg_syrk_smem_bytes(int np, int stages, int raw_stages, int fp16) {
   // [1 KB alignment slack | operand stages (hi + lo) | raw stages | barriers]
-  return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np) + (size_t)kLgRawStages * lg_syrk_raw_bytes(np) + 512;
+  return 1024 + (size_t)stages * 2 * lg_syrk_half_bytes(np, fp16) + (size_t)raw_stages * lg_syrk_raw_bytes(np) + 512;
 }
 
 constexpr int kLgSolveThreads = 512;
