@@ -71,7 +71,7 @@ typedef struct tob200_options {
   int32_t check_final_cost;        /* options.h:43 */
   int32_t use_step_quality_approx; /* options.h:46 */
   float grad_clipping;             /* options.h:49 */
-  int32_t use_ldlt;                /* options.h:59; 0 = H.inverse() path (gn.h:157-163), n <= 55 only */
+  int32_t use_ldlt;                /* options.h:59; 0 = H.inverse() path (gn.h:157-163): every n <= 2048 */
   int32_t H_is_full;               /* options.h:61 */
   float check_min_H_diag;          /* options.h:63 */
   int32_t save_last;               /* options.h:66 */
@@ -139,7 +139,9 @@ int tob200_copy_to_host(tob200_ctx *ctx, void *dst_host, const void *src_device,
 int64_t tob200_tiled_elems(int64_t B, int m, int n);
 /* Which kernel family serves (dtype, n): 1 thread-per-problem registers (n <= 12 float, n <= 8 double),
  * 2 warp-per-problem shared-memory tiles (n <= 55, float and double), 3 tensor-core J^T J + blocked
- * LDLT (56 <= n <= 512, float; n % 4 != 0 runs on a zero-padded copy), 0 none. */
+ * LDLT (56 <= n <= 512, float; n % 4 != 0 runs on a zero-padded copy), 4 the general family (double 56 <= n <= 2048,
+ * float 513 <= n <= 2048, and `use_ldlt = 0` above n = 55: canonical operation order, bit-identical to the CPU
+ * restatement, no tensor cores), 0 none (n > 2048: TOB200_ERR_UNSUPPORTED, never a fallback). */
 int tob200_kernel_family(int dtype, int n);
 
 /* ---- layout ----------------------------------------------------------------------------------- */
@@ -209,7 +211,7 @@ int tob200_lm_run_f64(tob200_ctx *ctx, const tob200_options *opt, const double *
 /* The same run that also returns Output::final_hessian (optimizer.h:313-316): the last H_ of every problem,
  * un-damped as SolverLM::Hessian() does (solvers/lm.h:157-171: diagonal / (1 + prev_lambda_)), widened to
  * double, [B][n][n] row-major, full symmetric.  Honoured only when options.save_last != 0 (options.h:66, the
- * reference's default); final_hessian may be NULL.  Every kernel family (n <= 512 float, n <= 55 double). */
+ * reference's default); final_hessian may be NULL.  Every kernel family (n <= 2048, float and double). */
 int tob200_lm_run_ex_f32(tob200_ctx *ctx, const tob200_options *opt, const float *A, const float *y,
                          float alpha, int layout, int64_t B, int m, int n, float *x,
                          tob200_result *results, double *final_hessian);
