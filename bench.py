@@ -474,7 +474,7 @@ def probes(ctx, name, cfg, A, y, x0, layout, family, tdt, opt):
     from tinyopt_b200 import api as tba
     m, n, s = cfg["m"], cfg["n"], elt(cfg)
     hbm_peak, hbm_src, _, _ = measured_peaks()
-    Bp = bounded_sample(cfg, 16 << 30)   # J is a second copy of A's size: keep A + J <= 32 GiB
+    Bp = min(int(x0.shape[0]), bounded_sample(cfg, 16 << 30))   # this rank's shard; J is a second copy of A's size: A + J <= 32 GiB
     tiles = (Bp + 31) // 32
     Ap, yp = (A[:tiles], y[:tiles]) if layout == tb.TILE32 else (A[:Bp], y[:Bp])
     xp = x0[:Bp].contiguous()
