@@ -54,6 +54,7 @@ SYMBOLS = {
     "tob200_last_error": (C.c_char_p, [_vp]),
     "tob200_launch_count": (_i64, [_vp]),
     "tob200_last_elapsed_ms": (_i, [_vp, C.POINTER(_f)]),
+    "tob200_set_exact": (_i, [_vp, _i]),
     "tob200_options_default": (None, [_PO]),
     "tob200_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "tob200_device_free": (_i, [_vp, _vp]),

@@ -174,6 +174,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.tob200_launch_count(self._h))
 
+    def set_exact(self, exact: bool = True):
+        """Mid-n float runs (13 <= n <= 55): bit-exact warp-per-problem kernel instead of the tensor-core one."""
+        self._ck(self._lib.tob200_set_exact(self._h, int(bool(exact))), "set_exact")
+
     def last_elapsed_ms(self) -> float:
         ms = C.c_float(0)
         self._ck(self._lib.tob200_last_elapsed_ms(self._h, C.byref(ms)), "tob200_last_elapsed_ms")

@@ -20,6 +20,7 @@
 #include "lg_params.h"
 #include "tpp_inst.cuh"
 #include "wpp_inst.cuh"
+#include "wtc_params.h"
 
 using namespace tob200;
 
@@ -50,6 +51,9 @@ struct tob200_ctx {
   int next_counter = 0;
   unsigned long long *tile_counter = nullptr;  // the counter of the launch being configured
   int wpp_stages = 1;  // env TOB200_WPP_STAGES (1: three CTAs per SM fit, measured best)
+  int wpp_tc = 1;      // env TOB200_WPP_TC / tob200_set_exact: 1 = mid-n float lm_run on the tensor-core kernel (wtc.cuh)
+  int wtc_prefetch = 6;  // env TOB200_WTC_PREFETCH: L2 prefetch distance of its loader, in 32-row stages
+  int wtc_debug = 0;     // env TOB200_WTC_DEBUG (timing experiments)
   // *_host entry points: upload / solve / download pipeline over chunks of the batch
   static constexpr int kMaxChunks = 16;
   int host_chunks = 4;  // env TOB200_HOST_CHUNKS
@@ -776,6 +780,32 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
                                results, final_hessian, n)) != TOB200_OK) {
       return rc;
     }
+  } else if (sizeof(T) == 4 && ctx->wpp_tc && opt->use_ldlt && !final_hessian && n >= kWtcMinN && n <= kWtcMaxN &&
+             m >= kWtcMinM && ((int64_t)m * n) % 4 == 0 && aligned16(A)) {
+    // mid-n tensor-core family (wtc.cuh): one persistent CTA per SM, eight problems in flight each
+    WtcParams p;
+    p.A = (const float *)A;
+    p.y = (const float *)y;
+    p.x = (float *)x;
+    p.results = results;
+    p.B = B;
+    p.m = m;
+    p.n = n;
+    p.opt = make_dev_options<float>(*opt);
+    p.alpha = (float)alpha;
+    p.alpha3 = 3.f * (float)alpha;
+    p.L = wtc_smem_best(n);
+    p.prefetch = ctx->wtc_prefetch;
+    p.debug = ctx->wtc_debug;
+    int64_t grid = ctx->num_sms;
+    const int64_t need = (B + kWtcSlots - 1) / kWtcSlots;
+    if (grid > need) grid = need;
+    if ((rc = ensure_scratch(ctx, 7, (size_t)grid * kWtcSlots * n * wtc_ldw(n) * sizeof(float))) != TOB200_OK) return rc;
+    p.hpersist = (float *)ctx->scratch[7];
+    if ((rc = next_counter(ctx)) != TOB200_OK) return rc;
+    p.counter = ctx->tile_counter;
+    CK(launch_wtc_lm_run(p, (int)grid, ctx->stream));
+    ctx->launches++;
   } else {
     WppRunParams<T> p;
     const int kind = opt->use_ldlt ? kWppRun : kWppRunInv;  // options.h:59
@@ -1131,6 +1161,9 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->tpp_stages = env_int("TOB200_TPP_STAGES", ctx->tpp_stages);
   ctx->tpp_ctas_per_sm = env_int("TOB200_TPP_CTAS_PER_SM", 0);
   ctx->wpp_stages = env_int("TOB200_WPP_STAGES", ctx->wpp_stages);
+  ctx->wpp_tc = env_int("TOB200_WPP_TC", ctx->wpp_tc);
+  ctx->wtc_prefetch = env_int("TOB200_WTC_PREFETCH", ctx->wtc_prefetch);
+  ctx->wtc_debug = env_int("TOB200_WTC_DEBUG", ctx->wtc_debug);
   ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
   ctx->lg_fp16 = (env_int("TOB200_LG_FP16", 1) != 0 && ctx->lg_tf32_terms == 3) ? 1 : 0;
   ctx->lg_raw_stages = env_int("TOB200_LG_RAW_STAGES", kLgRawStages);  // 2..5 measured equal on C5 (12.43 .. 12.57 ms): not the limiter
@@ -1183,6 +1216,12 @@ int tob200_sync(tob200_ctx *ctx) {
 const char *tob200_last_error(const tob200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int64_t tob200_launch_count(const tob200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tob200_set_exact(tob200_ctx *ctx, int exact) {
+  if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
+  ctx->wpp_tc = exact ? 0 : 1;
+  return TOB200_OK;
+}
 
 int tob200_last_elapsed_ms(tob200_ctx *ctx, float *ms) {
   if (!ctx || !ms) return fail(ctx, TOB200_ERR_INVALID, "NULL argument");

@@ -62,6 +62,12 @@ cudaError_t launch_lg_solve(const LgSolveParams &p, int grid, cudaStream_t st);
 int lg_syrk_stages(int np, int raw_stages, int fp16);
 }  // namespace tob200
 
+// wtc_kernels.cu (mid-n tensor-core family; parameter struct in wtc_params.h)
+namespace tob200 {
+struct WtcParams;
+cudaError_t launch_wtc_lm_run(const WtcParams &p, int grid, cudaStream_t st);
+}  // namespace tob200
+
 // gn_kernels.cu (general family; parameter structs in gn.cuh)
 namespace tob200 {
 template <typename T> struct GnAccumParams;

@@ -1,0 +1,754 @@
+// wtc.cuh — mid-n tensor-core family (13 <= n <= 55, float; config C4: n = 50, m = 500).
+//
+// tob200_lm_run_f32 for the sizes where H = J^T J is too big for FFMA register blocks to reach the HBM roofline
+// (the warp-per-problem kernel of wpp.cuh sits at the FP32 ridge and is bound by the shared-memory crossbar: DESIGN.md
+// §5.2) but too small to fill a tensor-core tile on its own.  One persistent CTA per SM keeps EIGHT problems ("slots")
+// in flight; two slots share one 128 x 128 FP32 accumulator in TMEM, whose two 64 x 64 diagonal blocks are their
+// Hessians (the operand rows 0..63 are the columns of slot A's Jacobian, rows 64..127 those of slot B's; the
+// off-diagonal blocks are computed and ignored).  Warp-specialised:
+//
+//   loader   (1 warp)   32-row chunks of both problems' A with cp.async.bulk through an mbarrier ring, L2 prefetch ahead
+//   t-warps  (2 warps)  lane = row: the canonical t = a_i . x chain, r_i, the row scale s_i, cost = sum r_i^2 in row order
+//   columns  (8 warps)  thread = column j: J_ij = s_i a_ij, g_j += J_ij r_i and H_jj += J_ij^2 in FP32, then
+//                       v = J_ij 2^e_j (a per-column power of two), hi = fp16(v), lo = fp16(v - hi), both stored
+//                       K-major into the UMMA operand ring
+//   MMA      (1 thread) tcgen05.mma.cta_group::1.kind::f16, M = N = 128, K = 16: hi hi' + hi lo' + lo hi' (22 significant
+//                       bits, the accuracy class of FP32 sums) into the pair's TMEM accumulator
+//   solvers  (8 warps)  one per slot: drain the slot's block from TMEM (tcgen05.ld) straight into the pivoted layout,
+//                       then everything the reference does with the accumulated system — exactly the code path of
+//                       the warp-per-problem family (wpp.cuh: Eigen's pivot order, the two-column LDL^T, LDLT::solve)
+//                       and the shared LM state machine (lm_state.cuh)
+//   helpers  (2 warps)  a warp can only read its own quarter of the TMEM lanes: rows 32..63 of a slot's block are
+//                       drained by a helper warp of the right quarter into a small staging tile
+//
+// The data pass of one pair overlaps the solves of the other three.  Parity: g, diag(H), cost and t are FP32 sums
+// (cost and t in the oracle's canonical order), the off-diagonal of H comes from the tensor core, so the family is
+// tolerance-held (1e-4 on x and the costs, iteration counts where the decisions clear FP32 noise), like the large-n
+// family; TOB200_WPP_TC=0 / tob200_set_exact() keeps the bit-exact warp-per-problem kernel.
+//
+// Reference path replaced: diff/optimize_autodiff.h:151-157, solvers/lm.h:60-120, solvers/gn.h:150-171,
+// math.h:232-240, optimizers/optimizer.h:243-539.
+#pragma once
+
+#include <cstdio>
+
+#include "common.cuh"
+#include "lm_state.cuh"
+#include "tc.cuh"
+#include "wpp.cuh"
+#include "wtc_params.h"
+
+namespace tob200 {
+
+enum WtcVec {
+  kVx = 0, kVlastdx, kVg, kVdg, kVdd, kVtemp, kVdxs, kVtb1, kVperm, kVinv, kVcs, kVci,
+  kVgp0, kVgp1, kVdp0, kVdp1, kVmp0, kVmp1, kVmisc
+};
+static_assert(kVmisc + 1 == kWtcVecs, "vector count");
+static_assert(kVtb1 == kVdxs + 1, "the LDLT's two-column buffer is dxs + tb1");
+
+enum WtcBar {
+  kBRawFull = 0, kBRawEmpty = 3, kBRsFull = 6, kBOpFull = 9, kBOpEmpty = 12,
+  kBAccFull = 15, kBFrontDone = 19, kBPairReady = 23, kBStageDone = 27, kBCount = 35
+};
+
+// warp roles (24 warps).  A warp reads the TMEM lanes [32 (warp % 4), +32): the solver of an A-side slot must be a
+// warp = 0 (mod 4), of a B-side slot (accumulator rows 64..127) a warp = 2 (mod 4): the even warps 0..14; the helpers
+// are warps 1 and 3 (lanes 32..63 and 96..127).
+#ifdef TOB200_WTC_TIMING
+__device__ long long g_wtc_tm[32];
+#define WTC_T0() long long wtc_t0__ = clock64()
+#define WTC_T(k) do { const long long t__ = clock64(); if (blockIdx.x == 0 && lane == 0) g_wtc_tm[k] += t__ - wtc_t0__; wtc_t0__ = t__; } while (0)
+#else
+#define WTC_T0()
+#define WTC_T(k)
+#endif
+
+constexpr int kWtcLoadWarp = 5, kWtcMmaWarp = 7, kWtcTWarp0 = 9, kWtcTWarp1 = 11;
+// column warps: 13, 15, 16 .. 21 (-> 0 .. 7)
+__device__ __forceinline__ int wtc_col_warp(int warp) { return warp == 13 ? 0 : (warp == 15 ? 1 : (warp >= 16 ? warp - 14 : -1)); }
+
+// mbarrier wait with a sleep between polls: the waits of this kernel are long (a whole data pass or a whole solve), and
+// twenty warps polling without a pause take the issue slots and the LSU from the warps that work (measured: 28 % of all
+// executed instructions were polls)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+// packed FP32 pairs (Blackwell FMUL2 / FFMA2 / FADD2: two IEEE operations per issue slot)
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// four consecutive floats of shared memory as two packed pairs
+__device__ __forceinline__ void lds_f2x2(uint32_t saddr, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
+}
+__device__ __forceinline__ uint32_t h2_absmax(uint32_t acc, uint32_t v) {  // per half: max(acc, |v|)
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2 *>(&acc), __habs2(*reinterpret_cast<const __half2 *>(&v)));
+  return *reinterpret_cast<const uint32_t *>(&r);
+}
+
+// 2^e as a float, |e| <= 100
+__device__ __forceinline__ float wtc_pow2(int e) { return __int_as_float((127 + e) << 23); }
+
+// per-column power of two: base 2^e in [2^(target-1), 2^target)
+__device__ __forceinline__ int wtc_scale_exp(float base, int target) {
+  if (!(base > 0.f) || !(base < 3.0e38f)) return 0;
+  int ex;
+  frexpf(base, &ex);
+  const int e = target - ex;
+  return e < -100 ? -100 : (e > 100 ? 100 : e);
+}
+
+// W <- P H P^T (lower triangle, pitch ldw) from the slot's accumulator block: rows 0..31 straight from TMEM (this
+// warp's lane quarter), rows 32.. from the helper's staging tile; the diagonal is the damped FP32 one.  Optionally the
+// unpermuted damped H_ to the persistent global copy (hp(i, j) = H(j, i), j <= i).
+__device__ __forceinline__ void wtc_layout(float *W, int ldw, int n, uint32_t taddr, const float *stg, const float *dd,
+                                           const int *inv, const float *ci, float *hp, int lane) {
+  const int j = lane;
+  const int aj = j < n ? inv[j] : 0;
+  const float cj = ci[j];
+#pragma unroll 1
+  for (int cb = 0; cb < kWtcNP; cb += 32) {
+    if (cb >= n) break;
+    uint32_t v[32];
+    tc_ld32(taddr + (uint32_t)cb, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int col = cb + c;
+      if (col > j && col < n) {
+        const float val = __fmul_rn(__fmul_rn(__uint_as_float(v[c]), cj), ci[col]);
+        const int b = inv[col];
+        W[(aj > b ? aj : b) * ldw + (aj > b ? b : aj)] = val;
+        if (hp) hp[col * ldw + j] = val;
+      }
+    }
+  }
+  const int j2 = 32 + lane;
+  if (j2 < n) {
+    const int a2 = inv[j2];
+    for (int col = j2 + 1; col < n; ++col) {
+      const float val = stg[lane * kWtcStgPitch + (col - 32)];
+      const int b = inv[col];
+      W[(a2 > b ? a2 : b) * ldw + (a2 > b ? b : a2)] = val;
+      if (hp) hp[col * ldw + j2] = val;
+    }
+  }
+  for (int r = lane; r < n; r += 32) {
+    const int a = inv[r];
+    W[a * ldw + a] = dd[r];
+    if (hp) hp[r * ldw + r] = dd[r];
+  }
+}
+
+// Everything after the data pass of one problem (mirrors wpp_after_pass / lm_after_pass).  Returns true when the
+// pass has to be REPEATED with new column scales (an FP16 operand overflowed: nothing of the state was touched).
+__device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOptions<float> &o, int n, int nres, int ldw,
+                                               float *V, float *W, const float *stg, float *hp, uint32_t taddr,
+                                               bool pass_rebuilt, int lane, int debug) {
+  using O = Ops<float>;
+  float *xs = V + kVx * kWtcNP, *last_dx = V + kVlastdx * kWtcNP, *g = V + kVg * kWtcNP, *dg = V + kVdg * kWtcNP;
+  float *dd = V + kVdd * kWtcNP, *temp = V + kVtemp * kWtcNP, *dxs = V + kVdxs * kWtcNP;
+  int *perm = reinterpret_cast<int *>(V + kVperm * kWtcNP), *inv = reinterpret_cast<int *>(V + kVinv * kWtcNP);
+  float *cs = V + kVcs * kWtcNP, *ci = V + kVci * kWtcNP;
+  const float cost_t = V[kVmisc * kWtcNP];
+#ifdef TOB200_WTC_TIMING
+  const bool tm_on = (threadIdx.x >> 5) == 0;
+#define WTC_TA(k) do { if (tm_on) WTC_T(k); } while (0)
+  WTC_T0();
+#else
+#define WTC_TA(k)
+#endif
+
+  int new_e[2] = {0, 0};
+  bool new_ok[2] = {false, false};
+  if (pass_rebuilt) {
+    bool ovf = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+      if (j < n) {
+        // the two row halves of every stage were summed by different warps: fixed combine order
+        g[j] = __fadd_rn(V[kVgp0 * kWtcNP + j], V[kVgp1 * kWtcNP + j]);
+        dg[j] = __fadd_rn(V[kVdp0 * kWtcNP + j], V[kVdp1 * kWtcNP + j]);
+        const float cms = fmaxf(V[kVmp0 * kWtcNP + j], V[kVmp1 * kWtcNP + j]);  // max_i |J_ij| 2^e_j (Inf: overflow)
+        if (!(cms < 60000.f)) {
+          // an operand of this column overflowed FP16: the true maximum is unknown, step the exponent down
+          ovf = true;
+          int ex;
+          frexpf(cs[j], &ex);  // cs = 2^(ex - 1)
+          new_e[h] = ex - 1 - 8 < -100 ? -100 : ex - 1 - 8;
+          new_ok[h] = true;
+        } else if (cms > 0.f) {
+          new_e[h] = wtc_scale_exp(__fmul_rn(cms, ci[j]), 11);
+          new_ok[h] = true;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, ovf)) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (new_ok[h]) {
+          cs[lane + 32 * h] = wtc_pow2(new_e[h]);
+          ci[lane + 32 * h] = wtc_pow2(-new_e[h]);
+        }
+      __syncwarp();
+      return true;
+    }
+    __syncwarp();
+  }
+
+  double cost;
+  bool built_ok = lm_normalize_cost(o, cost_t, nres, cost);
+  if (pass_rebuilt) {
+    s.num_builds++;
+    if (built_ok) {
+      if (o.grad_clipping != 0.f) {  // base.h:30-38
+        for (int j = lane; j < n; j += 32) {
+          float v = g[j];
+          v = v < -o.grad_clipping ? -o.grad_clipping : v;
+          v = v > o.grad_clipping ? o.grad_clipping : v;
+          g[j] = v;
+        }
+        __syncwarp();
+      }
+      if (o.check_min_H_diag > 0.f) {  // lm.h:82-86
+        bool low = false;
+        for (int j = lane; j < n; j += 32) low = low || (O::abs(dg[j]) < o.check_min_H_diag);
+        if (__any_sync(0xffffffffu, low)) built_ok = false;
+      }
+    }
+  }
+  // will a cost-only iteration possibly follow this one?  Only then must H_ outlive the next pass (optimizer.h:295)
+  const bool may_need_stale_h = !pass_rebuilt || (!(cost - s.final_cost < 0.0) && !(s.flags & kFlagLastWasSuccess));
+
+  bool solver_failed = true, early_return = false;
+  const uint8_t max_tries = lm_max_tries(o);
+  for (int attempt = 0; s.num_consec_failures <= max_tries; ++attempt) {
+    if (built_ok) {
+      double sc;
+      const bool damp = lm_damping_scale(s, o, pass_rebuilt, sc);  // lm.h:108-117
+      for (int j = lane; j < n; j += 32) {
+        const float base = pass_rebuilt ? dg[j] : hp[j * ldw + j];
+        dd[j] = damp ? (float)((double)base * sc) : base;
+      }
+      __syncwarp();
+      WTC_TA(21);
+      wpp_pivot_order(dd, n, perm, inv, lane);
+      WTC_TA(22);
+      if (pass_rebuilt) {
+        wtc_layout(W, ldw, n, taddr, stg, dd, inv, ci, may_need_stale_h ? hp : nullptr, lane);
+      } else {  // cost-only pass, or a retry of one: lay the persistent H_ out, publish its new diagonal
+        for (int e = lane; e < n * ldw; e += 32) {
+          const int i = e / ldw, j = e - i * ldw;
+          if (j <= i) {
+            const float val = i == j ? dd[i] : hp[e];
+            const int a = inv[i], b = inv[j];
+            W[(a > b ? a : b) * ldw + (a > b ? b : a)] = val;
+          }
+        }
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) hp[j * ldw + j] = dd[j];
+      }
+      __syncwarp();
+      WTC_TA(23);
+      if (debug & 2) {  // timing experiment: no factorisation (results invalid)
+        for (int j = lane; j < n; j += 32) dxs[j] = 0.f;
+        __syncwarp();
+        solver_failed = false;
+      } else {
+        const bool fact_ok = wpp_ldlt_factor<float>(W, ldw, n, temp, dxs, kWtcNP, lane);  // gn.h:150-156
+        WTC_TA(24);
+        if (fact_ok) {
+          for (int j = lane; j < n; j += 32) temp[j] = -g[j];
+          __syncwarp();
+          wpp_ldlt_solve<float>(W, ldw, n, perm, temp, dxs, lane);
+          solver_failed = false;
+        }
+        WTC_TA(25);
+      }
+    }
+    if (!solver_failed) break;
+    const int act = lm_on_solver_failure(s, o, cost, nres);
+    if (act == kLmEarlyReturn) early_return = true;
+    if (act != kLmRetry) break;
+    if (attempt >= 100000) break;
+  }
+
+  double dx_norm2 = 0.0, grad_norm2 = 0.0;
+  if (!solver_failed) {
+    dx_norm2 = (double)wpp_sqnorm<float>(dxs, n, lane);
+    if (o.min_grad_norm2_f > 0.0f) grad_norm2 = (double)wpp_sqnorm<float>(g, n, lane);
+  }
+  bool success, has_dx;
+  lm_finish_step(s, o, early_return, solver_failed, cost, nres, dx_norm2, grad_norm2, success, has_dx);
+  const int action = lm_update_action(s, o, success, has_dx);
+  if (action == kLmApplyDx || action == kLmProbeDx) {
+    for (int j = lane; j < n; j += 32) {
+      xs[j] = O::add(xs[j], dxs[j]);
+      last_dx[j] = dxs[j];
+    }
+  } else if (action == kLmRollBack) {
+    for (int j = lane; j < n; j += 32) xs[j] = O::add(xs[j], -last_dx[j]);
+  }
+  // column scales of the next pass from this pass's exact column maxima of J
+  if (pass_rebuilt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (new_ok[h]) {
+        cs[lane + 32 * h] = wtc_pow2(new_e[h]);
+        ci[lane + 32 * h] = wtc_pow2(-new_e[h]);
+      }
+  }
+  __syncwarp();
+  WTC_TA(26);
+  return false;
+}
+
+__global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid_constant__ WtcParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const WtcSmem &L = p.L;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.bars + kBCount * 8);
+  volatile long long *slot_prob = reinterpret_cast<volatile long long *>(smem + L.desc);  // [2][kWtcSlots]
+  const int n = p.n, m = p.m;
+  const int nchunks = (m + kWtcRows - 1) / kWtcRows;
+  const uint32_t R = (uint32_t)L.raw_stages, S = (uint32_t)L.op_stages;
+  float *rsr = reinterpret_cast<float *>(smem + L.rsr);  // [2: s, r][raw stage][side][32 rows]
+  constexpr int kRsrHalf = kWtcMaxRawStages * 2 * kWtcRows;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWtcMaxRawStages; ++s) {
+      mbar_init(&bars[kBRawFull + s], 1);
+      mbar_init(&bars[kBRawEmpty + s], kWtcColWarps);
+      mbar_init(&bars[kBRsFull + s], 2);
+      mbar_init(&bars[kBOpFull + s], kWtcColWarps);
+      mbar_init(&bars[kBOpEmpty + s], 1);
+    }
+    for (int q = 0; q < kWtcPairs; ++q) {
+      mbar_init(&bars[kBAccFull + q], 1);
+      mbar_init(&bars[kBFrontDone + q], kWtcColWarps + 2);
+      mbar_init(&bars[kBPairReady + q], 2);
+    }
+    for (int s = 0; s < kWtcSlots; ++s) mbar_init(&bars[kBStageDone + s], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {  // the whole TMEM of this SM: four 128 x 128 FP32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const bool is_solver = (warp & 1) == 0 && warp < 2 * kWtcSlots;
+  const bool is_helper = warp == 1 || warp == 3;
+  const int cw = wtc_col_warp(warp);
+  const bool is_front = warp == kWtcLoadWarp || warp == kWtcMmaWarp || warp == kWtcTWarp0 || warp == kWtcTWarp1 || cw >= 0;
+
+  if (is_solver) {
+    // ===================== solver: one warp per slot =====================
+    const int slot = warp >> 1, q = slot >> 1, b = slot & 1;
+    const int ldw = wtc_ldw(n);
+    float *V = reinterpret_cast<float *>(smem + L.vec + (size_t)slot * L.vec_stride);
+    float *W = reinterpret_cast<float *>(smem + L.w + (size_t)slot * L.w_stride);
+    const float *stg = reinterpret_cast<const float *>(smem + L.stg + (size_t)slot * L.stg_stride);
+    float *hp = p.hpersist + ((size_t)blockIdx.x * kWtcSlots + slot) * ((size_t)n * ldw);
+    const uint32_t taddr = tmem_base + ((uint32_t)(64 * b) << 16) + (uint32_t)(128 * q + 64 * b);
+    const bool is_lm = p.opt.solver_type == 0;
+    LmScalars<float> s;
+    s.reset_scalars(p.opt);
+    long long prob = -1;
+
+    // the first chunks of the problem's next pass on their way into L2 while the other pairs stream
+    auto prefetch_head = [&]() {
+      if (lane < 4 && lane < nchunks) {
+        const int row0 = lane * kWtcRows;
+        const int rows = (m - row0 < kWtcRows) ? (m - row0) : kWtcRows;
+        tma_prefetch_l2(p.A + ((size_t)prob * m + row0) * n, (uint32_t)rows * (uint32_t)n * 4u);
+      }
+    };
+    auto fetch = [&]() {
+      unsigned long long t = 0;
+      if (lane == 0) t = atomicAdd(p.counter, 1ull);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if ((int64_t)t >= p.B) {
+        prob = -1;
+        return;
+      }
+      prob = (long long)t;
+      prefetch_head();
+      for (int j = lane; j < kWtcNP; j += 32) {
+        V[kVx * kWtcNP + j] = j < n ? p.x[(size_t)prob * n + j] : 0.f;
+        V[kVlastdx * kWtcNP + j] = 0.f;
+      }
+      s.reset_scalars(p.opt);
+      // first estimate of the column scales: max |a_ij| over the first rows (s_i is unknown yet: 2^7 of headroom;
+      // an overflow is detected after the pass and the pass repeated with the exact maxima)
+      const float *Ap = p.A + (size_t)prob * m * n;
+      const int re = m < 32 ? m : 32;
+      float m0 = 0.f, m1 = 0.f;
+      for (int i = 0; i < re; ++i) {
+        if (lane < n) m0 = fmaxf(m0, fabsf(Ap[(size_t)i * n + lane]));
+        if (lane + 32 < n) m1 = fmaxf(m1, fabsf(Ap[(size_t)i * n + lane + 32]));
+      }
+      float gm = fmaxf(m0, m1);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, off));
+      const int e0 = lane < n ? wtc_scale_exp(m0 > 0.f ? m0 : gm, 9) : 0;
+      const int e1 = lane + 32 < n ? wtc_scale_exp(m1 > 0.f ? m1 : gm, 9) : 0;
+      V[kVcs * kWtcNP + lane] = wtc_pow2(e0);
+      V[kVci * kWtcNP + lane] = wtc_pow2(-e0);
+      V[kVcs * kWtcNP + lane + 32] = wtc_pow2(e1);
+      V[kVci * kWtcNP + lane + 32] = wtc_pow2(-e1);
+    };
+    fetch();
+    uint32_t v = 0, sv = 0;
+    WTC_T0();
+    for (;;) {
+      if (lane == 0) slot_prob[(v & 1u) * kWtcSlots + slot] = prob;
+      tc_fence_before();  // my tcgen05.ld of the accumulator precede the pair's next MMAs
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[kBPairReady + q]);
+      mbar_wait_sleep(&bars[kBPairReady + q], v & 1u, 64);
+      const long long pa = slot_prob[(v & 1u) * kWtcSlots + 2 * q], pb = slot_prob[(v & 1u) * kWtcSlots + 2 * q + 1];
+      if (pa < 0 && pb < 0) break;
+      if (slot == 0) WTC_T(0);  // waiting for the pair to be ready (the partner's solve)
+      if (prob >= 0) {
+        mbar_wait_sleep(&bars[kBFrontDone + q], v & 1u, 128);
+        mbar_wait_sleep(&bars[kBAccFull + q], v & 1u, 32);
+        mbar_wait_sleep(&bars[kBStageDone + slot], sv & 1u, 32);
+        ++sv;
+        tc_fence_after();
+        if (slot == 0) WTC_T(1);  // waiting for the data pass
+        const bool do_rebuild = !is_lm || s.rebuild();
+        const bool redo = wtc_after_pass(s, p.opt, n, m, ldw, V, W, stg, hp, taddr, do_rebuild, lane, p.debug);
+        if (slot == 0) WTC_T(2);  // after-pass
+        if (!redo && s.done()) {
+          for (int j = lane; j < n; j += 32) p.x[(size_t)prob * n + j] = V[kVx * kWtcNP + j];
+          if (lane == 0) lm_write_result(s, &p.results[prob]);
+          __syncwarp();
+          fetch();
+        } else {
+          prefetch_head();
+        }
+        if (slot == 0) WTC_T(3);  // write-back + fetch
+      }
+      ++v;
+    }
+  } else if (is_helper) {
+    // ===================== helper: rows 32..63 of the slots of one side =====================
+    const int b = warp >> 1;
+    uint32_t vpar = 0, fin = 0;
+    for (int q = 0; fin != 0xFu; q = (q + 1) & 3) {
+      if ((fin >> q) & 1u) continue;
+      const uint32_t par = (vpar >> q) & 1u;
+      mbar_wait_sleep(&bars[kBPairReady + q], par, 128);
+      const long long pa = slot_prob[par * kWtcSlots + 2 * q], pb = slot_prob[par * kWtcSlots + 2 * q + 1];
+      if (pa < 0 && pb < 0) {
+        fin |= 1u << q;
+        continue;
+      }
+      const int slot = 2 * q + b;
+      if ((b ? pb : pa) >= 0) {
+        mbar_wait_sleep(&bars[kBAccFull + q], par, 128);
+        tc_fence_after();
+        if (n > 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(64 * b + 32) << 16) + (uint32_t)(128 * q + 64 * b + 32), v);
+          tc_wait_ld();
+          const float *ci = reinterpret_cast<const float *>(smem + L.vec + (size_t)slot * L.vec_stride) + kVci * kWtcNP;
+          float *stg = reinterpret_cast<float *>(smem + L.stg + (size_t)slot * L.stg_stride);
+          const int j = 32 + lane;
+          const float cj = ci[j];
+#pragma unroll
+          for (int c = 0; c < kWtcStgPitch; ++c) {
+            const int col = 32 + c;
+            if (lane < kWtcStgPitch && col > j && col < n)
+              stg[lane * kWtcStgPitch + c] = __fmul_rn(__fmul_rn(__uint_as_float(v[c]), cj), ci[col]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[kBStageDone + slot]);
+      }
+      vpar ^= 1u << q;
+    }
+  } else if (is_front) {
+    // ===================== the data pass: loader, t-warps, column warps, MMA issuer =====================
+    const uint32_t ops_u32 = smem_u32(smem + L.ops);
+    uint32_t vpar = 0, fin = 0;
+    uint32_t st = 0, ph = 0, os = 0, oph = 0;  // raw ring stage / phase, operand ring stage / phase
+    WTC_T0();
+    const int tmk = warp == kWtcLoadWarp ? 4 : (warp == kWtcMmaWarp ? 8 : (warp == kWtcTWarp0 ? 12 : (cw == 0 ? 16 : 28)));
+    (void)tmk;
+    for (int q = 0; fin != 0xFu; q = (q + 1) & 3) {
+      if ((fin >> q) & 1u) continue;
+      const uint32_t par = (vpar >> q) & 1u;
+      mbar_wait_sleep(&bars[kBPairReady + q], par, 128);
+      WTC_T(tmk);  // waiting for a ready pair
+      const long long pa = slot_prob[par * kWtcSlots + 2 * q], pb = slot_prob[par * kWtcSlots + 2 * q + 1];
+      if (pa < 0 && pb < 0) {
+        fin |= 1u << q;
+        continue;
+      }
+      vpar ^= 1u << q;
+
+      if (warp == kWtcLoadWarp) {
+        for (int c = 0; c < nchunks; ++c) {
+          const int row0 = c * kWtcRows;
+          const int rows = (m - row0 < kWtcRows) ? (m - row0) : kWtcRows;
+          const uint32_t bytes = (uint32_t)rows * (uint32_t)n * 4u;
+          if (lane == 0) {
+            mbar_wait_sleep(&bars[kBRawEmpty + st], ph ^ 1u, 32);
+            WTC_T(5);
+            fence_proxy_async();  // the column warps' generic reads of this stage precede the async writes
+            mbar_expect_tx(&bars[kBRawFull + st], bytes * (uint32_t)((pa >= 0) + (pb >= 0)));
+            unsigned char *dst = smem + L.raw + (size_t)st * L.raw_stage;
+            if (pa >= 0) tma_bulk_g2s(dst, p.A + ((size_t)pa * m + row0) * n, bytes, &bars[kBRawFull + st]);
+            if (pb >= 0) tma_bulk_g2s(dst + L.raw_side, p.A + ((size_t)pb * m + row0) * n, bytes, &bars[kBRawFull + st]);
+          } else if (lane <= 2) {  // L2 prefetch of the same rows p.prefetch stages ahead
+            const long long pp = lane == 1 ? pa : pb;
+            const int cc = c + p.prefetch;
+            if (pp >= 0 && cc < nchunks) {
+              const int r0 = cc * kWtcRows;
+              const int rr = (m - r0 < kWtcRows) ? (m - r0) : kWtcRows;
+              tma_prefetch_l2(p.A + ((size_t)pp * m + r0) * n, (uint32_t)rr * (uint32_t)n * 4u);
+            }
+          }
+          __syncwarp();
+          WTC_T(6);
+          if (++st == R) { st = 0; ph ^= 1u; }
+        }
+      } else if (warp == kWtcTWarp0 || warp == kWtcTWarp1) {
+        // ---- lane = row: canonical t-chain, r_i, s_i; cost in row order ----
+        const int b = warp == kWtcTWarp1 ? 1 : 0;
+        const long long prob = b ? pb : pa;
+        const bool active = prob >= 0;
+        const int slot = 2 * q + b;
+        float *V = reinterpret_cast<float *>(smem + L.vec + (size_t)slot * L.vec_stride);
+        const float *xs = V + kVx * kWtcNP;
+        const float *yp = p.y + (size_t)(active ? prob : 0) * m;
+        float cost = 0.f;  // my rows' share of sum r_i^2
+        float ynext = (active && lane < m) ? yp[lane] : 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          const int row0 = c * kWtcRows;
+          const int rows = (m - row0 < kWtcRows) ? (m - row0) : kWtcRows;
+          const float ycur = ynext;
+          ynext = (active && row0 + kWtcRows + lane < m) ? yp[row0 + kWtcRows + lane] : 0.f;
+          mbar_wait_sleep(&bars[kBRawFull + st], ph, 32);
+          if (warp == kWtcTWarp0) WTC_T(13);
+          float *arow = reinterpret_cast<float *>(smem + L.raw + (size_t)st * L.raw_stage + (size_t)b * L.raw_side) + lane * n;
+          float ri = 0.f, sc = 0.f;
+          if (active && lane < rows) {
+            // t = a_i . x as four interleaved partial sums (fixed combine order): the chain is the latency of this warp
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            if ((n & 1) == 0) {
+              const float2 *a2 = reinterpret_cast<const float2 *>(arow);
+              const float2 *x2 = reinterpret_cast<const float2 *>(xs);
+              const int h = n / 2;
+              int j = 0;
+#pragma unroll 4
+              for (; j + 2 <= h; j += 2) {
+                const float2 av0 = a2[j], av1 = a2[j + 1], xv0 = x2[j], xv1 = x2[j + 1];
+                t0 = __fmaf_rn(av0.x, xv0.x, t0);
+                t1 = __fmaf_rn(av0.y, xv0.y, t1);
+                t2 = __fmaf_rn(av1.x, xv1.x, t2);
+                t3 = __fmaf_rn(av1.y, xv1.y, t3);
+              }
+              if (j < h) {
+                const float2 av0 = a2[j], xv0 = x2[j];
+                t0 = __fmaf_rn(av0.x, xv0.x, t0);
+                t1 = __fmaf_rn(av0.y, xv0.y, t1);
+              }
+            } else {
+              int j = 0;
+#pragma unroll 2
+              for (; j + 4 <= n; j += 4) {
+                t0 = __fmaf_rn(arow[j], xs[j], t0);
+                t1 = __fmaf_rn(arow[j + 1], xs[j + 1], t1);
+                t2 = __fmaf_rn(arow[j + 2], xs[j + 2], t2);
+                t3 = __fmaf_rn(arow[j + 3], xs[j + 3], t3);
+              }
+              for (; j < n; ++j) t0 = __fmaf_rn(arow[j], xs[j], t0);
+            }
+            const float t = __fadd_rn(__fadd_rn(t0, t1), __fadd_rn(t2, t3));
+            const float tt = __fmul_rn(t, t);
+            ri = __fmaf_rn(t, __fmaf_rn(p.alpha, tt, 1.f), -ycur);
+            sc = __fmaf_rn(p.alpha3, tt, 1.f);
+            cost = __fmaf_rn(ri, ri, cost);
+          } else if (lane >= rows) {
+            // a partial last chunk: the rows the bulk copy did not write hold another chunk's data: clear them, so that
+            // the column warps need no row guard (s_i = 0 alone would let a NaN through)
+            for (int j = 0; j < n; ++j) arow[j] = 0.f;
+          }
+          float *ssp = rsr + ((int)st * 2 + b) * kWtcRows, *srp = ssp + kRsrHalf;
+          ssp[lane] = sc;
+          srp[lane] = ri;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[kBRsFull + st]);
+          if (warp == kWtcTWarp0) WTC_T(14);
+          if (++st == R) { st = 0; ph ^= 1u; }
+        }
+        // cost: the lanes' shares combined by a fixed butterfly
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) cost = __fadd_rn(cost, __shfl_xor_sync(0xffffffffu, cost, off));
+        if (lane == 0) {
+          V[kVmisc * kWtcNP] = cost;
+          mbar_arrive(&bars[kBFrontDone + q]);
+        }
+        __syncwarp();
+      } else if (cw >= 0) {
+        // ---- thread = operand row (slot side, column j): FP32 sums of g_j and H_jj, FP16 hi / lo operands ----
+        // Warp (grp, quarter): rows [16 grp, 16 grp + 16) of every stage, operand rows [32 quarter, +32).  Two rows at
+        // a time as packed FP32 pairs.  Pad columns (j >= n) and idle slots read column n - 1 / stale bytes and are
+        // multiplied by zero: whatever they produce stays inside accumulator rows / columns nobody reads.
+        const int grp = cw >> 2;
+        const int rr = 32 * (cw & 3) + lane, b = rr >> 6, j = rr & 63;
+        const long long prob = b ? pb : pa;
+        const int slot = 2 * q + b;
+        float *V = reinterpret_cast<float *>(smem + L.vec + (size_t)slot * L.vec_stride);
+        const bool colok = prob >= 0 && j < n;
+        const float fs = colok ? V[kVcs * kWtcNP + j] : 0.f;
+        const unsigned long long fs2 = f2_pack(fs, fs);
+        unsigned long long g2 = 0ull, d2 = 0ull;  // (even rows, odd rows) partial sums
+        uint32_t mxh = 0u;                        // max |hi| of my column, per half
+        const uint32_t off0 = (uint32_t)(2 * grp) * 2048u + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
+        const uint32_t n4 = (uint32_t)n * 4u;
+        const uint32_t raw0 = smem_u32(smem + L.raw) + (uint32_t)b * L.raw_side + (uint32_t)((j < n ? j : n - 1) + 16 * grp * n) * 4u;
+        const uint32_t rs0 = smem_u32(rsr) + (uint32_t)(b * kWtcRows + 16 * grp) * 4u;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait_sleep(&bars[kBRsFull + st], ph, 32);
+          mbar_wait(&bars[kBRawFull + st], ph);
+          if (cw == 0) WTC_T(17);
+          const uint32_t sa = raw0 + st * L.raw_stage;
+          const uint32_t ss = rs0 + st * (uint32_t)(2 * kWtcRows * 4), sr = ss + (uint32_t)kRsrHalf * 4u;
+          uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            unsigned long long sc2[4], r2[4];
+            lds_f2x2(ss + (uint32_t)h * 32u, sc2[0], sc2[1]);
+            lds_f2x2(ss + (uint32_t)h * 32u + 16u, sc2[2], sc2[3]);
+            lds_f2x2(sr + (uint32_t)h * 32u, r2[0], r2[1]);
+            lds_f2x2(sr + (uint32_t)h * 32u + 16u, r2[2], r2[3]);
+            float a[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a[t] = lds_f32(sa + (uint32_t)(8 * h + t) * n4);
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              const unsigned long long jv = f2_mul(f2_pack(a[2 * t2], a[2 * t2 + 1]), sc2[t2]);  // J_ij = s_i a_ij
+              g2 = f2_fma(jv, r2[t2], g2);
+              d2 = f2_fma(jv, jv, d2);
+              const unsigned long long vv = f2_mul(jv, fs2);  // * 2^e_j (exact)
+              float v0, v1;
+              f2_unpack(vv, v0, v1);
+              const uint32_t hh = lg_pack_h2(v0, v1);
+              const unsigned long long ll = f2_sub(vv, f2_pack(lg_h_lo(hh), lg_h_hi(hh)));  // exact
+              float l0, l1;
+              f2_unpack(ll, l0, l1);
+              hi[h][t2] = hh;
+              lo[h][t2] = lg_pack_h2(l0, l1);
+              mxh = h2_absmax(mxh, hh);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[kBRawEmpty + st]);
+          if (cw == 0) WTC_T(18);
+          mbar_wait_sleep(&bars[kBOpEmpty + os], oph ^ 1u, 32);
+          if (cw == 0) WTC_T(19);
+          const uint32_t sb = ops_u32 + os * (uint32_t)kWtcOpStageBytes + off0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            sts_v4u(sb + (uint32_t)h * 2048u, hi[h][0], hi[h][1], hi[h][2], hi[h][3]);
+            sts_v4u(sb + (uint32_t)(kWtcOpStageBytes / 2) + (uint32_t)h * 2048u, lo[h][0], lo[h][1], lo[h][2], lo[h][3]);
+          }
+          fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[kBOpFull + os]);
+          if (cw == 0) WTC_T(20);
+          if (++st == R) { st = 0; ph ^= 1u; }
+          if (++os == S) { os = 0; oph ^= 1u; }
+        }
+        {
+          float ge, go, de, dO;
+          f2_unpack(g2, ge, go);
+          f2_unpack(d2, de, dO);
+          V[(kVgp0 + grp) * kWtcNP + j] = __fadd_rn(ge, go);
+          V[(kVdp0 + grp) * kWtcNP + j] = __fadd_rn(de, dO);
+          V[(kVmp0 + grp) * kWtcNP + j] = fmaxf(lg_h_lo(mxh), lg_h_hi(mxh));  // max_i |J_ij| 2^e_j as the FP16 operand saw it
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[kBFrontDone + q]);
+      } else {
+        // ---- MMA issuer: one thread ----
+        if (lane == 0) {
+          tc_fence_after();
+          const uint32_t idesc = tc_idesc_f16(128);
+          const uint32_t d = tmem_base + (uint32_t)(128 * q);
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait_sleep(&bars[kBOpFull + os], oph, 32);
+            WTC_T(9);
+            tc_fence_after();
+            const uint32_t sb0 = ops_u32 + os * (uint32_t)kWtcOpStageBytes;
+            if (!(p.debug & 1)) {
+#pragma unroll
+              for (int kk = 0; kk < kWtcRows / 16; ++kk) {
+                const uint32_t sb = sb0 + (uint32_t)(2 * kk) * 2048u;  // this K step: 8-row chunks 2 kk, 2 kk + 1
+                const uint64_t d_hi = tc_desc_k_major(sb, 2048u, 128u);
+                const uint64_t d_lo = tc_desc_k_major(sb + (uint32_t)(kWtcOpStageBytes / 2), 2048u, 128u);
+                tc_mma_f16(d, d_hi, d_hi, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+                tc_mma_f16(d, d_hi, d_lo, idesc, 1u);
+                tc_mma_f16(d, d_lo, d_hi, idesc, 1u);
+              }
+            }
+            tc_commit(&bars[kBOpEmpty + os]);  // arrives when the MMAs above have read the stage
+            if (c == nchunks - 1) tc_commit(&bars[kBAccFull + q]);
+            WTC_T(10);
+            if (++os == S) { os = 0; oph ^= 1u; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+#ifdef TOB200_WTC_TIMING
+  if (blockIdx.x == 0 && tid == 0) {
+    printf("wtc block 0 kcycles: solver0 wait-pair %lld wait-data %lld after-pass %lld fetch %lld | loader wait-pair %lld wait-empty %lld "
+           "issue %lld | mma wait-pair %lld wait-full %lld issue %lld | twarp wait-pair %lld wait-raw %lld work %lld | col wait-pair %lld "
+           "wait-rs %lld compute %lld wait-op %lld store %lld\n",
+           g_wtc_tm[0] / 1000, g_wtc_tm[1] / 1000, g_wtc_tm[2] / 1000, g_wtc_tm[3] / 1000, g_wtc_tm[4] / 1000, g_wtc_tm[5] / 1000,
+           g_wtc_tm[6] / 1000, g_wtc_tm[8] / 1000, g_wtc_tm[9] / 1000, g_wtc_tm[10] / 1000, g_wtc_tm[12] / 1000, g_wtc_tm[13] / 1000,
+           g_wtc_tm[14] / 1000, g_wtc_tm[16] / 1000, g_wtc_tm[17] / 1000, g_wtc_tm[18] / 1000, g_wtc_tm[19] / 1000, g_wtc_tm[20] / 1000);
+    printf("   after-pass of solver 0: gather+damp %lld pivot order %lld layout %lld factor %lld solve %lld state %lld\n", g_wtc_tm[21] / 1000,
+           g_wtc_tm[22] / 1000, g_wtc_tm[23] / 1000, g_wtc_tm[24] / 1000, g_wtc_tm[25] / 1000, g_wtc_tm[26] / 1000);
+    for (int k = 0; k < 32; ++k) g_wtc_tm[k] = 0;
+  }
+#endif
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+}  // namespace tob200
