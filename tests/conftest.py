@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# The parity suite pins the BIT-EXACT kernels against the oracle: mid-n float runs (13 <= n <= 55) take the
+# warp-per-problem kernel here (also in the C++ test binaries, which inherit the environment).  The library default for
+# those sizes — the tensor-core kernel of wtc.cuh, tolerance-held — is pinned by tests/test_gpu_wtc.py, which switches it
+# on explicitly (Context.set_exact(False)).
+os.environ.setdefault("TOB200_WPP_TC", "0")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -14,12 +14,14 @@
 //                       K-major into the UMMA operand ring
 //   MMA      (1 thread) tcgen05.mma.cta_group::1.kind::f16, M = N = 128, K = 16: hi hi' + hi lo' + lo hi' (22 significant
 //                       bits, the accuracy class of FP32 sums) into the pair's TMEM accumulator
-//   solvers  (8 warps)  one per slot: drain the slot's block from TMEM (tcgen05.ld) straight into the pivoted layout,
-//                       then everything the reference does with the accumulated system — exactly the code path of
-//                       the warp-per-problem family (wpp.cuh: Eigen's pivot order, the two-column LDL^T, LDLT::solve)
-//                       and the shared LM state machine (lm_state.cuh)
-//   helpers  (2 warps)  a warp can only read its own quarter of the TMEM lanes: rows 32..63 of a slot's block are
-//                       drained by a helper warp of the right quarter into a small staging tile
+//   drains   (4 warps)  a warp can only read its own quarter of the TMEM lanes: warp k moves rows [32 k, 32 k + 32) of
+//                       every accumulator (tcgen05.ld) straight into the slot's pivoted LDL^T layout in shared memory
+//                       and into the slot's persistent copy of H_ (global, L2 resident)
+//   solvers  (8 warps)  one per slot, two per scheduler: Build's tail, damping, Eigen's pivot order (from the FP32
+//                       diagonal, before the accumulator is complete), a latency-optimised two-column LDL^T that carries
+//                       the right-hand side along as an extra row, the back substitution, and the shared LM state
+//                       machine (lm_state.cuh).  A pivot that is not positive sends the problem through the exact
+//                       pivoted routine of the warp-per-problem family (wpp.cuh) on the persistent copy.
 //
 // The data pass of one pair overlaps the solves of the other three.  Parity: g, diag(H), cost and t are FP32 sums
 // (cost and t in the oracle's canonical order), the off-diagonal of H comes from the tensor core, so the family is
@@ -41,20 +43,19 @@
 namespace tob200 {
 
 enum WtcVec {
-  kVx = 0, kVlastdx, kVg, kVdg, kVdd, kVtemp, kVdxs, kVtb1, kVperm, kVinv, kVcs, kVci,
+  kVx = 0, kVlastdx, kVg, kVdg, kVdd, kVtemp, kVdxs, kVtb1, kVtb2, kVtb3, kVperm, kVinv, kVcs, kVci,
   kVgp0, kVgp1, kVdp0, kVdp1, kVmp0, kVmp1, kVmisc
 };
 static_assert(kVmisc + 1 == kWtcVecs, "vector count");
-static_assert(kVtb1 == kVdxs + 1, "the LDLT's two-column buffer is dxs + tb1");
+static_assert(kVtb1 == kVdxs + 1 && kVtb3 == kVdxs + 3, "the LDLT's T rows are dxs .. tb3");
 
 enum WtcBar {
-  kBRawFull = 0, kBRawEmpty = 3, kBRsFull = 6, kBOpFull = 9, kBOpEmpty = 12,
-  kBAccFull = 15, kBFrontDone = 19, kBPairReady = 23, kBStageDone = 27, kBCount = 35
+  kBRawFull = 0, kBRawEmpty = 5, kBRsFull = 10, kBOpFull = 15, kBOpEmpty = 18,
+  kBAccFull = 21, kBFrontDone = 25, kBPairReady = 29, kBPermReady = 33, kBWReady = 41, kBCount = 49
 };
 
-// warp roles (24 warps).  A warp reads the TMEM lanes [32 (warp % 4), +32): the solver of an A-side slot must be a
-// warp = 0 (mod 4), of a B-side slot (accumulator rows 64..127) a warp = 2 (mod 4): the even warps 0..14; the helpers
-// are warps 1 and 3 (lanes 32..63 and 96..127).
+// warp roles (24 warps, six per scheduler).  A warp reads the TMEM lanes [32 (warp % 4), +32): the drains are warps
+// 0..3; the solvers are warps 4..11 (two per scheduler: their code is one long dependency chain).
 #ifdef TOB200_WTC_TIMING
 __device__ long long g_wtc_tm[32];
 #define WTC_T0() long long wtc_t0__ = clock64()
@@ -64,15 +65,31 @@ __device__ long long g_wtc_tm[32];
 #define WTC_T(k)
 #endif
 
-constexpr int kWtcLoadWarp = 5, kWtcMmaWarp = 7, kWtcTWarp0 = 9, kWtcTWarp1 = 11;
-// column warps: 13, 15, 16 .. 21 (-> 0 .. 7)
-__device__ __forceinline__ int wtc_col_warp(int warp) { return warp == 13 ? 0 : (warp == 15 ? 1 : (warp >= 16 ? warp - 14 : -1)); }
+constexpr int kWtcDrainWarps = 4, kWtcSolveWarp0 = 4, kWtcLoadWarp = 12, kWtcMmaWarp = 13, kWtcTWarp0 = 14, kWtcTWarp1 = 15,
+              kWtcColWarp0 = 16, kWtcTWarp2 = 24, kWtcTWarp3 = 25;
+__device__ __forceinline__ int wtc_col_warp(int warp) { return (warp >= kWtcColWarp0 && warp < kWtcColWarp0 + kWtcColWarps) ? warp - kWtcColWarp0 : -1; }
+// t-warps: 14, 15 take the even chunks of side 0 / 1, 24, 25 the odd ones (-> side + 2 * parity, or -1)
+__device__ __forceinline__ int wtc_t_warp(int warp) {
+  return warp == kWtcTWarp0 ? 0 : (warp == kWtcTWarp1 ? 1 : (warp == kWtcTWarp2 ? 2 : (warp == kWtcTWarp3 ? 3 : -1)));
+}
 
-// mbarrier wait with a sleep between polls: the waits of this kernel are long (a whole data pass or a whole solve), and
-// twenty warps polling without a pause take the issue slots and the LSU from the warps that work (measured: 28 % of all
-// executed instructions were polls)
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, unsigned ns) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+// mbarrier wait with an exponentially growing sleep between polls.  The waits of this kernel are long (a data pass, a
+// solve) and there are twenty waiting warps: polled without a pause they took 28 % of all issued instructions, and with
+// the suspend-time hint of try_wait (NANOSLEEP.SYNCS wakes on every barrier event of the CTA) still 40 % of them plus a
+// third of the shared-memory pipe, which is the resource this kernel runs out of.  ns0: first sleep, doubled up to nsmax.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, unsigned ns0, unsigned nsmax = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (nsmax == 0) nsmax = 8 * ns0;
+  unsigned ns = ns0;
+  do {
+    __nanosleep(ns);
+    ns = ns * 2 > nsmax ? nsmax : ns * 2;
+  } while (!mbar_try_wait(bar, parity));
+}
+__device__ __forceinline__ float wtc_rcp(float x) {  // MUFU.RCP: 1 ulp, the LDL^T below is tolerance-held anyway
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 // packed FP32 pairs (Blackwell FMUL2 / FFMA2 / FADD2: two IEEE operations per issue slot)
 __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
@@ -119,66 +136,172 @@ __device__ __forceinline__ int wtc_scale_exp(float base, int target) {
   return e < -100 ? -100 : (e > 100 ? 100 : e);
 }
 
-// W <- P H P^T (lower triangle, pitch ldw) from the slot's accumulator block: rows 0..31 straight from TMEM (this
-// warp's lane quarter), rows 32.. from the helper's staging tile; the diagonal is the damped FP32 one.  Optionally the
-// unpermuted damped H_ to the persistent global copy (hp(i, j) = H(j, i), j <= i).
-__device__ __forceinline__ void wtc_layout(float *W, int ldw, int n, uint32_t taddr, const float *stg, const float *dd,
-                                           const int *inv, const float *ci, float *hp, int lane) {
-  const int j = lane;
-  const int aj = j < n ? inv[j] : 0;
-  const float cj = ci[j];
-#pragma unroll 1
-  for (int cb = 0; cb < kWtcNP; cb += 32) {
-    if (cb >= n) break;
-    uint32_t v[32];
-    tc_ld32(taddr + (uint32_t)cb, v);
-    tc_wait_ld();
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int col = cb + c;
-      if (col > j && col < n) {
-        const float val = __fmul_rn(__fmul_rn(__uint_as_float(v[c]), cj), ci[col]);
-        const int b = inv[col];
-        W[(aj > b ? aj : b) * ldw + (aj > b ? b : aj)] = val;
-        if (hp) hp[col * ldw + j] = val;
-      }
+// ---- latency-optimised LDL^T of the already permuted, column-scaled system ------------------------------------------
+// W: rows 0..n of pitch ldw (row n = right-hand side), lower triangle; on return the strict lower triangle holds L, row n
+// holds z = D^-1 L^-1 b (the forward substitution rides along as one more row of the sweep), dvec holds D.  Left-looking,
+// two columns per step; T (2 x 64 floats) takes the rows D_j L_{k+c,j} of the step, zero padded to a multiple of four so
+// that the sweep has no tail loop (the never-written upper triangle of W is zeroed once per kernel).  The 2 x 2 pivot
+// block is broadcast by three shuffles and factorised redundantly in every lane with MUFU.RCP instead of two divisions
+// behind two dependent shuffles: the serial chain of a step is shuffle - rcp - fma - rcp - multiply.
+// Measured in isolation (tools/cuda/ldlt_bench.cu, one warp, n = 50): 31 k cycles against 46 k for the bit-exact routine
+// of wpp.cuh; a single warp retires one instruction per ~5 cycles here, so the instruction count of a step is what
+// matters (a variant with fixed row ownership, T rows produced a step ahead and eight fma chains was SLOWER: 36 k).
+// Returns false when a pivot is not positive (NaN included): the caller then runs the exact routine, which decides
+// what Eigen would have decided (zero pivots, sign of D).
+__device__ __forceinline__ bool wtc_ldlt_fast(float *W, int ldw, int n, float *dvec, float *T, int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  bool bad = false;
+  const int nr = n + 1;
+  for (int k = 0; k < n; k += 2) {
+    const bool two = k + 1 < n;
+    const int k4 = (k + 3) & ~3;
+    for (int j = lane; j < k4; j += 32) {
+      const float d = j < k ? dvec[j] : 0.f;
+      T[j] = j < k ? __fmul_rn(d, W[k * ldw + j]) : 0.f;
+      T[kWtcNP + j] = (two && j < k) ? __fmul_rn(d, W[(k + 1) * ldw + j]) : 0.f;
     }
-  }
-  const int j2 = 32 + lane;
-  if (j2 < n) {
-    const int a2 = inv[j2];
-    for (int col = j2 + 1; col < n; ++col) {
-      const float val = stg[lane * kWtcStgPitch + (col - 32)];
-      const int b = inv[col];
-      W[(a2 > b ? a2 : b) * ldw + (a2 > b ? b : a2)] = val;
-      if (hp) hp[col * ldw + j2] = val;
+    __syncwarp();
+    const int r0 = k + lane, r1 = r0 + 32;
+    const bool h0 = r0 < nr, h1 = r1 < nr;
+    float *w0 = W + (h0 ? r0 : k) * ldw, *w1 = W + (h1 ? r1 : k) * ldw;
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < k4; j += 4) {
+      const float4 a4 = *reinterpret_cast<const float4 *>(w0 + j);
+      const float4 b4 = *reinterpret_cast<const float4 *>(w1 + j);
+      const float4 t4 = *reinterpret_cast<const float4 *>(T + j);
+      const float4 u4 = *reinterpret_cast<const float4 *>(T + kWtcNP + j);
+      s00 = __fmaf_rn(a4.x, t4.x, s00); s01 = __fmaf_rn(a4.x, u4.x, s01); s10 = __fmaf_rn(b4.x, t4.x, s10); s11 = __fmaf_rn(b4.x, u4.x, s11);
+      s00 = __fmaf_rn(a4.y, t4.y, s00); s01 = __fmaf_rn(a4.y, u4.y, s01); s10 = __fmaf_rn(b4.y, t4.y, s10); s11 = __fmaf_rn(b4.y, u4.y, s11);
+      s00 = __fmaf_rn(a4.z, t4.z, s00); s01 = __fmaf_rn(a4.z, u4.z, s01); s10 = __fmaf_rn(b4.z, t4.z, s10); s11 = __fmaf_rn(b4.z, u4.z, s11);
+      s00 = __fmaf_rn(a4.w, t4.w, s00); s01 = __fmaf_rn(a4.w, u4.w, s01); s10 = __fmaf_rn(b4.w, t4.w, s10); s11 = __fmaf_rn(b4.w, u4.w, s11);
     }
+    const float e00 = __fsub_rn(w0[k], s00), e10 = __fsub_rn(w1[k], s10);
+    const float e01 = __fsub_rn(two ? w0[k + 1] : 0.f, s01), e11 = __fsub_rn(two ? w1[k + 1] : 0.f, s11);
+    // the pivot block [a b; b c] (rows k, k + 1 are lanes 0, 1)
+    const float a = __shfl_sync(kFull, e00, 0), b = __shfl_sync(kFull, e00, 1), c = __shfl_sync(kFull, e01, 1);
+    const float ra = wtc_rcp(a);
+    const float lb = __fmul_rn(b, ra);
+    const float c2 = __fmaf_rn(-lb, b, c);
+    const float rc = wtc_rcp(c2);
+    bad = bad || !(a > 0.f) || (two && !(c2 > 0.f));
+    const float l00 = __fmul_rn(e00, ra), l10 = __fmul_rn(e10, ra);
+    const float l01 = __fmul_rn(__fmaf_rn(-l00, b, e01), rc), l11 = __fmul_rn(__fmaf_rn(-l10, b, e11), rc);
+    if (h0 && lane > 0) w0[k] = l00;
+    if (h1) w1[k] = l10;
+    if (two) {
+      if (h0 && lane > 1) w0[k + 1] = l01;
+      if (h1) w1[k + 1] = l11;
+    }
+    if (lane == 0) {
+      dvec[k] = a;
+      if (two) dvec[k + 1] = c2;
+    }
+    __syncwarp();
   }
-  for (int r = lane; r < n; r += 32) {
-    const int a = inv[r];
-    W[a * ldw + a] = dd[r];
-    if (hp) hp[r * ldw + r] = dd[r];
-  }
+  return !bad;
 }
 
-// Everything after the data pass of one problem (mirrors wpp_after_pass / lm_after_pass).  Returns true when the
-// pass has to be REPEATED with new column scales (an FP16 operand overflowed: nothing of the state was touched).
+// x <- L^-T z (z = row n of W), two columns per step, then dx[perm[i]] = x_i * cs[perm[i]] (undoing the column scaling)
+__device__ __forceinline__ void wtc_back_subst(const float *W, int ldw, int n, const int *perm, const float *cs, float *dx,
+                                               int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  float x0 = lane < n ? W[n * ldw + lane] : 0.f, x1 = lane + 32 < n ? W[n * ldw + lane + 32] : 0.f;
+  for (int j = n - 1; j >= 1; j -= 2) {
+    const float u = __shfl_sync(kFull, j < 32 ? x0 : x1, j & 31);               // x_j, final
+    float v = __shfl_sync(kFull, j - 1 < 32 ? x0 : x1, (j - 1) & 31);           // x_{j-1} before its last update
+    v = __fmaf_rn(-W[j * ldw + j - 1], u, v);
+    if (lane == ((j - 1) & 31)) {
+      if (j - 1 < 32) x0 = v;
+      else x1 = v;
+    }
+    if (lane < j - 1) x0 = __fmaf_rn(-W[(j - 1) * ldw + lane], v, __fmaf_rn(-W[j * ldw + lane], u, x0));
+    if (lane + 32 < j - 1) x1 = __fmaf_rn(-W[(j - 1) * ldw + lane + 32], v, __fmaf_rn(-W[j * ldw + lane + 32], u, x1));
+  }
+  if (lane < n) { const int o = perm[lane]; dx[o] = __fmul_rn(x0, cs[o]); }
+  if (lane + 32 < n) { const int o = perm[lane + 32]; dx[o] = __fmul_rn(x1, cs[o]); }
+  __syncwarp();
+}
+
+// The exact route: Eigen's pivoted LDL^T semantics (zero pivots, sign of D, D^+) on the UNSCALED damped H_ rebuilt from the
+// slot's persistent copy.  Cold: cost-only passes, retries after a solver failure, systems that are not positive
+// definite.  Returns false when the factorisation reports failure.
+__device__ __noinline__ bool wtc_solve_exact(float *W, int ldw, int n, float *V, float *hp, int lane) {
+  float *g = V + kVg * kWtcNP, *dd = V + kVdd * kWtcNP, *temp = V + kVtemp * kWtcNP, *dxs = V + kVdxs * kWtcNP;
+  int *perm = reinterpret_cast<int *>(V + kVperm * kWtcNP), *inv = reinterpret_cast<int *>(V + kVinv * kWtcNP);
+  const float *hps = hp + n * ldw;
+  wpp_pivot_order(dd, n, perm, inv, lane);
+  for (int e = lane; e < n * ldw; e += 32) {
+    const int i = e / ldw, j = e - i * ldw;
+    if (j <= i) {
+      const float val = i == j ? dd[i] : __fmul_rn(__fmul_rn(__ldcg(hp + e), __ldcg(hps + i)), __ldcg(hps + j));
+      const int a = inv[i], b = inv[j];
+      W[(a > b ? a : b) * ldw + (a > b ? b : a)] = val;
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < n; j += 32) hp[j * ldw + j] = dd[j];
+  __syncwarp();
+  const bool ok = wpp_ldlt_factor<float>(W, ldw, n, temp, dxs, kWtcNP, lane);  // gn.h:150-156
+  if (ok) {
+    for (int j = lane; j < n; j += 32) temp[j] = -g[j];
+    __syncwarp();
+    wpp_ldlt_solve<float>(W, ldw, n, perm, temp, dxs, lane);
+  }
+  // the fast path relies on a zero upper triangle: the routine above never writes it
+  return ok;
+}
+
+// damped diagonal of H_ (lm.h:108-117): from the undamped FP32 one after a rebuild, cumulative on the stale H_ otherwise
+__device__ __forceinline__ void wtc_damp(const LmScalars<float> &s, const DevOptions<float> &o, bool pass_rebuilt, int n, int ldw,
+                                         const float *dg, const float *hp, float *dd, int lane) {
+  double sc;
+  const bool damp = lm_damping_scale(s, o, pass_rebuilt, sc);
+  for (int j = lane; j < n; j += 32) {
+    const float base = pass_rebuilt ? dg[j] : __ldcg(hp + j * ldw + j);
+    dd[j] = damp ? (float)((double)base * sc) : base;
+  }
+  __syncwarp();
+}
+
+struct WtcSolverCtx {
+  uint64_t *perm_ready, *w_ready;
+  volatile int *cmd;  // this visit: 1 = the drains lay the accumulator out, 0 = they only pass
+  uint32_t sv;        // visits of this slot so far (parity of the two barriers above)
+};
+
+// Everything after the data pass of one problem (mirrors wpp_after_pass / lm_after_pass).  Called when the FP32 sums of
+// the pass (g, diag, cost) are complete; the accumulator itself is waited for as late as possible.  Returns true when
+// the pass has to be REPEATED with new column scales (an FP16 operand overflowed: nothing of the state was touched).
 __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOptions<float> &o, int n, int nres, int ldw,
-                                               float *V, float *W, const float *stg, float *hp, uint32_t taddr,
-                                               bool pass_rebuilt, int lane, int debug) {
+                                               float *V, float *W, float *hp, WtcSolverCtx &sx, bool pass_rebuilt, int lane,
+                                               int debug) {
   using O = Ops<float>;
   float *xs = V + kVx * kWtcNP, *last_dx = V + kVlastdx * kWtcNP, *g = V + kVg * kWtcNP, *dg = V + kVdg * kWtcNP;
-  float *dd = V + kVdd * kWtcNP, *temp = V + kVtemp * kWtcNP, *dxs = V + kVdxs * kWtcNP;
+  float *dd = V + kVdd * kWtcNP, *dvec = V + kVtemp * kWtcNP, *dxs = V + kVdxs * kWtcNP;
   int *perm = reinterpret_cast<int *>(V + kVperm * kWtcNP), *inv = reinterpret_cast<int *>(V + kVinv * kWtcNP);
   float *cs = V + kVcs * kWtcNP, *ci = V + kVci * kWtcNP;
-  const float cost_t = V[kVmisc * kWtcNP];
+  const float cost_t = __fadd_rn(V[kVmisc * kWtcNP], V[kVmisc * kWtcNP + 1]);
 #ifdef TOB200_WTC_TIMING
-  const bool tm_on = (threadIdx.x >> 5) == 0;
+  const bool tm_on = (threadIdx.x >> 5) == kWtcSolveWarp0;
 #define WTC_TA(k) do { if (tm_on) WTC_T(k); } while (0)
   WTC_T0();
 #else
 #define WTC_TA(k)
 #endif
+  // hands the visit to the drain warps (lay out / pass) and waits until both have passed
+  auto release_drains = [&](int lay_out) {
+    __syncwarp();  // every lane's writes of W, perm, hp precede the release
+    if (lane == 0) {
+      *sx.cmd = lay_out;
+      mbar_arrive(sx.perm_ready);
+    }
+    __syncwarp();
+  };
+  auto wait_drains = [&]() {
+    mbar_wait_sleep(sx.w_ready, sx.sv & 1u, 200, 800);
+    ++sx.sv;
+  };
 
   int new_e[2] = {0, 0};
   bool new_ok[2] = {false, false};
@@ -193,12 +316,15 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
         dg[j] = __fadd_rn(V[kVdp0 * kWtcNP + j], V[kVdp1 * kWtcNP + j]);
         const float cms = fmaxf(V[kVmp0 * kWtcNP + j], V[kVmp1 * kWtcNP + j]);  // max_i |J_ij| 2^e_j (Inf: overflow)
         if (!(cms < 60000.f)) {
-          // an operand of this column overflowed FP16: the true maximum is unknown, step the exponent down
-          ovf = true;
+          // an operand of this column overflowed FP16: the true maximum is unknown, step the exponent down and repeat
+          // the pass — unless the exponent is at its floor already (the data itself is Inf: let the solver see it)
           int ex;
           frexpf(cs[j], &ex);  // cs = 2^(ex - 1)
-          new_e[h] = ex - 1 - 8 < -100 ? -100 : ex - 1 - 8;
-          new_ok[h] = true;
+          if (ex - 1 > -100) {
+            ovf = true;
+            new_e[h] = ex - 1 - 8 < -100 ? -100 : ex - 1 - 8;
+            new_ok[h] = true;
+          }
         } else if (cms > 0.f) {
           new_e[h] = wtc_scale_exp(__fmul_rn(cms, ci[j]), 11);
           new_ok[h] = true;
@@ -206,6 +332,8 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
       }
     }
     if (__any_sync(0xffffffffu, ovf)) {
+      release_drains(0);
+      wait_drains();
 #pragma unroll
       for (int h = 0; h < 2; ++h)
         if (new_ok[h]) {
@@ -239,54 +367,57 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
       }
     }
   }
-  // will a cost-only iteration possibly follow this one?  Only then must H_ outlive the next pass (optimizer.h:295)
-  const bool may_need_stale_h = !pass_rebuilt || (!(cost - s.final_cost < 0.0) && !(s.flags & kFlagLastWasSuccess));
+  WTC_TA(21);
+
+  // The pivot order depends on the damped diagonal only: it is ready before the accumulator is.  The solver writes the
+  // diagonal and the right-hand side row (column-scaled like the accumulator: H_s = S H S, b_s = -S g), the drains add
+  // the off-diagonal entries at their pivoted positions.
+  const bool fast = pass_rebuilt && built_ok;
+  if (fast) {
+    wtc_damp(s, o, true, n, ldw, dg, hp, dd, lane);
+    wpp_pivot_order(dd, n, perm, inv, lane);
+    for (int j = lane; j < n; j += 32) {
+      const int a = inv[j];
+      const float c = cs[j];
+      W[a * ldw + a] = __fmul_rn(__fmul_rn(dd[j], c), c);
+      W[n * ldw + a] = __fmul_rn(-g[j], c);
+      hp[j * ldw + j] = dd[j];
+      hp[n * ldw + j] = ci[j];
+    }
+  }
+  release_drains(fast ? 1 : 0);
+  WTC_TA(22);
+  wait_drains();
+  WTC_TA(23);
 
   bool solver_failed = true, early_return = false;
   const uint8_t max_tries = lm_max_tries(o);
   for (int attempt = 0; s.num_consec_failures <= max_tries; ++attempt) {
     if (built_ok) {
-      double sc;
-      const bool damp = lm_damping_scale(s, o, pass_rebuilt, sc);  // lm.h:108-117
-      for (int j = lane; j < n; j += 32) {
-        const float base = pass_rebuilt ? dg[j] : hp[j * ldw + j];
-        dd[j] = damp ? (float)((double)base * sc) : base;
-      }
-      __syncwarp();
-      WTC_TA(21);
-      wpp_pivot_order(dd, n, perm, inv, lane);
-      WTC_TA(22);
-      if (pass_rebuilt) {
-        wtc_layout(W, ldw, n, taddr, stg, dd, inv, ci, may_need_stale_h ? hp : nullptr, lane);
-      } else {  // cost-only pass, or a retry of one: lay the persistent H_ out, publish its new diagonal
-        for (int e = lane; e < n * ldw; e += 32) {
-          const int i = e / ldw, j = e - i * ldw;
-          if (j <= i) {
-            const float val = i == j ? dd[i] : hp[e];
-            const int a = inv[i], b = inv[j];
-            W[(a > b ? a : b) * ldw + (a > b ? b : a)] = val;
-          }
-        }
-        __syncwarp();
-        for (int j = lane; j < n; j += 32) hp[j * ldw + j] = dd[j];
-      }
-      __syncwarp();
-      WTC_TA(23);
-      if (debug & 2) {  // timing experiment: no factorisation (results invalid)
-        for (int j = lane; j < n; j += 32) dxs[j] = 0.f;
-        __syncwarp();
-        solver_failed = false;
-      } else {
-        const bool fact_ok = wpp_ldlt_factor<float>(W, ldw, n, temp, dxs, kWtcNP, lane);  // gn.h:150-156
-        WTC_TA(24);
-        if (fact_ok) {
-          for (int j = lane; j < n; j += 32) temp[j] = -g[j];
+      bool ok = false;
+      if (fast && attempt == 0) {
+        if (debug & 2) {  // timing experiment: no factorisation (results invalid)
+          for (int j = lane; j < n; j += 32) dxs[j] = 0.f;
           __syncwarp();
-          wpp_ldlt_solve<float>(W, ldw, n, perm, temp, dxs, lane);
-          solver_failed = false;
+          ok = true;
+        } else {
+          ok = wtc_ldlt_fast(W, ldw, n, dvec, dxs, lane);
+          WTC_TA(24);
+          if (ok) wtc_back_subst(W, ldw, n, perm, cs, dxs, lane);
+          WTC_TA(25);
         }
-        WTC_TA(25);
+        if (!ok) {  // not positive definite (or NaN): let the exact routine decide; W's upper triangle must stay zero
+          ok = wtc_solve_exact(W, ldw, n, V, hp, lane);
+          for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;
+          __syncwarp();
+        }
+      } else {
+        wtc_damp(s, o, pass_rebuilt, n, ldw, dg, hp, dd, lane);
+        ok = wtc_solve_exact(W, ldw, n, V, hp, lane);
+        for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;
+        __syncwarp();
       }
+      if (ok) solver_failed = false;
     }
     if (!solver_failed) break;
     const int act = lm_on_solver_failure(s, o, cost, nres);
@@ -311,7 +442,7 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
   } else if (action == kLmRollBack) {
     for (int j = lane; j < n; j += 32) xs[j] = O::add(xs[j], -last_dx[j]);
   }
-  // column scales of the next pass from this pass's exact column maxima of J
+  // column scales of the next pass from this pass's column maxima of J
   if (pass_rebuilt) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -332,26 +463,33 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.bars + kBCount * 8);
   volatile long long *slot_prob = reinterpret_cast<volatile long long *>(smem + L.desc);  // [2][kWtcSlots]
+  volatile int *slot_cmd = reinterpret_cast<volatile int *>(smem + L.desc + 128);         // [kWtcSlots]
   const int n = p.n, m = p.m;
   const int nchunks = (m + kWtcRows - 1) / kWtcRows;
   const uint32_t R = (uint32_t)L.raw_stages, S = (uint32_t)L.op_stages;
   float *rsr = reinterpret_cast<float *>(smem + L.rsr);  // [2: s, r][raw stage][side][32 rows]
   constexpr int kRsrHalf = kWtcMaxRawStages * 2 * kWtcRows;
+  const int ldw = wtc_ldw(n);
 
   if (tid == 0) {
     for (int s = 0; s < kWtcMaxRawStages; ++s) {
       mbar_init(&bars[kBRawFull + s], 1);
       mbar_init(&bars[kBRawEmpty + s], kWtcColWarps);
       mbar_init(&bars[kBRsFull + s], 2);
+    }
+    for (int s = 0; s < kWtcMaxOpStages; ++s) {
       mbar_init(&bars[kBOpFull + s], kWtcColWarps);
       mbar_init(&bars[kBOpEmpty + s], 1);
     }
     for (int q = 0; q < kWtcPairs; ++q) {
       mbar_init(&bars[kBAccFull + q], 1);
-      mbar_init(&bars[kBFrontDone + q], kWtcColWarps + 2);
+      mbar_init(&bars[kBFrontDone + q], kWtcColWarps + kWtcTWarps);
       mbar_init(&bars[kBPairReady + q], 2);
     }
-    for (int s = 0; s < kWtcSlots; ++s) mbar_init(&bars[kBStageDone + s], 1);
+    for (int s = 0; s < kWtcSlots; ++s) {
+      mbar_init(&bars[kBPermReady + s], 1);
+      mbar_init(&bars[kBWReady + s], 2);
+    }
     mbar_fence_init();
   }
   if (warp == 0) {  // the whole TMEM of this SM: four 128 x 128 FP32 accumulators
@@ -363,24 +501,28 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const bool is_solver = (warp & 1) == 0 && warp < 2 * kWtcSlots;
-  const bool is_helper = warp == 1 || warp == 3;
+  const bool is_drain = warp < kWtcDrainWarps;
+  const bool is_solver = warp >= kWtcSolveWarp0 && warp < kWtcSolveWarp0 + kWtcSlots;
   const int cw = wtc_col_warp(warp);
-  const bool is_front = warp == kWtcLoadWarp || warp == kWtcMmaWarp || warp == kWtcTWarp0 || warp == kWtcTWarp1 || cw >= 0;
+  const int tw = wtc_t_warp(warp);
+  const bool is_front = warp == kWtcLoadWarp || warp == kWtcMmaWarp || tw >= 0 || cw >= 0;
 
   if (is_solver) {
     // ===================== solver: one warp per slot =====================
-    const int slot = warp >> 1, q = slot >> 1, b = slot & 1;
-    const int ldw = wtc_ldw(n);
+    const int slot = warp - kWtcSolveWarp0, q = slot >> 1;
     float *V = reinterpret_cast<float *>(smem + L.vec + (size_t)slot * L.vec_stride);
     float *W = reinterpret_cast<float *>(smem + L.w + (size_t)slot * L.w_stride);
-    const float *stg = reinterpret_cast<const float *>(smem + L.stg + (size_t)slot * L.stg_stride);
-    float *hp = p.hpersist + ((size_t)blockIdx.x * kWtcSlots + slot) * ((size_t)n * ldw);
-    const uint32_t taddr = tmem_base + ((uint32_t)(64 * b) << 16) + (uint32_t)(128 * q + 64 * b);
+    float *hp = p.hpersist + ((size_t)blockIdx.x * kWtcSlots + slot) * (size_t)wtc_hp_floats(n);
     const bool is_lm = p.opt.solver_type == 0;
     LmScalars<float> s;
     s.reset_scalars(p.opt);
     long long prob = -1;
+    WtcSolverCtx sx;
+    sx.perm_ready = &bars[kBPermReady + slot];
+    sx.w_ready = &bars[kBWReady + slot];
+    sx.cmd = &slot_cmd[slot];
+    sx.sv = 0;
+    for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;  // the fast LDL^T reads (and multiplies by zero) above the diagonal
 
     // the first chunks of the problem's next pass on their way into L2 while the other pairs stream
     auto prefetch_head = [&]() {
@@ -406,7 +548,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
       }
       s.reset_scalars(p.opt);
       // first estimate of the column scales: max |a_ij| over the first rows (s_i is unknown yet: 2^7 of headroom;
-      // an overflow is detected after the pass and the pass repeated with the exact maxima)
+      // an overflow is detected after the pass and the pass repeated with smaller scales)
       const float *Ap = p.A + (size_t)prob * m * n;
       const int re = m < 32 ? m : 32;
       float m0 = 0.f, m1 = 0.f;
@@ -425,26 +567,21 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
       V[kVci * kWtcNP + lane + 32] = wtc_pow2(-e1);
     };
     fetch();
-    uint32_t v = 0, sv = 0;
+    uint32_t v = 0;
     WTC_T0();
     for (;;) {
       if (lane == 0) slot_prob[(v & 1u) * kWtcSlots + slot] = prob;
-      tc_fence_before();  // my tcgen05.ld of the accumulator precede the pair's next MMAs
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[kBPairReady + q]);
-      mbar_wait_sleep(&bars[kBPairReady + q], v & 1u, 64);
+      mbar_wait_sleep(&bars[kBPairReady + q], v & 1u, 200, 1600);
       const long long pa = slot_prob[(v & 1u) * kWtcSlots + 2 * q], pb = slot_prob[(v & 1u) * kWtcSlots + 2 * q + 1];
       if (pa < 0 && pb < 0) break;
       if (slot == 0) WTC_T(0);  // waiting for the pair to be ready (the partner's solve)
       if (prob >= 0) {
-        mbar_wait_sleep(&bars[kBFrontDone + q], v & 1u, 128);
-        mbar_wait_sleep(&bars[kBAccFull + q], v & 1u, 32);
-        mbar_wait_sleep(&bars[kBStageDone + slot], sv & 1u, 32);
-        ++sv;
-        tc_fence_after();
+        mbar_wait_sleep(&bars[kBFrontDone + q], v & 1u, 400, 3200);
         if (slot == 0) WTC_T(1);  // waiting for the data pass
         const bool do_rebuild = !is_lm || s.rebuild();
-        const bool redo = wtc_after_pass(s, p.opt, n, m, ldw, V, W, stg, hp, taddr, do_rebuild, lane, p.debug);
+        const bool redo = wtc_after_pass(s, p.opt, n, m, ldw, V, W, hp, sx, do_rebuild, lane, p.debug);
         if (slot == 0) WTC_T(2);  // after-pass
         if (!redo && s.done()) {
           for (int j = lane; j < n; j += 32) p.x[(size_t)prob * n + j] = V[kVx * kWtcNP + j];
@@ -458,43 +595,58 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
       }
       ++v;
     }
-  } else if (is_helper) {
-    // ===================== helper: rows 32..63 of the slots of one side =====================
-    const int b = warp >> 1;
-    uint32_t vpar = 0, fin = 0;
+  } else if (is_drain) {
+    // ===================== drain: TMEM lanes [32 warp, +32) of every accumulator =====================
+    // warp k: side b = k / 2 (accumulator rows 64 b ..), rows [32 hh, 32 hh + 32) of the slot's H, hh = k % 2.  Only the
+    // upper triangle (col > row) is moved: to W(max, min) of the pivoted positions and to the persistent copy
+    // hp(col, row) (coalesced: lane = row).  The values stay column-scaled; the solver keeps the scale vector beside them.
+    const int b = warp >> 1, hh = warp & 1;
+    uint32_t vpar = 0, fin = 0, svm = 0;  // svm: parity of each slot's visit count (bit q)
     for (int q = 0; fin != 0xFu; q = (q + 1) & 3) {
       if ((fin >> q) & 1u) continue;
       const uint32_t par = (vpar >> q) & 1u;
-      mbar_wait_sleep(&bars[kBPairReady + q], par, 128);
+      mbar_wait_sleep(&bars[kBPairReady + q], par, 200, 1600);
       const long long pa = slot_prob[par * kWtcSlots + 2 * q], pb = slot_prob[par * kWtcSlots + 2 * q + 1];
       if (pa < 0 && pb < 0) {
         fin |= 1u << q;
         continue;
       }
+      vpar ^= 1u << q;
       const int slot = 2 * q + b;
-      if ((b ? pb : pa) >= 0) {
-        mbar_wait_sleep(&bars[kBAccFull + q], par, 128);
-        tc_fence_after();
-        if (n > 32) {
+      if ((b ? pb : pa) < 0) continue;
+      mbar_wait_sleep(&bars[kBPermReady + slot], (svm >> q) & 1u, 400, 1600);
+      svm ^= 1u << q;
+      const int lay_out = slot_cmd[slot];
+      mbar_wait_sleep(&bars[kBAccFull + q], par, 100, 800);
+      tc_fence_after();
+      if (lay_out && 32 * hh < n) {
+        const float *V = reinterpret_cast<const float *>(smem + L.vec + (size_t)slot * L.vec_stride);
+        const int *inv = reinterpret_cast<const int *>(V + kVinv * kWtcNP);
+        float *W = reinterpret_cast<float *>(smem + L.w + (size_t)slot * L.w_stride);
+        float *hp = p.hpersist + ((size_t)blockIdx.x * kWtcSlots + slot) * (size_t)wtc_hp_floats(n);
+        const int j = 32 * hh + lane;  // my row of H
+        const int aj = j < n ? inv[j] : 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(64 * b + 32 * hh) << 16) + (uint32_t)(128 * q + 64 * b);
+#pragma unroll 1
+        for (int cb = 32 * hh; cb < n; cb += 32) {
           uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(64 * b + 32) << 16) + (uint32_t)(128 * q + 64 * b + 32), v);
+          tc_ld32(taddr + (uint32_t)cb, v);
           tc_wait_ld();
-          const float *ci = reinterpret_cast<const float *>(smem + L.vec + (size_t)slot * L.vec_stride) + kVci * kWtcNP;
-          float *stg = reinterpret_cast<float *>(smem + L.stg + (size_t)slot * L.stg_stride);
-          const int j = 32 + lane;
-          const float cj = ci[j];
 #pragma unroll
-          for (int c = 0; c < kWtcStgPitch; ++c) {
-            const int col = 32 + c;
-            if (lane < kWtcStgPitch && col > j && col < n)
-              stg[lane * kWtcStgPitch + c] = __fmul_rn(__fmul_rn(__uint_as_float(v[c]), cj), ci[col]);
+          for (int c = 0; c < 32; ++c) {
+            const int col = cb + c;
+            if (col > j && col < n) {
+              const float val = __uint_as_float(v[c]);
+              const int bb = inv[col];
+              W[(aj > bb ? aj : bb) * ldw + (aj > bb ? bb : aj)] = val;
+              hp[col * ldw + j] = val;
+            }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[kBStageDone + slot]);
       }
-      vpar ^= 1u << q;
+      tc_fence_before();  // my tcgen05.ld of the accumulator precede the pair's next MMAs
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[kBWReady + slot]);
     }
   } else if (is_front) {
     // ===================== the data pass: loader, t-warps, column warps, MMA issuer =====================
@@ -502,12 +654,12 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
     uint32_t vpar = 0, fin = 0;
     uint32_t st = 0, ph = 0, os = 0, oph = 0;  // raw ring stage / phase, operand ring stage / phase
     WTC_T0();
-    const int tmk = warp == kWtcLoadWarp ? 4 : (warp == kWtcMmaWarp ? 8 : (warp == kWtcTWarp0 ? 12 : (cw == 0 ? 16 : 28)));
+    const int tmk = warp == kWtcLoadWarp ? 4 : (warp == kWtcMmaWarp ? 8 : (tw == 0 ? 12 : (cw == 0 ? 16 : 28)));
     (void)tmk;
     for (int q = 0; fin != 0xFu; q = (q + 1) & 3) {
       if ((fin >> q) & 1u) continue;
       const uint32_t par = (vpar >> q) & 1u;
-      mbar_wait_sleep(&bars[kBPairReady + q], par, 128);
+      mbar_wait_sleep(&bars[kBPairReady + q], par, 200, 1600);
       WTC_T(tmk);  // waiting for a ready pair
       const long long pa = slot_prob[par * kWtcSlots + 2 * q], pb = slot_prob[par * kWtcSlots + 2 * q + 1];
       if (pa < 0 && pb < 0) {
@@ -522,7 +674,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           const int rows = (m - row0 < kWtcRows) ? (m - row0) : kWtcRows;
           const uint32_t bytes = (uint32_t)rows * (uint32_t)n * 4u;
           if (lane == 0) {
-            mbar_wait_sleep(&bars[kBRawEmpty + st], ph ^ 1u, 32);
+            mbar_wait_sleep(&bars[kBRawEmpty + st], ph ^ 1u, 100, 400);
             WTC_T(5);
             fence_proxy_async();  // the column warps' generic reads of this stage precede the async writes
             mbar_expect_tx(&bars[kBRawFull + st], bytes * (uint32_t)((pa >= 0) + (pb >= 0)));
@@ -542,9 +694,9 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           WTC_T(6);
           if (++st == R) { st = 0; ph ^= 1u; }
         }
-      } else if (warp == kWtcTWarp0 || warp == kWtcTWarp1) {
-        // ---- lane = row: canonical t-chain, r_i, s_i; cost in row order ----
-        const int b = warp == kWtcTWarp1 ? 1 : 0;
+      } else if (tw >= 0) {
+        // ---- lane = row: t = a_i . x, r_i, s_i, my share of the cost; this warp takes every other chunk of its side ----
+        const int b = tw & 1, tpar = tw >> 1;
         const long long prob = b ? pb : pa;
         const bool active = prob >= 0;
         const int slot = 2 * q + b;
@@ -552,18 +704,24 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         const float *xs = V + kVx * kWtcNP;
         const float *yp = p.y + (size_t)(active ? prob : 0) * m;
         float cost = 0.f;  // my rows' share of sum r_i^2
-        float ynext = (active && lane < m) ? yp[lane] : 0.f;
+        float ynext = (active && tpar * kWtcRows + lane < m) ? yp[tpar * kWtcRows + lane] : 0.f;
         for (int c = 0; c < nchunks; ++c) {
+          if ((c & 1) != tpar) {  // the other warp's chunk
+            if (++st == R) { st = 0; ph ^= 1u; }
+            continue;
+          }
           const int row0 = c * kWtcRows;
           const int rows = (m - row0 < kWtcRows) ? (m - row0) : kWtcRows;
           const float ycur = ynext;
-          ynext = (active && row0 + kWtcRows + lane < m) ? yp[row0 + kWtcRows + lane] : 0.f;
-          mbar_wait_sleep(&bars[kBRawFull + st], ph, 32);
-          if (warp == kWtcTWarp0) WTC_T(13);
+          ynext = (active && row0 + 2 * kWtcRows + lane < m) ? yp[row0 + 2 * kWtcRows + lane] : 0.f;
+          mbar_wait_sleep(&bars[kBRawFull + st], ph, 100, 400);
+          if (tw == 0) WTC_T(13);
           float *arow = reinterpret_cast<float *>(smem + L.raw + (size_t)st * L.raw_stage + (size_t)b * L.raw_side) + lane * n;
           float ri = 0.f, sc = 0.f;
           if (active && lane < rows) {
-            // t = a_i . x as four interleaved partial sums (fixed combine order): the chain is the latency of this warp
+            // t = a_i . x as four interleaved partial sums (fixed combine order): the chain is the latency of this warp.
+            // (x held in registers - all of it, or the first 32 entries - was measured SLOWER: 2.0 k cycles per chunk
+            // against 1.4 k; the unrolled predicated code and its spills cost more than the broadcast loads)
             float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
             if ((n & 1) == 0) {
               const float2 *a2 = reinterpret_cast<const float2 *>(arow);
@@ -609,14 +767,14 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           srp[lane] = ri;
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[kBRsFull + st]);
-          if (warp == kWtcTWarp0) WTC_T(14);
+          if (tw == 0) WTC_T(14);
           if (++st == R) { st = 0; ph ^= 1u; }
         }
         // cost: the lanes' shares combined by a fixed butterfly
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) cost = __fadd_rn(cost, __shfl_xor_sync(0xffffffffu, cost, off));
         if (lane == 0) {
-          V[kVmisc * kWtcNP] = cost;
+          V[kVmisc * kWtcNP + tpar] = cost;  // the solver adds the two warps' shares
           mbar_arrive(&bars[kBFrontDone + q]);
         }
         __syncwarp();
@@ -640,7 +798,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         const uint32_t raw0 = smem_u32(smem + L.raw) + (uint32_t)b * L.raw_side + (uint32_t)((j < n ? j : n - 1) + 16 * grp * n) * 4u;
         const uint32_t rs0 = smem_u32(rsr) + (uint32_t)(b * kWtcRows + 16 * grp) * 4u;
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait_sleep(&bars[kBRsFull + st], ph, 32);
+          mbar_wait_sleep(&bars[kBRsFull + st], ph, 100, 400);
           mbar_wait(&bars[kBRawFull + st], ph);
           if (cw == 0) WTC_T(17);
           const uint32_t sa = raw0 + st * L.raw_stage;
@@ -676,7 +834,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[kBRawEmpty + st]);
           if (cw == 0) WTC_T(18);
-          mbar_wait_sleep(&bars[kBOpEmpty + os], oph ^ 1u, 32);
+          mbar_wait_sleep(&bars[kBOpEmpty + os], oph ^ 1u, 100, 400);
           if (cw == 0) WTC_T(19);
           const uint32_t sb = ops_u32 + os * (uint32_t)kWtcOpStageBytes + off0;
 #pragma unroll
@@ -708,7 +866,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           const uint32_t idesc = tc_idesc_f16(128);
           const uint32_t d = tmem_base + (uint32_t)(128 * q);
           for (int c = 0; c < nchunks; ++c) {
-            mbar_wait_sleep(&bars[kBOpFull + os], oph, 32);
+            mbar_wait_sleep(&bars[kBOpFull + os], oph, 100, 400);
             WTC_T(9);
             tc_fence_after();
             const uint32_t sb0 = ops_u32 + os * (uint32_t)kWtcOpStageBytes;

@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-{
-for w in 1 2 4 8 16; do ./tools/cuda/_ldlt_bench 50 $w 1; done
-./tools/cuda/_ldlt_bench 50 8 148
-./tools/cuda/_ldlt_bench 32 1 1
-./tools/cuda/_ldlt_bench 20 1 1
-} > gpurun_out/ldlt_bench.txt 2>&1
-cat gpurun_out/ldlt_bench.txt
+timeout 900 python -m pytest tests/test_gpu_wtc.py -m gpu -q --timeout 600 > gpurun_out/pytest_wtc_a.log 2>&1
+echo "rc=$?"; tail -30 gpurun_out/pytest_wtc_a.log
