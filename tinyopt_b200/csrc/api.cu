@@ -800,7 +800,7 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     int64_t grid = ctx->num_sms;
     const int64_t need = (B + kWtcSlots - 1) / kWtcSlots;
     if (grid > need) grid = need;
-    if ((rc = ensure_scratch(ctx, 7, (size_t)grid * kWtcSlots * n * wtc_ldw(n) * sizeof(float))) != TOB200_OK) return rc;
+    if ((rc = ensure_scratch(ctx, 7, (size_t)grid * kWtcSlots * wtc_hp_floats(n) * sizeof(float))) != TOB200_OK) return rc;
     p.hpersist = (float *)ctx->scratch[7];
     if ((rc = next_counter(ctx)) != TOB200_OK) return rc;
     p.counter = ctx->tile_counter;
