@@ -348,8 +348,8 @@ def run_config(name, args, env, steps, warmup, sampler, pinned, headline):
 
     # mid-n float runs take the tensor-core kernel (wtc.cuh, tolerance-held) by default: time the bit-exact
     # warp-per-problem kernel on the same inputs beside it (tob200_set_exact)
-    wtc = (family == 2 and cfg["dtype"] == "f32" and os.environ.get("TOB200_WPP_TC", "1") != "0" and n >= 13 and m >= 64
-           and (m * n) % 4 == 0)
+    wtc = (family == 2 and cfg["dtype"] == "f32" and os.environ.get("TOB200_WPP_TC", "1") != "0" and n >= 28 and m >= 192
+           and (m * n) % 4 == 0)   # api.cu: lm_run_impl (kWtcMinN, kWtcMinM)
     exact_rec = None
     if wtc:
         ctx.set_exact(True)

@@ -180,6 +180,8 @@ class Context {
     throw Error(rc, msg);
   }
   void sync() const { check(tob200_sync(ctx_), "tob200_sync"); }
+  /// Mid-n float runs (13 <= n <= 55): the bit-exact warp-per-problem kernel instead of the tensor-core one (tob200_set_exact)
+  void set_exact(bool exact = true) const { check(tob200_set_exact(ctx_, exact ? 1 : 0), "tob200_set_exact"); }
 
  private:
   tob200_ctx *ctx_ = nullptr;

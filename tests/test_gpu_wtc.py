@@ -64,9 +64,9 @@ def check(xg, rg, xo, ro, robust, min_robust=0.0, tol=1e-4):
 
 
 @pytest.mark.parametrize("B,m,n", [(1, 500, 50), (7, 500, 50), (9, 500, 50), (300, 500, 50),   # partial CTAs, idle slots, odd pair counts
-                                   (64, 64, 13), (40, 96, 27), (40, 100, 28), (33, 200, 32), (33, 132, 33),
-                                   (50, 77, 52), (40, 260, 55), (25, 501, 44),                   # rows not a multiple of the 32-row stage
-                                   (30, 100, 51), (30, 68, 35)])                                 # odd n: scalar t-chain, single last LDLT column
+                                   (64, 192, 28), (40, 196, 32), (33, 200, 32), (33, 204, 33),   # n <= 32: one drain warp per side
+                                   (50, 231, 52), (40, 260, 55), (25, 501, 44),                  # rows not a multiple of the 32-row stage
+                                   (30, 300, 51), (30, 268, 35)])                                # odd n: scalar t-chain, single last LDLT column
 def test_wtc_lm_run_parity(ctx, B, m, n):
     assert (m * n) % 4 == 0  # the shapes the tensor-core path takes (others fall back to the exact kernel: test below)
     A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=1000 * n + m)
@@ -156,12 +156,12 @@ def test_wtc_badly_scaled_columns_and_overflow_redo(ctx):
 def test_wtc_degenerate_systems_take_the_exact_route(ctx):
     """A zero column (zero pivot: Eigen's D⁺), two equal columns (rank deficient JᵀJ, solved through the damping), a NaN and
     an Inf in A: the outcomes of the exact kernel, problem by problem."""
-    B, m, n = 48, 128, 30
+    B, m, n = 48, 256, 30
     A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=31)
     A[0, :, 7] = 0.0
     A[1, :, 9] = A[1, :, 3]
     A[2, 17, 5] = np.nan
-    A[3, 64, 2] = np.inf
+    A[3, 164, 2] = np.inf
     A[4] = 0.0
     xe, re_ = gpu_run(ctx, A, y, x0, FLOAT_OPTS, exact=True)
     xg, rg = gpu_run(ctx, A, y, x0, FLOAT_OPTS)
@@ -182,9 +182,10 @@ def test_wtc_degenerate_systems_take_the_exact_route(ctx):
 
 
 def test_shapes_outside_the_tensor_core_path_run_the_exact_kernel(ctx):
-    """(m n) % 4 != 0, short problems (m < 64), double precision and `use_ldlt = 0` never reach wtc.cuh: bit-identical to the oracle."""
+    """(m n) % 4 != 0, short problems (m < 192), n < 28, double precision and `use_ldlt = 0` never reach wtc.cuh: bit-identical
+    to the oracle."""
     import tinyopt_b200 as tb
-    for (B, m, n, kw) in [(20, 75, 15, {}), (20, 40, 20, {}), (20, 128, 20, dict(use_ldlt=0))]:
+    for (B, m, n, kw) in [(20, 225, 31, {}), (20, 100, 50, {}), (20, 300, 20, {}), (20, 256, 40, dict(use_ldlt=0))]:
         A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=3)
         kw = {**FLOAT_OPTS, **kw}
         xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))

@@ -8,9 +8,9 @@
 
 namespace tob200 {
 
-constexpr int kWtcMinN = 13;       // below: thread-per-problem family
+constexpr int kWtcMinN = 28;       // below, the 4 x 4-block warp-per-problem kernels are faster (measured: DESIGN.md §5.5); the kernel itself runs n >= 13
 constexpr int kWtcMaxN = 55;       // above: large-n family
-constexpr int kWtcMinM = 64;       // shorter problems are not worth a tensor-core pass
+constexpr int kWtcMinM = 192;      // shorter problems are dominated by the solve: the exact kernel is as fast (measured)
 constexpr int kWtcSlots = 8;       // problems in flight per CTA
 constexpr int kWtcPairs = 4;       // two slots share one 128 x 128 accumulator (its two 64 x 64 diagonal blocks)
 constexpr int kWtcNP = 64;         // operand rows per slot

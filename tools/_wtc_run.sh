@@ -1,12 +1,4 @@
 mkdir -p gpurun_out
-{
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -8
-timeout 900 python bench.py --config C4 --steps 5 --warmup 3 > gpurun_out/bench_C4_r2e.json 2> gpurun_out/bench_C4_r2e.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_C4_r2e.err
-} > gpurun_out/wtc10.txt 2>&1
-cat gpurun_out/wtc10.txt
-python - <<'P'
-import json
-r=json.loads(open('gpurun_out/bench_C4_r2e.json').read().strip().splitlines()[-1])
-print(r['value'], r['ms_per_step'], json.dumps(r['roofline'])[:1500])
-print('e2e', r.get('e2e'))
-P
+timeout 900 python -m pytest tests/test_gpu_wtc.py tests/test_gpu_parity.py -m gpu -q --timeout 600 > gpurun_out/pytest_wtc_b.log 2>&1
+echo "rc=$?"; tail -12 gpurun_out/pytest_wtc_b.log
+timeout 300 python bench.py --config C4 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-probes 2>/dev/null | python -c "import sys,json; r=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(r['value'], r['roofline']['kernel'], r['roofline']['frac'], r['roofline']['traffic'])"
