@@ -54,6 +54,7 @@ struct tob200_ctx {
   int wpp_tc = 1;      // env TOB200_WPP_TC / tob200_set_exact: 1 = mid-n float lm_run on the tensor-core kernel (wtc.cuh)
   int wtc_prefetch = 6;  // env TOB200_WTC_PREFETCH: L2 prefetch distance of its loader, in 32-row stages
   int wtc_debug = 0;     // env TOB200_WTC_DEBUG (timing experiments)
+  int wtc_raw_stages = 0, wtc_op_stages = 0;  // env TOB200_WTC_RAW / TOB200_WTC_OPS: ring depths (0: the deepest that fit)
   // *_host entry points: upload / solve / download pipeline over chunks of the batch
   static constexpr int kMaxChunks = 16;
   int host_chunks = 4;  // env TOB200_HOST_CHUNKS
@@ -795,6 +796,10 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
     p.alpha = (float)alpha;
     p.alpha3 = 3.f * (float)alpha;
     p.L = wtc_smem_best(n);
+    if (ctx->wtc_raw_stages > 0 && ctx->wtc_op_stages > 0) {  // tuning override (env TOB200_WTC_RAW / TOB200_WTC_OPS)
+      const WtcSmem L2 = wtc_smem_plan(n, ctx->wtc_raw_stages, ctx->wtc_op_stages);
+      if (ctx->wtc_raw_stages <= kWtcMaxRawStages && ctx->wtc_op_stages <= kWtcMaxOpStages && L2.total <= 232448u) p.L = L2;
+    }
     p.prefetch = ctx->wtc_prefetch;
     p.debug = ctx->wtc_debug;
     int64_t grid = ctx->num_sms;
@@ -1164,6 +1169,8 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->wpp_tc = env_int("TOB200_WPP_TC", ctx->wpp_tc);
   ctx->wtc_prefetch = env_int("TOB200_WTC_PREFETCH", ctx->wtc_prefetch);
   ctx->wtc_debug = env_int("TOB200_WTC_DEBUG", ctx->wtc_debug);
+  ctx->wtc_raw_stages = env_int("TOB200_WTC_RAW", 0);
+  ctx->wtc_op_stages = env_int("TOB200_WTC_OPS", 0);
   ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
   ctx->lg_fp16 = (env_int("TOB200_LG_FP16", 1) != 0 && ctx->lg_tf32_terms == 3) ? 1 : 0;
   ctx->lg_raw_stages = env_int("TOB200_LG_RAW_STAGES", kLgRawStages);  // 2..5 measured equal on C5 (12.43 .. 12.57 ms): not the limiter

@@ -77,9 +77,14 @@ __device__ __forceinline__ int wtc_t_warp(int warp) {
 // solve) and there are twenty waiting warps: polled without a pause they took 28 % of all issued instructions, and with
 // the suspend-time hint of try_wait (NANOSLEEP.SYNCS wakes on every barrier event of the CTA) still 40 % of them plus a
 // third of the shared-memory pipe, which is the resource this kernel runs out of.  ns0: first sleep, doubled up to nsmax.
+#ifndef TOB200_WTC_SLEEP_DIV
+#define TOB200_WTC_SLEEP_DIV 1
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, unsigned ns0, unsigned nsmax = 0) {
   if (mbar_try_wait(bar, parity)) return;
   if (nsmax == 0) nsmax = 8 * ns0;
+  ns0 /= TOB200_WTC_SLEEP_DIV;
+  nsmax /= TOB200_WTC_SLEEP_DIV;
   unsigned ns = ns0;
   do {
     __nanosleep(ns);
@@ -266,8 +271,10 @@ __device__ __forceinline__ void wtc_damp(const LmScalars<float> &s, const DevOpt
 
 struct WtcSolverCtx {
   uint64_t *perm_ready, *w_ready;
-  volatile int *cmd;  // this visit: 1 = the drains lay the accumulator out, 0 = they only pass
+  volatile int *cmd;  // this visit: bit 0 = the drains lay the accumulator out (else they only pass), bit 1 = they also
+                      // write the slot's persistent copy of H_
   uint32_t sv;        // visits of this slot so far (parity of the two barriers above)
+  bool force_hp;      // the next pass must keep a persistent copy (the last one turned out to need it and had none)
 };
 
 // Everything after the data pass of one problem (mirrors wpp_after_pass / lm_after_pass).  Called when the FP32 sums of
@@ -373,6 +380,16 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
   // diagonal and the right-hand side row (column-scaled like the accumulator: H_s = S H S, b_s = -S g), the drains add
   // the off-diagonal entries at their pivoted positions.
   const bool fast = pass_rebuilt && built_ok;
+  // Will a cost-only iteration possibly follow this one (optimizer.h:295)?  Only then — or when the last attempt found the
+  // system not positive definite and had no copy to hand to the exact routine — does H_ have to outlive the accumulator:
+  // the 10 KB per problem the drains would otherwise write every pass are 7 % of the kernel's DRAM traffic and 8 % of its
+  // shared-memory-pipe wavefronts.
+#ifdef TOB200_WTC_ALWAYS_PERSIST
+  const bool persist = fast;
+#else
+  const bool persist = fast && (sx.force_hp || (!(cost - s.final_cost < 0.0) && !(s.flags & kFlagLastWasSuccess)));
+#endif
+  sx.force_hp = false;
   if (fast) {
     wtc_damp(s, o, true, n, ldw, dg, hp, dd, lane);
     wpp_pivot_order(dd, n, perm, inv, lane);
@@ -381,11 +398,13 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
       const float c = cs[j];
       W[a * ldw + a] = __fmul_rn(__fmul_rn(dd[j], c), c);
       W[n * ldw + a] = __fmul_rn(-g[j], c);
-      hp[j * ldw + j] = dd[j];
-      hp[n * ldw + j] = ci[j];
+      if (persist) {
+        hp[j * ldw + j] = dd[j];
+        hp[n * ldw + j] = ci[j];
+      }
     }
   }
-  release_drains(fast ? 1 : 0);
+  release_drains(fast ? (persist ? 3 : 1) : 0);
   WTC_TA(22);
   wait_drains();
   WTC_TA(23);
@@ -407,6 +426,14 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
           WTC_TA(25);
         }
         if (!ok) {  // not positive definite (or NaN): let the exact routine decide; W's upper triangle must stay zero
+          if (!persist) {
+            // no copy of H_ was kept: repeat the data pass once with the copy requested (rare: singular / indefinite systems)
+            for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;
+            __syncwarp();
+            s.num_builds--;
+            sx.force_hp = true;
+            return true;
+          }
           ok = wtc_solve_exact(W, ldw, n, V, hp, lane);
           for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;
           __syncwarp();
@@ -522,6 +549,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
     sx.w_ready = &bars[kBWReady + slot];
     sx.cmd = &slot_cmd[slot];
     sx.sv = 0;
+    sx.force_hp = false;
     for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;  // the fast LDL^T reads (and multiplies by zero) above the diagonal
 
     // the first chunks of the problem's next pass on their way into L2 while the other pairs stream
@@ -619,7 +647,8 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
       const int lay_out = slot_cmd[slot];
       mbar_wait_sleep(&bars[kBAccFull + q], par, 100, 800);
       tc_fence_after();
-      if (lay_out && 32 * hh < n) {
+      if ((lay_out & 1) && 32 * hh < n) {
+        const bool keep = (lay_out & 2) != 0;
         const float *V = reinterpret_cast<const float *>(smem + L.vec + (size_t)slot * L.vec_stride);
         const int *inv = reinterpret_cast<const int *>(V + kVinv * kWtcNP);
         float *W = reinterpret_cast<float *>(smem + L.w + (size_t)slot * L.w_stride);
@@ -636,10 +665,15 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           for (int c = 0; c < 32; ++c) {
             const int col = cb + c;
             if (col > j && col < n) {
-              const float val = __uint_as_float(v[c]);
               const int bb = inv[col];
-              W[(aj > bb ? aj : bb) * ldw + (aj > bb ? bb : aj)] = val;
-              hp[col * ldw + j] = val;
+              W[(aj > bb ? aj : bb) * ldw + (aj > bb ? bb : aj)] = __uint_as_float(v[c]);
+            }
+          }
+          if (keep) {  // (its own loop: a predicate on every store of the loop above cost 2 % of the kernel)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int col = cb + c;
+              if (col > j && col < n) hp[col * ldw + j] = __uint_as_float(v[c]);
             }
           }
         }

@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_wtc.py tests/test_gpu_parity.py -m gpu -q --timeout 600 > gpurun_out/pytest_wtc_b.log 2>&1
-echo "rc=$?"; tail -12 gpurun_out/pytest_wtc_b.log
-timeout 300 python bench.py --config C4 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-probes 2>/dev/null | python -c "import sys,json; r=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(r['value'], r['roofline']['kernel'], r['roofline']['frac'], r['roofline']['traffic'])"
+{
+for rep in 1 2; do
+for v in "" base; do
+  if [ -n "$v" ]; then export TOB200_LIB_OVERRIDE=$PWD/tinyopt_b200/libtinyopt_b200_$v.so; else unset TOB200_LIB_OVERRIDE; fi
+  echo "== variant '$v'"; timeout 120 python tools/wtc_check.py 131072 500 50 3 2>&1 | sed -n 2p
+done
+done
+} > gpurun_out/wtc16.txt 2>&1
+cat gpurun_out/wtc16.txt
