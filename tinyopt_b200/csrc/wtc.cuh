@@ -77,6 +77,10 @@ __device__ __forceinline__ int wtc_t_warp(int warp) {
 // solve) and there are twenty waiting warps: polled without a pause they took 28 % of all issued instructions, and with
 // the suspend-time hint of try_wait (NANOSLEEP.SYNCS wakes on every barrier event of the CTA) still 40 % of them plus a
 // third of the shared-memory pipe, which is the resource this kernel runs out of.  ns0: first sleep, doubled up to nsmax.
+#ifndef TOB200_WTC_COL_ALT
+#define TOB200_WTC_COL_ALT 0
+#endif
+constexpr int kWtcColArrive = TOB200_WTC_COL_ALT ? kWtcColWarps / 2 : kWtcColWarps;  // column warps that work on one chunk
 #ifndef TOB200_WTC_SLEEP_DIV
 #define TOB200_WTC_SLEEP_DIV 1
 #endif
@@ -207,6 +211,103 @@ __device__ __forceinline__ bool wtc_ldlt_fast(float *W, int ldw, int n, float *d
   return !bad;
 }
 
+// The same factorisation, FOUR columns per step (13 steps at n = 50 instead of 25: the per-step overhead — T rows, two warp
+// barriers, loop control — is what a lone warp pays for, tools/cuda/ldlt_bench.cu).  The 4 x 4 pivot block travels by ten
+// shuffles and is factorised redundantly in every lane (four MUFU.RCP in the chain); k is a multiple of four, so a row's
+// four new entries are one 16-byte load and one 16-byte store.  T: 4 x 64 floats.  Same result contract as wtc_ldlt_fast.
+__device__ __forceinline__ bool wtc_ldlt_fast4(float *W, int ldw, int n, float *dvec, float *T, int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  bool bad = false;
+  const int nr = n + 1;
+  for (int k = 0; k < n; k += 4) {
+    const int ncol = n - k < 4 ? n - k : 4;  // columns of this step (the last step may have fewer)
+    for (int j = lane; j < k; j += 32) {
+      const float d = dvec[j];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) T[c * kWtcNP + j] = c < ncol ? __fmul_rn(d, W[(k + c) * ldw + j]) : 0.f;
+    }
+    __syncwarp();
+    const int r0 = k + lane, r1 = r0 + 32;
+    const bool h0 = r0 < nr, h1 = r1 < nr;
+    float *w0 = W + (h0 ? r0 : k) * ldw, *w1 = W + (h1 ? r1 : k) * ldw;
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int j = 0; j < k; j += 4) {
+      const float4 a4 = *reinterpret_cast<const float4 *>(w0 + j), b4 = *reinterpret_cast<const float4 *>(w1 + j);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 t4 = *reinterpret_cast<const float4 *>(T + c * kWtcNP + j);
+        s0[c] = __fmaf_rn(a4.x, t4.x, s0[c]); s1[c] = __fmaf_rn(b4.x, t4.x, s1[c]);
+        s0[c] = __fmaf_rn(a4.y, t4.y, s0[c]); s1[c] = __fmaf_rn(b4.y, t4.y, s1[c]);
+        s0[c] = __fmaf_rn(a4.z, t4.z, s0[c]); s1[c] = __fmaf_rn(b4.z, t4.z, s1[c]);
+        s0[c] = __fmaf_rn(a4.w, t4.w, s0[c]); s1[c] = __fmaf_rn(b4.w, t4.w, s1[c]);
+      }
+    }
+    const float4 a4 = *reinterpret_cast<const float4 *>(w0 + k), b4 = *reinterpret_cast<const float4 *>(w1 + k);
+    float e0[4] = {a4.x - s0[0], a4.y - s0[1], a4.z - s0[2], a4.w - s0[3]};
+    float e1[4] = {b4.x - s1[0], b4.y - s1[1], b4.z - s1[2], b4.w - s1[3]};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c >= ncol) { e0[c] = 0.f; e1[c] = 0.f; }
+    // pivot block P (lower triangle; rows k .. k + 3 are lanes 0 .. 3); missing columns become identity columns
+    const float p00 = __shfl_sync(kFull, e0[0], 0);
+    float p10 = __shfl_sync(kFull, e0[0], 1), p11 = __shfl_sync(kFull, e0[1], 1);
+    float p20 = __shfl_sync(kFull, e0[0], 2), p21 = __shfl_sync(kFull, e0[1], 2), p22 = __shfl_sync(kFull, e0[2], 2);
+    float p30 = __shfl_sync(kFull, e0[0], 3), p31 = __shfl_sync(kFull, e0[1], 3), p32 = __shfl_sync(kFull, e0[2], 3),
+          p33 = __shfl_sync(kFull, e0[3], 3);
+    if (ncol < 2) { p10 = 0.f; p11 = 1.f; }   // rows k + ncol .. are not pivot rows (row n is the right-hand side)
+    if (ncol < 3) { p20 = 0.f; p21 = 0.f; p22 = 1.f; }
+    if (ncol < 4) { p30 = 0.f; p31 = 0.f; p32 = 0.f; p33 = 1.f; }
+    const float q0 = wtc_rcp(p00);
+    const float l10 = __fmul_rn(p10, q0), l20 = __fmul_rn(p20, q0), l30 = __fmul_rn(p30, q0);
+    const float d1 = __fmaf_rn(-l10, p10, p11);
+    const float q1 = wtc_rcp(d1);
+    const float m21 = __fmaf_rn(-l20, p10, p21), m31 = __fmaf_rn(-l30, p10, p31);
+    const float l21 = __fmul_rn(m21, q1), l31 = __fmul_rn(m31, q1);
+    const float d2 = __fmaf_rn(-l21, m21, __fmaf_rn(-l20, p20, p22));
+    const float q2 = wtc_rcp(d2);
+    const float m32 = __fmaf_rn(-l31, m21, __fmaf_rn(-l30, p20, p32));
+    const float l32 = __fmul_rn(m32, q2);
+    const float d3 = __fmaf_rn(-l32, m32, __fmaf_rn(-l31, m31, __fmaf_rn(-l30, p30, p33)));
+    const float q3 = wtc_rcp(d3);
+    bad = bad || !(p00 > 0.f) || !(d1 > 0.f) || !(d2 > 0.f) || !(d3 > 0.f);
+    // my rows: L_rc = M_rc / D_c, M_rc = e_rc - sum_{c' < c} L_rc' M_{k+c, c'}
+    float x0[4], x1[4];
+    x0[0] = __fmul_rn(e0[0], q0);
+    x1[0] = __fmul_rn(e1[0], q0);
+    x0[1] = __fmul_rn(__fmaf_rn(-x0[0], p10, e0[1]), q1);
+    x1[1] = __fmul_rn(__fmaf_rn(-x1[0], p10, e1[1]), q1);
+    x0[2] = __fmul_rn(__fmaf_rn(-x0[1], m21, __fmaf_rn(-x0[0], p20, e0[2])), q2);
+    x1[2] = __fmul_rn(__fmaf_rn(-x1[1], m21, __fmaf_rn(-x1[0], p20, e1[2])), q2);
+    x0[3] = __fmul_rn(__fmaf_rn(-x0[2], m32, __fmaf_rn(-x0[1], m31, __fmaf_rn(-x0[0], p30, e0[3]))), q3);
+    x1[3] = __fmul_rn(__fmaf_rn(-x1[2], m32, __fmaf_rn(-x1[1], m31, __fmaf_rn(-x1[0], p30, e1[3]))), q3);
+    if (ncol == 4 && lane >= 4) {
+      if (h0) *reinterpret_cast<float4 *>(w0 + k) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+    } else if (h0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < ncol && lane > c) w0[k + c] = x0[c];
+    }
+    if (h1) {
+      if (ncol == 4) {
+        *reinterpret_cast<float4 *>(w1 + k) = make_float4(x1[0], x1[1], x1[2], x1[3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < ncol) w1[k + c] = x1[c];
+      }
+    }
+    if (lane == 0) {
+      dvec[k] = p00;
+      if (ncol > 1) dvec[k + 1] = d1;
+      if (ncol > 2) dvec[k + 2] = d2;
+      if (ncol > 3) dvec[k + 3] = d3;
+    }
+    __syncwarp();
+  }
+  return !bad;
+}
+
 // x <- L^-T z (z = row n of W), two columns per step, then dx[perm[i]] = x_i * cs[perm[i]] (undoing the column scaling)
 __device__ __forceinline__ void wtc_back_subst(const float *W, int ldw, int n, const int *perm, const float *cs, float *dx,
                                                int lane) {
@@ -267,6 +368,16 @@ __device__ __forceinline__ void wtc_damp(const LmScalars<float> &s, const DevOpt
     dd[j] = damp ? (float)((double)base * sc) : base;
   }
   __syncwarp();
+}
+
+// sum of squares of a shared vector: lane shares + a fixed butterfly (the bit-exact kernels sum sequentially: 50 dependent fmas
+// of one lane; here the order only has to be deterministic)
+__device__ __forceinline__ float wtc_sqnorm(const float *v, int n, int lane) {
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s = __fmaf_rn(v[j], v[j], s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, off));
+  return s;
 }
 
 struct WtcSolverCtx {
@@ -392,6 +503,8 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
   sx.force_hp = false;
   if (fast) {
     wtc_damp(s, o, true, n, ldw, dg, hp, dd, lane);
+    // (re-using the previous pass's order when it still sorts the new diagonal was measured slower: the diagonal entries of a
+    //  well-scaled problem are nearly equal, so their order changes with every step and the check is pure overhead)
     wpp_pivot_order(dd, n, perm, inv, lane);
     for (int j = lane; j < n; j += 32) {
       const int a = inv[j];
@@ -420,7 +533,7 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
           __syncwarp();
           ok = true;
         } else {
-          ok = wtc_ldlt_fast(W, ldw, n, dvec, dxs, lane);
+          ok = wtc_ldlt_fast4(W, ldw, n, dvec, dxs, lane);
           WTC_TA(24);
           if (ok) wtc_back_subst(W, ldw, n, perm, cs, dxs, lane);
           WTC_TA(25);
@@ -455,8 +568,8 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
 
   double dx_norm2 = 0.0, grad_norm2 = 0.0;
   if (!solver_failed) {
-    dx_norm2 = (double)wpp_sqnorm<float>(dxs, n, lane);
-    if (o.min_grad_norm2_f > 0.0f) grad_norm2 = (double)wpp_sqnorm<float>(g, n, lane);
+    dx_norm2 = (double)wtc_sqnorm(dxs, n, lane);
+    if (o.min_grad_norm2_f > 0.0f) grad_norm2 = (double)wtc_sqnorm(g, n, lane);
   }
   bool success, has_dx;
   lm_finish_step(s, o, early_return, solver_failed, cost, nres, dx_norm2, grad_norm2, success, has_dx);
@@ -501,11 +614,11 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
   if (tid == 0) {
     for (int s = 0; s < kWtcMaxRawStages; ++s) {
       mbar_init(&bars[kBRawFull + s], 1);
-      mbar_init(&bars[kBRawEmpty + s], kWtcColWarps);
+      mbar_init(&bars[kBRawEmpty + s], kWtcColArrive);
       mbar_init(&bars[kBRsFull + s], 2);
     }
     for (int s = 0; s < kWtcMaxOpStages; ++s) {
-      mbar_init(&bars[kBOpFull + s], kWtcColWarps);
+      mbar_init(&bars[kBOpFull + s], kWtcColArrive);
       mbar_init(&bars[kBOpEmpty + s], 1);
     }
     for (int q = 0; q < kWtcPairs; ++q) {
@@ -569,7 +682,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         return;
       }
       prob = (long long)t;
-      prefetch_head();
+        prefetch_head();
       for (int j = lane; j < kWtcNP; j += 32) {
         V[kVx * kWtcNP + j] = j < n ? p.x[(size_t)prob * n + j] : 0.f;
         V[kVlastdx * kWtcNP + j] = 0.f;
@@ -827,8 +940,68 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         const unsigned long long fs2 = f2_pack(fs, fs);
         unsigned long long g2 = 0ull, d2 = 0ull;  // (even rows, odd rows) partial sums
         uint32_t mxh = 0u;                        // max |hi| of my column, per half
-        const uint32_t off0 = (uint32_t)(2 * grp) * 2048u + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
         const uint32_t n4 = (uint32_t)n * 4u;
+#if TOB200_WTC_COL_ALT
+        // Variant: the two sets of four warps take ALTERNATE chunks (all 32 rows of a chunk each): half the barrier
+        // operations per element and two chunk periods to finish one, operands stored K chunk by K chunk.
+        const uint32_t off0 = (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
+        const uint32_t raw0 = smem_u32(smem + L.raw) + (uint32_t)b * L.raw_side + (uint32_t)(j < n ? j : n - 1) * 4u;
+        const uint32_t rs0 = smem_u32(rsr) + (uint32_t)(b * kWtcRows) * 4u;
+        for (int c = 0; c < nchunks; ++c) {
+          if ((c & 1) != grp) {
+            if (++st == R) { st = 0; ph ^= 1u; }
+            if (++os == S) { os = 0; oph ^= 1u; }
+            continue;
+          }
+          mbar_wait_sleep(&bars[kBRsFull + st], ph, 100, 400);
+          mbar_wait(&bars[kBRawFull + st], ph);
+          mbar_wait_sleep(&bars[kBOpEmpty + os], oph ^ 1u, 100, 400);
+          if (cw == 0) WTC_T(17);
+          const uint32_t sa = raw0 + st * L.raw_stage;
+          const uint32_t ss = rs0 + st * (uint32_t)(2 * kWtcRows * 4), sr = ss + (uint32_t)kRsrHalf * 4u;
+          const uint32_t sb = ops_u32 + os * (uint32_t)kWtcOpStageBytes + off0;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            unsigned long long sc2[4], r2[4];
+            lds_f2x2(ss + (uint32_t)h * 32u, sc2[0], sc2[1]);
+            lds_f2x2(ss + (uint32_t)h * 32u + 16u, sc2[2], sc2[3]);
+            lds_f2x2(sr + (uint32_t)h * 32u, r2[0], r2[1]);
+            lds_f2x2(sr + (uint32_t)h * 32u + 16u, r2[2], r2[3]);
+            float a[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a[t] = lds_f32(sa + (uint32_t)(8 * h + t) * n4);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) {
+              const unsigned long long jv = f2_mul(f2_pack(a[2 * t2], a[2 * t2 + 1]), sc2[t2]);  // J_ij = s_i a_ij
+              g2 = f2_fma(jv, r2[t2], g2);
+              d2 = f2_fma(jv, jv, d2);
+              const unsigned long long vv = f2_mul(jv, fs2);  // * 2^e_j (exact)
+              float v0, v1;
+              f2_unpack(vv, v0, v1);
+              const uint32_t hh = lg_pack_h2(v0, v1);
+              const unsigned long long ll = f2_sub(vv, f2_pack(lg_h_lo(hh), lg_h_hi(hh)));  // exact
+              float l0, l1;
+              f2_unpack(ll, l0, l1);
+              hi[t2] = hh;
+              lo[t2] = lg_pack_h2(l0, l1);
+              mxh = h2_absmax(mxh, hh);
+            }
+            sts_v4u(sb + (uint32_t)h * 2048u, hi[0], hi[1], hi[2], hi[3]);
+            sts_v4u(sb + (uint32_t)(kWtcOpStageBytes / 2) + (uint32_t)h * 2048u, lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bars[kBRawEmpty + st]);
+            mbar_arrive(&bars[kBOpFull + os]);
+          }
+          if (cw == 0) WTC_T(18);
+          if (++st == R) { st = 0; ph ^= 1u; }
+          if (++os == S) { os = 0; oph ^= 1u; }
+        }
+#else
+        const uint32_t off0 = (uint32_t)(2 * grp) * 2048u + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
         const uint32_t raw0 = smem_u32(smem + L.raw) + (uint32_t)b * L.raw_side + (uint32_t)((j < n ? j : n - 1) + 16 * grp * n) * 4u;
         const uint32_t rs0 = smem_u32(rsr) + (uint32_t)(b * kWtcRows + 16 * grp) * 4u;
         for (int c = 0; c < nchunks; ++c) {
@@ -883,6 +1056,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           if (++st == R) { st = 0; ph ^= 1u; }
           if (++os == S) { os = 0; oph ^= 1u; }
         }
+#endif
         {
           float ge, go, de, dO;
           f2_unpack(g2, ge, go);

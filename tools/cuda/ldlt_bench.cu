@@ -50,12 +50,29 @@ __global__ void bench(const float *H, int n, int ldw, int reps, long long *out) 
     for (int j = lane; j < n; j += 32) W[n * ldw + inv[j]] = g[j];
     __syncwarp();
     long long t2 = clock64();
-    ok = wtc_ldlt_fast(W, ldw, n, temp, vec + 8 * 64, lane) && ok;
+    ok = wtc_ldlt_fast(W, ldw, n, temp, tb, lane) && ok;
     long long t3 = clock64();
     wtc_back_subst(W, ldw, n, perm, cs1, x, lane);
     long long t4 = clock64();
     tf2 += t3 - t2; ts2 += t4 - t3;
   }
+  long long tf4 = 0;
+  for (int r = 0; r < reps; ++r) {
+    for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e / n, j = e % n;
+      if (j <= i) { const int a = inv[i], b = inv[j]; W[(a > b ? a : b) * ldw + (a > b ? b : a)] = H[i * n + j]; }
+    }
+    for (int j = lane; j < n; j += 32) W[n * ldw + inv[j]] = g[j];
+    __syncwarp();
+    long long t2 = clock64();
+    ok = wtc_ldlt_fast4(W, ldw, n, temp, vec + 8 * 64, lane) && ok;
+    long long t3 = clock64();
+    wtc_back_subst(W, ldw, n, perm, cs1, x, lane);
+    tf4 += t3 - t2;
+  }
+  if (lane == 0 && blockIdx.x == 0 && w == 0) { out[113] = tf4 / reps; out[114] = (long long)(x[0] * 1e6f); }
   if (lane == 0 && blockIdx.x == 0 && w == 0) { out[110] = tf2 / reps; out[111] = ts2 / reps; out[112] = (long long)(x[0] * 1e6f); }
   if (lane == 0 && blockIdx.x == 0) { out[3 * w] = tp / reps; out[3 * w + 1] = tf / reps; out[3 * w + 2] = ts / reps; }
   if (!ok && lane == 0) out[100] = 1;
@@ -85,6 +102,7 @@ int main(int argc, char **argv) {
   { long long pr[8]; cudaMemcpyFromSymbol(pr, g_ldlt_prof, sizeof(pr)); int steps = 50 * warps * blocks * ((n + 1) / 2);
     printf("   fast factor per step (cycles, lane 0): sweep + next T %lld pivot block %lld finish + store + sync %lld\n", pr[1] / steps, pr[2] / steps, pr[3] / steps); }
 #endif
+  printf("   fast4: factor %lld x0=%lld\n", out[113], out[114]);
   printf("   fast: factor %lld back-substitution %lld x0=%lld\n", out[110], out[111], out[112]);
   if (warps > 1) printf("   last warp: pivot %lld factor %lld solve %lld\n", out[3 * (warps - 1)], out[3 * (warps - 1) + 1], out[3 * (warps - 1) + 2]);
   return 0;
