@@ -42,6 +42,11 @@
 
 namespace tob200 {
 
+#ifndef TOB200_WTC_SWEEP_UNROLL
+#define TOB200_WTC_SWEEP_UNROLL 1  // the LDL^T sweep's j loop (2 measured: see DESIGN.md)
+#endif
+constexpr int kWtcSweepUnroll = TOB200_WTC_SWEEP_UNROLL;
+
 enum WtcVec {
   kVx = 0, kVlastdx, kVg, kVdg, kVdd, kVtemp, kVdxs, kVtb1, kVtb2, kVtb3, kVperm, kVinv, kVcs, kVci,
   kVgp0, kVgp1, kVdp0, kVdp1, kVmp0, kVmp1, kVmisc
@@ -231,7 +236,7 @@ __device__ __forceinline__ bool wtc_ldlt_fast4(float *W, int ldw, int n, float *
     const bool h0 = r0 < nr, h1 = r1 < nr;
     float *w0 = W + (h0 ? r0 : k) * ldw, *w1 = W + (h1 ? r1 : k) * ldw;
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll kWtcSweepUnroll
     for (int j = 0; j < k; j += 4) {
       const float4 a4 = *reinterpret_cast<const float4 *>(w0 + j), b4 = *reinterpret_cast<const float4 *>(w1 + j);
 #pragma unroll
@@ -380,6 +385,33 @@ __device__ __forceinline__ float wtc_sqnorm(const float *v, int n, int lane) {
   return s;
 }
 
+// Eigen's pivot order of the damped diagonal (pos2orig in perm, orig2pos in inv), rank-count fast path of
+// wpp_pivot_order with half the work per key: position = number of larger keys; ties and NaNs show up as two keys landing
+// on one position (checked after the fact: perm[inv[i]] == i) or as a zero key, and go through the exact replay of wpp.cuh.
+// keys: 64 words of scratch.
+__device__ __forceinline__ void wtc_pivot_order(const float *dd, int n, int *perm, int *inv, uint32_t *keys, int lane) {
+  const int i0 = lane, i1 = lane + 32;
+  uint32_t k0 = 0, k1 = 0;  // 0: NaN or beyond n, otherwise 1 + bits(|d|) (monotone in |d|)
+  if (i0 < n) { const float v = fabsf(dd[i0]); k0 = (v != v) ? 0u : __float_as_uint(v) + 1u; }
+  if (i1 < n) { const float v = fabsf(dd[i1]); k1 = (v != v) ? 0u : __float_as_uint(v) + 1u; }
+  keys[i0] = k0;
+  keys[i1] = k1;
+  __syncwarp();
+  int gt0 = 0, gt1 = 0;
+  const int n4 = (n + 3) & ~3;  // keys beyond n are 0: never greater
+#pragma unroll 2
+  for (int j = 0; j < n4; j += 4) {
+    const uint4 kj = *reinterpret_cast<const uint4 *>(keys + j);
+    gt0 += (kj.x > k0) + (kj.y > k0) + (kj.z > k0) + (kj.w > k0);
+    gt1 += (kj.x > k1) + (kj.y > k1) + (kj.z > k1) + (kj.w > k1);
+  }
+  if (i0 < n) { perm[gt0] = i0; inv[i0] = gt0; }
+  if (i1 < n) { perm[gt1] = i1; inv[i1] = gt1; }
+  __syncwarp();
+  const bool amb = (i0 < n && (k0 == 0u || perm[gt0] != i0)) || (i1 < n && (k1 == 0u || perm[gt1] != i1));
+  if (__any_sync(0xffffffffu, amb)) wpp_pivot_order(dd, n, perm, inv, lane);
+}
+
 struct WtcSolverCtx {
   uint64_t *perm_ready, *w_ready;
   volatile int *cmd;  // this visit: bit 0 = the drains lay the accumulator out (else they only pass), bit 1 = they also
@@ -505,7 +537,7 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
     wtc_damp(s, o, true, n, ldw, dg, hp, dd, lane);
     // (re-using the previous pass's order when it still sorts the new diagonal was measured slower: the diagonal entries of a
     //  well-scaled problem are nearly equal, so their order changes with every step and the check is pure overhead)
-    wpp_pivot_order(dd, n, perm, inv, lane);
+    wtc_pivot_order(dd, n, perm, inv, reinterpret_cast<uint32_t *>(dxs), lane);  // (dxs is free until the factorisation)
     for (int j = lane; j < n; j += 32) {
       const int a = inv[j];
       const float c = cs[j];
