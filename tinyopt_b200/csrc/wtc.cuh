@@ -75,7 +75,7 @@ constexpr int kWtcDrainWarps = 4, kWtcSolveWarp0 = 4, kWtcLoadWarp = 12, kWtcMma
 __device__ __forceinline__ int wtc_col_warp(int warp) { return (warp >= kWtcColWarp0 && warp < kWtcColWarp0 + kWtcColWarps) ? warp - kWtcColWarp0 : -1; }
 // t-warps: 14, 15 take the even chunks of side 0 / 1, 24, 25 the odd ones (-> side + 2 * parity, or -1)
 __device__ __forceinline__ int wtc_t_warp(int warp) {
-  return warp == kWtcTWarp0 ? 0 : (warp == kWtcTWarp1 ? 1 : (warp == kWtcTWarp2 ? 2 : (warp == kWtcTWarp3 ? 3 : -1)));
+  return warp == kWtcTWarp0 ? 0 : (warp == kWtcTWarp1 ? 1 : ((warp >= kWtcTWarp2 && warp < kWtcTWarp2 + kWtcTWarps - 2) ? 2 + warp - kWtcTWarp2 : -1));
 }
 
 // mbarrier wait with an exponentially growing sleep between polls.  The waits of this kernel are long (a data pass, a
@@ -431,7 +431,7 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
   float *dd = V + kVdd * kWtcNP, *dvec = V + kVtemp * kWtcNP, *dxs = V + kVdxs * kWtcNP;
   int *perm = reinterpret_cast<int *>(V + kVperm * kWtcNP), *inv = reinterpret_cast<int *>(V + kVinv * kWtcNP);
   float *cs = V + kVcs * kWtcNP, *ci = V + kVci * kWtcNP;
-  const float cost_t = __fadd_rn(V[kVmisc * kWtcNP], V[kVmisc * kWtcNP + 1]);
+  const float cost_t = __fadd_rn(__fadd_rn(V[kVmisc * kWtcNP], V[kVmisc * kWtcNP + 1]), V[kVmisc * kWtcNP + 2]);  // the t-warps' shares
 #ifdef TOB200_WTC_TIMING
   const bool tm_on = (threadIdx.x >> 5) == kWtcSolveWarp0;
 #define WTC_TA(k) do { if (tm_on) WTC_T(k); } while (0)
@@ -883,16 +883,17 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         const float *xs = V + kVx * kWtcNP;
         const float *yp = p.y + (size_t)(active ? prob : 0) * m;
         float cost = 0.f;  // my rows' share of sum r_i^2
+        constexpr int kTStride = kWtcTWarps / 2;  // this warp takes every kTStride-th chunk of its side
         float ynext = (active && tpar * kWtcRows + lane < m) ? yp[tpar * kWtcRows + lane] : 0.f;
         for (int c = 0; c < nchunks; ++c) {
-          if ((c & 1) != tpar) {  // the other warp's chunk
+          if (kTStride > 1 && (c % kTStride) != tpar) {  // another warp's chunk
             if (++st == R) { st = 0; ph ^= 1u; }
             continue;
           }
           const int row0 = c * kWtcRows;
           const int rows = (m - row0 < kWtcRows) ? (m - row0) : kWtcRows;
           const float ycur = ynext;
-          ynext = (active && row0 + 2 * kWtcRows + lane < m) ? yp[row0 + 2 * kWtcRows + lane] : 0.f;
+          ynext = (active && row0 + kTStride * kWtcRows + lane < m) ? yp[row0 + kTStride * kWtcRows + lane] : 0.f;
           mbar_wait_sleep(&bars[kBRawFull + st], ph, 100, 400);
           if (tw == 0) WTC_T(13);
           float *arow = reinterpret_cast<float *>(smem + L.raw + (size_t)st * L.raw_stage + (size_t)b * L.raw_side) + lane * n;
@@ -954,6 +955,8 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         for (int off = 16; off > 0; off >>= 1) cost = __fadd_rn(cost, __shfl_xor_sync(0xffffffffu, cost, off));
         if (lane == 0) {
           V[kVmisc * kWtcNP + tpar] = cost;  // the solver adds the two warps' shares
+          if (kTStride == 1) V[kVmisc * kWtcNP + 1] = 0.f;
+          if (kTStride < 3) V[kVmisc * kWtcNP + 2 + tpar] = 0.f;
           mbar_arrive(&bars[kBFrontDone + q]);
         }
         __syncwarp();

@@ -18,8 +18,11 @@ constexpr int kWtcRows = 32;       // rows of A per stage == two K = 16 steps of
 constexpr int kWtcMaxRawStages = 5;
 constexpr int kWtcMaxOpStages = 3;
 constexpr int kWtcColWarps = 8;    // (row half of the stage) x (32 operand rows)
-constexpr int kWtcThreads = 832;   // 26 warps, roles in wtc.cuh
-constexpr int kWtcTWarps = 4;      // two per side, alternating chunks
+#ifndef TOB200_WTC_TWARPS
+#define TOB200_WTC_TWARPS 4
+#endif
+constexpr int kWtcTWarps = TOB200_WTC_TWARPS;             // 4: two per side, alternating chunks; 2: one per side
+constexpr int kWtcThreads = (24 + kWtcTWarps - 2) * 32;   // 24 / 26 / 28 warps (80 / 72 / 72 registers), roles in wtc.cuh
 constexpr int kWtcOpStageBytes = 2 * 128 * kWtcRows * 2;  // hi + lo, 128 operand rows, FP16
 constexpr int kWtcVecs = 21;       // 64-float vectors per slot (enum WtcVec in wtc.cuh)
 
