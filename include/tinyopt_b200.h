@@ -123,7 +123,7 @@ int64_t tob200_launch_count(const tob200_ctx *ctx);
 /* Device time in ms of the last compute entry point (CUDA events on the context's stream;
  * blocks until that work has finished). */
 int tob200_last_elapsed_ms(tob200_ctx *ctx, float *ms);
-/* exact != 0: tob200_lm_run_f32 for 28 <= n <= 55 (and m >= 192, m n % 4 == 0, use_ldlt) runs the warp-per-problem FFMA kernel, whose every sum is the CPU
+/* exact != 0: tob200_lm_run_f32 and tob200_build_solve_f32 for 28 <= n <= 55 (and m >= 192, m n % 4 == 0, use_ldlt) run the warp-per-problem FFMA kernel, whose every sum is the CPU
  * restatement's canonical fma chain (bit-identical results), instead of the default tensor-core kernel (wtc.cuh:
  * H = J^T J off-diagonal from tcgen05.mma with an FP16 hi / lo split, held to the float tolerance of 1e-4).  The
  * environment variable TOB200_WPP_TC=0 selects the same at tob200_create time. */

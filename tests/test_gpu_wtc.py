@@ -218,3 +218,40 @@ def test_wtc_full_c4_shard_properties(ctx):
     ctx.set_exact(False)
     assert (ref.results["num_iters"] == r["num_iters"]).mean() >= 0.999
     assert rel_err_rows(out.x.cpu().numpy(), ref.x.cpu().numpy()).max() <= 1e-4
+
+
+# ---- tob200_build_solve_f32 on the tensor-core kernel (materialised J, r: the SolverType seam's Build + Solve) ----------
+def oracle_build_solve_batch(J, r, lam):
+    B, m, n = J.shape
+    dx = np.zeros((B, n), J.dtype); cost = np.zeros(B); st = np.zeros(B, np.int32)
+    H = np.zeros((B, n, n), J.dtype); g = np.zeros((B, n), J.dtype)
+    for p in range(B):
+        o = O.build_solve(J[p], r[p], float(lam[p]))
+        st[p] = o["status"]; cost[p] = o["cost"]; H[p] = o["H"]; g[p] = o["g"]
+        if o["status"] == 0:
+            dx[p] = o["dx"]
+    return dx, cost, st, H, g
+
+
+@pytest.mark.parametrize("B,m,n", [(64, 500, 50), (9, 231, 52), (40, 260, 55), (33, 204, 33), (50, 192, 28), (30, 300, 51)])
+def test_wtc_build_solve_parity(ctx, B, m, n):
+    import tinyopt_b200 as tb
+    A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=11)
+    r, J = O.synth_eval(A, y, x0)
+    lam = np.full(B, np.float32(1e-4), np.float32)
+    lam[::3] = 0
+    if B > 8:
+        J[5, :, 3] = 0.0      # a zero column: zero pivot, Eigen's D+ (the exact route, after one repeated pass)
+        J[7] = 0.0            # the all-zero system
+    dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+    for want in (False, True):
+        out = ctx.build_solve(torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(lam).cuda(), layout=tb.PROBLEM_MAJOR,
+                              want_H=want, want_g=want)
+        ctx.sync()
+        assert np.array_equal(out["status"].cpu().numpy(), st), (B, m, n, out["status"].cpu().numpy(), st)
+        ok = st == 0
+        assert rel_err_rows(out["dx"].cpu().numpy()[ok], dx[ok]).max() <= 1e-4, (B, m, n)
+        assert (np.abs(out["cost"].cpu().numpy() - cost) / np.maximum(cost, 1e-30)).max() <= 1e-5
+        if want:
+            assert rel_err_rows(out["g"].cpu().numpy(), g).max() <= 1e-5 or np.abs(g).max() == 0
+            assert rel_err_rows(out["H"].cpu().numpy(), H).max() <= 1e-5

@@ -308,6 +308,35 @@ int wpp_launch(tob200_ctx *ctx, int n, int kind, const void *params, const TppLa
 }
 
 
+// launch geometry / scratch of the mid-n tensor-core kernel (wtc.cuh)
+inline bool wtc_takes(const tob200_ctx *ctx, int elt, int64_t m, int n, const void *A) {
+  return elt == 4 && ctx->wpp_tc && n >= kWtcMinN && n <= kWtcMaxN && m >= kWtcMinM && (m * n) % 4 == 0 && aligned16(A);
+}
+int wtc_configure(tob200_ctx *ctx, const float *A, const float *y, int64_t B, int m, int n, WtcParams *p, int64_t *grid_out) {
+  p->A = A;
+  p->y = y;
+  p->B = B;
+  p->m = m;
+  p->n = n;
+  p->L = wtc_smem_best(n);
+  if (ctx->wtc_raw_stages > 0 && ctx->wtc_op_stages > 0) {  // tuning override (env TOB200_WTC_RAW / TOB200_WTC_OPS)
+    const WtcSmem L2 = wtc_smem_plan(n, ctx->wtc_raw_stages, ctx->wtc_op_stages);
+    if (ctx->wtc_raw_stages <= kWtcMaxRawStages && ctx->wtc_op_stages <= kWtcMaxOpStages && L2.total <= 232448u) p->L = L2;
+  }
+  p->prefetch = ctx->wtc_prefetch;
+  p->debug = ctx->wtc_debug;
+  int64_t grid = ctx->num_sms;
+  const int64_t need = (B + kWtcSlots - 1) / kWtcSlots;
+  if (grid > need) grid = need;
+  int rc = ensure_scratch(ctx, 7, (size_t)grid * kWtcSlots * wtc_hp_floats(n) * sizeof(float));
+  if (rc != TOB200_OK) return rc;
+  p->hpersist = (float *)ctx->scratch[7];
+  if ((rc = next_counter(ctx)) != TOB200_OK) return rc;
+  p->counter = ctx->tile_counter;
+  *grid_out = grid;
+  return TOB200_OK;
+}
+
 // ---- large-n family (lg.cuh): host-orchestrated eval -> syrk -> solve per LM iteration ------------
 enum LgSlot { kLgH = 8, kLgHd, kLgG, kLgCost, kLgScale, kLgRec, kLgLastDx, kLgW, kLgActive, kLgDg };
 constexpr int kLgAmaxSlot = 6;  // [B] max |J_ij| per problem for the FP16-split J^T J (a free scratch slot)
@@ -710,6 +739,23 @@ int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_
                                     cost, (float *)H_out, (float *)g_out, status)) != TOB200_OK) {
       return rc;
     }
+  } else if (wtc_takes(ctx, (int)sizeof(T), m, n, J)) {
+    // the tensor-core kernel in its Build + Solve mode (materialised J, r)
+    WtcParams p{};
+    int64_t grid = 0;
+    if ((rc = wtc_configure(ctx, (const float *)J, (const float *)r, B, m, n, &p, &grid)) != TOB200_OK) return rc;
+    tob200_options dflt;
+    tob200_options_default(&dflt);
+    p.opt = make_dev_options<float>(dflt);
+    p.mode = 1;
+    p.lambda = (const float *)lambda;
+    p.dx = (float *)dx;
+    p.cost_out = cost;
+    p.H_out = (float *)H_out;
+    p.g_out = (float *)g_out;
+    p.status = status;
+    CK(launch_wtc_lm_run(p, (int)grid, ctx->stream));
+    ctx->launches++;
   } else {
     WppBuildSolveParams<T> p;
     if ((rc = wpp_configure<T>(ctx, n, m, B, kWppBuildSolve, J, r, &p.d, &cfg)) != TOB200_OK) return rc;
@@ -781,34 +827,17 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
                                results, final_hessian, n)) != TOB200_OK) {
       return rc;
     }
-  } else if (sizeof(T) == 4 && ctx->wpp_tc && opt->use_ldlt && !final_hessian && n >= kWtcMinN && n <= kWtcMaxN &&
-             m >= kWtcMinM && ((int64_t)m * n) % 4 == 0 && aligned16(A)) {
+  } else if (opt->use_ldlt && !final_hessian && wtc_takes(ctx, (int)sizeof(T), m, n, A)) {
     // mid-n tensor-core family (wtc.cuh): one persistent CTA per SM, eight problems in flight each
-    WtcParams p;
-    p.A = (const float *)A;
-    p.y = (const float *)y;
+    WtcParams p{};
+    int64_t grid = 0;
+    if ((rc = wtc_configure(ctx, (const float *)A, (const float *)y, B, m, n, &p, &grid)) != TOB200_OK) return rc;
     p.x = (float *)x;
     p.results = results;
-    p.B = B;
-    p.m = m;
-    p.n = n;
     p.opt = make_dev_options<float>(*opt);
     p.alpha = (float)alpha;
     p.alpha3 = 3.f * (float)alpha;
-    p.L = wtc_smem_best(n);
-    if (ctx->wtc_raw_stages > 0 && ctx->wtc_op_stages > 0) {  // tuning override (env TOB200_WTC_RAW / TOB200_WTC_OPS)
-      const WtcSmem L2 = wtc_smem_plan(n, ctx->wtc_raw_stages, ctx->wtc_op_stages);
-      if (ctx->wtc_raw_stages <= kWtcMaxRawStages && ctx->wtc_op_stages <= kWtcMaxOpStages && L2.total <= 232448u) p.L = L2;
-    }
-    p.prefetch = ctx->wtc_prefetch;
-    p.debug = ctx->wtc_debug;
-    int64_t grid = ctx->num_sms;
-    const int64_t need = (B + kWtcSlots - 1) / kWtcSlots;
-    if (grid > need) grid = need;
-    if ((rc = ensure_scratch(ctx, 7, (size_t)grid * kWtcSlots * wtc_hp_floats(n) * sizeof(float))) != TOB200_OK) return rc;
-    p.hpersist = (float *)ctx->scratch[7];
-    if ((rc = next_counter(ctx)) != TOB200_OK) return rc;
-    p.counter = ctx->tile_counter;
+    p.mode = 0;
     CK(launch_wtc_lm_run(p, (int)grid, ctx->stream));
     ctx->launches++;
   } else {

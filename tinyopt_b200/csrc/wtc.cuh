@@ -82,10 +82,7 @@ __device__ __forceinline__ int wtc_t_warp(int warp) {
 // solve) and there are twenty waiting warps: polled without a pause they took 28 % of all issued instructions, and with
 // the suspend-time hint of try_wait (NANOSLEEP.SYNCS wakes on every barrier event of the CTA) still 40 % of them plus a
 // third of the shared-memory pipe, which is the resource this kernel runs out of.  ns0: first sleep, doubled up to nsmax.
-#ifndef TOB200_WTC_COL_ALT
-#define TOB200_WTC_COL_ALT 0
-#endif
-constexpr int kWtcColArrive = TOB200_WTC_COL_ALT ? kWtcColWarps / 2 : kWtcColWarps;  // column warps that work on one chunk
+constexpr int kWtcColArrive = kWtcColWarps;  // column warps that work on one chunk (all of them: alternating sets measured slower)
 #ifndef TOB200_WTC_SLEEP_DIV
 #define TOB200_WTC_SLEEP_DIV 1
 #endif
@@ -628,6 +625,106 @@ __device__ __forceinline__ bool wtc_after_pass(LmScalars<float> &s, const DevOpt
   return false;
 }
 
+// tob200_build_solve_f32 on this family: one Build + Solve of a problem whose J and r were handed in (SolverLM::Build,
+// solvers/lm.h:60-120, + SolverGN::Solve, gn.h:150-171): cost, g, the damped H_, dx.  Same machinery as the LM pass, no state.
+// Returns true when the pass has to be repeated (FP16 overflow of a column, or a copy of H_ needed after all).
+__device__ __forceinline__ bool wtc_build_solve_pass(const WtcParams &p, long long prob, int n, int ldw, float *V, float *W,
+                                                     float *hp, WtcSolverCtx &sx, int lane) {
+  float *g = V + kVg * kWtcNP, *dg = V + kVdg * kWtcNP, *dd = V + kVdd * kWtcNP, *dvec = V + kVtemp * kWtcNP;
+  float *dxs = V + kVdxs * kWtcNP, *cs = V + kVcs * kWtcNP, *ci = V + kVci * kWtcNP;
+  int *perm = reinterpret_cast<int *>(V + kVperm * kWtcNP), *inv = reinterpret_cast<int *>(V + kVinv * kWtcNP);
+  const float cost_t = __fadd_rn(__fadd_rn(V[kVmisc * kWtcNP], V[kVmisc * kWtcNP + 1]), V[kVmisc * kWtcNP + 2]);
+  auto release_drains = [&](int cmd) {
+    __syncwarp();
+    if (lane == 0) {
+      *sx.cmd = cmd;
+      mbar_arrive(sx.perm_ready);
+    }
+    __syncwarp();
+  };
+  auto wait_drains = [&]() {
+    mbar_wait_sleep(sx.w_ready, sx.sv & 1u, 200, 800);
+    ++sx.sv;
+  };
+  bool ovf = false;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    if (j < n) {
+      g[j] = __fadd_rn(V[kVgp0 * kWtcNP + j], V[kVgp1 * kWtcNP + j]);
+      dg[j] = __fadd_rn(V[kVdp0 * kWtcNP + j], V[kVdp1 * kWtcNP + j]);
+      const float cms = fmaxf(V[kVmp0 * kWtcNP + j], V[kVmp1 * kWtcNP + j]);
+      if (!(cms < 60000.f)) {
+        int ex;
+        frexpf(cs[j], &ex);
+        if (ex - 1 > -100) {
+          ovf = true;
+          const int e = ex - 1 - 8 < -100 ? -100 : ex - 1 - 8;
+          cs[j] = wtc_pow2(e);
+          ci[j] = wtc_pow2(-e);
+        }
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, ovf)) {
+    release_drains(0);
+    wait_drains();
+    return true;
+  }
+  __syncwarp();
+  const float lam = p.lambda ? p.lambda[prob] : 0.f;
+  const double sc = 1.0 + (double)lam;  // solvers/lm.h:108-117
+  for (int j = lane; j < n; j += 32) dd[j] = lam > 0.f ? (float)((double)dg[j] * sc) : dg[j];
+  __syncwarp();
+  if (lane == 0) p.cost_out[prob] = (double)cost_t;
+  if (p.g_out)
+    for (int j = lane; j < n; j += 32) p.g_out[(size_t)prob * n + j] = g[j];
+  const bool persist = sx.force_hp || p.H_out != nullptr;
+  sx.force_hp = false;
+  wtc_pivot_order(dd, n, perm, inv, reinterpret_cast<uint32_t *>(dxs), lane);
+  for (int j = lane; j < n; j += 32) {
+    const int a = inv[j];
+    const float c = cs[j];
+    W[a * ldw + a] = __fmul_rn(__fmul_rn(dd[j], c), c);
+    W[n * ldw + a] = __fmul_rn(-g[j], c);
+    if (persist) {
+      hp[j * ldw + j] = dd[j];
+      hp[n * ldw + j] = ci[j];
+    }
+  }
+  release_drains(persist ? 3 : 1);
+  wait_drains();
+  if (p.H_out) {  // damped H_, full symmetric, from the persistent copy (column-scaled: undone here)
+    float *Ho = p.H_out + (size_t)prob * n * n;
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e / n, j = e - i * n;
+      const int a = i > j ? i : j, b = i > j ? j : i;
+      Ho[e] = i == j ? dd[i] : __fmul_rn(__fmul_rn(__ldcg(hp + a * ldw + b), ci[a]), ci[b]);
+    }
+  }
+  bool ok = wtc_ldlt_fast4(W, ldw, n, dvec, dxs, lane);
+  if (ok) {
+    wtc_back_subst(W, ldw, n, perm, cs, dxs, lane);
+  } else {
+    if (!persist) {  // no copy of H_ for the exact routine: repeat the pass with the copy requested
+      for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;
+      __syncwarp();
+      sx.force_hp = true;
+      return true;
+    }
+    ok = wtc_solve_exact(W, ldw, n, V, hp, lane);
+    for (int e = lane; e < (n + 1) * ldw; e += 32) W[e] = 0.f;
+    __syncwarp();
+  }
+  if (ok)
+    for (int j = lane; j < n; j += 32) p.dx[(size_t)prob * n + j] = dxs[j];
+  if (lane == 0) p.status[prob] = ok ? 0 : 1;
+  __syncwarp();
+  return false;
+}
+
+// kMode 0: tob200_lm_run_f32 (the whole LM loop of the polynomial family), 1: tob200_build_solve_f32 (materialised J, r)
+template <int kMode>
 __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid_constant__ WtcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -716,7 +813,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
       prob = (long long)t;
         prefetch_head();
       for (int j = lane; j < kWtcNP; j += 32) {
-        V[kVx * kWtcNP + j] = j < n ? p.x[(size_t)prob * n + j] : 0.f;
+        V[kVx * kWtcNP + j] = (j < n && p.x) ? p.x[(size_t)prob * n + j] : 0.f;
         V[kVlastdx * kWtcNP + j] = 0.f;
       }
       s.reset_scalars(p.opt);
@@ -753,6 +850,12 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
       if (prob >= 0) {
         mbar_wait_sleep(&bars[kBFrontDone + q], v & 1u, 400, 3200);
         if (slot == 0) WTC_T(1);  // waiting for the data pass
+        if constexpr (kMode == 1) {  // tob200_build_solve: one pass per problem
+          const bool again = wtc_build_solve_pass(p, prob, n, ldw, V, W, hp, sx, lane);
+          if (!again) fetch();
+          ++v;
+          continue;
+        }
         const bool do_rebuild = !is_lm || s.rebuild();
         const bool redo = wtc_after_pass(s, p.opt, n, m, ldw, V, W, hp, sx, do_rebuild, lane, p.debug);
         if (slot == 0) WTC_T(2);  // after-pass
@@ -898,7 +1001,11 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           if (tw == 0) WTC_T(13);
           float *arow = reinterpret_cast<float *>(smem + L.raw + (size_t)st * L.raw_stage + (size_t)b * L.raw_side) + lane * n;
           float ri = 0.f, sc = 0.f;
-          if (active && lane < rows) {
+          if (kMode == 1 && active && lane < rows) {  // materialised blocks: the row IS the Jacobian row, y the residual
+            ri = ycur;
+            sc = 1.f;
+            cost = __fmaf_rn(ri, ri, cost);
+          } else if (active && lane < rows) {
             // t = a_i . x as four interleaved partial sums (fixed combine order): the chain is the latency of this warp.
             // (x held in registers - all of it, or the first 32 entries - was measured SLOWER: 2.0 k cycles per chunk
             // against 1.4 k; the unrolled predicated code and its spills cost more than the broadcast loads)
@@ -976,66 +1083,6 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         unsigned long long g2 = 0ull, d2 = 0ull;  // (even rows, odd rows) partial sums
         uint32_t mxh = 0u;                        // max |hi| of my column, per half
         const uint32_t n4 = (uint32_t)n * 4u;
-#if TOB200_WTC_COL_ALT
-        // Variant: the two sets of four warps take ALTERNATE chunks (all 32 rows of a chunk each): half the barrier
-        // operations per element and two chunk periods to finish one, operands stored K chunk by K chunk.
-        const uint32_t off0 = (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
-        const uint32_t raw0 = smem_u32(smem + L.raw) + (uint32_t)b * L.raw_side + (uint32_t)(j < n ? j : n - 1) * 4u;
-        const uint32_t rs0 = smem_u32(rsr) + (uint32_t)(b * kWtcRows) * 4u;
-        for (int c = 0; c < nchunks; ++c) {
-          if ((c & 1) != grp) {
-            if (++st == R) { st = 0; ph ^= 1u; }
-            if (++os == S) { os = 0; oph ^= 1u; }
-            continue;
-          }
-          mbar_wait_sleep(&bars[kBRsFull + st], ph, 100, 400);
-          mbar_wait(&bars[kBRawFull + st], ph);
-          mbar_wait_sleep(&bars[kBOpEmpty + os], oph ^ 1u, 100, 400);
-          if (cw == 0) WTC_T(17);
-          const uint32_t sa = raw0 + st * L.raw_stage;
-          const uint32_t ss = rs0 + st * (uint32_t)(2 * kWtcRows * 4), sr = ss + (uint32_t)kRsrHalf * 4u;
-          const uint32_t sb = ops_u32 + os * (uint32_t)kWtcOpStageBytes + off0;
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            unsigned long long sc2[4], r2[4];
-            lds_f2x2(ss + (uint32_t)h * 32u, sc2[0], sc2[1]);
-            lds_f2x2(ss + (uint32_t)h * 32u + 16u, sc2[2], sc2[3]);
-            lds_f2x2(sr + (uint32_t)h * 32u, r2[0], r2[1]);
-            lds_f2x2(sr + (uint32_t)h * 32u + 16u, r2[2], r2[3]);
-            float a[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) a[t] = lds_f32(sa + (uint32_t)(8 * h + t) * n4);
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int t2 = 0; t2 < 4; ++t2) {
-              const unsigned long long jv = f2_mul(f2_pack(a[2 * t2], a[2 * t2 + 1]), sc2[t2]);  // J_ij = s_i a_ij
-              g2 = f2_fma(jv, r2[t2], g2);
-              d2 = f2_fma(jv, jv, d2);
-              const unsigned long long vv = f2_mul(jv, fs2);  // * 2^e_j (exact)
-              float v0, v1;
-              f2_unpack(vv, v0, v1);
-              const uint32_t hh = lg_pack_h2(v0, v1);
-              const unsigned long long ll = f2_sub(vv, f2_pack(lg_h_lo(hh), lg_h_hi(hh)));  // exact
-              float l0, l1;
-              f2_unpack(ll, l0, l1);
-              hi[t2] = hh;
-              lo[t2] = lg_pack_h2(l0, l1);
-              mxh = h2_absmax(mxh, hh);
-            }
-            sts_v4u(sb + (uint32_t)h * 2048u, hi[0], hi[1], hi[2], hi[3]);
-            sts_v4u(sb + (uint32_t)(kWtcOpStageBytes / 2) + (uint32_t)h * 2048u, lo[0], lo[1], lo[2], lo[3]);
-          }
-          fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&bars[kBRawEmpty + st]);
-            mbar_arrive(&bars[kBOpFull + os]);
-          }
-          if (cw == 0) WTC_T(18);
-          if (++st == R) { st = 0; ph ^= 1u; }
-          if (++os == S) { os = 0; oph ^= 1u; }
-        }
-#else
         const uint32_t off0 = (uint32_t)(2 * grp) * 2048u + (uint32_t)(rr >> 3) * 128u + (uint32_t)(rr & 7) * 16u;
         const uint32_t raw0 = smem_u32(smem + L.raw) + (uint32_t)b * L.raw_side + (uint32_t)((j < n ? j : n - 1) + 16 * grp * n) * 4u;
         const uint32_t rs0 = smem_u32(rsr) + (uint32_t)(b * kWtcRows + 16 * grp) * 4u;
@@ -1091,7 +1138,6 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           if (++st == R) { st = 0; ph ^= 1u; }
           if (++os == S) { os = 0; oph ^= 1u; }
         }
-#endif
         {
           float ge, go, de, dO;
           f2_unpack(g2, ge, go);

@@ -5,11 +5,13 @@
 namespace tob200 {
 
 cudaError_t launch_wtc_lm_run(const WtcParams &p, int grid, cudaStream_t st) {
+  const void *fn = p.mode == 1 ? (const void *)wtc_lm_run_kernel<1> : (const void *)wtc_lm_run_kernel<0>;
   {
-    cudaError_t e = raise_smem_limit((const void *)wtc_lm_run_kernel, p.L.total);
+    cudaError_t e = raise_smem_limit(fn, p.L.total);
     if (e != cudaSuccess) return e;
   }
-  wtc_lm_run_kernel<<<(unsigned)grid, kWtcThreads, p.L.total, st>>>(p);
+  if (p.mode == 1) wtc_lm_run_kernel<1><<<(unsigned)grid, kWtcThreads, p.L.total, st>>>(p);
+  else wtc_lm_run_kernel<0><<<(unsigned)grid, kWtcThreads, p.L.total, st>>>(p);
   return cudaGetLastError();
 }
 

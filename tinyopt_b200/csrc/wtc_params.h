@@ -88,6 +88,14 @@ struct WtcParams {
   WtcSmem L;
   int prefetch;                 // L2 prefetch distance of the loader, in stages
   int debug;                    // timing experiments (env TOB200_WTC_DEBUG): 1 no MMAs, 2 no LDLT (results invalid)
+  // mode 1: one Build + Solve per problem from materialised blocks (tob200_build_solve_f32): A = J, y = r, no LM state
+  int mode;
+  const float *lambda;          // [B] or nullptr
+  float *dx;                    // [B][n]   (written for accepted problems only)
+  double *cost_out;             // [B] sum r^2
+  float *H_out;                 // [B][n][n] damped H_, full symmetric, or nullptr
+  float *g_out;                 // [B][n] or nullptr
+  int32_t *status;              // [B] 0 solved, 1 the factorisation rejected the system
 };
 
 }  // namespace tob200
