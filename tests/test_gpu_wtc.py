@@ -255,3 +255,21 @@ def test_wtc_build_solve_parity(ctx, B, m, n):
         if want:
             assert rel_err_rows(out["g"].cpu().numpy(), g).max() <= 1e-5 or np.abs(g).max() == 0
             assert rel_err_rows(out["H"].cpu().numpy(), H).max() <= 1e-5
+
+
+@pytest.mark.parametrize("n", list(range(28, 56)))
+def test_wtc_every_size(ctx, n):
+    """Every n of the family (pitch of the LDLᵀ matrix, last step of 1..4 columns, one or two drain warps per side, odd n)."""
+    B, m = 24, 256 if (256 * n) % 4 == 0 else 260
+    A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=n)
+    xo, ro, robust = oracle_run(A, y, x0, FLOAT_OPTS)
+    xg, rg = gpu_run(ctx, A, y, x0, FLOAT_OPTS)
+    check(xg, rg, xo, ro, robust)
+    r, J = O.synth_eval(A, y, x0)
+    lam = np.full(B, np.float32(1e-4), np.float32)
+    dx, cost, st, H, g = oracle_build_solve_batch(J, r, lam)
+    out = ctx.build_solve(torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(lam).cuda(), want_H=True, want_g=True)
+    ctx.sync()
+    assert np.array_equal(out["status"].cpu().numpy(), st)
+    assert rel_err_rows(out["dx"].cpu().numpy(), dx).max() <= 1e-4
+    assert rel_err_rows(out["H"].cpu().numpy(), H).max() <= 1e-5 and rel_err_rows(out["g"].cpu().numpy(), g).max() <= 1e-5

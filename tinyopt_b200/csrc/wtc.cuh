@@ -959,11 +959,15 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
             mbar_wait_sleep(&bars[kBRawEmpty + st], ph ^ 1u, 100, 400);
             WTC_T(5);
             fence_proxy_async();  // the column warps' generic reads of this stage precede the async writes
-            mbar_expect_tx(&bars[kBRawFull + st], bytes * (uint32_t)((pa >= 0) + (pb >= 0)));
-            unsigned char *dst = smem + L.raw + (size_t)st * L.raw_stage;
-            if (pa >= 0) tma_bulk_g2s(dst, p.A + ((size_t)pa * m + row0) * n, bytes, &bars[kBRawFull + st]);
-            if (pb >= 0) tma_bulk_g2s(dst + L.raw_side, p.A + ((size_t)pb * m + row0) * n, bytes, &bars[kBRawFull + st]);
-          } else if (lane <= 2) {  // L2 prefetch of the same rows p.prefetch stages ahead
+            if (p.debug & 4) {  // timing experiment: no copies (the stages keep whatever they hold)
+              mbar_arrive(&bars[kBRawFull + st]);
+            } else {
+              mbar_expect_tx(&bars[kBRawFull + st], bytes * (uint32_t)((pa >= 0) + (pb >= 0)));
+              unsigned char *dst = smem + L.raw + (size_t)st * L.raw_stage;
+              if (pa >= 0) tma_bulk_g2s(dst, p.A + ((size_t)pa * m + row0) * n, bytes, &bars[kBRawFull + st]);
+              if (pb >= 0) tma_bulk_g2s(dst + L.raw_side, p.A + ((size_t)pb * m + row0) * n, bytes, &bars[kBRawFull + st]);
+            }
+          } else if (lane <= 2 && !(p.debug & 4)) {  // L2 prefetch of the same rows p.prefetch stages ahead
             const long long pp = lane == 1 ? pa : pb;
             const int cc = c + p.prefetch;
             if (pp >= 0 && cc < nchunks) {
@@ -1089,8 +1093,8 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait_sleep(&bars[kBRsFull + st], ph, 100, 400);
           mbar_wait(&bars[kBRawFull + st], ph);
-          if (cw == 0) WTC_T(17);
           const uint32_t sa = raw0 + st * L.raw_stage;
+          if (cw == 0) WTC_T(17);
           const uint32_t ss = rs0 + st * (uint32_t)(2 * kWtcRows * 4), sr = ss + (uint32_t)kRsrHalf * 4u;
           uint32_t hi[2][4], lo[2][4];
 #pragma unroll
