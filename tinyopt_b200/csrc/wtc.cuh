@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           if (tw == 0) WTC_T(13);
           float *arow = reinterpret_cast<float *>(smem + L.raw + (size_t)st * L.raw_stage + (size_t)b * L.raw_side) + lane * n;
           float ri = 0.f, sc = 0.f;
-          if (kMode == 1 && active && lane < rows) {  // materialised blocks: the row IS the Jacobian row, y the residual
+          if ((kMode == 1 || (p.debug & 8)) && active && lane < rows) {  // materialised blocks (debug 8: timing experiment, no t-chain): the row IS the Jacobian row, y the residual
             ri = ycur;
             sc = 1.f;
             cost = __fmaf_rn(ri, ri, cost);
