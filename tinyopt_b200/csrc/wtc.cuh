@@ -959,15 +959,12 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
             mbar_wait_sleep(&bars[kBRawEmpty + st], ph ^ 1u, 100, 400);
             WTC_T(5);
             fence_proxy_async();  // the column warps' generic reads of this stage precede the async writes
-            if (p.debug & 4) {  // timing experiment: no copies (the stages keep whatever they hold)
-              mbar_arrive(&bars[kBRawFull + st]);
-            } else {
-              mbar_expect_tx(&bars[kBRawFull + st], bytes * (uint32_t)((pa >= 0) + (pb >= 0)));
-              unsigned char *dst = smem + L.raw + (size_t)st * L.raw_stage;
-              if (pa >= 0) tma_bulk_g2s(dst, p.A + ((size_t)pa * m + row0) * n, bytes, &bars[kBRawFull + st]);
-              if (pb >= 0) tma_bulk_g2s(dst + L.raw_side, p.A + ((size_t)pb * m + row0) * n, bytes, &bars[kBRawFull + st]);
-            }
-          } else if (lane <= 2 && !(p.debug & 4)) {  // L2 prefetch of the same rows p.prefetch stages ahead
+            // (a run without these copies - stale stages, results invalid - is no faster: 17.0 against 17.2 M it/s)
+            mbar_expect_tx(&bars[kBRawFull + st], bytes * (uint32_t)((pa >= 0) + (pb >= 0)));
+            unsigned char *dst = smem + L.raw + (size_t)st * L.raw_stage;
+            if (pa >= 0) tma_bulk_g2s(dst, p.A + ((size_t)pa * m + row0) * n, bytes, &bars[kBRawFull + st]);
+            if (pb >= 0) tma_bulk_g2s(dst + L.raw_side, p.A + ((size_t)pb * m + row0) * n, bytes, &bars[kBRawFull + st]);
+          } else if (lane <= 2) {  // L2 prefetch of the same rows p.prefetch stages ahead
             const long long pp = lane == 1 ? pa : pb;
             const int cc = c + p.prefetch;
             if (pp >= 0 && cc < nchunks) {
@@ -1005,7 +1002,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1) wtc_lm_run_kernel(const __grid
           if (tw == 0) WTC_T(13);
           float *arow = reinterpret_cast<float *>(smem + L.raw + (size_t)st * L.raw_stage + (size_t)b * L.raw_side) + lane * n;
           float ri = 0.f, sc = 0.f;
-          if ((kMode == 1 || (p.debug & 8)) && active && lane < rows) {  // materialised blocks (debug 8: timing experiment, no t-chain): the row IS the Jacobian row, y the residual
+          if (kMode == 1 && active && lane < rows) {  // materialised blocks: the row IS the Jacobian row, y the residual: the row IS the Jacobian row, y the residual
             ri = ycur;
             sc = 1.f;
             cost = __fmaf_rn(ri, ri, cost);
