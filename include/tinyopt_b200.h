@@ -237,10 +237,16 @@ int tob200_lm_run_host_f64(tob200_ctx *ctx, const tob200_options *opt, const dou
  * rebuild flag, H_, grad_, Output counters) lives on the device.  Each tob200_solver_step is one
  * Optimizer_::Step + the OptimizeAcc update (optimizer.h:266-309) for every still-running problem,
  * fed with the residual blocks the caller's lambda produced at the current x.
- * n <= 55, float and double (kernel families 1 and 2); bit-identical to tob200_lm_run_* for the same
- * residual blocks. */
+ * Every n <= 2048, float and double: n <= 55 on kernel families 1 and 2 (bit-identical to tob200_lm_run_* for
+ * the same residual blocks), above on the general family 4 in both precisions (the reference's dynamic-size
+ * solver has no size cap, math.h:232-240; bit-identical to the CPU oracle fed with the same J, r). */
 int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob200_options *opt,
                          tob200_solver **out);
+/* flags: TOB200_SOLVER_GENERAL runs the solver on the general family whatever n is (needed by
+ * tob200_solver_step_cost_*). */
+#define TOB200_SOLVER_GENERAL 1
+int tob200_solver_create_ex(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob200_options *opt, int flags,
+                            tob200_solver **out);
 int tob200_solver_destroy(tob200_solver *s);
 /* Reset all problems (solvers/lm.h:46-52 reset()) and set x <- x0 ([B][n], device). */
 int tob200_solver_reset(tob200_solver *s, const void *x0);
@@ -251,6 +257,15 @@ void *tob200_solver_x(tob200_solver *s);
 const int32_t *tob200_solver_needs(tob200_solver *s);
 int tob200_solver_step_f32(tob200_solver *s, const float *J, const float *r, int layout, int m);
 int tob200_solver_step_f64(tob200_solver *s, const double *J, const double *r, int layout, int m);
+/* tob200_solver_step with the pass's `Cost::cost` supplied by the caller ([B] doubles, device) instead of
+ * being formed as r^T r: accumulation functors return what they like - diff/num_diff.h:300-305 returns the
+ * NORM of the residuals, not its square.  grad_ = J^T r and H_ = J^T J as in tob200_solver_step; the residual
+ * count is m.  General family only (tob200_solver_create_ex with TOB200_SOLVER_GENERAL), else
+ * TOB200_ERR_UNSUPPORTED. */
+int tob200_solver_step_cost_f32(tob200_solver *s, const float *J, const float *r, int layout, int m,
+                                const double *cost);
+int tob200_solver_step_cost_f64(tob200_solver *s, const double *J, const double *r, int layout, int m,
+                                const double *cost);
 /* The manual accumulation contract `acc(x, grad, H) -> Cost` (docs/API.md:37-57,137-170; examples
  * tests/optimize_easy.cpp:35-80 (Rosenbrock with its true Hessian), tests/types.cpp:97-108,
  * benchmarks/dense.cpp:57-66 ("Prior n": a diagonal H)): the caller's lambda has filled, for every problem,

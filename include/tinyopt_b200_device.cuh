@@ -641,6 +641,255 @@ cudaError_t OptimizeBatchManualWarp(const F &f, T *x, int64_t B, const tob200_op
   return detail::launch_warp<T, N, false, F>(f, x, B, options, results, stream);
 }
 
+
+// ================================================================================================
+// Any n up to 2048, run-time n (the reference's dynamic-size path: `Optimize(x, residuals)` with a VecX, no size
+// cap, math.h:232-240): the same functor source as the warp family above, evaluated by one warp per problem into
+// MATERIALISED residual blocks J [B][m][n], r [B][m] in HBM, which then go through the SolverType seam of the
+// library (tob200_solver_*: n <= 55 on the fused step kernels, above on the general family) in a host-driven
+// Step loop — the structure of `Optimizer_::OptimizeAcc` itself (optimizer.h:243-327).  Unlike the kernels above
+// this one links the library (-ltinyopt_b200).  Three ways to the Jacobian:
+//   * OptimizeBatchAutoDiffLarge   — Jets (diff/optimize_autodiff.h:33-166): 64 parameters per sweep (every lane
+//     carries d/dx_{base+lane}, d/dx_{base+lane+32}), ceil(n / 64) sweeps of the functor per rebuild pass;
+//   * OptimizeBatchManualLarge     — the functor supplies its own rows: emit(r, [&](int j) { return J_ij; });
+//   * OptimizeBatchNumDiffLarge    — numeric differentiation (diff/num_diff.h:57-126, 284-309: kForward, kCentral
+//     (default), kFastCentral, h = FloatEpsilon = 1e-7f / 1e-4f): every lane perturbs ITS OWN parameter, so 32
+//     columns of J come out of one lockstep sweep; the Cost is the residual NORM with m residuals, as the
+//     reference's `CreateNumDiffFunc2` returns it (num_diff.h:300-305), handed over by tob200_solver_step_cost_*.
+// Cost-only Steps (solvers/gn.h:98-105) sweep the functor once with plain T.  The functor must emit exactly m
+// residuals per sweep and be free of lane-dependent control flow.
+// ================================================================================================
+enum NumDiffMethod { kForward = 0, kCentral = 1, kFastCentral = 2 };  // diff/num_diff.h:20-52
+
+template <typename T>
+struct LargeXJet {
+  const T *xg;
+  int lane, base;
+  __device__ __forceinline__ Jet<T, 2> operator[](int j) const {
+    Jet<T, 2> r;
+    r.a = xg[j];
+    r.v[0] = (base + lane == j) ? (T)1 : (T)0;
+    r.v[1] = (base + lane + 32 == j) ? (T)1 : (T)0;
+    return r;
+  }
+};
+template <typename T>
+struct LargeXScalar {
+  const T *xg;
+  __device__ __forceinline__ T operator[](int j) const { return xg[j]; }
+};
+template <typename T>
+struct LargeXNum {  // PlusEq(y, dx) with dx = +-h e_mine (num_diff.h:96-113)
+  const T *xg;
+  int mine;
+  T step;
+  __device__ __forceinline__ T operator[](int j) const {
+    const T v = xg[j];
+    return j == mine ? Ops<T>::add(v, step) : v;
+  }
+};
+
+template <typename T>
+struct LargeXNumFast {  // kFastCentral's second point: y = (x + h e_mine) + (-2h e_mine)
+  const T *xg;
+  int mine;
+  T h, m2h;
+  __device__ __forceinline__ T operator[](int j) const {
+    const T v = xg[j];
+    return j == mine ? Ops<T>::add(Ops<T>::add(v, h), m2h) : v;
+  }
+};
+
+template <typename T>
+struct LargeEmit {
+  enum Mode { kScalar = 0, kJet = 1, kManual = 2, kNumPlus = 3, kNumMinus = 4, kNumForward = 5 };
+  T *Jp, *rp;  // the problem's J [m][n] and r [m]
+  int n, lane, base, mode, row;
+  T inv_den;   // numeric differentiation: the divisor 2h or h
+  __device__ __forceinline__ void operator()(const Jet<T, 2> &r) {
+    T *Jr = Jp + (size_t)row * n;
+    if (base + lane < n) Jr[base + lane] = r.v[0];
+    if (base + lane + 32 < n) Jr[base + lane + 32] = r.v[1];
+    if (base == 0 && lane == 0) rp[row] = r.a;
+    ++row;
+  }
+  __device__ __forceinline__ void operator()(T r) {
+    const int c = base + lane;
+    T *Je = Jp + (size_t)row * n + c;
+    if (mode == kScalar) {
+      if (lane == 0) rp[row] = r;
+    } else if (c < n) {
+      if (mode == kNumPlus) *Je = r;                                               // res_plus
+      else if (mode == kNumMinus) *Je = Ops<T>::div(Ops<T>::sub(*Je, r), inv_den);  // (res_plus - res_minus) / (2 h)
+      else *Je = Ops<T>::div(Ops<T>::sub(r, rp[row]), inv_den);                     // (res_plus - res) / h
+    }
+    ++row;
+  }
+  /// residual with its own Jacobian row: jf(j) = d r / d x_j (every lane passes the same r and the same jf)
+  template <typename JF>
+  __device__ __forceinline__ void operator()(T r, JF jf) {
+    T *Jr = Jp + (size_t)row * n;
+    for (int j = lane; j < n; j += 32) Jr[j] = jf(j);
+    if (lane == 0) rp[row] = r;
+    ++row;
+  }
+};
+
+namespace detail {
+
+// kind 0: Jets, 1: manual rows, 2: numeric differentiation
+template <typename T, int kKind, typename F>
+__global__ void __launch_bounds__(128) functor_eval_kernel(F f, const T *x, const int32_t *needs, T *J, T *r, int64_t B, int n,
+                                                          int m, int method, T h) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pr = warp0; pr < B; pr += nwarps) {
+    const int need = needs[pr];
+    if (need < 0) continue;  // finished
+    const T *xg = x + (size_t)pr * n;
+    LargeEmit<T> emit;
+    emit.Jp = J + (size_t)pr * m * n;
+    emit.rp = r + (size_t)pr * m;
+    emit.n = n; emit.lane = lane; emit.base = 0; emit.row = 0; emit.inv_den = (T)1;
+    if constexpr (kKind == 1) {
+      emit.mode = need ? LargeEmit<T>::kManual : LargeEmit<T>::kScalar;
+      f(pr, LargeXScalar<T>{xg}, emit, need != 0);
+    } else if constexpr (kKind == 0) {
+      if (!need) {
+        emit.mode = LargeEmit<T>::kScalar;
+        f(pr, LargeXScalar<T>{xg}, emit);
+      } else {
+        emit.mode = LargeEmit<T>::kJet;
+        for (int base = 0; base < n; base += 64) {
+          emit.base = base;
+          emit.row = 0;
+          f(pr, LargeXJet<T>{xg, lane, base}, emit);
+        }
+      }
+    } else {
+      emit.mode = LargeEmit<T>::kScalar;
+      f(pr, LargeXScalar<T>{xg}, emit);  // `const auto res = residuals(x)` (num_diff.h:293)
+      if (need) {
+        __syncwarp();  // kNumForward reads lane 0's r
+        const T two_h = Ops<T>::mul((T)2, h);
+        for (int base = 0; base < n; base += 32) {
+          const int mine = base + lane < n ? base + lane : -1;
+          emit.base = base;
+          emit.row = 0;
+          if (method == kForward) {
+            emit.mode = LargeEmit<T>::kNumForward;
+            emit.inv_den = h;
+            f(pr, LargeXNum<T>{xg, mine, h}, emit);
+          } else {
+            emit.mode = LargeEmit<T>::kNumPlus;
+            f(pr, LargeXNum<T>{xg, mine, h}, emit);
+            emit.row = 0;
+            emit.mode = LargeEmit<T>::kNumMinus;
+            emit.inv_den = two_h;
+            if (method == kCentral) {
+              f(pr, LargeXNum<T>{xg, mine, -h}, emit);  // y = x; dx[r] = -h
+            } else {  // kFastCentral: y = (x + h) + (-2h) (num_diff.h:104-106)
+              f(pr, LargeXNumFast<T>{xg, mine, h, Ops<T>::mul((T)-2, h)}, emit);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Cost(res.norm(), res.size()) of num_diff.h:305: sqrt of the canonical chain over the rows, one thread per problem
+template <typename T>
+__global__ void norm_cost_kernel(const T *r, const int32_t *needs, int64_t B, int m, double *cost) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B || needs[p] < 0) return;
+  const T *rp = r + (size_t)p * m;
+  T c = (T)0;
+  for (int i = 0; i < m; ++i) c = Ops<T>::fma(rp[i], rp[i], c);
+  cost[p] = (double)sqrt(c);
+}
+
+inline int large_step(tob200_solver *s, const float *J, const float *r, int m, const double *cost) {
+  return cost ? tob200_solver_step_cost_f32(s, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, m, cost)
+              : tob200_solver_step_f32(s, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, m);
+}
+inline int large_step(tob200_solver *s, const double *J, const double *r, int m, const double *cost) {
+  return cost ? tob200_solver_step_cost_f64(s, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, m, cost)
+              : tob200_solver_step_f64(s, J, r, TOB200_LAYOUT_PROBLEM_MAJOR, m);
+}
+
+template <typename T, int kKind, typename F>
+int optimize_large(tob200_ctx *ctx, const F &f, T *x, int64_t B, int n, int m, const tob200_options &options,
+                   tob200_result *results, int method, T h) {
+  if (!ctx || !x || !results || B < 0 || n < 1 || m < 1) return TOB200_ERR_INVALID;
+  if (B == 0) return TOB200_OK;
+  tob200_solver *s = nullptr;
+  int rc = tob200_solver_create_ex(ctx, sizeof(T) == 4 ? TOB200_F32 : TOB200_F64, B, n, &options,
+                                   kKind == 2 ? TOB200_SOLVER_GENERAL : 0, &s);
+  if (rc != TOB200_OK) return rc;
+  T *J = nullptr, *r = nullptr;
+  double *cost = nullptr;
+  auto done = [&](int code) {
+    cudaFree(J); cudaFree(r); cudaFree(cost);
+    tob200_solver_destroy(s);
+    return code;
+  };
+  if (cudaMalloc(&J, (size_t)B * m * n * sizeof(T)) != cudaSuccess) return done(TOB200_ERR_NOMEM);
+  if (cudaMalloc(&r, (size_t)B * m * sizeof(T)) != cudaSuccess) return done(TOB200_ERR_NOMEM);
+  if (kKind == 2 && cudaMalloc(&cost, (size_t)B * sizeof(double)) != cudaSuccess) return done(TOB200_ERR_NOMEM);
+  if ((rc = tob200_solver_reset(s, x)) != TOB200_OK) return done(rc);
+  const T *xs = static_cast<const T *>(tob200_solver_x(s));
+  const int32_t *needs = tob200_solver_needs(s);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t grid = (B + 3) / 4;
+  if (grid > 8 * (int64_t)sms) grid = 8 * (int64_t)sms;
+  const int max_steps = options.max_iters + 2;  // optimizer.h:248-250
+  for (int step = 0; step < max_steps; ++step) {
+    int64_t active = 0;
+    if ((rc = tob200_solver_num_active(s, &active)) != TOB200_OK) return done(rc);  // synchronises the library's stream
+    if (active == 0) break;
+    functor_eval_kernel<T, kKind, F><<<(unsigned)grid, 128>>>(f, xs, needs, J, r, B, n, m, method, h);
+    if (kKind == 2) norm_cost_kernel<T><<<(unsigned)((B + 127) / 128), 128>>>(r, needs, B, m, cost);
+    if (cudaDeviceSynchronize() != cudaSuccess) return done(TOB200_ERR_CUDA);
+    if ((rc = large_step(s, J, r, m, cost)) != TOB200_OK) return done(rc);
+  }
+  if ((rc = tob200_solver_results(s, results)) != TOB200_OK) return done(rc);
+  if ((rc = tob200_sync(ctx)) != TOB200_OK) return done(rc);
+  if (cudaMemcpy(x, xs, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToDevice) != cudaSuccess) return done(TOB200_ERR_CUDA);
+  return done(TOB200_OK);
+}
+
+}  // namespace detail
+
+/// tinyopt::Optimize(x, residuals, options) with automatic differentiation, any n <= 2048 (run-time n, m residuals).
+/// f : `template <typename X, typename E> __device__ void operator()(int64_t p, const X &x, E &emit) const`
+/// Returns a tob200_status; x [B][n] and results [B] are device arrays.
+template <typename T, typename F>
+int OptimizeBatchAutoDiffLarge(tob200_ctx *ctx, const F &f, T *x, int64_t B, int n, int m, const tob200_options &options,
+                               tob200_result *results) {
+  return detail::optimize_large<T, 0, F>(ctx, f, x, B, n, m, options, results, 0, (T)0);
+}
+/// The accumulation contract with the functor's own Jacobian rows, any n <= 2048.
+/// f : `template <typename X, typename E> __device__ void operator()(int64_t p, const X &x, E &emit, bool want_jacobian) const`
+///     — emit(r, [&](int j) { return J_ij; }) per residual, or emit(r) when !want_jacobian
+template <typename T, typename F>
+int OptimizeBatchManualLarge(tob200_ctx *ctx, const F &f, T *x, int64_t B, int n, int m, const tob200_options &options,
+                             tob200_result *results) {
+  return detail::optimize_large<T, 1, F>(ctx, f, x, B, n, m, options, results, 0, (T)0);
+}
+/// tinyopt::Optimize with numeric differentiation (diff/num_diff.h: `CreateNumDiffFunc2(x, residuals, method, h)` handed
+/// to the optimizer), any n <= 2048.  f as for OptimizeBatchAutoDiffLarge (it is only ever called with plain T).
+/// h <= 0 selects the reference's default FloatEpsilon<T>() (math.h:297-301: 1e-7f in double, 1e-4f in float).
+template <typename T, typename F>
+int OptimizeBatchNumDiffLarge(tob200_ctx *ctx, const F &f, T *x, int64_t B, int n, int m, const tob200_options &options,
+                              tob200_result *results, NumDiffMethod method = kCentral, T h = (T)0) {
+  if (!(h > (T)0)) h = sizeof(T) == 4 ? (T)1e-4f : (T)1e-7f;
+  return detail::optimize_large<T, 2, F>(ctx, f, x, B, n, m, options, results, (int)method, h);
+}
+
 }  // namespace device
 }  // namespace b200
 }  // namespace tinyopt

@@ -319,7 +319,7 @@ def synth_eval(A: np.ndarray, y: np.ndarray, x: np.ndarray, alpha: float = ALPHA
 
 def synth_lm_run(A: np.ndarray, y: np.ndarray, x0: np.ndarray, options: Options | None = None,
                  alpha: float = ALPHA, nthreads: int = 0, fast: bool = False, reverse_rows: bool = False,
-                 want_hessian: bool = False, robust: tuple | None = None):
+                 want_hessian: bool = False, robust: tuple | None = None, numdiff: tuple | None = None):
     """Batched LM over the family.  Returns (x[B,n], results structured array, threads used).
     fast=True runs the -DTOO_FAST build (same results, scheduled for throughput).  reverse_rows=True
     (census only) sums the residual rows m-1 .. 0: another valid order, NOT the canonical one."""
@@ -332,6 +332,8 @@ def synth_lm_run(A: np.ndarray, y: np.ndarray, x0: np.ndarray, options: Options 
     l.too_census_set_row_order(C.c_int(1 if reverse_rows else 0))
     # robust = (kind 1..7, th2): every residual goes through that M-estimator inside the accumulation
     l.too_synth_set_robust(C.c_int(robust[0] if robust else 0), C.c_double(robust[1] if robust else 1.0))
+    # numdiff = (method 1 kForward / 2 kCentral / 3 kFastCentral, h or 0 for FloatEpsilon): diff/num_diff.h instead of the analytic J
+    l.too_synth_set_numdiff(C.c_int(numdiff[0] if numdiff else 0), C.c_double(numdiff[1] if numdiff else 0.0))
     fh = np.zeros((B, n, n)) if want_hessian else None
     try:
         fn = getattr(l, f"too_synth_lm_run_fh_{_suf(A.dtype)}")
@@ -341,6 +343,7 @@ def synth_lm_run(A: np.ndarray, y: np.ndarray, x0: np.ndarray, options: Options 
     finally:
         l.too_census_set_row_order(C.c_int(0))
         l.too_synth_set_robust(C.c_int(0), C.c_double(1.0))
+        l.too_synth_set_numdiff(C.c_int(0), C.c_double(0.0))
     if want_hessian:
         return x, res, used, fh   # Output::final_hessian per problem (optimizer.h:313-316), un-damped
     return x, res, used

@@ -57,6 +57,11 @@ void too_census_set_row_order(int rev) { too_census_row_order_ = rev; }
 static int too_synth_robust_kind_ = 0;
 static double too_synth_robust_th2_ = 1.0;
 void too_synth_set_robust(int kind, double th2) { too_synth_robust_kind_ = kind; too_synth_robust_th2_ = th2; }
+/* numeric-differentiation variant of the family (diff/num_diff.h:57-126, 284-309): method 0 = off (analytic J),
+ * 1 = kForward, 2 = kCentral, 3 = kFastCentral; h <= 0 = FloatEpsilon<Scalar>() (math.h:297-301) */
+static int too_synth_numdiff_method_ = 0;
+static double too_synth_numdiff_h_ = 0.0;
+void too_synth_set_numdiff(int method, double h) { too_synth_numdiff_method_ = method; too_synth_numdiff_h_ = h; }
 
 /* stateless counter RNG of the synthetic family:
  * u(seed,p,k) = splitmix64-finaliser(seed ^ (p * golden + k)) */

@@ -179,6 +179,11 @@ int too_synth_lm_run_fh_f32(int64_t B, int m, int n, const float *A, const float
  * too_synth_lm_run_* goes through M-estimator `kind` (1 Truncated, 2 Huber, 3 Tukey, 4 Arctan, 5 Cauchy,
  * 6 GemanMcClure, 7 BlakeZisserman) with squared threshold th2:  cost += loss, grad += J^T r * scale, H += J^T J. */
 void too_synth_set_robust(int kind, double th2);
+/* Numeric-differentiation variant (diff/num_diff.h:57-126 NumEval, :284-309 CreateNumDiffFunc2): while method != 0 the
+ * family's Jacobian is estimated column by column from the residual function (1 kForward, 2 kCentral - the
+ * reference's default -, 3 kFastCentral; h <= 0: FloatEpsilon<Scalar>()), grad = J^T res, H = J^T J, and the Cost is
+ * the residual NORM with m residuals, as the reference's lambda returns it.  Global state like set_robust. */
+void too_synth_set_numdiff(int method, double h);
 
 int too_max_threads(void);
 

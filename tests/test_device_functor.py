@@ -91,3 +91,21 @@ def test_device_functor_on_gpu(tmp_path):
             assert same.mean() > 0.9, (f.name, same.mean())
             err = np.abs(xg - xo)[same].max(axis=1) / np.maximum(np.abs(xo)[same].max(axis=1), 1e-300)
             assert err.max() < 1e-9, (f.name, err.max())
+
+    # run-time n (the *Large drivers): the manual functor through the SolverType seam == the oracle bit for bit in both
+    # precisions and for every n; numeric differentiation (diff/num_diff.h, central differences, the NORM as cost) ==
+    # the oracle's numdiff variant bit for bit
+    ldumps = sorted(tmp_path.glob("large_*.bin"))
+    assert len(ldumps) == 10, ldumps
+    for f in ldumps:
+        tag, dt, n, m, B = re.match(r"large_(\w+)_(f\d+)_n(\d+)_m(\d+)_B(\d+)\.bin", f.name).groups()
+        n, m, B = int(n), int(m), int(B)
+        rec = np.fromfile(f, np.float64).reshape(B, 4 + n)
+        npdt = np.float32 if dt == "f32" else np.float64
+        kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dt == "f32" else {}
+        A, y, xs, x0 = O.synth_generate(B, m, n, npdt)
+        xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw), numdiff=(2, 0.0) if tag == "numdiff" else None)
+        iters, stop, cost, fails, xg = rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4:]
+        assert np.array_equal(iters, ro["num_iters"]) and np.array_equal(stop, ro["stop_reason"]), f.name
+        assert np.array_equal(fails, ro["num_failures"]) and np.array_equal(cost, ro["final_cost"]), f.name
+        assert np.array_equal(xg, xo.astype(np.float64)), f.name

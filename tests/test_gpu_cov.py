@@ -71,6 +71,28 @@ def test_inv_cov_large_bitexact(ctx, n):
     assert st[2] == 1 and ms[2] == 0
 
 
+@pytest.mark.parametrize("dtype,n", [(np.float64, 65), (np.float64, 96), (np.float64, 200), (np.float64, 513),
+                                     (np.float32, 513), (np.float32, 700)])
+def test_inv_cov_general_family_bitexact(ctx, dtype, n):
+    """InvCov above the specialised kernels' sizes (double n > 64, float n > 512): the general family's LDLT + every
+    column of the identity at once, each entry in the oracle's update order."""
+    rng = np.random.default_rng(n)
+    B = 3
+    A = np.stack([spd(rng, n, dtype) for _ in range(B)])
+    A[1][np.tril_indices(n, -1)] = -3.0
+    A[2] = -A[2]
+    cov, ms, st = ctx.inv_cov(torch.from_numpy(A).cuda())
+    ctx.sync()
+    cov, ms, st = cov.cpu().numpy(), ms.cpu().numpy(), st.cpu().numpy()
+    for p in range(B):
+        ref = O.inv_cov(A[p])
+        assert (ref is None) == (st[p] == 1), (n, p)
+        if ref is not None:
+            assert np.array_equal(cov[p], ref), (n, p, np.abs(cov[p] - ref).max())
+            assert ms[p] == np.sqrt(ref.max())
+    assert st[2] == 1 and ms[2] == 0
+
+
 def test_inv_cov_is_the_inverse(ctx):
     """tests/cov.cpp:20-42 style: InvCov(H) * H = I to 1e-5 (double)."""
     rng = np.random.default_rng(5)

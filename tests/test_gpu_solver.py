@@ -401,3 +401,99 @@ def test_hg_singular_normal_matrix_float(ctx):
     outs = oracle_hg(x0, acc4, {}, np.float32)
     assert_hg_parity(x, res, outs)
     assert np.abs(x[:, 0:2] + x[:, 2:4] + x[:, 4:6] - 10).max() < 1e-5
+
+
+# ---- the seam above n = 55: the general kernel family behind tob200_solver_* (gn.cuh) --------------------------------
+@pytest.mark.parametrize("dtype,B,m,n", [(np.float64, 9, 150, 56), (np.float32, 7, 200, 72), (np.float64, 5, 260, 130),
+                                         (np.float32, 3, 640, 300), (np.float64, 2, 300, 257), (np.float32, 2, 700, 600)])
+def test_solver_seam_above_55_matches_oracle(ctx, dtype, B, m, n):
+    """`Optimizer_<SolverLM>` with a user lambda has no size cap (math.h:232-240): the host-driven loop on the general
+    family, fed with the family's residual blocks, == the oracle bit for bit in both precisions; Output::final_hessian and
+    Output::Covariance() (InvCov of the un-damped H_, in double) follow."""
+    import tinyopt_b200 as tb
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dtype == np.float32 else {}
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype, p0=5)
+    xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, tdt, p0=5, layout=tb.PROBLEM_MAJOR)
+    s = tb.BatchSolver(ctx, B, n, tdt, tb.options(**kw))
+    s.reset(dx0)
+    assert s.num_active() == B and (s.needs.cpu().numpy() == 1).all()
+    steps = 0
+    while s.num_active() > 0 and steps < 200:
+        r, J = ctx.synth_eval(dA, dy, s.x, layout=tb.PROBLEM_MAJOR)
+        s.step(J, r, layout=tb.PROBLEM_MAJOR)
+        steps += 1
+    res = s.results()
+    assert (s.needs.cpu().numpy() == -1).all()
+    assert np.array_equal(res["num_iters"], ro["num_iters"])
+    assert np.array_equal(res["stop_reason"], ro["stop_reason"])
+    assert np.array_equal(s.x.cpu().numpy(), xo)
+    assert np.array_equal(res["final_cost"], ro["final_cost"])
+    assert np.array_equal(res["last_lambda"], ro["last_lambda"])
+    H = s.final_hessian().cpu().numpy()
+    assert np.array_equal(H, np.swapaxes(H, 1, 2))
+    cov, st = s.covariance()
+    ctx.sync()
+    assert (st.cpu().numpy() == 0).all()
+    assert np.array_equal(cov[0].cpu().numpy(), O.inv_cov(H[0]))
+    eye_err = np.abs(np.einsum("bij,bjk->bik", cov.cpu().numpy(), H) - np.eye(n)).max()
+    assert eye_err < 1e-8, eye_err
+    ms = s.max_std_dev().cpu().numpy()
+    assert np.array_equal(ms, np.sqrt(cov.cpu().numpy().reshape(B, -1).max(axis=1)))
+    s.close()
+
+
+@pytest.mark.parametrize("dtype,n", [(torch.float64, 64), (torch.float32, 100), (torch.float64, 300)])
+def test_hg_prior_above_55(ctx, dtype, n):
+    """"Prior n" (benchmarks/dense.cpp:57-66) with user-filled accumulators above n = 55: only H.diagonal() is filled, the
+    lower triangle is poisoned, cost is a scalar Cost; bit for bit against the oracle run with the same numpy lambda."""
+    import tinyopt_b200 as tb
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    rng = np.random.default_rng(n)
+    B = 5
+    y = rng.uniform(-1, 1, (B, n)).astype(npdt)
+    sd = rng.uniform(-1, 1, (B, n)).astype(npdt)
+    sd[np.abs(sd) < 0.05] = npdt(0.3)
+
+    def acc(p, v, want):
+        res = ((v - y[p]) / sd[p]).astype(npdt)
+        cost = npdt(0)
+        for r in res:
+            cost = npdt(cost + npdt(r * r))
+        g = H = None
+        if want:
+            g = (res / sd[p]).astype(npdt)
+            H = np.diag((npdt(1) / sd[p]) ** 2).astype(npdt)
+        return g, H, float(cost), 1
+
+    x0 = rng.uniform(-1, 1, (B, n)).astype(npdt)
+    kw = {} if npdt == np.float64 else dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)
+    x, res, Hf = drive_hg(ctx, x0, acc, tb.options(**kw), dtype)
+    outs = oracle_hg(x0, acc, kw, npdt)
+    assert_hg_parity(x, res, outs)
+    assert np.abs(x - y).max() < (1e-6 if npdt == np.float64 else 1e-3) and (res["stop_reason"] > 0).all()
+
+
+def test_solver_seam_above_55_option_variants(ctx):
+    """Gauss-Newton, use_ldlt = false, cost normalisation and gradient clipping through the seam at n = 64 (double)."""
+    import tinyopt_b200 as tb
+    B, m, n = 4, 160, 64
+    A, y, xs, x0 = O.synth_generate(B, m, n, np.float64, p0=11)
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, torch.float64, p0=11, layout=tb.PROBLEM_MAJOR)
+    for kw in (dict(solver_type=1), dict(use_ldlt=0), dict(normalize=1, downscale_by_2=1), dict(grad_clipping=0.05, max_iters=8),
+               dict(damping_init=10.0)):
+        xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+        s = tb.BatchSolver(ctx, B, n, torch.float64, tb.options(**kw))
+        s.reset(dx0)
+        steps = 0
+        while s.num_active() > 0 and steps < 200:
+            r, J = ctx.synth_eval(dA, dy, s.x, layout=tb.PROBLEM_MAJOR)
+            s.step(J, r, layout=tb.PROBLEM_MAJOR)
+            steps += 1
+        res = s.results()
+        assert np.array_equal(res["num_iters"], ro["num_iters"]), kw
+        assert np.array_equal(res["stop_reason"], ro["stop_reason"]), kw
+        assert np.array_equal(s.x.cpu().numpy(), xo), kw
+        assert np.array_equal(res["final_cost"], ro["final_cost"]), kw
+        s.close()

@@ -126,3 +126,25 @@ def test_fast_build_is_bit_identical(B, m, n, dtype, kw):
         assert np.array_equal(x1, x2)
         for k in r1.dtype.names:
             assert np.array_equal(r1[k], r2[k]), k
+
+
+@pytest.mark.parametrize("dtype,method", [(np.float64, 2), (np.float64, 1), (np.float64, 3), (np.float32, 2)])
+def test_numdiff_variant_of_the_family(dtype, method):
+    """diff/num_diff.h restated (NumEval :57-126, CreateNumDiffFunc2 :284-309): the Jacobian from central / forward /
+    fast-central differences with h = FloatEpsilon, the Cost the residual NORM.  Pinned the way tests/num_diff.cpp pins
+    the reference: the estimate agrees with the analytic Jacobian to the method's order (same minimiser as the analytic
+    run), and here additionally: final_cost is the norm (sqrt of the analytic run's r^T r at the same point)."""
+    B, m, n = 6, 40, 7
+    kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dtype == np.float32 else {}
+    A, y, xs, x0 = O.synth_generate(B, m, n, dtype)
+    xa, ra, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+    xn, rn, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw), numdiff=(method, 0.0))
+    assert (rn["stop_reason"] > 0).all() and (ra["stop_reason"] > 0).all()
+    tol = {(np.float64, 2): 1e-7, (np.float64, 1): 1e-5, (np.float64, 3): 1e-7, (np.float32, 2): 5e-3}[(dtype, method)]
+    assert np.abs(xn - xa).max() / np.abs(xa).max() < tol
+    # the cost of the numdiff run is a norm: compare with the analytic run's squared norm at (nearly) the same point
+    assert np.allclose(rn["final_cost"] ** 2, ra["final_cost"], rtol=1e-3)
+    assert (rn["final_num_residuals"] == m).all()
+    # the switch is off again: the analytic family is what runs by default
+    xb, rb, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+    assert np.array_equal(xa, xb)

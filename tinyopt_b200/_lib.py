@@ -84,6 +84,9 @@ SYMBOLS = {
     "tob200_solver_needs": (_vp, [_vp]),
     "tob200_solver_step_f32": (_i, [_vp, _vp, _vp, _i, _i]),
     "tob200_solver_step_f64": (_i, [_vp, _vp, _vp, _i, _i]),
+    "tob200_solver_create_ex": (_i, [_vp, _i, _i64, _i, _PO, _i, C.POINTER(_vp)]),
+    "tob200_solver_step_cost_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "tob200_solver_step_cost_f64": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "tob200_solver_step_hg_f32": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "tob200_solver_step_hg_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "tob200_solver_num_active": (_i, [_vp, C.POINTER(_i64)]),

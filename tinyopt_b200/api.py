@@ -368,12 +368,16 @@ class BatchSolver:
     """A batch of `Optimizer_<SolverLM>` whose state lives on the device; the caller evaluates the
     residual blocks (its own lambda, AD, ...) at `x` and feeds them to `step`."""
 
-    def __init__(self, ctx: Context, B: int, n: int, dtype: torch.dtype, opt: Options | None = None):
+    def __init__(self, ctx: Context, B: int, n: int, dtype: torch.dtype, opt: Options | None = None, *,
+                 general: bool = False):
+        """Any n <= 2048 (n > 55 runs on the general kernel family); `general=True` forces that family for a small n
+        too (TOB200_SOLVER_GENERAL: needed by `step(..., cost=...)`)."""
         self.ctx, self.B, self.n, self.dtype = ctx, B, n, dtype
         self.opt = opt if opt is not None else options()
         h = C.c_void_p()
-        ctx._ck(ctx._lib.tob200_solver_create(ctx._h, 0 if dtype == torch.float32 else 1, B, n,
-                                              C.byref(self.opt), C.byref(h)), "tob200_solver_create")
+        ctx._ck(ctx._lib.tob200_solver_create_ex(ctx._h, 0 if dtype == torch.float32 else 1, B, n,
+                                                 C.byref(self.opt), 1 if general else 0, C.byref(h)),
+                "tob200_solver_create_ex")
         self._h = h
 
     def close(self):
@@ -409,9 +413,18 @@ class BatchSolver:
         """[B] int32: 1 rebuild (J and r), 0 cost only (r), -1 finished."""
         return self._wrap(self.ctx._lib.tob200_solver_needs(self._h), (self.B,), torch.int32)
 
-    def step(self, J: torch.Tensor, r: torch.Tensor, layout: int | None = None):
+    def step(self, J: torch.Tensor, r: torch.Tensor, layout: int | None = None, cost: torch.Tensor | None = None):
+        """One Step from the residual blocks at the current x.  `cost` ([B] float64): the pass's Cost::cost as the
+        caller's accumulation functor returns it (tob200_solver_step_cost_*; e.g. the residual NORM of
+        diff/num_diff.h:300-305) instead of r^T r - general family only."""
         layout = _layout_of(J, layout)
         m = r.shape[1]
+        if cost is not None:
+            cost = cost.to(dtype=torch.float64, device=self.ctx.device).contiguous()
+            fn = getattr(self.ctx._lib, f"tob200_solver_step_cost_{_suf(self.dtype)}")
+            self.ctx._ck(fn(self._h, _p(J.contiguous()), _p(r.contiguous()), layout, m, _p(cost)), "tob200_solver_step_cost")
+            self._keep = (cost,)
+            return
         fn = getattr(self.ctx._lib, f"tob200_solver_step_{_suf(self.dtype)}")
         self.ctx._ck(fn(self._h, _p(J.contiguous()), _p(r.contiguous()), layout, m), "tob200_solver_step")
 

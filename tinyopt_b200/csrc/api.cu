@@ -36,7 +36,7 @@ struct tob200_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // scratch for PROBLEM_MAJOR -> TILE32 conversion and for the *_host entry points
   // (slots 0-1 layout conversion, 2-5 host entry points, 7 warp-per-problem H_, 8-19 large-n family)
-  static constexpr int kScratchSlots = 24;
+  static constexpr int kScratchSlots = 28;
   void *scratch[kScratchSlots] = {};
   size_t scratch_bytes[kScratchSlots] = {};
   std::map<std::tuple<int, int, int, int, size_t>, int> occupancy;  // (dtype, n, kind, block, smem) -> CTAs/SM
@@ -960,8 +960,10 @@ struct tob200_solver {
   int32_t *needs = nullptr;
   unsigned long long *n_active = nullptr;  // device
   bool is_reset = false;
-  int family = 1;          // 1: thread per problem (H_, grad_ tile-interleaved), 2: warp per problem ([B][NP * LDW], [B][NP])
+  int family = 1;          // 1: thread per problem (H_, grad_ tile-interleaved), 2: warp per problem ([B][NP * LDW], [B][NP]),
+                           // 4: general family, n > 55 (H_ [B][n][n] upper triangle, grad_ [B][n]; rec = LmScalars<T>)
   size_t h_bytes = 0, g_bytes = 0;
+  void *hd = nullptr, *cost = nullptr;  // family 4: the damped diagonal of H_ [B][n], the pass's cost [B]
 };
 
 namespace {
@@ -973,8 +975,56 @@ struct StepHG {  // tob200_solver_step_hg_*: caller-filled accumulators instead 
   const int32_t *nres = nullptr;
 };
 
+// The seam above n = 55 on the general kernel family (gn.cuh): gn_accum_kernel forms cost, grad_, H_ from the
+// caller's residual blocks (canonical chains, rows in order: bit-identical to the oracle fed with the same J, r),
+// gn_solve_kernel runs Build's tail, Solve, Step and the OptimizeAcc update.
 template <typename T>
-int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m, int reset, const StepHG<T> *hg = nullptr) {
+int gn_solver_step(tob200_solver *s, const T *J, const T *r, int m, int reset, const StepHG<T> *hg, const double *cost_in) {
+  tob200_ctx *ctx = s->ctx;
+  const int n = s->n;
+  const int64_t B = s->B;
+  const DevOptions<T> dopt = make_dev_options<T>(s->opt);
+  LmScalars<T> *rec = (LmScalars<T> *)s->rec;
+  if (reset) {
+    CK(launch_gn_init<T>(rec, dopt, (T *)s->last_dx, B, n, ctx->stream, s->needs));
+    ctx->launches++;
+    const unsigned long long all = (unsigned long long)B;
+    CK(cudaMemcpyAsync(s->n_active, &all, sizeof(all), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // `all` is a stack variable
+    return TOB200_OK;
+  }
+  const int grid = (int)(B < 2 * ctx->num_sms ? B : 2 * ctx->num_sms);
+  int rc;
+  if ((rc = ensure_scratch(ctx, kGnW, (size_t)grid * n * n * sizeof(T))) != TOB200_OK) return rc;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  const int is_lm = s->opt.solver_type == 0;
+  if (hg) {
+    CK(launch_gn_import_hg<T>(hg->grad, hg->H, rec, is_lm, B, n, (T *)s->g, (T *)s->H, ctx->stream));
+  } else {
+    if ((rc = ensure_scratch(ctx, kGnRs, (size_t)B * 2 * (m > 0 ? m : 1) * sizeof(T))) != TOB200_OK) return rc;
+    GnAccumParams<T> ap;
+    ap.A = J; ap.y = r; ap.x = nullptr; ap.rec = rec; ap.rs = (T *)ctx->scratch[kGnRs]; ap.g = (T *)s->g; ap.H = (T *)s->H;
+    ap.cost = (T *)s->cost; ap.B = B; ap.m = m; ap.n = n; ap.synth = 0; ap.is_lm = is_lm; ap.alpha = (T)0; ap.alpha3 = (T)0;
+    CK(launch_gn_accum<T>(ap, ctx->num_sms, ctx->stream));
+  }
+  ctx->launches++;
+  GnSolveParams<T> vp;
+  vp.H = (T *)s->H; vp.hd = (T *)s->hd; vp.g = (T *)s->g; vp.cost = (const T *)s->cost; vp.W = (T *)ctx->scratch[kGnW];
+  vp.B = B; vp.n = n; vp.nres = m; vp.mode = 0; vp.opt = dopt; vp.rec = rec; vp.x = (T *)s->x; vp.last_dx = (T *)s->last_dx;
+  vp.results = nullptr; vp.n_active = s->n_active; vp.lambda = nullptr; vp.dx = nullptr; vp.cost_out = nullptr;
+  vp.status = nullptr; vp.use_ldlt = s->opt.use_ldlt; vp.needs = s->needs;
+  if (hg) { vp.cost_d = hg->cost; vp.nres_arr = hg->nres; }
+  else if (cost_in) vp.cost_d = cost_in;
+  CK(cudaMemsetAsync(s->n_active, 0, sizeof(unsigned long long), ctx->stream));
+  CK(launch_gn_solve<T>(vp, grid, ctx->stream));
+  ctx->launches++;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  return TOB200_OK;
+}
+
+template <typename T>
+int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m, int reset, const StepHG<T> *hg = nullptr,
+                     const double *cost_in = nullptr) {
   if (!s) return fail(nullptr, TOB200_ERR_INVALID, "solver is NULL");
   tob200_ctx *ctx = s->ctx;
   if (s->dtype != dtype_of<T>()) return fail(ctx, TOB200_ERR_INVALID, "solver dtype mismatch");
@@ -995,6 +1045,8 @@ int solver_step_impl(tob200_solver *s, const T *J, const T *r, int layout, int m
     int rc = to_native_layout<T>(ctx, s->family, layout, B, m, n, &J, &r);
     if (rc != TOB200_OK) return rc;
   }
+  if (s->family == 4) return gn_solver_step<T>(s, J, r, m, reset, hg, cost_in);
+  if (cost_in) return fail(ctx, TOB200_ERR_UNSUPPORTED, "tob200_solver_step_cost: general family only (TOB200_SOLVER_GENERAL)");
   if (s->family == 2) {  // warp per problem (wpp_step.cuh)
     WppStepParams<T> p;
     TppLaunch cfg;
@@ -1085,8 +1137,23 @@ int inv_cov_impl(tob200_ctx *ctx, const T *H, int64_t B, int n, T *cov, T *max_s
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     return TOB200_OK;
   }
-  if (sizeof(T) != 4 || n > kLgMaxN)
-    return fail(ctx, TOB200_ERR_UNSUPPORTED, "InvCov: n <= 64 (float, double) or n <= 512 (float)");
+  if (sizeof(T) != 4 || n > kLgMaxN) {  // general family: double above n = 64, float above n = 512 (gn.cuh, mode 3)
+    if (n > kGnMaxN) return fail(ctx, TOB200_ERR_UNSUPPORTED, "InvCov: n above 2048 has no kernel");
+    const int grid = (int)(B < 2 * ctx->num_sms ? B : 2 * ctx->num_sms);
+    int rc;
+    if ((rc = ensure_scratch(ctx, kGnW, (size_t)grid * n * n * sizeof(T))) != TOB200_OK) return rc;
+    if ((rc = ensure_scratch(ctx, 24, (size_t)grid * n * n * sizeof(T))) != TOB200_OK) return rc;
+    GnSolveParams<T> vp;
+    vp.H = const_cast<T *>(H); vp.hd = nullptr; vp.g = nullptr; vp.cost = nullptr; vp.W = (T *)ctx->scratch[kGnW]; vp.B = B;
+    vp.n = n; vp.nres = 0; vp.mode = 3; vp.opt = DevOptions<T>(); vp.rec = nullptr; vp.x = nullptr; vp.last_dx = nullptr;
+    vp.results = nullptr; vp.n_active = nullptr; vp.lambda = nullptr; vp.dx = nullptr; vp.cost_out = nullptr; vp.status = status;
+    vp.use_ldlt = 1; vp.Y = (T *)ctx->scratch[24]; vp.cov = cov; vp.max_std = max_std;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_gn_solve<T>(vp, grid, ctx->stream));
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    return TOB200_OK;
+  }
   LgBuffers b;
   int rc = lg_prepare(ctx, B, 0, n, false, false, &b);
   if (rc != TOB200_OK) return rc;
@@ -1461,15 +1528,21 @@ int tob200_lm_run_host_f64(tob200_ctx *ctx, const tob200_options *opt, const dou
 // ---- solver object -------------------------------------------------------------------------------
 int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob200_options *opt,
                          tob200_solver **out) {
+  return tob200_solver_create_ex(ctx, dtype, B, n, opt, 0, out);
+}
+
+int tob200_solver_create_ex(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob200_options *opt, int flags,
+                            tob200_solver **out) {
   if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
   if (!out) return fail(ctx, TOB200_ERR_INVALID, "out is NULL");
   *out = nullptr;
   int rc = check_options(ctx, opt);
   if (rc != TOB200_OK) return rc;
   if (B < 1 || n < 1) return fail(ctx, TOB200_ERR_INVALID, "need B >= 1 and n >= 1");
-  const int family = tob200_kernel_family(dtype, n);
-  if (family != 1 && family != 2)
-    return fail(ctx, TOB200_ERR_UNSUPPORTED, "solver: n has no kernel yet for this dtype (n <= 55)");
+  int family = tob200_kernel_family(dtype, n);
+  if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "solver: n above 2048 has no kernel");
+  if (family == 3) family = 4;  // the seam above n = 55 runs on the general (bit-exact) family in both precisions
+  if (flags & TOB200_SOLVER_GENERAL) family = 4;
   DeviceGuard guard(ctx->device);
   tob200_solver *s = new (std::nothrow) tob200_solver();
   if (!s) return fail(ctx, TOB200_ERR_NOMEM, "host allocation failed");
@@ -1481,7 +1554,8 @@ int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob
   s->opt = *opt;
   const size_t elt = dtype == TOB200_F32 ? 4 : 8;
   const size_t ntiles = (size_t)((B + kTile - 1) / kTile);
-  const size_t rec_bytes = dtype == TOB200_F32 ? sizeof(StateRec<float>) : sizeof(StateRec<double>);
+  size_t rec_bytes = dtype == TOB200_F32 ? sizeof(StateRec<float>) : sizeof(StateRec<double>);
+  if (family == 4) rec_bytes = dtype == TOB200_F32 ? sizeof(LmScalars<float>) : sizeof(LmScalars<double>);
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void **p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -1493,10 +1567,15 @@ int tob200_solver_create(tob200_ctx *ctx, int dtype, int64_t B, int n, const tob
   if (family == 1) {
     s->h_bytes = elt * ntiles * tri_count(n) * kTile;
     s->g_bytes = elt * ntiles * n * kTile;
-  } else {
+  } else if (family == 2) {
     const int np = wpp_nb_for(n) * wpp_blk_for(n);
     s->h_bytes = elt * (size_t)B * np * wpp_ldw(np);
     s->g_bytes = elt * (size_t)B * np;
+  } else {
+    s->h_bytes = elt * (size_t)B * n * n;
+    s->g_bytes = elt * (size_t)B * n;
+    alloc(&s->hd, elt * B * n);
+    alloc(&s->cost, elt * B);
   }
   alloc(&s->H, s->h_bytes);
   alloc(&s->g, s->g_bytes);
@@ -1521,6 +1600,8 @@ int tob200_solver_destroy(tob200_solver *s) {
   cudaFree(s->g);
   cudaFree(s->needs);
   cudaFree(s->n_active);
+  cudaFree(s->hd);
+  cudaFree(s->cost);
   delete s;
   return TOB200_OK;
 }
@@ -1534,6 +1615,7 @@ int tob200_solver_reset(tob200_solver *s, const void *x0) {
   CK(cudaMemcpyAsync(s->x, x0, elt * s->B * s->n, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemsetAsync(s->H, 0, s->h_bytes, ctx->stream));
   CK(cudaMemsetAsync(s->g, 0, s->g_bytes, ctx->stream));
+  if (s->hd) CK(cudaMemsetAsync(s->hd, 0, elt * s->B * s->n, ctx->stream));
   int rc = s->dtype == TOB200_F32 ? solver_step_impl<float>(s, nullptr, nullptr, 0, 0, 1)
                                   : solver_step_impl<double>(s, nullptr, nullptr, 0, 0, 1);
   if (rc == TOB200_OK) s->is_reset = true;
@@ -1548,6 +1630,15 @@ int tob200_solver_step_f32(tob200_solver *s, const float *J, const float *r, int
 }
 int tob200_solver_step_f64(tob200_solver *s, const double *J, const double *r, int layout, int m) {
   return solver_step_impl<double>(s, J, r, layout, m, 0);
+}
+
+int tob200_solver_step_cost_f32(tob200_solver *s, const float *J, const float *r, int layout, int m, const double *cost) {
+  if (!cost) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "cost is NULL");
+  return solver_step_impl<float>(s, J, r, layout, m, 0, nullptr, cost);
+}
+int tob200_solver_step_cost_f64(tob200_solver *s, const double *J, const double *r, int layout, int m, const double *cost) {
+  if (!cost) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "cost is NULL");
+  return solver_step_impl<double>(s, J, r, layout, m, 0, nullptr, cost);
 }
 
 int tob200_solver_step_hg_f32(tob200_solver *s, const float *grad, const float *H, const double *cost,
@@ -1578,6 +1669,12 @@ int tob200_solver_results(tob200_solver *s, tob200_result *results) {
   if (!s || !results) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "NULL argument");
   tob200_ctx *ctx = s->ctx;
   DeviceGuard guard(ctx->device);
+  if (s->family == 4) {
+    if (s->dtype == TOB200_F32) CK(launch_gn_results<float>((const LmScalars<float> *)s->rec, s->B, results, ctx->stream));
+    else CK(launch_gn_results<double>((const LmScalars<double> *)s->rec, s->B, results, ctx->stream));
+    ctx->launches++;
+    return TOB200_OK;
+  }
   const unsigned grid = (unsigned)((s->B + 255) / 256);
   if (s->dtype == TOB200_F32)
     results_kernel<float><<<grid, 256, 0, ctx->stream>>>((const StateRec<float> *)s->rec, s->B, results);
@@ -1592,6 +1689,16 @@ int tob200_solver_final_hessian(tob200_solver *s, double *H) {
   if (!s || !H) return fail(s ? s->ctx : nullptr, TOB200_ERR_INVALID, "NULL argument");
   tob200_ctx *ctx = s->ctx;
   DeviceGuard guard(ctx->device);
+  if (s->family == 4) {
+    if (s->dtype == TOB200_F32)
+      CK((launch_gn_export_h<float, double>((const float *)s->H, (const float *)s->hd, (const LmScalars<float> *)s->rec, nullptr,
+                                            s->opt.solver_type, s->B, s->n, H, ctx->stream)));
+    else
+      CK((launch_gn_export_h<double, double>((const double *)s->H, (const double *)s->hd, (const LmScalars<double> *)s->rec,
+                                             nullptr, s->opt.solver_type, s->B, s->n, H, ctx->stream)));
+    ctx->launches++;
+    return TOB200_OK;
+  }
   if (s->family == 2) {
     const int np = wpp_nb_for(s->n) * wpp_blk_for(s->n), ldw = wpp_ldw(np);
     if (s->dtype == TOB200_F32)

@@ -189,6 +189,15 @@ struct GnSolveParams {
   double *cost_out;
   int32_t *status;
   int use_ldlt;
+  // the SolverType seam above n = 55 (tob200_solver_*, family 4): what the next Step needs from the caller, and the
+  // cost / residual count of user-filled accumulators (tob200_solver_step_hg_*: Cost::cost is a double, cost.h:93)
+  int32_t *needs = nullptr;           // [B] or nullptr
+  const double *cost_d = nullptr;     // [B] or nullptr: replaces cost[]
+  const int32_t *nres_arr = nullptr;  // [B] or nullptr: replaces nres
+  // mode 3 (InvCov, math.h:44-57): H -> cov = LDLT(H).solve(Identity), MaxStdDev (solvers/lm.h:176-187)
+  T *Y = nullptr;        // [grid][n][n] second workspace
+  T *cov = nullptr;      // [B][n][n] or nullptr
+  T *max_std = nullptr;  // [B] or nullptr
 };
 
 // shared memory of gn_solve_kernel, in scalars: dd | temp | rhs / y | keys(perm, inv as ints share the tail)
@@ -386,6 +395,74 @@ __global__ void __launch_bounds__(kGnThreads) gn_solve_kernel(const __grid_const
     T *gp = p.g + (size_t)pr * n;
     bool pass_rebuilt = true;
     __syncthreads();
+    if (p.mode == 3) {  // InvCov(H) = H.ldlt().solve(Identity) (math.h:44-57), MaxStdDev (solvers/lm.h:176-187)
+      T *Cp = p.cov ? p.cov + (size_t)pr * n * n : nullptr;
+      if (n == 1) {  // m.inverse() of a 1 x 1 (math.h:49-50), unprotected as in the reference
+        if (tid == 0) {
+          const T v = O::div((T)1, Hp[0]);
+          if (Cp) Cp[0] = v;
+          if (p.max_std) p.max_std[pr] = sqrt(v);
+          p.status[pr] = 0;
+        }
+        continue;
+      }
+      for (int j = tid; j < n; j += kGnThreads) dd[j] = Hp[(size_t)j * n + j];
+      __syncthreads();
+      gn_pivot_order<T>(dd, n, perm, inv, &sh_flag);
+      for (int64_t e = tid; e < (int64_t)n * n; e += kGnThreads) {
+        const int b = (int)(e / n), a = (int)(e % n);
+        if (a < b) continue;
+        const int ia = perm[a], ib = perm[b];
+        W[e] = ia < ib ? Hp[(size_t)ia * n + ib] : Hp[(size_t)ib * n + ia];
+      }
+      __syncthreads();
+      const bool ok = gn_ldlt_factor<T>(W, n, temp, misc);
+      T best = (T)0;
+      bool have = false;
+      if (ok) {
+        // every column of the identity at once: thread = right-hand side c, Y(i, c) at Y[i * n + c] (coalesced over
+        // c), each entry taking its updates in the oracle's order (ldlt_solve_: j = 0 .. i-1, then j = n-1 .. i+1)
+        T *Y = p.Y + (size_t)blockIdx.x * n * n;
+#define GW(i, j) W[(size_t)(j) * n + (i)]
+        for (int c = tid; c < n; c += kGnThreads) {
+          for (int i = 0; i < n; ++i) {
+            T sacc = perm[i] == c ? (T)1 : (T)0;  // P e_c
+            for (int j = 0; j < i; ++j) sacc = O::fma(-GW(i, j), Y[(size_t)j * n + c], sacc);
+            Y[(size_t)i * n + c] = sacc;
+          }
+          for (int i = 0; i < n; ++i) {
+            const T d = GW(i, i);
+            const T v = Y[(size_t)i * n + c];
+            Y[(size_t)i * n + c] = (O::abs(d) > O::min_normal()) ? O::div(v, d) : (T)0;
+          }
+          for (int i = n - 1; i >= 0; --i) {
+            T sacc = Y[(size_t)i * n + c];
+            for (int j = n - 1; j > i; --j) sacc = O::fma(-GW(j, i), Y[(size_t)j * n + c], sacc);
+            Y[(size_t)i * n + c] = sacc;
+          }
+          for (int i = 0; i < n; ++i) {  // x = P^T y
+            const T v = Y[(size_t)i * n + c];
+            if (Cp) Cp[(size_t)perm[i] * n + c] = v;
+            if (!have || v > best) { best = v; have = true; }  // maxCoeff
+          }
+        }
+#undef GW
+      }
+      if (p.max_std) {
+        __shared__ T red_best[kGnThreads];
+        __shared__ int red_have[kGnThreads];
+        red_best[tid] = best;
+        red_have[tid] = have;
+        __syncthreads();
+        if (tid == 0) {
+          for (int t = 1; t < kGnThreads; ++t)
+            if (red_have[t] && (!have || red_best[t] > best)) { best = red_best[t]; have = true; }
+          p.max_std[pr] = ok ? sqrt(best) : (T)0;
+        }
+      }
+      if (tid == 0) p.status[pr] = ok ? 0 : 1;
+      continue;
+    }
     if (p.mode == 0) {
       if (tid == 0) s = p.rec[pr];
       __syncthreads();
@@ -394,10 +471,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_solve_kernel(const __grid_const
     }
     double cost = 0.0;
     bool built_ok = true;
+    const int nres = p.nres_arr ? p.nres_arr[pr] : p.nres;
     if (p.mode == 0) {
       if (tid == 0) {
         double c;
-        const bool ok = lm_normalize_cost(p.opt, p.cost[pr], p.nres, c);
+        const bool ok = p.cost_d ? lm_normalize_cost_d(p.opt, p.cost_d[pr], nres, c)
+                                 : lm_normalize_cost(p.opt, p.cost[pr], nres, c);
         if (pass_rebuilt) s.num_builds++;
         sh_cost = c;
         sh_built_ok = ok;
@@ -471,7 +550,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_solve_kernel(const __grid_const
       }
       if (!solver_failed) break;
       if (p.mode != 0) break;
-      if (tid == 0) sh_act = lm_on_solver_failure(s, p.opt, cost, p.nres);
+      if (tid == 0) sh_act = lm_on_solver_failure(s, p.opt, cost, nres);
       __syncthreads();
       const int act = sh_act;
       if (act == kLmEarlyReturn) early_return = true;
@@ -495,7 +574,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_solve_kernel(const __grid_const
           for (int j = 0; j < n; ++j) gn = O::fma(gp[j], gp[j], gn);
       }
       bool success, has_dx;
-      lm_finish_step(s, p.opt, early_return, solver_failed, cost, p.nres, (double)dn, (double)gn, success, has_dx);
+      lm_finish_step(s, p.opt, early_return, solver_failed, cost, nres, (double)dn, (double)gn, success, has_dx);
       sh_act = lm_update_action(s, p.opt, success, has_dx);
     }
     __syncthreads();
@@ -511,8 +590,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_solve_kernel(const __grid_const
     }
     if (tid == 0) {
       p.rec[pr] = s;
-      if (s.done()) lm_write_result(s, &p.results[pr]);
+      if (s.done()) { if (p.results) lm_write_result(s, &p.results[pr]); }
       else local_active++;
+      if (p.needs) p.needs[pr] = s.done() ? -1 : ((s.rebuild() || p.opt.solver_type != 0) ? 1 : 0);
     }
   }
   (void)sh_norm;
@@ -520,14 +600,38 @@ __global__ void __launch_bounds__(kGnThreads) gn_solve_kernel(const __grid_const
 }
 
 template <typename T>
-__global__ void gn_init_kernel(LmScalars<T> *rec, DevOptions<T> opt, T *last_dx, int64_t B, int n) {
+__global__ void gn_init_kernel(LmScalars<T> *rec, DevOptions<T> opt, T *last_dx, int64_t B, int n, int32_t *needs) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     LmScalars<T> s;
     s.reset_scalars(opt);
     rec[i] = s;
+    if (needs) needs[i] = 1;
   }
   if (i < B * n) last_dx[i] = (T)0;
+}
+
+// tob200_solver_step_hg_* above n = 55: the caller's grad / H (upper triangle read, docs/API.md:170) become the
+// solver-owned grad_ / H_ of the problems whose Step rebuilds; the others keep theirs (stale H_, re-damped)
+template <typename T>
+__global__ void gn_import_hg_kernel(const T *grad, const T *Hin, const LmScalars<T> *rec, int is_lm, int64_t B, int n, T *g,
+                                    T *H) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * n * n) return;
+  const int64_t pr = e / ((int64_t)n * n);
+  const LmScalars<T> s = rec[pr];
+  if (s.done() || (is_lm && !s.rebuild())) return;
+  const int ij = (int)(e % ((int64_t)n * n));
+  const int i = ij / n, j = ij % n;
+  if (i <= j) H[e] = Hin[e];
+  if (i == 0) g[(size_t)pr * n + j] = grad[(size_t)pr * n + j];
+}
+
+// the Output scalars of every problem, finished or not (tob200_solver_results)
+template <typename T>
+__global__ void gn_results_kernel(const LmScalars<T> *rec, int64_t B, tob200_result *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) lm_write_result(rec[i], &out[i]);
 }
 
 // Output::final_hessian / H_out: upper triangle + persistent (damped) diagonal -> full symmetric

@@ -7,9 +7,26 @@
 namespace tob200 {
 
 template <typename T>
-cudaError_t launch_gn_init(LmScalars<T> *rec, const DevOptions<T> &opt, T *last_dx, int64_t B, int n, cudaStream_t st) {
+cudaError_t launch_gn_init(LmScalars<T> *rec, const DevOptions<T> &opt, T *last_dx, int64_t B, int n, cudaStream_t st,
+                           int32_t *needs) {
   const int64_t total = B * n;
-  gn_init_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rec, opt, last_dx, B, n);
+  gn_init_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rec, opt, last_dx, B, n, needs);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_gn_import_hg(const T *grad, const T *Hin, const LmScalars<T> *rec, int is_lm, int64_t B, int n, T *g, T *H,
+                                cudaStream_t st) {
+  const int64_t total = B * n * n;
+  if (total <= 0) return cudaSuccess;
+  gn_import_hg_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(grad, Hin, rec, is_lm, B, n, g, H);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_gn_results(const LmScalars<T> *rec, int64_t B, tob200_result *out, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  gn_results_kernel<T><<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rec, B, out);
   return cudaGetLastError();
 }
 
@@ -43,7 +60,10 @@ cudaError_t launch_gn_export_h(const T *H, const T *hd, const LmScalars<T> *rec,
 }
 
 #define TOB200_GN_INST(T)                                                                                                   \
-  template cudaError_t launch_gn_init<T>(LmScalars<T> *, const DevOptions<T> &, T *, int64_t, int, cudaStream_t);            \
+  template cudaError_t launch_gn_init<T>(LmScalars<T> *, const DevOptions<T> &, T *, int64_t, int, cudaStream_t, int32_t *); \
+  template cudaError_t launch_gn_import_hg<T>(const T *, const T *, const LmScalars<T> *, int, int64_t, int, T *, T *,       \
+                                              cudaStream_t);                                                                \
+  template cudaError_t launch_gn_results<T>(const LmScalars<T> *, int64_t, tob200_result *, cudaStream_t);                   \
   template cudaError_t launch_gn_accum<T>(const GnAccumParams<T> &, int, cudaStream_t);                                      \
   template cudaError_t launch_gn_solve<T>(const GnSolveParams<T> &, int, cudaStream_t);                                      \
   template cudaError_t launch_gn_export_h<T, double>(const T *, const T *, const LmScalars<T> *, const T *, int, int64_t,    \

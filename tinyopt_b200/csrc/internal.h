@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/tinyopt_b200.h"
+
 #include <map>
 #include <mutex>
 #include <utility>
@@ -73,7 +75,13 @@ namespace tob200 {
 template <typename T> struct GnAccumParams;
 template <typename T> struct GnSolveParams;
 template <typename T>
-cudaError_t launch_gn_init(LmScalars<T> *rec, const DevOptions<T> &opt, T *last_dx, int64_t B, int n, cudaStream_t st);
+cudaError_t launch_gn_init(LmScalars<T> *rec, const DevOptions<T> &opt, T *last_dx, int64_t B, int n, cudaStream_t st,
+                           int32_t *needs = nullptr);
+template <typename T>
+cudaError_t launch_gn_import_hg(const T *grad, const T *Hin, const LmScalars<T> *rec, int is_lm, int64_t B, int n, T *g, T *H,
+                                cudaStream_t st);
+template <typename T>
+cudaError_t launch_gn_results(const LmScalars<T> *rec, int64_t B, tob200_result *out, cudaStream_t st);
 template <typename T>
 cudaError_t launch_gn_accum(const GnAccumParams<T> &p, int num_sms, cudaStream_t st);
 template <typename T>
