@@ -342,7 +342,8 @@ std::vector<Output> OptimizeBatch(const Context &ctx, Scalar *xs, int64_t B, int
 /// nullptr is the reference's `nullptr_t` cost-only call (solvers/gn.h:98-105).  The user may fill a true
 /// Hessian (tests/optimize_easy.cpp:35-80), a diagonal prior (benchmarks/dense.cpp:57-66), per-block
 /// `J^T J` sums (tests/types.cpp:97-108) ... — the device runs Build's tail, damping, Solve, Step and the
-/// OptimizeAcc update for every still-running problem (tob200_solver_step_hg_*).  n <= 55.
+/// OptimizeAcc update for every still-running problem (tob200_solver_step_hg_*).  Every n <= 2048 (above n = 55 on the
+/// general kernel family).
 template <typename Scalar, typename Acc>
 std::vector<Output> OptimizeBatchAcc(const Context &ctx, Scalar *xs, int64_t B, int n, Acc &&acc,
                                      const Options &options = Options()) {
