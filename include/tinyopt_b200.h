@@ -279,6 +279,17 @@ int tob200_solver_step_hg_f32(tob200_solver *s, const float *grad, const float *
                               const int32_t *num_residuals);
 int tob200_solver_step_hg_f64(tob200_solver *s, const double *grad, const double *H, const double *cost,
                               const int32_t *num_residuals);
+/* The same contract for accumulation functors whose H is SPARSE (the reference selects its sparse solver from the
+ * lambda's H type, optimize.h:27-33; tests/sparse.cpp:19-85): H arrives as triplets with ONE pattern for the whole batch -
+ * rows / cols: [nnz] int32 HOST arrays; values: [B][nnz] device.  Duplicates are summed in triplet order (Eigen's
+ * setFromTriplets), entries below the diagonal are ignored (`SimplicialLDLT<_, Upper>`, math.h:267-277).  The values are
+ * scattered into a dense upper triangle and solved by the dense pivoted LDL^T of the path: the same solution as the sparse
+ * factorisation's up to rounding for the positive definite systems LM produces; an indefinite H is rejected (the dense
+ * reference semantics) where SimplicialLDLT would go on.  n <= 2048.  Synchronises the stream once (pattern upload). */
+int tob200_solver_step_hg_sparse_f32(tob200_solver *s, const float *grad, const int32_t *rows, const int32_t *cols, int nnz,
+                                     const float *values, const double *cost, const int32_t *num_residuals);
+int tob200_solver_step_hg_sparse_f64(tob200_solver *s, const double *grad, const int32_t *rows, const int32_t *cols, int nnz,
+                                     const double *values, const double *cost, const int32_t *num_residuals);
 /* Number of problems still running (synchronises the stream). */
 int tob200_solver_num_active(tob200_solver *s, int64_t *n_active);
 /* Copy the per-problem results to `results` ([B], device). */

@@ -308,6 +308,36 @@ static void test_accumulation_contract(const Context &ctx) {
   for (size_t i = 0; i < x.size(); ++i) worst = std::fmax(worst, std::fabs(x[i] - y[i]));
   CHECK(worst < 1e-3f);
   for (int64_t p = 0; p < B; ++p) CHECK(po[p].Converged());
+  // the same contract above n = 55 (the reference's dynamic-size solver has no cap, math.h:232-240): "Prior 80" in double
+  {
+    const int nl = 80;
+    const int64_t Bl = 6;
+    std::vector<double> yl(Bl * nl), sl(Bl * nl), xl(Bl * nl);
+    for (auto &v : yl) v = rnd();
+    for (auto &v : sl) { v = rnd(); if (std::fabs(v) < 0.05) v = 0.3; }
+    for (auto &v : xl) v = rnd();
+    auto prior_l = [&](size_t p, const double *xv, double *grad, double *H) {
+      Cost c;
+      double acc = 0.0;
+      for (int j = 0; j < nl; ++j) {
+        const double res = (xv[j] - yl[p * nl + j]) / sl[p * nl + j];
+        acc += res * res;
+        if (grad) {
+          grad[j] = res / sl[p * nl + j];
+          H[j * nl + j] = (1.0 / sl[p * nl + j]) * (1.0 / sl[p * nl + j]);
+        }
+      }
+      c.cost = acc;
+      c.num_resisuals = 1;
+      return c;
+    };
+    auto pl = OptimizeBatchAcc<double>(ctx, xl.data(), Bl, nl, prior_l);
+    double wl = 0.0;
+    for (size_t i = 0; i < xl.size(); ++i) wl = std::fmax(wl, std::fabs(xl[i] - yl[i]));
+    CHECK(wl < 1e-6);
+    for (int64_t p = 0; p < Bl; ++p) CHECK(pl[p].Converged());
+    std::printf("accumulation contract above n = 55: Prior 80 (double): max |x - y| = %.2e\n", wl);
+  }
   std::printf("accumulation contract: Rosenbrock (true Hessian) iters[0]=%d failures[0]=%d, converged %d/%d; Prior 12: max |x - y| = %.2e\n",
               (int)outs[0].num_iters, (int)outs[0].num_failures, conv, (int)B, (double)worst);
 }

@@ -497,3 +497,57 @@ def test_solver_seam_above_55_option_variants(ctx):
         assert np.array_equal(s.x.cpu().numpy(), xo), kw
         assert np.array_equal(res["final_cost"], ro["final_cost"]), kw
         s.close()
+
+
+# ---- sparse H in the accumulation signature (tests/sparse.cpp:19-57) -------------------------------------------------
+@pytest.mark.parametrize("dtype,n", [(torch.float64, 100), (torch.float32, 10), (torch.float64, 12)])
+def test_hg_sparse_reference_case(ctx, dtype, n):
+    """tests/sparse.cpp "tinyopt_sparse" (n = 100, double) and "tinyopt_sparse_ad" (n = 10, float): res = 10 x - 2,
+    grad = J^T res with J = 10 I, H = J^T J handed over as TRIPLETS (here with a duplicated diagonal entry, 60 + 40, and
+    junk below the diagonal that a `SimplicialLDLT<_, Upper>` never reads), Cost(res.norm(), res.size()).  Reference
+    assertions: Succeeded, Converged, min / max of x == 0.2 +- 1e-5; and bit for bit against the oracle's dense run of the
+    same lambda."""
+    import tinyopt_b200 as tb
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    rng = np.random.default_rng(7 + n)
+    B = 5
+    x0 = rng.uniform(-1, 1, (B, n)).astype(npdt)
+    rows = np.concatenate([np.arange(n), np.arange(n), np.arange(1, n)]).astype(np.int32)   # diag twice + sub-diagonal junk
+    cols = np.concatenate([np.arange(n), np.arange(n), np.arange(0, n - 1)]).astype(np.int32)
+
+    def acc(p, v, want):
+        res = (npdt(10) * v - npdt(2)).astype(npdt)
+        c = npdt(0)
+        for r in res:
+            c = npdt(c + npdt(r * r))
+        cost = float(np.sqrt(c))
+        if want:
+            return (npdt(10) * res).astype(npdt), np.diag(np.full(n, 100, npdt)), cost, n
+        return None, None, cost, n
+
+    kw = dict(check_final_cost=0)
+    if npdt == np.float32:
+        kw.update(min_rerr_dec=1e-5, min_step_norm2=1e-9)
+    s = tb.BatchSolver(ctx, B, n, dtype, tb.options(**kw))
+    s.reset(torch.from_numpy(x0).cuda())
+    steps = 0
+    while s.num_active() > 0 and steps < 100:
+        x = s.x.cpu().numpy()
+        needs = s.needs.cpu().numpy()
+        g = np.zeros((B, n), npdt); c = np.zeros(B); nr = np.full(B, n, np.int32)
+        vals = np.zeros((B, 3 * n - 1), npdt)
+        for p in range(B):
+            if needs[p] < 0:
+                continue
+            gp, Hp, c[p], nr[p] = acc(p, x[p], needs[p] == 1)
+            if needs[p] == 1:
+                g[p] = gp
+                vals[p, :n] = 60; vals[p, n:2 * n] = 40; vals[p, 2 * n:] = np.nan
+        s.step_hg_sparse(torch.from_numpy(g), rows, cols, torch.from_numpy(vals), torch.from_numpy(c), torch.from_numpy(nr))
+        steps += 1
+    res = s.results()
+    x = s.x.cpu().numpy()
+    s.close()
+    assert (res["stop_reason"] > 0).all()
+    assert abs(x.min() - 0.2) < 1e-5 and abs(x.max() - 0.2) < 1e-5
+    assert_hg_parity(x, res, oracle_hg(x0, acc, kw, npdt))

@@ -87,6 +87,8 @@ SYMBOLS = {
     "tob200_solver_create_ex": (_i, [_vp, _i, _i64, _i, _PO, _i, C.POINTER(_vp)]),
     "tob200_solver_step_cost_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "tob200_solver_step_cost_f64": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "tob200_solver_step_hg_sparse_f32": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tob200_solver_step_hg_sparse_f64": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "tob200_solver_step_hg_f32": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "tob200_solver_step_hg_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "tob200_solver_num_active": (_i, [_vp, C.POINTER(_i64)]),

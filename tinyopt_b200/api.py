@@ -444,6 +444,26 @@ class BatchSolver:
         self.ctx._ck(fn(self._h, _p(grad), _p(H), _p(cost), _p(nres)), "tob200_solver_step_hg")
         self._keep = (grad, H, cost, nres)  # the launch is asynchronous: keep the converted copies alive
 
+    def step_hg_sparse(self, grad: torch.Tensor, rows, cols, values: torch.Tensor, cost: torch.Tensor,
+                       num_residuals: torch.Tensor | None = None):
+        """One Step from a SPARSE user-filled H (tob200_solver_step_hg_sparse_*; the reference's
+        `acc(x, grad, SparseMatrix &H)` signature, tests/sparse.cpp): rows / cols [nnz] (host, one pattern for the batch),
+        values [B, nnz]; duplicates are summed in triplet order, entries below the diagonal ignored."""
+        dev = self.ctx.device
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int32))
+        cols = np.ascontiguousarray(np.asarray(cols, dtype=np.int32))
+        nnz = int(rows.shape[0])
+        grad = grad.to(dtype=self.dtype, device=dev).contiguous()
+        values = values.to(dtype=self.dtype, device=dev).contiguous()
+        cost = cost.to(dtype=torch.float64, device=dev).contiguous()
+        if num_residuals is None:
+            num_residuals = torch.ones((self.B,), dtype=torch.int32, device=dev)
+        nres = num_residuals.to(dtype=torch.int32, device=dev).contiguous()
+        fn = getattr(self.ctx._lib, f"tob200_solver_step_hg_sparse_{_suf(self.dtype)}")
+        self.ctx._ck(fn(self._h, _p(grad), rows.ctypes.data_as(C.c_void_p), cols.ctypes.data_as(C.c_void_p), nnz, _p(values),
+                        _p(cost), _p(nres)), "tob200_solver_step_hg_sparse")
+        self._keep = (grad, values, cost, nres)
+
     def num_active(self) -> int:
         v = C.c_int64(0)
         self.ctx._ck(self.ctx._lib.tob200_solver_num_active(self._h, C.byref(v)), "tob200_solver_num_active")

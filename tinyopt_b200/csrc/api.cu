@@ -5,6 +5,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1652,6 +1654,88 @@ int tob200_solver_step_hg_f64(tob200_solver *s, const double *grad, const double
   StepHG<double> hg;
   hg.grad = grad; hg.H = H; hg.cost = cost; hg.nres = num_residuals;
   return solver_step_impl<double>(s, nullptr, nullptr, 0, 0, 0, &hg);
+}
+
+}  // extern "C"
+
+// ---- sparse H in the accumulation signature (optimize.h:27-33 selects the solver from the lambda's H type; tests/sparse.cpp)
+// One triplet pattern for the whole batch, values per problem.  Duplicated (row, col) entries are summed in triplet order
+// (what Eigen's setFromTriplets does), entries below the diagonal are ignored (`SimplicialLDLT<_, Upper>` reads the upper
+// triangle, math.h:270).  The values are scattered into a dense upper triangle and go through the dense pivoted LDL^T of the
+// path (tob200_solver_step_hg_*): for the positive definite systems LM produces (J^T J, damped) that is the same solution as
+// the sparse factorisation's up to rounding; unlike SimplicialLDLT it REJECTS an indefinite H (the dense reference semantics).
+namespace {
+template <typename T>
+__global__ void sparse_to_dense_kernel(const T *vals, const int32_t *dest, const int32_t *start, const int32_t *order, int64_t B,
+                                       int nnz, int nd, int n, T *H) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * nd) return;
+  const int64_t pr = e / nd;
+  const int d = (int)(e % nd);
+  const T *v = vals + (size_t)pr * nnz;
+  T sum = v[order[start[d]]];
+  for (int k = start[d] + 1; k < start[d + 1]; ++k) sum = Ops<T>::add(sum, v[order[k]]);
+  H[(size_t)pr * n * n + dest[d]] = sum;
+}
+
+template <typename T>
+int step_hg_sparse_impl(tob200_solver *s, const T *grad, const int32_t *rows, const int32_t *cols, int nnz, const T *values,
+                        const double *cost, const int32_t *nres) {
+  if (!s) return fail(nullptr, TOB200_ERR_INVALID, "solver is NULL");
+  tob200_ctx *ctx = s->ctx;
+  if (nnz < 0 || (nnz > 0 && (!rows || !cols || !values))) return fail(ctx, TOB200_ERR_INVALID, "bad triplet arrays");
+  const int n = s->n;
+  const int64_t B = s->B;
+  // group the kept triplets by destination, original order inside a group
+  std::vector<std::pair<int32_t, int32_t>> key;  // (dest, triplet)
+  key.reserve((size_t)nnz);
+  for (int k = 0; k < nnz; ++k) {
+    if (rows[k] < 0 || cols[k] < 0 || rows[k] >= n || cols[k] >= n) return fail(ctx, TOB200_ERR_INVALID, "triplet index out of range");
+    if (rows[k] <= cols[k]) key.emplace_back(rows[k] * n + cols[k], k);
+  }
+  std::stable_sort(key.begin(), key.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+  std::vector<int32_t> pack;  // dest[nd] | start[nd + 1] | order[kept]
+  std::vector<int32_t> dest, start, order;
+  for (size_t k = 0; k < key.size(); ++k) {
+    if (k == 0 || key[k].first != key[k - 1].first) { dest.push_back(key[k].first); start.push_back((int32_t)k); }
+    order.push_back(key[k].second);
+  }
+  start.push_back((int32_t)key.size());
+  const int nd = (int)dest.size();
+  pack.insert(pack.end(), dest.begin(), dest.end());
+  pack.insert(pack.end(), start.begin(), start.end());
+  pack.insert(pack.end(), order.begin(), order.end());
+  DeviceGuard guard(ctx->device);
+  int rc;
+  if ((rc = ensure_scratch(ctx, 25, (size_t)B * n * n * sizeof(T))) != TOB200_OK) return rc;
+  if ((rc = ensure_scratch(ctx, 26, pack.size() * sizeof(int32_t) + 16)) != TOB200_OK) return rc;
+  T *Hd = (T *)ctx->scratch[25];
+  int32_t *dp = (int32_t *)ctx->scratch[26];
+  CK(cudaMemsetAsync(Hd, 0, (size_t)B * n * n * sizeof(T), ctx->stream));
+  if (nd > 0) {
+    CK(cudaMemcpyAsync(dp, pack.data(), pack.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // `pack` is a local
+    const int64_t total = B * nd;
+    sparse_to_dense_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(values, dp, dp + nd, dp + 2 * nd + 1, B, nnz,
+                                                                                       nd, n, Hd);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  StepHG<T> hg;
+  hg.grad = grad; hg.H = Hd; hg.cost = cost; hg.nres = nres;
+  return solver_step_impl<T>(s, nullptr, nullptr, 0, 0, 0, &hg);
+}
+}  // namespace
+
+extern "C" {
+
+int tob200_solver_step_hg_sparse_f32(tob200_solver *s, const float *grad, const int32_t *rows, const int32_t *cols, int nnz,
+                                     const float *values, const double *cost, const int32_t *num_residuals) {
+  return step_hg_sparse_impl<float>(s, grad, rows, cols, nnz, values, cost, num_residuals);
+}
+int tob200_solver_step_hg_sparse_f64(tob200_solver *s, const double *grad, const int32_t *rows, const int32_t *cols, int nnz,
+                                     const double *values, const double *cost, const int32_t *num_residuals) {
+  return step_hg_sparse_impl<double>(s, grad, rows, cols, nnz, values, cost, num_residuals);
 }
 
 int tob200_solver_num_active(tob200_solver *s, int64_t *n_active) {
