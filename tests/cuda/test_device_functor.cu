@@ -450,11 +450,10 @@ static void test_large(tob200_ctx *ctx, int64_t B, int m, int n, double tol) {
   tob200_options_default(&opt);
   if (sizeof(T) == 4) { opt.min_rerr_dec = 1e-5f; opt.min_step_norm2 = 1e-9f; }
   for (T *q : {xa, xb, xc, xd}) CU(cudaMemcpy(q, x0, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToDevice));
+  CU(cudaDeviceSynchronize());  // device-to-device copies do not block the host, and the library's stream is non-blocking
   // reference run: the library's own device-resident loop; bit-exact (oracle-pinned) kernels for every n
-  CHECK(tob200_set_exact(ctx, 1) == TOB200_OK);
   CHECK(lm_run(ctx, &opt, A, y, B, m, n, xa, ra) == TOB200_OK);
   CHECK(tob200_sync(ctx) == TOB200_OK);
-  CHECK(tob200_set_exact(ctx, 0) == TOB200_OK);
   PolyLargeManual<T> fm{A, y, m, n, (T)0.1, (T)3 * (T)0.1};
   CHECK((dev::OptimizeBatchManualLarge<T>(ctx, fm, xb, B, n, m, opt, rb)) == TOB200_OK);
   PolyLargeAuto<T> fa{A, y, m, n, (T)0.1};
@@ -501,6 +500,17 @@ static void test_large(tob200_ctx *ctx, int64_t B, int m, int n, double tol) {
   CHECK(worst_nd / xmax <= (sizeof(T) == 8 ? 1e-6 : 5e-3));
   dump_run<T>("manual", n, m, B, hb, qb);
   dump_run<T>("numdiff", n, m, B, hd, qd);
+  if (n == 6 || n == 40) {  // the other two methods of diff/num_diff.h:20-52, and an explicit step h
+    for (int method : {0, 2}) {
+      CU(cudaMemcpy(xd, x0, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToDevice));
+      CU(cudaDeviceSynchronize());
+      CHECK((dev::OptimizeBatchNumDiffLarge<T>(ctx, fc, xd, B, n, m, opt, rd, (dev::NumDiffMethod)method,
+                                               method == 2 ? (T)(sizeof(T) == 8 ? 1e-6 : 5e-4) : (T)0)) == TOB200_OK);
+      CU(cudaMemcpy(hd.data(), xd, hd.size() * sizeof(T), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(qd.data(), rd, qd.size() * sizeof(tob200_result), cudaMemcpyDeviceToHost));
+      dump_run<T>(method == 0 ? "numdiffFwd" : "numdiffFast", n, m, B, hd, qd);
+    }
+  }
   std::printf("large<%s> n=%d m=%d B=%lld: manual rows %s lm_run (%lld/%lld same decisions, max rel dx %.2e); Jets: %lld/%lld, "
               "%.2e; numeric differentiation: all converged, %.2e from the analytic solution\n",
               sizeof(T) == 8 ? "double" : "float", n, m, (long long)B, exact_ref ? "== (bit for bit)" : "~", (long long)same_m,
@@ -558,6 +568,9 @@ int main() {
     std::printf("tob200_create failed: %s\n", tob200_last_error(nullptr));
     return 3;
   }
+  // the reference runs below are the library's BIT-EXACT kernels (the mid-n float default is the tolerance-held
+  // tensor-core kernel): a functor with the canonical op sequence must reproduce them bit for bit
+  if (tob200_set_exact(ctx, 1) != TOB200_OK) return 3;
   test_sqrt2();
   test_family<double, 6>(ctx, 4096, 30, 1e-10);
   test_family<float, 12>(ctx, 4096, 200, 1e-4);

@@ -96,7 +96,7 @@ def test_device_functor_on_gpu(tmp_path):
     # precisions and for every n; numeric differentiation (diff/num_diff.h, central differences, the NORM as cost) ==
     # the oracle's numdiff variant bit for bit
     ldumps = sorted(tmp_path.glob("large_*.bin"))
-    assert len(ldumps) == 10, ldumps
+    assert len(ldumps) == 14, ldumps
     for f in ldumps:
         tag, dt, n, m, B = re.match(r"large_(\w+)_(f\d+)_n(\d+)_m(\d+)_B(\d+)\.bin", f.name).groups()
         n, m, B = int(n), int(m), int(B)
@@ -104,7 +104,10 @@ def test_device_functor_on_gpu(tmp_path):
         npdt = np.float32 if dt == "f32" else np.float64
         kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9) if dt == "f32" else {}
         A, y, xs, x0 = O.synth_generate(B, m, n, npdt)
-        xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw), numdiff=(2, 0.0) if tag == "numdiff" else None)
+        # numdiff: kCentral with h = FloatEpsilon; numdiffFwd: kForward; numdiffFast: kFastCentral with an explicit h
+        nd = {"manual": None, "numdiff": (2, 0.0), "numdiffFwd": (1, 0.0),
+              "numdiffFast": (3, float(npdt(1e-6 if dt == "f64" else 5e-4)))}[tag]
+        xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw), numdiff=nd)
         iters, stop, cost, fails, xg = rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4:]
         assert np.array_equal(iters, ro["num_iters"]) and np.array_equal(stop, ro["stop_reason"]), f.name
         assert np.array_equal(fails, ro["num_failures"]) and np.array_equal(cost, ro["final_cost"]), f.name
