@@ -113,6 +113,27 @@ def test_jtj_matches_float64(ctx, B, m, n):
         assert derr < 5e-6 and oerr < 4e-6, (B, m, n, derr, oerr)
 
 
+@pytest.mark.parametrize("B,m,n", [(2, 2048, 512), (7, 333, 400), (3, 100, 509), (149, 40, 512)])
+def test_jtj_cluster_multicast_is_identical(ctx, B, m, n, monkeypatch):
+    """TOB200_LG_MC=1: the J^T J kernel launched as clusters of two CTAs, the raw stages both units of a problem read
+    multicast by the TMA unit (A leaves HBM / L2 once for the two wide strips).  Same operands, same MMAs, same order:
+    the result must be BIT-identical to the default launch (ragged rows, padded n, more problems than clusters)."""
+    import tinyopt_b200 as tb
+    rng = np.random.default_rng(m + n)
+    J = torch.from_numpy(rng.uniform(-1, 1, (B, m, n)).astype(np.float32)).cuda()
+    s = torch.from_numpy(rng.uniform(0.5, 1.5, (B, m)).astype(np.float32)).cuda()
+    H0 = ctx.jtj(J, s)
+    ctx.sync()
+    monkeypatch.setenv("TOB200_LG_MC", "1")
+    c2 = tb.Context(0)
+    try:
+        H1 = c2.jtj(J, s)
+        c2.sync()
+        assert torch.equal(H0, H1)
+    finally:
+        c2.close()
+
+
 # ---- a1 + a5 + a6: one Build + Solve -----------------------------------------------------------------
 @pytest.mark.parametrize("B,m,n", [(4, 256, 64), (3, 300, 100), (3, 1024, 256), (2, 2048, 512),
                                    (4, 256, 57), (3, 300, 101), (2, 900, 258), (2, 1100, 511)])  # n % 4 != 0: padded copy

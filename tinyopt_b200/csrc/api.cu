@@ -65,6 +65,7 @@ struct tob200_ctx {
   // large-n family: 3 = 3xTF32 (hi*hi + hi*lo + lo*hi, FP32-level accuracy), 1 = plain TF32
   int lg_tf32_terms = 3;  // env TOB200_LG_TF32_TERMS
   int lg_raw_stages = kLgRawStages;  // env TOB200_LG_RAW_STAGES (2..6)
+  int lg_mc = 0;          // env TOB200_LG_MC: 1 = JtJ kernel as clusters of two CTAs with TMA multicast of the shared raw stages
   int lg_fp16 = 1;        // env TOB200_LG_FP16: 1 = FP16 hi / lo split (kind::f16), 0 = TF32 split (kind::tf32)
   // device time of the last large-n call by phase (0 eval, 1 syrk, 2 solve): CUDA event pairs
   static constexpr int kMaxPhaseEvents = 3 * 80;
@@ -469,6 +470,9 @@ LgSyrkParams lg_syrk_params(tob200_ctx *ctx, const LgBuffers &b, const float *A,
   sp.is_lm = is_lm;
   sp.debug = env_int("TOB200_LG_DEBUG", 0);
   sp.half_bytes = lg_syrk_half_bytes(b.np, sp.fp16);
+  // cluster multicast of the raw stages both units of a problem read (lg.cuh): four strips, FP16 split, tensor map, m rows
+  // in whole 16-row stages for both wide strips (they are: same RS), an even grid
+  sp.mc = (ctx->lg_mc && sp.nstrips == 4 && sp.fp16 && sp.use_tmap && !(sp.debug & 4) && B >= 1 && (ctx->num_sms % 2) == 0) ? 1 : 0;
   return sp;
 }
 
@@ -1271,6 +1275,7 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->wtc_op_stages = env_int("TOB200_WTC_OPS", 0);
   ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
   ctx->lg_fp16 = (env_int("TOB200_LG_FP16", 1) != 0 && ctx->lg_tf32_terms == 3) ? 1 : 0;
+  ctx->lg_mc = env_int("TOB200_LG_MC", 0);
   ctx->lg_raw_stages = env_int("TOB200_LG_RAW_STAGES", kLgRawStages);  // 2..5 measured equal on C5 (12.43 .. 12.57 ms): not the limiter
   if (ctx->lg_raw_stages < 2) ctx->lg_raw_stages = 2;
   if (ctx->lg_raw_stages > 6) ctx->lg_raw_stages = 6;

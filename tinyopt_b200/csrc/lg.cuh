@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(raw) + (size_t)p.raw_stages * lg_syrk_raw_bytes(p.np));
   uint64_t *full = bars, *empty = bars + kLgMaxStages, *tmem_full = bars + 2 * kLgMaxStages, *tmem_empty = tmem_full + 1;
   uint64_t *raw_full = tmem_empty + 1, *raw_empty = raw_full + kLgMaxStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kLgMaxStages);
+  uint64_t *peer_empty = raw_empty + kLgMaxStages;  // multicast mode, CTA 0: CTA 1 has released raw stage s
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(peer_empty + kLgMaxStages);
+  const bool mc = p.mc != 0;
+  const uint32_t crank = mc ? cluster_ctarank() : 0u;
   // Ring geometry per strip.  The operand region (p.stages stages of the widest strip) and the raw region
   // (kLgRawStages of them) are re-cut for every strip into stages of ITS width ncs, so a strip of 128 / 256
   // columns runs 8 / 4 stages deep in the bytes that give the 512-column strip two: the narrow strips
@@ -253,6 +256,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     for (int s = 0; s < kLgMaxStages; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], kLgProdWarps);
+      mbar_init(&peer_empty[s], 1);
     }
     mbar_fence_init();
   }
@@ -263,6 +267,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (mc) cluster_sync_all();  // the peer's barriers are initialised before anybody arrives on them remotely
   const uint32_t tmem_base = *tmem_slot;
 
   // Work unit = (problem, pair of strips {h, nstrips - 1 - h}): both units of a problem cost the same
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
   auto unit_of = [&](int64_t idx, int64_t &pr, int &h) {
     pr = idx / upp;
     h = (int)(idx % upp);
-    if (rotate) h = (int)((h + (idx - blockIdx.x) / gridDim.x) % upp);
+    if (rotate && !mc) h = (int)((h + (idx - blockIdx.x) / gridDim.x) % upp);  // (multicast: h == rank in the cluster)
   };
   const int m = p.m, n = p.n, np = p.np;
 
@@ -286,6 +291,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
     // rows >= m belong to the next problem: the producers select 0 for both.
     // lane 0 owns the barrier; lane b < nbox issues the copy of box b, lane 16 + b its L2 prefetch
     uint32_t rawe_bits = 0, item = 0;  // bit s: parity of the use count of raw stage s
+    uint32_t peer_bits = 0;            // multicast mode, CTA 0: the same for peer_empty
     for (int64_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
       int64_t pr; int h;
       unit_of(idx, pr, h);
@@ -298,6 +304,29 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         uint32_t hb, S, R, rs = 0;
         int RS;
         ring_geom(ncs, RS, hb, S, R);
+        const bool mc1 = mc && half == 0;  // strips 0 (CTA 0) and 1 (CTA 1) in lockstep: CTA 0 loads for both
+        if (mc1 && crank == 1) {
+          // CTA 1 only relays: when its producers have released raw stage rs it posts the bytes it expects (its three
+          // boxes) on its own raw_full and tells CTA 0, which issues the multicast copies.  Same ring depth as CTA 0.
+          uint32_t hb0, S0, R0;
+          int RS0;
+          ring_geom(np, RS0, hb0, S0, R0);
+          const int ksteps1 = (m + RS - 1) / RS;
+          if (item > 0 && lane == 0) mbar_wait(tmem_full, (item - 1u) & 1u);
+          __syncwarp();
+          for (int ks = 0; ks < ksteps1; ++ks) {
+            if (lane == 0) {
+              mbar_wait(&raw_empty[rs], ((rawe_bits >> rs) & 1u) ^ 1u);
+              fence_proxy_async();
+              mbar_expect_tx(&raw_full[rs], (uint32_t)((ncs + kLgBoxCols - 1) / kLgBoxCols) * kBoxBytes);
+              mbar_arrive_remote(&peer_empty[rs], 0u);
+            }
+            __syncwarp();
+            rawe_bits ^= 1u << rs;
+            if (++rs == R0) rs = 0;
+          }
+          continue;
+        }
         const int ksteps = (m + RS - 1) / RS;
         const int ncg = (ncs + kLgBoxCols - 1) / kLgBoxCols;
         const int nbox = ncg * (RS / kLgStageK);  // boxes per stage (<= 4): box b = (row box b / ncg, column box b % ncg)
@@ -324,6 +353,10 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
           const int rows = (m - row0 < RS) ? (m - row0) : RS;
           if (lane == 0) {
             mbar_wait(&raw_empty[rs], ((rawe_bits >> rs) & 1u) ^ 1u);
+            if (mc1) {  // ... and CTA 1 has released the same stage of ITS ring
+              mbar_wait_cluster(&peer_empty[rs], (peer_bits >> rs) & 1u);
+              peer_bits ^= 1u << rs;
+            }
             fence_proxy_async();  // the producers' generic reads of this stage precede the async writes
             if (p.debug & 4) mbar_arrive(&raw_full[rs]);  // timing experiment: no copies
             else if (p.use_tmap) mbar_expect_tx(&raw_full[rs], raw_stage);  // OOB parts of a box count too
@@ -334,8 +367,12 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
             unsigned char *dst = reinterpret_cast<unsigned char *>(raw) + (size_t)rs * raw_stage;
             if (p.use_tmap) {
               if (lane < nbox) {
-                tma_load_box(dst + (size_t)lane * kBoxBytes, &p.tmap, c0 + kLgBoxCols * (lane % ncg),
-                             grow0 + row0 + kLgStageK * (lane / ncg), &raw_full[rs]);
+                if (mc1 && (lane % ncg) > 0)  // columns >= 128: strip 1 needs them too
+                  tma_load_box_multicast(dst + (size_t)lane * kBoxBytes, &p.tmap, c0 + kLgBoxCols * (lane % ncg),
+                                         grow0 + row0 + kLgStageK * (lane / ncg), &raw_full[rs], (uint16_t)3);
+                else
+                  tma_load_box(dst + (size_t)lane * kBoxBytes, &p.tmap, c0 + kLgBoxCols * (lane % ncg),
+                               grow0 + row0 + kLgStageK * (lane / ncg), &raw_full[rs]);
               } else if (lane >= 16 && lane - 16 < nbox) {
                 const int prow = row0 + pf * RS + kLgStageK * ((lane - 16) / ncg);
                 if (prow < m) tma_prefetch_box(&p.tmap, c0 + kLgBoxCols * ((lane - 16) % ncg), grow0 + prow);
@@ -382,7 +419,15 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       ring_geom(ncs, RS, hb, S, R);
       const int ksteps = (m + RS - 1) / RS;
       const int ncg = (ncs + kLgBoxCols - 1) / kLgBoxCols;
-      const uint32_t raw_stage = (uint32_t)(ncg * (RS / kLgStageK)) * kBoxBytes;
+      uint32_t raw_stage = (uint32_t)(ncg * (RS / kLgStageK)) * kBoxBytes;
+      uint32_t box_shift = 0;
+      if (mc && half == 0 && crank == 1) {  // multicast phase: the raw stages have CTA 0's geometry (strip 0: one box more,
+        uint32_t hb0, S0;                   // in front) and ring depth
+        int RS0;
+        ring_geom(np, RS0, hb0, S0, R);
+        raw_stage = (uint32_t)((ncg + 1) * (RS / kLgStageK)) * kBoxBytes;
+        box_shift = 1;
+      }
       const int per = 2 * ncg;
       const int kc = w / per, cg = (w % per) >> 1, hq = w & 1;
       const bool mine = kc < RS / 8;
@@ -404,8 +449,8 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
         for (int t = 0; t < 8; ++t) sc[t] = __shfl_sync(0xffffffffu, sc_cur, t);
         mbar_wait(&raw_full[rs], (rawf_bits >> rs) & 1u);
         // row 8 kc + t of the stage sits in row box kc / 2, row 8 (kc % 2) + t of the box
-        const uint32_t rsrc = raw_u32 + rs * raw_stage + (uint32_t)((kc >> 1) * ncg) * kBoxBytes +
-                              (uint32_t)(8 * (kc & 1)) * (kLgBoxCols * 4u);
+        const uint32_t rsrc = raw_u32 + rs * raw_stage + (uint32_t)((kc >> 1) * (ncg + (int)box_shift)) * kBoxBytes +
+                              box_shift * kBoxBytes + (uint32_t)(8 * (kc & 1)) * (kLgBoxCols * 4u);
         const int row0 = ks * RS + 8 * kc;
         if ((p.debug & 2) || !mine) {  // idle warp (or timing experiment): barrier protocol only
           mbar_wait(&empty[st], ((empty_bits >> st) & 1u) ^ 1u);
@@ -683,6 +728,7 @@ __global__ void __launch_bounds__(kLgSyrkThreads, 1) lg_syrk_kernel(const __grid
       g_syrk_strip_count[r] = 0;
     }
   }
+  if (mc) cluster_sync_all();  // nobody leaves while its peer may still signal it
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 

@@ -124,6 +124,22 @@ cudaError_t launch_lg_syrk(const LgSyrkParams &p, int num_sms, cudaStream_t st) 
   int64_t grid = num_sms;  // one CTA per SM: each owns the SM's whole TMEM
   const int64_t total = (int64_t)((p.nstrips + 1) / 2) * p.B;  // work units: strip pairs
   if (grid > total) grid = total;
+  if (p.mc) {  // clusters of two CTAs = the two units of a problem (total is even here)
+    grid &= ~(int64_t)1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kLgSyrkThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, lg_syrk_kernel, p);
+  }
   lg_syrk_kernel<<<(unsigned)grid, kLgSyrkThreads, smem, st>>>(p);
   return cudaGetLastError();
 }

@@ -72,6 +72,9 @@ struct LgSyrkParams {
   int is_lm;
   int debug;           // timing experiments only (env TOB200_LG_DEBUG): 1 no MMAs, 2 no transform, 4 no copies
   uint32_t half_bytes; // bytes of the hi (== lo) part of a stage == of a raw stage: kLgStageK x max(128, np) floats
+  int mc;              // 1: launched as clusters of two CTAs (the two units of a problem); while both stream their first,
+                       // wide strips (0 and 1 of four), CTA 0 loads every raw stage ONCE and the TMA unit multicasts the
+                       // three column boxes both need to CTA 1 (nstrips == 4, fp16, tensor map only)
 };
 
 __host__ __device__ inline uint32_t lg_syrk_half_bytes(int np, int fp16 = 0) {

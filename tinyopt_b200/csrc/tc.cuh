@@ -117,6 +117,48 @@ __device__ __forceinline__ void tma_load_box(void *smem_dst, const CUtensorMap *
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c), "r"(r), "r"(smem_u32(bar))
       : "memory");
 }
+// the same box delivered to every CTA of the cluster named in `cta_mask` (same CTA-relative destination and mbarrier
+// offsets in each of them; each destination's mbarrier receives the box's bytes)
+__device__ __forceinline__ void tma_load_box_multicast(void *smem_dst, const CUtensorMap *tmap, int c, int r, uint64_t *bar,
+                                                       uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], "
+      "[%4], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c), "r"(r), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// ---- thread-block cluster helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same CTA-relative address in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// wait with cluster-scope acquire (the arrival comes from another CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void tma_prefetch_box(const CUtensorMap *tmap, int c, int r) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
                "r"(c), "r"(r)
