@@ -126,7 +126,10 @@ int tob200_last_elapsed_ms(tob200_ctx *ctx, float *ms);
 /* exact != 0: tob200_lm_run_f32 and tob200_build_solve_f32 for 28 <= n <= 55 (and m >= 192, m n % 4 == 0, use_ldlt) run the warp-per-problem FFMA kernel, whose every sum is the CPU
  * restatement's canonical fma chain (bit-identical results), instead of the default tensor-core kernel (wtc.cuh:
  * H = J^T J off-diagonal from tcgen05.mma with an FP16 hi / lo split, held to the float tolerance of 1e-4).  The
- * environment variable TOB200_WPP_TC=0 selects the same at tob200_create time. */
+ * environment variable TOB200_WPP_TC=0 selects the same at tob200_create time.
+ * exact >= 2 additionally runs float 56 <= n <= 512 (tob200_lm_run_f32 / tob200_build_solve_f32: by default the
+ * tcgen05 J^T J family, tolerance-held) on the general kernel family, whose results are bit-identical to the CPU
+ * restatement - several times slower, for callers who want reproducibility down to the last bit (env TOB200_LG_EXACT=1). */
 int tob200_set_exact(tob200_ctx *ctx, int exact);
 
 void tob200_options_default(tob200_options *opt); /* == tinyopt::Options{} */

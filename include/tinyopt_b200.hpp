@@ -233,6 +233,14 @@ inline int solver_step_hg(tob200_solver *s, const float *g, const float *H, cons
 inline int solver_step_hg(tob200_solver *s, const double *g, const double *H, const double *c, const int32_t *nr) {
   return tob200_solver_step_hg_f64(s, g, H, c, nr);
 }
+inline int solver_step_hg_sparse(tob200_solver *s, const float *g, const int32_t *rows, const int32_t *cols, int nnz,
+                                 const float *v, const double *c, const int32_t *nr) {
+  return tob200_solver_step_hg_sparse_f32(s, g, rows, cols, nnz, v, c, nr);
+}
+inline int solver_step_hg_sparse(tob200_solver *s, const double *g, const int32_t *rows, const int32_t *cols, int nnz,
+                                 const double *v, const double *c, const int32_t *nr) {
+  return tob200_solver_step_hg_sparse_f64(s, g, rows, cols, nnz, v, c, nr);
+}
 inline int lm_run_host(tob200_ctx *c, const tob200_options *o, const float *A, const float *y, float alpha, int64_t B,
                        int m, int n, float *x, tob200_result *res) {
   return tob200_lm_run_host_f32(c, o, A, y, alpha, TOB200_LAYOUT_PROBLEM_MAJOR, B, m, n, x, res);
@@ -411,6 +419,73 @@ std::vector<Output> OptimizeBatchAcc(const Context &ctx, Scalar *xs, int64_t B, 
     outs[(size_t)p] = to_output(res[(size_t)p]);
     if (!Hf.empty()) outs[(size_t)p].final_hessian.assign(Hf.begin() + (size_t)p * nn, Hf.begin() + (size_t)(p + 1) * nn);
   }
+  return outs;
+}
+
+/// The accumulation contract with a SPARSE H (the reference selects its sparse solver from the lambda's H type,
+/// optimize.h:27-33; tests/sparse.cpp:19-57): the batch shares one triplet pattern (rows, cols: nnz entries; duplicates
+/// are summed in triplet order as Eigen's setFromTriplets does, entries below the diagonal are ignored as
+/// `SimplicialLDLT<_, Upper>` ignores them), `Cost acc(p, x, grad, values)` fills grad (n) and the nnz triplet VALUES of
+/// its problem (both pre-zeroed; nullptr on cost-only calls).  Solved by the dense pivoted LDL^T of the path
+/// (tob200_solver_step_hg_sparse_*).
+template <typename Scalar, typename Acc>
+std::vector<Output> OptimizeBatchAccSparse(const Context &ctx, Scalar *xs, int64_t B, int n, const std::vector<int32_t> &rows,
+                                           const std::vector<int32_t> &cols, Acc &&acc, const Options &options = Options()) {
+  if (B < 0 || n < 1 || rows.size() != cols.size()) throw std::invalid_argument("OptimizeBatchAccSparse: bad sizes");
+  std::vector<Output> outs((size_t)B);
+  if (B == 0) return outs;
+  const int nnz = (int)rows.size();
+  const tob200_options pod = options.pod();
+  tob200_solver *solver = nullptr;
+  ctx.check(tob200_solver_create(ctx.get(), scalar_traits<Scalar>::dtype, B, n, &pod, &solver), "tob200_solver_create");
+  struct Guard {
+    tob200_solver *s;
+    ~Guard() { tob200_solver_destroy(s); }
+  } guard{solver};
+  {
+    DeviceBuffer<Scalar> x0(ctx, (size_t)B * n);
+    x0.upload(xs, (size_t)B * n);
+    ctx.check(tob200_solver_reset(solver, x0.data()), "tob200_solver_reset");
+    ctx.sync();
+  }
+  std::vector<Scalar> g((size_t)B * n), v((size_t)B * (nnz > 0 ? nnz : 1)), x((size_t)B * n);
+  std::vector<double> cost((size_t)B, 0.0);
+  std::vector<int32_t> nres((size_t)B, 1), needs((size_t)B);
+  DeviceBuffer<Scalar> dg(ctx, g.size()), dv(ctx, v.size());
+  DeviceBuffer<double> dc(ctx, cost.size());
+  DeviceBuffer<int32_t> dn(ctx, nres.size());
+  int64_t active = B;
+  while (active > 0) {
+    ctx.check(tob200_copy_to_host(ctx.get(), x.data(), tob200_solver_x(solver), x.size() * sizeof(Scalar)), "copy x");
+    ctx.check(tob200_copy_to_host(ctx.get(), needs.data(), tob200_solver_needs(solver), needs.size() * sizeof(int32_t)),
+              "copy needs");
+    for (int64_t p = 0; p < B; ++p) {
+      if (needs[(size_t)p] < 0) continue;
+      Scalar *gp = nullptr, *vp = nullptr;
+      if (needs[(size_t)p] == 1) {
+        gp = &g[(size_t)p * n];
+        vp = &v[(size_t)p * nnz];
+        std::fill(gp, gp + n, (Scalar)0);
+        std::fill(vp, vp + nnz, (Scalar)0);
+      }
+      const Cost c = acc((size_t)p, (const Scalar *)&x[(size_t)p * n], gp, vp);
+      cost[(size_t)p] = c.cost;
+      nres[(size_t)p] = c.num_resisuals;
+    }
+    dg.upload(g.data(), g.size());
+    dv.upload(v.data(), v.size());
+    dc.upload(cost.data(), cost.size());
+    dn.upload(nres.data(), nres.size());
+    ctx.check(detail::solver_step_hg_sparse(solver, dg.data(), rows.data(), cols.data(), nnz, dv.data(), dc.data(), dn.data()),
+              "tob200_solver_step_hg_sparse");
+    ctx.check(tob200_solver_num_active(solver, &active), "tob200_solver_num_active");
+  }
+  DeviceBuffer<tob200_result> dres(ctx, (size_t)B);
+  ctx.check(tob200_solver_results(solver, dres.data()), "tob200_solver_results");
+  std::vector<tob200_result> res((size_t)B);
+  dres.download(res.data(), (size_t)B);
+  ctx.check(tob200_copy_to_host(ctx.get(), xs, tob200_solver_x(solver), (size_t)B * n * sizeof(Scalar)), "copy x");
+  for (int64_t p = 0; p < B; ++p) outs[(size_t)p] = to_output(res[(size_t)p]);
   return outs;
 }
 

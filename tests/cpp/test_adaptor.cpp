@@ -338,6 +338,39 @@ static void test_accumulation_contract(const Context &ctx) {
     for (int64_t p = 0; p < Bl; ++p) CHECK(pl[p].Converged());
     std::printf("accumulation contract above n = 55: Prior 80 (double): max |x - y| = %.2e\n", wl);
   }
+  // tests/sparse.cpp:19-57 "tinyopt_sparse": res = 10 x - 2 over 100 parameters, H = J^T J handed over as triplets (diagonal),
+  // Cost(res.norm(), res.size()), check_final_cost = false; reference assertions: converged, min / max of x == 0.2 +- 1e-5
+  {
+    const int ns = 100;
+    const int64_t Bs = 3;
+    std::vector<double> xsp(Bs * ns);
+    for (auto &v : xsp) v = rnd();
+    std::vector<int32_t> rws(ns), cls(ns);
+    for (int i = 0; i < ns; ++i) rws[i] = cls[i] = i;
+    Options so;
+    so.check_final_cost = false;
+    auto sparse_acc = [&](size_t, const double *xv, double *grad, double *vals) {
+      Cost c;
+      double acc = 0.0;
+      for (int j = 0; j < ns; ++j) {
+        const double res = 10.0 * xv[j] - 2.0;
+        acc += res * res;
+        if (grad) {
+          grad[j] = 10.0 * res;
+          vals[j] = 100.0;
+        }
+      }
+      c.cost = std::sqrt(acc);
+      c.num_resisuals = ns;
+      return c;
+    };
+    auto sp = OptimizeBatchAccSparse<double>(ctx, xsp.data(), Bs, ns, rws, cls, sparse_acc, so);
+    double lo = 1e300, hi = -1e300;
+    for (double v : xsp) { lo = std::fmin(lo, v); hi = std::fmax(hi, v); }
+    for (int64_t p = 0; p < Bs; ++p) CHECK(sp[p].Succeeded() && sp[p].Converged());
+    CHECK(std::fabs(lo - 0.2) < 1e-5 && std::fabs(hi - 0.2) < 1e-5);
+    std::printf("sparse accumulation signature (tests/sparse.cpp): min x = %.9f, max x = %.9f\n", lo, hi);
+  }
   std::printf("accumulation contract: Rosenbrock (true Hessian) iters[0]=%d failures[0]=%d, converged %d/%d; Prior 12: max |x - y| = %.2e\n",
               (int)outs[0].num_iters, (int)outs[0].num_failures, conv, (int)B, (double)worst);
 }

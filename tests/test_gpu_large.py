@@ -134,6 +134,28 @@ def test_jtj_cluster_multicast_is_identical(ctx, B, m, n, monkeypatch):
         c2.close()
 
 
+@pytest.mark.parametrize("B,m,n", [(5, 200, 64), (3, 600, 257), (2, 1100, 512)])
+def test_set_exact_2_runs_the_bit_exact_family(ctx, B, m, n):
+    """tob200_set_exact(ctx, 2): float 56 <= n <= 512 through the general family - x, iteration counts, stop reasons,
+    final costs, lambda and Build + Solve bit for bit against the oracle (the default tensor-core family is tolerance-held)."""
+    import tinyopt_b200 as tb
+    kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)
+    A, y, xs, x0 = O.synth_generate(B, m, n, np.float32, p0=9)
+    xo, ro, _ = O.synth_lm_run(A, y, x0, O.default_options(**kw))
+    dA, dy, _, dx0 = ctx.synth_generate(B, m, n, torch.float32, p0=9, layout=tb.PROBLEM_MAJOR)
+    ctx.set_exact(2)
+    try:
+        out = ctx.optimize_batch(dA, dy, dx0, tb.options(**kw))
+        ctx.sync()
+    finally:
+        ctx.set_exact(True)   # what the suite runs with (conftest: TOB200_WPP_TC=0)
+    assert np.array_equal(out.results["num_iters"], ro["num_iters"])
+    assert np.array_equal(out.results["stop_reason"], ro["stop_reason"])
+    assert np.array_equal(out.x.cpu().numpy(), xo)
+    assert np.array_equal(out.results["final_cost"], ro["final_cost"])
+    assert np.array_equal(out.results["last_lambda"], ro["last_lambda"])
+
+
 # ---- a1 + a5 + a6: one Build + Solve -----------------------------------------------------------------
 @pytest.mark.parametrize("B,m,n", [(4, 256, 64), (3, 300, 100), (3, 1024, 256), (2, 2048, 512),
                                    (4, 256, 57), (3, 300, 101), (2, 900, 258), (2, 1100, 511)])  # n % 4 != 0: padded copy

@@ -174,9 +174,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.tob200_launch_count(self._h))
 
-    def set_exact(self, exact: bool = True):
-        """Mid-n float runs (13 <= n <= 55): bit-exact warp-per-problem kernel instead of the tensor-core one."""
-        self._ck(self._lib.tob200_set_exact(self._h, int(bool(exact))), "set_exact")
+    def set_exact(self, exact: bool | int = True):
+        """Mid-n float runs (13 <= n <= 55): bit-exact warp-per-problem kernel instead of the tensor-core one.
+        exact=2: float 56 <= n <= 512 on the general (bit-exact) family as well, instead of the tcgen05 one."""
+        self._ck(self._lib.tob200_set_exact(self._h, int(exact)), "set_exact")
 
     def last_elapsed_ms(self) -> float:
         ms = C.c_float(0)

@@ -65,6 +65,7 @@ struct tob200_ctx {
   // large-n family: 3 = 3xTF32 (hi*hi + hi*lo + lo*hi, FP32-level accuracy), 1 = plain TF32
   int lg_tf32_terms = 3;  // env TOB200_LG_TF32_TERMS
   int lg_raw_stages = kLgRawStages;  // env TOB200_LG_RAW_STAGES (2..6)
+  int lg_exact = 0;       // tob200_set_exact(ctx, 2) / env TOB200_LG_EXACT: float 56 <= n <= 512 on the general (bit-exact) family
   int lg_mc = 0;          // env TOB200_LG_MC: 1 = JtJ kernel as clusters of two CTAs with TMA multicast of the shared raw stages
   int lg_fp16 = 1;        // env TOB200_LG_FP16: 1 = FP16 hi / lo split (kind::f16), 0 = TF32 split (kind::tf32)
   // device time of the last large-n call by phase (0 eval, 1 syrk, 2 solve): CUDA event pairs
@@ -700,8 +701,9 @@ int build_solve_impl(tob200_ctx *ctx, const T *J, const T *r, int layout, int64_
   if (!J || !r || !dx || !cost || !status) return fail(ctx, TOB200_ERR_INVALID, "NULL buffer");
   if (!aligned16(J) || !aligned16(r)) return fail(ctx, TOB200_ERR_INVALID, "J and r must be 16-byte aligned");
   DeviceGuard guard(ctx->device);
-  const int family = tob200_kernel_family(dtype_of<T>(), n);
+  int family = tob200_kernel_family(dtype_of<T>(), n);
   if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "build_solve: n is above the largest supported size (2048)");
+  if (family == 3 && ctx->lg_exact) family = 4;  // tob200_set_exact(ctx, 2): the bit-exact general family
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   int rc = to_native_layout<T>(ctx, family, layout, B, m, n, &J, &r);
   if (rc != TOB200_OK) return rc;
@@ -791,6 +793,7 @@ int lm_run_impl(tob200_ctx *ctx, const tob200_options *opt, const T *A, const T 
   int family = tob200_kernel_family(dtype_of<T>(), n);
   if (family == 0) return fail(ctx, TOB200_ERR_UNSUPPORTED, "lm_run: n is above the largest supported size (2048)");
   if (!opt->use_ldlt && family == 3) family = 4;  // hessian.use_ldlt = false (H.inverse()): the general family's LU
+  if (family == 3 && ctx->lg_exact) family = 4;   // tob200_set_exact(ctx, 2): the bit-exact general family
   if (record_events) CK(cudaEventRecord(ctx->ev0, ctx->stream));
   if ((rc = to_native_layout<T>(ctx, family, layout, B, m, n, &A, &y)) != TOB200_OK) return rc;
   if (!opt->save_last) final_hessian = nullptr;  // options.h:66 (hessian.save_last)
@@ -1276,6 +1279,7 @@ int tob200_create(tob200_ctx **out, int device, void *stream) {
   ctx->lg_tf32_terms = env_int("TOB200_LG_TF32_TERMS", ctx->lg_tf32_terms) == 1 ? 1 : 3;
   ctx->lg_fp16 = (env_int("TOB200_LG_FP16", 1) != 0 && ctx->lg_tf32_terms == 3) ? 1 : 0;
   ctx->lg_mc = env_int("TOB200_LG_MC", 0);
+  ctx->lg_exact = env_int("TOB200_LG_EXACT", 0);
   ctx->lg_raw_stages = env_int("TOB200_LG_RAW_STAGES", kLgRawStages);  // 2..5 measured equal on C5 (12.43 .. 12.57 ms): not the limiter
   if (ctx->lg_raw_stages < 2) ctx->lg_raw_stages = 2;
   if (ctx->lg_raw_stages > 6) ctx->lg_raw_stages = 6;
@@ -1330,6 +1334,7 @@ int64_t tob200_launch_count(const tob200_ctx *ctx) { return ctx ? ctx->launches 
 int tob200_set_exact(tob200_ctx *ctx, int exact) {
   if (!ctx) return fail(nullptr, TOB200_ERR_INVALID, "ctx is NULL");
   ctx->wpp_tc = exact ? 0 : 1;
+  ctx->lg_exact = exact >= 2 ? 1 : 0;
   return TOB200_OK;
 }
 
