@@ -409,6 +409,7 @@ int main() {
     test_family_equivalence<float>(ctx, 12, 40);
     test_family_equivalence<float>(ctx, 20, 64);    // warp-per-problem family behind the same SolverType seam
     test_family_equivalence<double>(ctx, 30, 90);
+    test_family_equivalence<double>(ctx, 64, 150);  // above n = 55: the general family behind the seam and behind lm_run
     test_accumulation_contract(ctx);
     test_multi_device();
     test_misuse(ctx);
