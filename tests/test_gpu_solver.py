@@ -551,3 +551,86 @@ def test_hg_sparse_reference_case(ctx, dtype, n):
     assert (res["stop_reason"] > 0).all()
     assert abs(x.min() - 0.2) < 1e-5 and abs(x.max() - 0.2) < 1e-5
     assert_hg_parity(x, res, oracle_hg(x0, acc, kw, npdt))
+
+
+# ---- tob200_solver_step_cost: the Cost is what the caller's accumulation functor returns (diff/num_diff.h:284-309) ----
+def test_step_cost_numdiff_host_lambda(ctx):
+    """`CreateNumDiffFunc2(x, residuals)` handed to the optimizer, with the residuals as a HOST lambda (numpy, float): an
+    exponential fit r_i = a exp(b t_i) + c - y_i, J from central differences with h = FloatEpsilon<float> = 1e-4f
+    (diff/num_diff.h:57-126), grad = J^T r, H = J^T J, Cost(res.norm(), res.size()) (:305).  The device gets J, r and that
+    cost (tob200_solver_step_cost_f32, general family); the oracle runs the same lambda, its g / H formed with the
+    canonical fma chains (float fma emulated exactly in double).  Bit for bit."""
+    import tinyopt_b200 as tb
+    f32 = np.float32
+    B, n, m = 6, 3, 24
+    rng = np.random.default_rng(5)
+    t = np.linspace(0, 1, m).astype(f32)
+    truth = np.stack([rng.uniform(0.5, 2.0, B), rng.uniform(-1.5, 1.0, B), rng.uniform(-0.5, 0.5, B)], 1).astype(f32)
+    yv = (truth[:, 0:1] * np.exp(truth[:, 1:2] * t) + truth[:, 2:3] + 0.01 * rng.standard_normal((B, m))).astype(f32)
+    x0 = (truth + 0.2 * rng.uniform(-1, 1, (B, n))).astype(f32)
+    h = f32(1e-4)
+
+    def res(p, x):
+        return (f32(x[0]) * np.exp(f32(x[1]) * t).astype(f32) + f32(x[2]) - yv[p]).astype(f32)
+
+    def numeval(p, x):   # NumEval, Method::kCentral
+        x = x.astype(f32)
+        r = res(p, x)
+        J = np.zeros((m, n), f32)
+        for k in range(n):
+            yp = x.copy(); yp[k] = f32(x[k] + h)
+            ym = x.copy(); ym[k] = f32(x[k] + f32(-h))
+            J[:, k] = ((res(p, yp) - res(p, ym)).astype(f32) / f32(f32(2) * h)).astype(f32)
+        return r, J
+
+    def fma32(a, b, c):
+        return f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    def norm32(r):
+        c = f32(0)
+        for v in r:
+            c = fma32(v, v, c)
+        return float(np.sqrt(c, dtype=f32))
+
+    kw = dict(min_rerr_dec=1e-5, min_step_norm2=1e-9)
+    s = tb.BatchSolver(ctx, B, n, torch.float32, tb.options(**kw), general=True)
+    s.reset(torch.from_numpy(x0).cuda())
+    steps = 0
+    while s.num_active() > 0 and steps < 100:
+        x = s.x.cpu().numpy()
+        r = np.zeros((B, m), f32); J = np.zeros((B, m, n), f32); c = np.zeros(B)
+        for p in range(B):
+            r[p], J[p] = numeval(p, x[p])
+            c[p] = norm32(r[p])
+        s.step(torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda(), layout=tb.PROBLEM_MAJOR, cost=torch.from_numpy(c))
+        steps += 1
+    resu = s.results()
+    xg = s.x.cpu().numpy()
+    s.close()
+    # a small-n solver without the flag refuses the cost override (the fused step kernels form r^T r themselves)
+    s2 = tb.BatchSolver(ctx, B, n, torch.float32, tb.options(**kw))
+    s2.reset(torch.from_numpy(x0).cuda())
+    with pytest.raises(RuntimeError):
+        s2.step(torch.from_numpy(J).cuda(), torch.from_numpy(r).cuda(), layout=tb.PROBLEM_MAJOR, cost=torch.from_numpy(c))
+    s2.close()
+    for p in range(B):
+        def acc(xv, g, H, p=p):
+            r_, J_ = numeval(p, xv)
+            if g is not None:
+                for j in range(n):
+                    gj = f32(0)
+                    for i in range(m):
+                        gj = fma32(J_[i, j], r_[i], gj)
+                    g[j] = gj
+                    for k in range(j, n):
+                        hjk = f32(0)
+                        for i in range(m):
+                            hjk = fma32(J_[i, j], J_[i, k], hjk)
+                        H[j, k] = hjk
+                        H[k, j] = hjk
+            return norm32(r_), m
+        o = O.optimize(x0[p], acc, O.default_options(**kw), dtype=f32)
+        assert resu["num_iters"][p] == o.num_iters and resu["stop_reason"][p] == o.stop_reason, (p, resu["num_iters"][p], o.num_iters)
+        assert np.array_equal(xg[p], o.x), (p, xg[p], o.x)
+        assert resu["final_cost"][p] == o.final_cost and resu["final_num_residuals"][p] == m
+        assert o.stop_reason > 0 and np.abs(o.x - truth[p]).max() < 0.3
