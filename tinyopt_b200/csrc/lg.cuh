@@ -51,7 +51,10 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
   float *wbuf = xs + lg_np(n);
   float *sbuf = wbuf + 16;
   float *cbuf = sbuf + 16;
-  float *stages = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(cbuf + 16) + 127) & ~(uintptr_t)127);
+  // (an OFFSET rounded up, not the address: a pointer that went through an integer keeps no address space and every read of
+  //  a stage became a generic LD, scoreboarded like a global access, instead of an LDS)
+  const size_t stage_off = ((size_t)(reinterpret_cast<unsigned char *>(cbuf + 16) - smem) + 127) & ~(size_t)127;
+  float *stages = reinterpret_cast<float *>(smem + stage_off);
   const uint32_t stage_elems = (uint32_t)kLgEvalRows * n;
   if (tid == 0) {
     for (int s = 0; s < kLgEvalStages; ++s) mbar_init(&bars[s], 1);
