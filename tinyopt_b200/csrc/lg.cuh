@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
     float cacc = 0.f;   // lane 0 of warp w: sum of r_i^2 over its rows
     for (int c = 0; c < nchunks; ++c, ++it) {
       const uint32_t st = it % kLgEvalStages, ph = (it / kLgEvalStages) & 1u;
+      const int row = c * kLgEvalRows + warp;
+      const float yrow = (row < m && p.y) ? yp[row] : 0.f;  // in flight while the chunk lands
       mbar_wait(&bars[st], ph);
       const float *sa = stages + (size_t)st * stage_elems;
-      const int row = c * kLgEvalRows + warp;
       // ---- warp = row: t_i, r_i, s_i ----
       if (row < m) {
         float ri, sc = 1.f;
@@ -113,10 +114,10 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, off));
           const float t2 = __fmul_rn(t, t);
-          ri = __fmaf_rn(t, __fmaf_rn(p.alpha, t2, 1.f), -yp[row]);
+          ri = __fmaf_rn(t, __fmaf_rn(p.alpha, t2, 1.f), -yrow);
           sc = __fmaf_rn(p.alpha3, t2, 1.f);
         } else {
-          ri = p.y ? yp[row] : 0.f;
+          ri = yrow;
           if (p.scale_in) sc = p.scale_in[(size_t)pr * m + row];
         }
         if (lane == 0) {
@@ -144,15 +145,28 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
           sv[4 * q] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
         }
         const float *ap = sa + tid;
+        if (nrows == kLgEvalRows) {  // every chunk but the last: no per-row guard, the sixteen loads issue back to back
+          float av[kLgEvalRows];
 #pragma unroll
-        for (int i = 0; i < kLgEvalRows; ++i) {
-          if (i >= nrows) break;  // (rows the TMA did not write may hold anything)
-          const float a = *ap;
-          ap += n;
-          gacc = __fmaf_rn(a, wv[i], gacc);
-          const float jv = __fmul_rn(sv[i], a);
-          dacc = __fmaf_rn(jv, jv, dacc);
-          amx = fmaxf(amx, fabsf(jv));
+          for (int i = 0; i < kLgEvalRows; ++i) av[i] = ap[(size_t)i * n];
+#pragma unroll
+          for (int i = 0; i < kLgEvalRows; ++i) {
+            gacc = __fmaf_rn(av[i], wv[i], gacc);
+            const float jv = __fmul_rn(sv[i], av[i]);
+            dacc = __fmaf_rn(jv, jv, dacc);
+            amx = fmaxf(amx, fabsf(jv));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kLgEvalRows; ++i) {
+            if (i >= nrows) break;  // (rows the TMA did not write may hold anything)
+            const float a = *ap;
+            ap += n;
+            gacc = __fmaf_rn(a, wv[i], gacc);
+            const float jv = __fmul_rn(sv[i], a);
+            dacc = __fmaf_rn(jv, jv, dacc);
+            amx = fmaxf(amx, fabsf(jv));
+          }
         }
       }
       __syncthreads();  // the stage and wbuf are free again
