@@ -48,9 +48,9 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
   const int n = p.n, m = p.m;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
   float *xs = reinterpret_cast<float *>(smem + 64);
-  float *wbuf = xs + lg_np(n);
-  float *sbuf = wbuf + 16;
-  float *cbuf = sbuf + 16;
+  float *wbuf2 = xs + lg_np(n);  // [2][16] row weights s_i r_i, double buffered: ONE barrier per chunk (below)
+  float *sbuf2 = wbuf2 + 32;     // [2][16] row scales s_i
+  float *cbuf = sbuf2 + 32;
   // (an OFFSET rounded up, not the address: a pointer that went through an integer keeps no address space and every read of
   //  a stage became a generic LD, scoreboarded like a global access, instead of an LDS)
   const size_t stage_off = ((size_t)(reinterpret_cast<unsigned char *>(cbuf + 16) - smem) + 127) & ~(size_t)127;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
       const float yrow = (row < m && p.y) ? yp[row] : 0.f;  // in flight while the chunk lands
       mbar_wait(&bars[st], ph);
       const float *sa = stages + (size_t)st * stage_elems;
+      float *wbuf = wbuf2 + 16 * (c & 1), *sbuf = sbuf2 + 16 * (c & 1);
       // ---- warp = row: t_i, r_i, s_i ----
       if (row < m) {
         float ri, sc = 1.f;
@@ -130,7 +131,15 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
         wbuf[warp] = 0.f;
         sbuf[warp] = 0.f;
       }
+      // The only barrier of the chunk: this chunk's row weights are visible, and every thread is through the column
+      // pass of the chunk before - whose stage can be refilled now, and whose weight buffer the NEXT row pass may
+      // overwrite (the weights alternate between two buffers, so the row pass of chunk c + 1 runs beside the column
+      // pass of chunk c).
       __syncthreads();
+      if (tid == 0 && c >= 1 && c - 1 + kLgEvalStages < nchunks) {
+        fence_proxy_async();
+        issue(c - 1 + kLgEvalStages, (it - 1) % kLgEvalStages);
+      }
       // ---- thread = column: g_j += sum_i (s_i r_i) a_ij, rows in order ----
       if (rebuild && tid < n) {
         // (the kernel issues ~60 % of its cycles: the per-row weights come in as four 16-byte broadcast loads each,
@@ -169,12 +178,9 @@ __global__ void __launch_bounds__(kLgEvalThreads, 2) lg_eval_kernel(const __grid
           }
         }
       }
-      __syncthreads();  // the stage and wbuf are free again
-      if (tid == 0 && c + kLgEvalStages < nchunks) {
-        fence_proxy_async();
-        issue(c + kLgEvalStages, st);
-      }
     }
+    __syncthreads();  // the last column pass is through: the stages and both weight buffers are free
+    float *wbuf = wbuf2;
     if (rebuild && tid < n) {
       p.g[(size_t)pr * n + tid] = gacc;
       if (p.dg) p.dg[(size_t)pr * n + tid] = dacc;

@@ -37,8 +37,8 @@ struct LgEvalParams {
 };
 
 __host__ __device__ inline size_t lg_eval_smem_bytes(int n) {
-  // [bars 64 | x n | w 16 | s 16 | cost 16 | stages * 16 rows * n]
-  return 64 + (size_t)lg_np(n) * 4 + 3 * 64 + (size_t)kLgEvalStages * kLgEvalRows * n * 4 + 128;
+  // [bars 64 | x n | w 2 x 16 | s 2 x 16 | cost 16 | stages * 16 rows * n]
+  return 64 + (size_t)lg_np(n) * 4 + 5 * 64 + (size_t)kLgEvalStages * kLgEvalRows * n * 4 + 128;
 }
 
 constexpr int kLgEpiWarps = 4;    // warps 0..3: TMEM lane quadrant == warp id
