@@ -477,3 +477,64 @@ def test_inverse_path_guard_and_singular_system():
     assert bad.stop_reason == K["kSystemHasNaNOrInf"]
     good = O.optimize(np.array([1.0, 1.0]), rank1, O.default_options())
     assert good.Converged() and good.x[0] == pytest.approx(2.0, abs=1e-6) and good.x[1] == 1.0
+
+
+# ---- diff/num_diff.h: numeric differentiation handed to the optimizer ---------------------------------------------------
+def _create_numdiff_func2(residuals, method="central", h=None, dtype=np.float64):
+    """`CreateNumDiffFunc2(x, residuals, method, h)` (diff/num_diff.h:284-309) over `NumEval` (:57-126) as an accumulation
+    lambda for O.optimize: J column by column from f(x + h e_r) and f(x - h e_r) (kCentral), (f(x + h e_r) - f(x)) / h
+    (kForward) or the second point at (x_r + h) - 2h (kFastCentral); grad = J^T res, H = J^T J;
+    Cost(res.norm(), res.size()) - the NORM.  h defaults to FloatEpsilon (math.h:297-301)."""
+    T = np.dtype(dtype).type
+    h = T(np.float32(1e-7 if dtype == np.float64 else 1e-4)) if h is None else T(h)
+
+    def acc(x, g, H):
+        x = np.asarray(x, dtype)
+        res = np.atleast_1d(residuals(x)).astype(dtype)
+        if g is not None:
+            J = np.zeros((res.size, x.size), dtype)
+            for r in range(x.size):
+                y = x.copy(); y[r] = T(x[r] + h)
+                rp = np.atleast_1d(residuals(y)).astype(dtype)
+                if method == "forward":
+                    J[:, r] = (rp - res) / h
+                else:
+                    if method == "central":
+                        y = x.copy(); y[r] = T(x[r] + T(-h))
+                    else:
+                        y[r] = T(y[r] + T(-2) * h)
+                    rm = np.atleast_1d(residuals(y)).astype(dtype)
+                    J[:, r] = (rp - rm) / (T(2) * h)
+            g[:] = J.T @ res
+            H[:, :] = J.T @ J
+        return float(np.sqrt((res * res).sum(dtype=dtype))), int(res.size)
+    return acc
+
+
+def test_numdiff_gradient_matches_reference_assertions():
+    """tests/diff.cpp:59-86 `TestCreateNumDiffFunc2`: loss = 2 (x - y_prior) at x = 0: g == 2 res (+-1e-5), for a
+    random prior; the scalar float case r = x - 2: g == res (+-1e-3)."""
+    rng = np.random.default_rng(3)
+    yp = rng.uniform(-1, 1, 3)
+    acc = _create_numdiff_func2(lambda x: 2 * (x - yp))
+    g = np.zeros(3); H = np.zeros((3, 3))
+    cost, nres = acc(np.zeros(3), g, H)
+    res = 2 * (np.zeros(3) - yp)
+    assert np.abs(g - 2 * res).max() < 1e-5 and nres == 3
+    assert abs(cost - np.linalg.norm(res)) < 1e-12          # the NORM, not its square (num_diff.h:305)
+    assert np.abs(H - 4 * np.eye(3)).max() < 1e-5
+    accf = _create_numdiff_func2(lambda x: x - np.float32(2), dtype=np.float32)
+    g1 = np.zeros(1, np.float32); H1 = np.zeros((1, 1), np.float32)
+    accf(np.zeros(1, np.float32), g1, H1)
+    assert abs(g1[0] - (-2.0)) < 1e-3
+
+
+@pytest.mark.parametrize("method", ["central", "forward", "fast"])
+def test_numdiff_optimizer_converges(method):
+    """tests/optimizers.cpp:100-120: loss = x - y_prior, y_prior = (3, 2, 1), x0 = 0, `CreateNumDiffFunc2` handed to
+    `Optimizer_<SolverLM<Mat3>>`: Succeeded and Converged (and it lands on the prior)."""
+    yp = np.array([3.0, 2.0, 1.0])
+    o = O.optimize(np.zeros(3), _create_numdiff_func2(lambda x: x - yp, method), O.default_options())
+    assert o.stop_reason > 0                                  # Succeeded() && Converged()
+    assert np.abs(o.x - yp).max() < 1e-5
+    assert o.final_cost < 1e-5 and o.num_iters <= 10
