@@ -538,3 +538,26 @@ def test_numdiff_optimizer_converges(method):
     assert o.stop_reason > 0                                  # Succeeded() && Converged()
     assert np.abs(o.x - yp).max() < 1e-5
     assert o.final_cost < 1e-5 and o.num_iters <= 10
+
+
+def test_sparse_reference_case_through_the_dense_restatement():
+    """tests/sparse.cpp:19-57 "tinyopt_sparse": res = 10 x - 2 over 100 parameters, H = J^T J (diagonal, handed over as a
+    sparse matrix in the reference), Cost(res.norm(), res.size()), check_final_cost = false.  The product solves the
+    scattered triplets with the dense pivoted LDLT (tob200_solver_step_hg_sparse_*); for this positive definite H that is
+    the sparse factorisation's answer: the reference's assertions hold for the dense restatement (Succeeded, Converged,
+    min / max of x == 0.2 +- 1e-5)."""
+    rng = np.random.default_rng(11)
+    n = 100
+    x0 = rng.uniform(-1, 1, n)
+
+    def acc(x, g, H):
+        res = 10 * x - 2.0
+        if g is not None:
+            g[:] = 10 * res
+            H[:, :] = 0
+            H[np.arange(n), np.arange(n)] = 100.0
+        return float(np.linalg.norm(res)), n
+
+    o = O.optimize(x0, acc, O.default_options(check_final_cost=0))
+    assert o.stop_reason > 0
+    assert abs(o.x.min() - 0.2) < 1e-5 and abs(o.x.max() - 0.2) < 1e-5
